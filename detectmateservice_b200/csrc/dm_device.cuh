@@ -1,0 +1,93 @@
+// dm_device.cuh -- device-side data structures and helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dmdetect.h"
+#include "dm_hash.h"
+
+#define DM_STATS_WORDS (8 + DM_MAX_KEYS)   // layout of dm_stats_t as uint64 words
+
+// Monitored keys, as the kernels see them (copied to shared memory per CTA).
+struct DmKeys {
+    uint32_t n;
+    uint32_t len[DM_MAX_KEYS];
+    uint64_t salt[DM_MAX_KEYS];
+    uint8_t bytes[DM_MAX_KEYS][DM_MAX_KEYLEN];
+};
+
+// Per-batch header written by the kernels, read back by the host.
+struct DmBatchHeader {
+    unsigned long long n_newlines;
+    unsigned long long n_lines;        // records in the batch (R-tok L1)
+    unsigned long long n_anomalies;    // records with score > 0
+    unsigned int anomaly_list_count;   // entries appended to the anomaly list (may exceed cap)
+    unsigned int error;                // DM_DEVERR_* bits
+};
+
+#define DM_DEVERR_TABLE_FULL 1u
+#define DM_DEVERR_TOO_MANY_LINES 2u
+#define DM_DEVERR_NOVEL_OVERFLOW 4u
+
+// Known-set table: open addressing, linear probing, 0 = empty slot.
+struct DmTable {
+    unsigned long long* slots;
+    uint32_t mask;                     // capacity - 1
+    uint32_t limit;                    // max entries (load limit)
+    unsigned long long* count;         // entries
+    unsigned long long* novel;         // keys inserted since creation, in insertion order
+    unsigned long long* novel_count;
+    uint32_t novel_cap;
+};
+
+__device__ __forceinline__ uint32_t dm_slot_of(uint64_t key, uint32_t mask) {
+    return ((uint32_t)key ^ (uint32_t)(key >> 32)) & mask;
+}
+
+__device__ __forceinline__ bool dm_table_contains(const DmTable& t, uint64_t key) {
+    uint32_t i = dm_slot_of(key, t.mask);
+    for (uint32_t probes = 0; probes <= t.mask; ++probes) {
+        unsigned long long v = __ldg(t.slots + i);
+        if (v == key) return true;
+        if (v == 0ull) return false;
+        i = (i + 1) & t.mask;
+    }
+    return false;
+}
+
+// Returns true if this call inserted the key (it was not present).
+__device__ __forceinline__ bool dm_table_insert(const DmTable& t, uint64_t key, unsigned int* err) {
+    uint32_t i = dm_slot_of(key, t.mask);
+    for (uint32_t probes = 0; probes <= t.mask; ++probes) {
+        unsigned long long v = atomicCAS(t.slots + i, 0ull, (unsigned long long)key);
+        if (v == 0ull) {
+            unsigned long long c = atomicAdd(t.count, 1ull);
+            if (c + 1 > t.limit) atomicOr(err, DM_DEVERR_TABLE_FULL);
+            unsigned long long j = atomicAdd(t.novel_count, 1ull);
+            if (j < t.novel_cap) t.novel[j] = key; else atomicOr(err, DM_DEVERR_NOVEL_OVERFLOW);
+            return true;
+        }
+        if (v == key) return false;
+        i = (i + 1) & t.mask;
+    }
+    atomicOr(err, DM_DEVERR_TABLE_FULL);
+    return false;
+}
+
+// 4-bit mask of the bytes of w equal to the replicated byte pattern pat (bit j = byte j).
+__device__ __forceinline__ uint32_t dm_nib_eq(uint32_t w, uint32_t pat) {
+    uint32_t m = __vcmpeq4(w, pat) & 0x08040201u;
+    return (m * 0x01010101u) >> 24;
+}
+
+// 16-bit mask over a 16-byte chunk.
+__device__ __forceinline__ uint32_t dm_mask16_eq(uint4 v, uint32_t pat) {
+    return dm_nib_eq(v.x, pat) | (dm_nib_eq(v.y, pat) << 4) | (dm_nib_eq(v.z, pat) << 8) |
+           (dm_nib_eq(v.w, pat) << 12);
+}
+
+__device__ __forceinline__ uint32_t dm_lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}

@@ -1,0 +1,546 @@
+// dmdetect.cu -- host side of libdmdetect.so: the C ABI of include/dmdetect.h.
+//
+// Replaces, for one message of raw records, the Python call chain
+//   Service.process -> CoreComponent.process -> NewValueDetector.train/detect
+// (/root/reference/src/service/core.py:176-206; detector in the un-vendored
+// detectmatelibrary).  No CPU path: every entry point that computes needs the device.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "dm_device.cuh"
+#include "dm_kernels_v1.cuh"
+#include "dm_kernels_tile.cuh"
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int dm_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DM_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return dm_fail(DM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                           __FILE__, __LINE__);                                               \
+    } while (0)
+
+extern "C" const char* dm_last_error(void) { return g_err; }
+extern "C" int dm_abi_version(void) { return DM_ABI_VERSION; }
+
+extern "C" uint64_t dm_table_key(uint32_t field, const uint8_t* value, uint32_t len) {
+    return dm_make_key(dm_fp64_bytes(value, len), dm_field_salt(field));
+}
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+struct dm_handle {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;       // the handle's own stream
+    cudaStream_t last_stream = nullptr;  // stream of the most recent enqueue
+    uint64_t max_batch_bytes = 0, max_lines = 0;
+    uint32_t table_log2 = 0;
+    uint32_t n_keys = 0;
+    int kernel_variant = 0;              // 0 = v1 (line index + warp per record), 1 = fused tile kernel
+
+    DmKeys h_keys;
+    DmKeys* d_keys = nullptr;
+    uint8_t* d_in = nullptr;             // staging for host input
+    uint32_t* d_tile_counts = nullptr;
+    uint32_t* d_tile_base = nullptr;
+    uint32_t* d_line_start = nullptr;
+    uint8_t* d_flags = nullptr;
+    float* d_scores = nullptr;
+    DmBatchHeader* d_hdr = nullptr;
+    DmBatchHeader* h_hdr = nullptr;      // pinned
+    dm_anomaly_t* d_anoms = nullptr;
+    uint32_t anomaly_cap = 0;
+    unsigned long long* d_stats = nullptr;         // DM_STATS_WORDS
+    unsigned long long* d_stats_exported = nullptr;
+    unsigned long long* d_stats_global = nullptr;
+    unsigned long long* h_stats = nullptr;         // pinned
+    DmTable table;
+    uint64_t novel_exported = 0;         // novel keys already shipped in a window
+    DmTileScratch tile;                  // fused-kernel scratch
+    uint64_t last_nbytes = 0;
+    // measurement support
+    bool profile = false;
+    std::vector<cudaEvent_t> ev;         // pairs: ev[2i] start, ev[2i+1] stop
+    size_t ev_used = 0;
+    uint64_t launches = 0;               // kernels launched since dm_create
+};
+
+static const size_t DM_PROFILE_PAIRS = 4096;
+
+static void dm_prof_mark(dm_handle* h, cudaStream_t st, int which) {
+    if (!h->profile || h->ev_used / 2 >= DM_PROFILE_PAIRS) return;
+    if (which == 0 && (h->ev_used & 1)) return;
+    if (which == 1 && !(h->ev_used & 1)) return;
+    cudaEventRecord(h->ev[h->ev_used], st);
+    h->ev_used++;
+}
+
+static const uint32_t DM_WINDOW_KEYS = 1u << 16;    // keys one rank can ship per window
+
+static int dm_pick_stream(dm_handle* h, void* stream, cudaStream_t* out) {
+    *out = stream ? (cudaStream_t)stream : h->stream;
+    h->last_stream = *out;
+    return DM_OK;
+}
+
+extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, const uint32_t* key_lens,
+                         uint64_t max_batch_bytes, uint64_t max_lines, uint32_t table_log2_slots,
+                         dm_handle** out) {
+    if (!out) return dm_fail(DM_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_keys > DM_MAX_KEYS) return dm_fail(DM_ERR_ARG, "n_keys %u > %d", n_keys, DM_MAX_KEYS);
+    if (n_keys && (!keys_blob || !key_lens)) return dm_fail(DM_ERR_ARG, "keys missing");
+    if (max_batch_bytes == 0 || max_batch_bytes > 0xFFFFFF00ull)
+        return dm_fail(DM_ERR_ARG, "max_batch_bytes must be in 1..2^32-256");
+    if (table_log2_slots < 10 || table_log2_slots > 28)
+        return dm_fail(DM_ERR_ARG, "table_log2_slots must be in 10..28");
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev <= 0)
+        return dm_fail(DM_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path",
+                       ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    if (device < 0 || device >= n_dev) return dm_fail(DM_ERR_ARG, "device %d out of range (0..%d)", device, n_dev - 1);
+    cudaDeviceProp prop;
+    DM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return dm_fail(DM_ERR_NO_DEVICE, "device %d is sm_%d%d; libdmdetect is built for sm_100a only", device,
+                       prop.major, prop.minor);
+    DM_CUDA(cudaSetDevice(device));
+
+    dm_handle* h = new (std::nothrow) dm_handle();
+    if (!h) return dm_fail(DM_ERR_ARG, "out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->max_batch_bytes = max_batch_bytes;
+    h->max_lines = max_lines ? max_lines : std::max<uint64_t>(max_batch_bytes / 8, 1024);
+    h->table_log2 = table_log2_slots;
+    h->n_keys = n_keys;
+    memset(&h->h_keys, 0, sizeof(DmKeys));
+    h->h_keys.n = n_keys;
+    uint64_t off = 0;
+    for (uint32_t k = 0; k < n_keys; ++k) {
+        uint32_t len = key_lens[k];
+        if (len == 0 || len > DM_MAX_KEYLEN) { delete h; return dm_fail(DM_ERR_ARG, "key %u: length %u not in 1..%d", k, len, DM_MAX_KEYLEN); }
+        for (uint32_t i = 0; i < len; ++i) {
+            uint8_t c = keys_blob[off + i];
+            if (c == 0x20 || c == 0x22 || c == 0x27 || c == 0x3D || c == 0x0A) { delete h; return dm_fail(DM_ERR_ARG, "key %u holds a separator byte 0x%02x", k, c); }
+            h->h_keys.bytes[k][i] = c;
+        }
+        for (uint32_t j = 0; j < k; ++j)
+            if (h->h_keys.len[j] == len && memcmp(h->h_keys.bytes[j], h->h_keys.bytes[k], len) == 0) { delete h; return dm_fail(DM_ERR_ARG, "key %u duplicates key %u", k, j); }
+        h->h_keys.len[k] = len;
+        h->h_keys.salt[k] = dm_field_salt(k);
+        off += len;
+    }
+
+    DM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->last_stream = h->stream;
+    const uint64_t n_tiles_max = (max_batch_bytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES + 1;
+    DM_CUDA(cudaMalloc(&h->d_keys, sizeof(DmKeys)));
+    DM_CUDA(cudaMemcpy(h->d_keys, &h->h_keys, sizeof(DmKeys), cudaMemcpyHostToDevice));
+    DM_CUDA(cudaMalloc(&h->d_in, max_batch_bytes + 256));
+    DM_CUDA(cudaMemset(h->d_in, 0, max_batch_bytes + 256));
+    DM_CUDA(cudaMalloc(&h->d_tile_counts, n_tiles_max * sizeof(uint32_t)));
+    DM_CUDA(cudaMalloc(&h->d_tile_base, n_tiles_max * sizeof(uint32_t)));
+    DM_CUDA(cudaMalloc(&h->d_line_start, (h->max_lines + 2) * sizeof(uint32_t)));
+    DM_CUDA(cudaMalloc(&h->d_flags, h->max_lines + 16));
+    DM_CUDA(cudaMalloc(&h->d_scores, (h->max_lines + 4) * sizeof(float)));
+    DM_CUDA(cudaMalloc(&h->d_hdr, sizeof(DmBatchHeader)));
+    DM_CUDA(cudaMemset(h->d_hdr, 0, sizeof(DmBatchHeader)));
+    DM_CUDA(cudaHostAlloc(&h->h_hdr, sizeof(DmBatchHeader), cudaHostAllocDefault));
+    memset(h->h_hdr, 0, sizeof(DmBatchHeader));
+    h->anomaly_cap = (uint32_t)std::min<uint64_t>(h->max_lines, 1u << 20);
+    DM_CUDA(cudaMalloc(&h->d_anoms, (uint64_t)h->anomaly_cap * sizeof(dm_anomaly_t)));
+    DM_CUDA(cudaMalloc(&h->d_stats, 3 * DM_STATS_WORDS * sizeof(unsigned long long)));
+    DM_CUDA(cudaMemset(h->d_stats, 0, 3 * DM_STATS_WORDS * sizeof(unsigned long long)));
+    h->d_stats_exported = h->d_stats + DM_STATS_WORDS;
+    h->d_stats_global = h->d_stats + 2 * DM_STATS_WORDS;
+    DM_CUDA(cudaHostAlloc(&h->h_stats, DM_STATS_WORDS * sizeof(unsigned long long), cudaHostAllocDefault));
+
+    const uint64_t cap = 1ull << table_log2_slots;
+    h->table.mask = (uint32_t)(cap - 1);
+    h->table.limit = (uint32_t)(cap / 2);
+    h->table.novel_cap = (uint32_t)(cap / 2);
+    DM_CUDA(cudaMalloc(&h->table.slots, cap * sizeof(unsigned long long)));
+    DM_CUDA(cudaMemset(h->table.slots, 0, cap * sizeof(unsigned long long)));
+    DM_CUDA(cudaMalloc(&h->table.novel, (cap / 2) * sizeof(unsigned long long)));
+    DM_CUDA(cudaMalloc(&h->table.count, 2 * sizeof(unsigned long long)));
+    DM_CUDA(cudaMemset(h->table.count, 0, 2 * sizeof(unsigned long long)));
+    h->table.novel_count = h->table.count + 1;
+
+    int rc = dm_tile_scratch_create(&h->tile, max_batch_bytes, h->sm_count);
+    if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "tile scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    const char* env = getenv("DM_KERNEL");
+    if (env && strcmp(env, "v1") == 0) h->kernel_variant = 0;
+    if (env && strcmp(env, "tile") == 0) h->kernel_variant = 1;
+    DM_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return DM_OK;
+}
+
+extern "C" int dm_profile_enable(dm_handle* h, int on) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    DM_CUDA(cudaSetDevice(h->device));
+    if (on && h->ev.empty()) {
+        h->ev.resize(2 * DM_PROFILE_PAIRS);
+        for (auto& e : h->ev) DM_CUDA(cudaEventCreate(&e));
+    }
+    h->profile = on != 0;
+    h->ev_used = 0;
+    return DM_OK;
+}
+
+extern "C" int dm_profile_read(dm_handle* h, double* kernel_ms_sum, uint64_t* n_timed, uint64_t* kernels_launched_total) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    double sum = 0.0;
+    const size_t pairs = h->ev_used / 2;
+    for (size_t i = 0; i < pairs; ++i) {
+        float ms = 0.f;
+        DM_CUDA(cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]));
+        sum += ms;
+    }
+    h->ev_used = 0;
+    if (kernel_ms_sum) *kernel_ms_sum = sum;
+    if (n_timed) *n_timed = pairs;
+    if (kernels_launched_total) *kernels_launched_total = h->launches;
+    return DM_OK;
+}
+
+extern "C" int dm_destroy(dm_handle* h) {
+    if (!h) return DM_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& e : h->ev) cudaEventDestroy(e);
+    dm_tile_scratch_destroy(&h->tile);
+    cudaFree(h->d_keys); cudaFree(h->d_in); cudaFree(h->d_tile_counts); cudaFree(h->d_tile_base);
+    cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
+    cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
+    cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return DM_OK;
+}
+
+static int dm_check_device_errors(dm_handle* h) {
+    unsigned int err = h->h_hdr->error;
+    if (err & DM_DEVERR_TABLE_FULL)
+        return dm_fail(DM_ERR_TABLE_FULL, "known-set table over its load limit (2^%u slots); recreate with a larger table_log2_slots", h->table_log2);
+    if (err & DM_DEVERR_NOVEL_OVERFLOW)
+        return dm_fail(DM_ERR_TABLE_FULL, "more than %u distinct values learnt; novel-key list full", h->table.novel_cap);
+    if (err & DM_DEVERR_TOO_MANY_LINES)
+        return dm_fail(DM_ERR_CAPACITY, "batch holds more than max_lines=%llu records", (unsigned long long)h->max_lines);
+    return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------------------
+extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbytes, int buf_on_device,
+                                uint64_t n_train_lines, uint8_t* flags_out, float* scores_out,
+                                uint64_t out_cap_lines, int out_on_device, uint64_t* n_lines_out,
+                                uint64_t* n_anomalies_out, void* stream_) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    if (nbytes > h->max_batch_bytes)
+        return dm_fail(DM_ERR_CAPACITY, "message of %llu bytes exceeds max_batch_bytes=%llu", (unsigned long long)nbytes, (unsigned long long)h->max_batch_bytes);
+    if (nbytes && !buf) return dm_fail(DM_ERR_ARG, "buf is NULL");
+    if (buf_on_device && (((uintptr_t)buf) & 15)) return dm_fail(DM_ERR_ARG, "device buf must be 16-byte aligned");
+    DM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st;
+    dm_pick_stream(h, stream_, &st);
+
+    const uint8_t* d_buf = buf;
+    if (!buf_on_device) {
+        if (nbytes) DM_CUDA(cudaMemcpyAsync(h->d_in, buf, nbytes, cudaMemcpyHostToDevice, st));
+        DM_CUDA(cudaMemsetAsync(h->d_in + nbytes, 0, 64, st));
+        d_buf = h->d_in;
+    }
+    const bool host_out = !out_on_device && (flags_out || scores_out);
+    uint8_t* d_flags = (out_on_device && flags_out) ? flags_out : h->d_flags;
+    float* d_scores = (out_on_device && scores_out) ? scores_out : h->d_scores;
+    const uint64_t dev_cap = out_on_device ? ((flags_out || scores_out) ? out_cap_lines : h->max_lines) : h->max_lines;
+    // when only one of the two outputs is a caller device buffer the other stays internal
+    const uint64_t cap_flags = (out_on_device && flags_out) ? out_cap_lines : h->max_lines;
+    const uint64_t cap_scores = (out_on_device && scores_out) ? out_cap_lines : h->max_lines;
+    const uint64_t out_cap = std::min(cap_flags, cap_scores);
+    (void)dev_cap;
+
+    DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
+    h->last_nbytes = nbytes;
+
+    if (h->kernel_variant == 0) {
+        const uint32_t n_tiles = (uint32_t)((nbytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES);
+        const int grid_tiles = std::max(1, std::min<int>((int)n_tiles, h->sm_count * 8));
+        dm_k_count_newlines<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts);
+        dm_k_scan_tiles<<<1, 1024, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts, h->d_tile_base,
+                                             h->d_line_start, h->max_lines, n_train_lines, h->d_hdr, h->d_stats);
+        dm_k_line_starts<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_base,
+                                                                  h->d_line_start, h->max_lines);
+        DmDetectArgs a;
+        a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
+        a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
+        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats;
+        const int grid = h->sm_count * 8;
+        if (n_train_lines > 0) {
+            a.line_lo = 0; a.line_hi = n_train_lines;
+            dm_k_detect_lines<true><<<grid, 256, 0, st>>>(a);
+        }
+        a.line_lo = n_train_lines; a.line_hi = ~0ull;
+        dm_prof_mark(h, st, 0);
+        dm_k_detect_lines<false><<<grid, 256, 0, st>>>(a);
+        dm_prof_mark(h, st, 1);
+        h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
+    } else {
+        dm_prof_mark(h, st, 0);
+        const int rc = dm_tile_launch(&h->tile, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,
+                                out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st);
+        dm_prof_mark(h, st, 1);
+        if (rc < 0) return dm_fail(DM_ERR_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->launches += (uint64_t)rc;
+    }
+    DM_CUDA(cudaGetLastError());
+
+    const bool want_sync = host_out || n_lines_out || n_anomalies_out;
+    if (!want_sync) return DM_OK;
+
+    DM_CUDA(cudaMemcpyAsync(h->h_hdr, h->d_hdr, sizeof(DmBatchHeader), cudaMemcpyDeviceToHost, st));
+    DM_CUDA(cudaStreamSynchronize(st));
+    int rc = dm_check_device_errors(h);
+    if (rc != DM_OK) return rc;
+    const uint64_t n_lines = h->h_hdr->n_lines;
+    if (n_lines_out) *n_lines_out = n_lines;
+    if (n_anomalies_out) *n_anomalies_out = h->h_hdr->n_anomalies;
+    if (host_out) {
+        if (n_lines > out_cap_lines)
+            return dm_fail(DM_ERR_CAPACITY, "batch holds %llu records, output capacity is %llu", (unsigned long long)n_lines, (unsigned long long)out_cap_lines);
+        if (flags_out && n_lines) DM_CUDA(cudaMemcpyAsync(flags_out, h->d_flags, n_lines, cudaMemcpyDeviceToHost, st));
+        if (scores_out && n_lines) DM_CUDA(cudaMemcpyAsync(scores_out, h->d_scores, n_lines * sizeof(float), cudaMemcpyDeviceToHost, st));
+        DM_CUDA(cudaStreamSynchronize(st));
+    }
+    return DM_OK;
+}
+
+extern "C" int dm_sync(dm_handle* h, uint64_t* n_lines_out, uint64_t* n_anomalies_out) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaMemcpyAsync(h->h_hdr, h->d_hdr, sizeof(DmBatchHeader), cudaMemcpyDeviceToHost, h->last_stream));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    int rc = dm_check_device_errors(h);
+    if (rc != DM_OK) return rc;
+    if (n_lines_out) *n_lines_out = h->h_hdr->n_lines;
+    if (n_anomalies_out) *n_anomalies_out = h->h_hdr->n_anomalies;
+    return DM_OK;
+}
+
+extern "C" int dm_get_anomalies(dm_handle* h, dm_anomaly_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!h || !n_out) return dm_fail(DM_ERR_ARG, "NULL argument");
+    DM_CUDA(cudaSetDevice(h->device));
+    int rc = dm_sync(h, nullptr, nullptr);
+    if (rc != DM_OK) return rc;
+    const uint32_t total = h->h_hdr->anomaly_list_count;
+    *n_out = total;
+    const uint32_t have = std::min(total, h->anomaly_cap);
+    if (!out || cap == 0 || have == 0) return DM_OK;
+    std::vector<dm_anomaly_t> tmp(have);
+    DM_CUDA(cudaMemcpy(tmp.data(), h->d_anoms, (uint64_t)have * sizeof(dm_anomaly_t), cudaMemcpyDeviceToHost));
+    std::sort(tmp.begin(), tmp.end(), [](const dm_anomaly_t& a, const dm_anomaly_t& b) { return a.line < b.line; });
+    memcpy(out, tmp.data(), (uint64_t)std::min(have, cap) * sizeof(dm_anomaly_t));
+    return DM_OK;
+}
+
+static void dm_words_to_stats(const unsigned long long* w, dm_stats_t* out) {
+    out->lines = w[0]; out->train_lines = w[1]; out->detect_lines = w[2]; out->anomalies = w[3];
+    out->score_sum = w[4]; out->bytes = w[5]; out->known_keys = w[6];
+    for (int k = 0; k < DM_MAX_KEYS; ++k) out->unknown_per_key[k] = w[8 + k];
+}
+
+extern "C" int dm_get_stats(dm_handle* h, dm_stats_t* out) {
+    if (!h || !out) return dm_fail(DM_ERR_ARG, "NULL argument");
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    DM_CUDA(cudaMemcpy(h->h_stats, h->d_stats, DM_STATS_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    dm_words_to_stats(h->h_stats, out);
+    unsigned long long cnt = 0;
+    DM_CUDA(cudaMemcpy(&cnt, h->table.count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    out->known_keys = cnt;
+    return DM_OK;
+}
+
+extern "C" int dm_get_global_stats(dm_handle* h, dm_stats_t* out) {
+    if (!h || !out) return dm_fail(DM_ERR_ARG, "NULL argument");
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    DM_CUDA(cudaMemcpy(h->h_stats, h->d_stats_global, DM_STATS_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    dm_words_to_stats(h->h_stats, out);
+    return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// known-set export / import / reset
+// ---------------------------------------------------------------------------------------
+__global__ void dm_k_insert_keys(DmTable t, const unsigned long long* __restrict__ keys, uint64_t n, unsigned int* err) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long k = keys[i];
+        if (k) dm_table_insert(t, k, err);
+    }
+}
+
+extern "C" int dm_export_known(dm_handle* h, uint64_t* keys_out, uint64_t cap, uint64_t* n_out) {
+    if (!h || !n_out) return dm_fail(DM_ERR_ARG, "NULL argument");
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    unsigned long long cnt[2];
+    DM_CUDA(cudaMemcpy(cnt, h->table.count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    // the novel list holds every key in insertion order (bounded by DM_NOVEL_CAP, checked at insert)
+    const uint64_t n = std::min<uint64_t>(cnt[1], h->table.novel_cap);
+    *n_out = n;
+    if (keys_out && cap) {
+        std::vector<unsigned long long> tmp(n);
+        if (n) DM_CUDA(cudaMemcpy(tmp.data(), h->table.novel, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        std::sort(tmp.begin(), tmp.end());
+        memcpy(keys_out, tmp.data(), std::min<uint64_t>(n, cap) * sizeof(uint64_t));
+    }
+    return DM_OK;
+}
+
+extern "C" int dm_import_known(dm_handle* h, const uint64_t* keys, uint64_t n) {
+    if (!h || (n && !keys)) return dm_fail(DM_ERR_ARG, "NULL argument");
+    if (n == 0) return DM_OK;
+    DM_CUDA(cudaSetDevice(h->device));
+    unsigned long long* d_tmp = nullptr;
+    DM_CUDA(cudaMalloc(&d_tmp, n * sizeof(unsigned long long)));
+    DM_CUDA(cudaMemcpy(d_tmp, keys, n * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), h->last_stream));
+    dm_k_insert_keys<<<std::max(1, (int)std::min<uint64_t>((n + 255) / 256, 1024)), 256, 0, h->last_stream>>>(h->table, d_tmp, n, &h->d_hdr->error);
+    DM_CUDA(cudaGetLastError());
+    int rc = dm_sync(h, nullptr, nullptr);
+    cudaFree(d_tmp);
+    return rc;
+}
+
+extern "C" int dm_reset(dm_handle* h) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    DM_CUDA(cudaMemset(h->table.slots, 0, ((uint64_t)h->table.mask + 1) * sizeof(unsigned long long)));
+    DM_CUDA(cudaMemset(h->table.count, 0, 2 * sizeof(unsigned long long)));
+    DM_CUDA(cudaMemset(h->d_stats, 0, 3 * DM_STATS_WORDS * sizeof(unsigned long long)));
+    DM_CUDA(cudaMemset(h->d_hdr, 0, sizeof(DmBatchHeader)));
+    h->novel_exported = 0;
+    return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU window exchange
+//   buffer layout (uint64 words): [0, DM_STATS_WORDS) statistics delta, summed over ranks;
+//   with_keys: then per rank r a segment [count, key_0 .. key_{DM_WINDOW_KEYS-1}] that only
+//   rank r fills, so the SUM all-reduce concatenates the segments.
+// ---------------------------------------------------------------------------------------
+extern "C" uint64_t dm_window_words(dm_handle* h, uint32_t world, int with_keys) {
+    (void)h;
+    return (uint64_t)DM_STATS_WORDS + (with_keys ? (uint64_t)world * (1ull + DM_WINDOW_KEYS) : 0ull);
+}
+
+__global__ void dm_k_window_export(unsigned long long* __restrict__ out, uint64_t n_words,
+                                   unsigned long long* __restrict__ stats, unsigned long long* __restrict__ exported,
+                                   const unsigned long long* __restrict__ table_count,
+                                   const unsigned long long* __restrict__ novel, uint64_t novel_from, uint64_t novel_to,
+                                   uint64_t seg_off, int with_keys) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nth = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = tid; i < n_words; i += nth) {
+        unsigned long long v = 0;
+        if (i < DM_STATS_WORDS) {
+            unsigned long long cur = (i == 6) ? 0ull : stats[i];
+            v = cur - exported[i];
+            exported[i] = cur;
+        } else if (with_keys && i >= seg_off && i < seg_off + 1 + DM_WINDOW_KEYS) {
+            const uint64_t j = i - seg_off;
+            if (j == 0) v = novel_to - novel_from;
+            else if (novel_from + j - 1 < novel_to) v = novel[novel_from + j - 1];
+        }
+        out[i] = v;
+    }
+    (void)table_count;
+}
+
+__global__ void dm_k_window_import(const unsigned long long* __restrict__ in, uint32_t world, uint32_t self_rank,
+                                   unsigned long long* __restrict__ global_stats, DmTable t, unsigned int* err,
+                                   int with_keys) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nth = (uint64_t)gridDim.x * blockDim.x;
+    if (tid < DM_STATS_WORDS) global_stats[tid] += in[tid];
+    if (!with_keys) return;
+    for (uint32_t r = 0; r < world; ++r) {
+        if (r == self_rank) continue;            // own keys are already in the local table
+        const uint64_t seg = (uint64_t)DM_STATS_WORDS + (uint64_t)r * (1ull + DM_WINDOW_KEYS);
+        const uint64_t cnt = in[seg];
+        for (uint64_t j = tid; j < cnt && j < DM_WINDOW_KEYS; j += nth) {
+            unsigned long long k = in[seg + 1 + j];
+            if (k) dm_table_insert(t, k, err);
+        }
+    }
+}
+
+extern "C" int dm_window_export(dm_handle* h, uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream_) {
+    if (!h || !dev_buf || rank >= world) return dm_fail(DM_ERR_ARG, "bad window arguments");
+    DM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st;
+    dm_pick_stream(h, stream_, &st);
+    uint64_t novel_to = h->novel_exported;
+    if (with_keys) {
+        // the number of keys learnt so far is needed on the host to bound the segment
+        unsigned long long cnt[2];
+        DM_CUDA(cudaMemcpyAsync(cnt, h->table.count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        DM_CUDA(cudaStreamSynchronize(st));
+        novel_to = std::min<uint64_t>(cnt[1], h->table.novel_cap);
+        if (novel_to - h->novel_exported > DM_WINDOW_KEYS)
+            return dm_fail(DM_ERR_CAPACITY, "%llu keys learnt in one window, at most %u can be exchanged; shorten the training window",
+                           (unsigned long long)(novel_to - h->novel_exported), DM_WINDOW_KEYS);
+    }
+    const uint64_t n_words = dm_window_words(h, world, with_keys);
+    const uint64_t seg_off = (uint64_t)DM_STATS_WORDS + (uint64_t)rank * (1ull + DM_WINDOW_KEYS);
+    dm_k_window_export<<<std::max(1, (int)std::min<uint64_t>((n_words + 255) / 256, 2048)), 256, 0, st>>>(
+        (unsigned long long*)dev_buf, n_words, h->d_stats, h->d_stats_exported, h->table.count, h->table.novel,
+        h->novel_exported, novel_to, seg_off, with_keys);
+    DM_CUDA(cudaGetLastError());
+    h->novel_exported = novel_to;
+    return DM_OK;
+}
+
+extern "C" int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream_) {
+    if (!h || !dev_buf || rank >= world) return dm_fail(DM_ERR_ARG, "bad window arguments");
+    DM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st;
+    dm_pick_stream(h, stream_, &st);
+    dm_k_window_import<<<with_keys ? 256 : 1, 256, 0, st>>>((const unsigned long long*)dev_buf, world, rank,
+                                                          h->d_stats_global, h->table, &h->d_hdr->error, with_keys);
+    DM_CUDA(cudaGetLastError());
+    if (with_keys) {
+        // keys received from peers are in the table now but must not be re-exported
+        unsigned long long cnt[2];
+        DM_CUDA(cudaMemcpyAsync(cnt, h->table.count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        DM_CUDA(cudaStreamSynchronize(st));
+        h->novel_exported = std::min<uint64_t>(cnt[1], h->table.novel_cap);
+    }
+    return DM_OK;
+}

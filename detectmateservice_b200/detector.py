@@ -1,0 +1,190 @@
+"""DeviceDetector -- thin ctypes wrapper of one libdmdetect handle (one GPU).
+
+Host code stays Python; all tokenizing, hashing, set membership and scoring run in the
+sm_100a kernels behind include/dmdetect.h.  PyTorch tensors are used only as device /
+pinned-host buffer containers whose raw pointers are handed to the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+
+BytesLike = Union[bytes, bytearray, memoryview, np.ndarray]
+
+
+def _as_key_bytes(k: Union[str, bytes]) -> bytes:
+    return k if isinstance(k, bytes) else k.encode("utf-8")
+
+
+class DeviceDetector:
+    """NewValueDetector state (known-value table + running statistics) on one B200.
+
+    keys: the monitored field names, in monitor order (field k <-> bit k of the masks).
+    """
+
+    def __init__(self, keys: Sequence[Union[str, bytes]], device: int = 0,
+                 max_batch_bytes: int = 32 << 20, max_lines: int = 0, table_log2_slots: int = 20):
+        self._lib = _lib.load()
+        self.keys: List[bytes] = [_as_key_bytes(k) for k in keys]
+        self.device = int(device)
+        self.max_batch_bytes = int(max_batch_bytes)
+        blob = b"".join(self.keys)
+        lens = (C.c_uint32 * max(1, len(self.keys)))(*[len(k) for k in self.keys])
+        h = C.c_void_p()
+        _lib.check(self._lib.dm_create(self.device, len(self.keys), blob, lens, self.max_batch_bytes,
+                                       int(max_lines), int(table_log2_slots), C.byref(h)))
+        self._h = h
+        self.max_lines = int(max_lines) if max_lines else max(self.max_batch_bytes // 8, 1024)
+        self._pin_flags = None
+        self._pin_scores = None
+        self._pin_in = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.dm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    # ------------------------------------------------------------------ helpers
+    def _pinned_outputs(self):
+        if self._pin_flags is None:
+            import torch
+            self._pin_flags = torch.empty(self.max_lines, dtype=torch.uint8, pin_memory=True)
+            self._pin_scores = torch.empty(self.max_lines, dtype=torch.float32, pin_memory=True)
+        return self._pin_flags, self._pin_scores
+
+    @staticmethod
+    def _host_ptr(buf: BytesLike) -> Tuple[int, int, object]:
+        """(address, nbytes, keepalive) of a host buffer without copying."""
+        if isinstance(buf, np.ndarray):
+            a = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+            return a.ctypes.data, a.size, a
+        if isinstance(buf, bytes):
+            return C.cast(C.c_char_p(buf), C.c_void_p).value or 0, len(buf), buf
+        mv = memoryview(buf).cast("B")
+        a = np.frombuffer(mv, dtype=np.uint8)
+        return a.ctypes.data, a.size, a
+
+    # ------------------------------------------------------------------ hot path, host buffers
+    def process_lines(self, buf: BytesLike, n_train_lines: int = 0, copy: bool = True
+                      ) -> Tuple[np.ndarray, np.ndarray]:
+        """One message of '\\n'-terminated raw records in host memory.  The first
+        n_train_lines records are training data.  Returns (flags uint8[n], scores float32[n])."""
+        ptr, n, keep = self._host_ptr(buf)
+        pf, ps = self._pinned_outputs()
+        n_lines = C.c_uint64()
+        n_anom = C.c_uint64()
+        _lib.check(self._lib.dm_process_lines(self._h, ptr, n, 0, int(n_train_lines), pf.data_ptr(), ps.data_ptr(),
+                                              self.max_lines, 0, C.byref(n_lines), C.byref(n_anom), None))
+        del keep
+        k = n_lines.value
+        f = pf.numpy()[:k]
+        s = ps.numpy()[:k]
+        self.last_n_anomalies = n_anom.value
+        return (f.copy(), s.copy()) if copy else (f, s)
+
+    def stage_pinned(self, buf: BytesLike):
+        """Copy a host message into the detector's pinned staging buffer; returns a uint8
+        numpy view usable as input of process_lines (fast H2D path)."""
+        import torch
+        if self._pin_in is None:
+            self._pin_in = torch.empty(self.max_batch_bytes + 64, dtype=torch.uint8, pin_memory=True)
+        ptr, n, keep = self._host_ptr(buf)
+        view = self._pin_in.numpy()[:n]
+        C.memmove(view.ctypes.data, ptr, n)
+        del keep
+        return view
+
+    # ------------------------------------------------------------------ hot path, device buffers
+    def enqueue_device(self, data_ptr: int, nbytes: int, n_train_lines: int = 0, flags_ptr: int = 0,
+                       scores_ptr: int = 0, out_cap_lines: int = 0, stream: int = 0) -> None:
+        """Enqueue one device-resident message on `stream` (a raw cudaStream_t, 0 = the
+        handle's own stream) without synchronising.  Pointers are raw device addresses
+        (e.g. torch.Tensor.data_ptr()); the message buffer needs 16 bytes of slack."""
+        _lib.check(self._lib.dm_process_lines(self._h, data_ptr, int(nbytes), 1, int(n_train_lines),
+                                              flags_ptr or None, scores_ptr or None, int(out_cap_lines), 1,
+                                              None, None, stream or None))
+
+    def sync(self) -> Tuple[int, int]:
+        n_lines = C.c_uint64()
+        n_anom = C.c_uint64()
+        _lib.check(self._lib.dm_sync(self._h, C.byref(n_lines), C.byref(n_anom)))
+        return n_lines.value, n_anom.value
+
+    # ------------------------------------------------------------------ results / state
+    def anomalies(self, cap: int = 1 << 20) -> List[Tuple[int, int, int]]:
+        n = C.c_uint32()
+        _lib.check(self._lib.dm_get_anomalies(self._h, None, 0, C.byref(n)))
+        k = min(n.value, cap)
+        if k == 0:
+            return []
+        arr = (_lib.Anomaly * k)()
+        _lib.check(self._lib.dm_get_anomalies(self._h, arr, k, C.byref(n)))
+        k = min(k, n.value)
+        return [(arr[i].line, arr[i].mask, arr[i].offset) for i in range(k)]
+
+    def stats(self) -> dict:
+        st = _lib.Stats()
+        _lib.check(self._lib.dm_get_stats(self._h, C.byref(st)))
+        return st.as_dict(len(self.keys))
+
+    def global_stats(self) -> dict:
+        st = _lib.Stats()
+        _lib.check(self._lib.dm_get_global_stats(self._h, C.byref(st)))
+        return st.as_dict(len(self.keys))
+
+    def export_known(self) -> np.ndarray:
+        n = C.c_uint64()
+        _lib.check(self._lib.dm_export_known(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), dtype=np.uint64)
+        _lib.check(self._lib.dm_export_known(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def import_known(self, keys: np.ndarray) -> None:
+        a = np.ascontiguousarray(keys, dtype=np.uint64)
+        _lib.check(self._lib.dm_import_known(self._h, a.ctypes.data_as(C.POINTER(C.c_uint64)), a.size))
+
+    def reset(self) -> None:
+        _lib.check(self._lib.dm_reset(self._h))
+
+    def table_key(self, field: int, value: bytes) -> int:
+        return int(self._lib.dm_table_key(int(field), value, len(value)))
+
+    # ------------------------------------------------------------------ measurement
+    def profile_enable(self, on: bool = True) -> None:
+        _lib.check(self._lib.dm_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> Tuple[float, int, int]:
+        """(summed dominant-kernel ms, launches timed, kernels launched since creation)."""
+        ms = C.c_double()
+        n = C.c_uint64()
+        tot = C.c_uint64()
+        _lib.check(self._lib.dm_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(tot)))
+        return ms.value, n.value, tot.value
+
+    # ------------------------------------------------------------------ multi-GPU window
+    def window_words(self, world: int, with_keys: bool) -> int:
+        return int(self._lib.dm_window_words(self._h, int(world), int(with_keys)))
+
+    def window_export(self, dev_ptr: int, rank: int, world: int, with_keys: bool, stream: int = 0) -> None:
+        _lib.check(self._lib.dm_window_export(self._h, dev_ptr, rank, world, int(with_keys), stream or None))
+
+    def window_import(self, dev_ptr: int, rank: int, world: int, with_keys: bool, stream: int = 0) -> None:
+        _lib.check(self._lib.dm_window_import(self._h, dev_ptr, rank, world, int(with_keys), stream or None))

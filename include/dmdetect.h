@@ -1,0 +1,145 @@
+/*
+ * dmdetect.h -- C ABI of libdmdetect.so, the B200 (sm_100a) detector hot path.
+ *
+ * The reference has no FFI: its hot path is the Python call chain
+ *   Engine._run_loop            /root/reference/src/service/features/engine.py:153-217
+ *     -> Service.process        /root/reference/src/service/core.py:176-206
+ *       -> CoreComponent.process (detectmatelibrary, un-vendored; contract in
+ *                                 /root/reference/docs/interfaces.md:23-35)
+ * This header is what a `process(bytes) -> bytes | None` implementation binds instead of
+ * the library's Python detector; INTEGRATION.md shows the ctypes stub.  Plain pointers and
+ * sizes only -- no torch / CUDA runtime types cross the boundary (a CUDA stream is passed
+ * as an opaque void*, NULL = the handle's own stream).
+ *
+ * Conventions
+ *   - every entry point returns 0 on success or a negative DM_ERR_* code; the message of
+ *     the last failure on the calling thread is dm_last_error().  Nothing throws.
+ *   - one handle = one device = one caller thread at a time (the reference calls process()
+ *     from the single EngineLoop thread only, engine.py:80-82).
+ *   - the caller owns every buffer it passes in; the library owns its tables and scratch
+ *     (allocated once in dm_create, no per-call cudaMalloc).
+ *   - there is NO CPU fallback: without a usable CUDA device dm_create fails.
+ */
+#ifndef DMDETECT_H
+#define DMDETECT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_ABI_VERSION 1
+#define DM_MAX_KEYS 32      /* monitored fields per detector                         */
+#define DM_MAX_KEYLEN 32    /* bytes per monitored key                                */
+
+#define DM_OK 0
+#define DM_ERR_ARG (-1)       /* bad argument                                         */
+#define DM_ERR_CUDA (-2)      /* CUDA runtime / launch failure (see dm_last_error)    */
+#define DM_ERR_NO_DEVICE (-3) /* no usable sm_100 device: the product has no CPU path */
+#define DM_ERR_CAPACITY (-4)  /* batch larger than the handle was created for         */
+#define DM_ERR_TABLE_FULL (-5)/* known-set table over its load limit                  */
+#define DM_ERR_STATE (-6)     /* call not valid in the handle's current state         */
+
+typedef struct dm_handle dm_handle;
+
+/* Running statistics of one handle (the "per-window running statistics" that are
+ * all-reduced across GPUs; replaces the Python-side counters the reference keeps in
+ * core.py:24-61 for lines/bytes, plus what NewValueDetector reports per alert). */
+typedef struct {
+    uint64_t lines;          /* records seen (training + detection)                   */
+    uint64_t train_lines;    /* records consumed as training data                     */
+    uint64_t detect_lines;   /* records scored                                        */
+    uint64_t anomalies;      /* records with score > 0                                */
+    uint64_t score_sum;      /* sum of scores (scores are small integers)             */
+    uint64_t bytes;          /* input bytes consumed                                  */
+    uint64_t known_keys;     /* entries in the known-set table                        */
+    uint64_t unknown_per_key[DM_MAX_KEYS]; /* alerts per monitored field             */
+} dm_stats_t;
+
+/* One anomalous record of the last batch. */
+typedef struct {
+    uint32_t line;    /* record index inside the batch                                */
+    uint32_t mask;    /* bit k set = monitored field k held an unknown value          */
+    uint64_t offset;  /* byte offset of the record's first byte inside the batch      */
+} dm_anomaly_t;
+
+const char* dm_last_error(void);
+int dm_abi_version(void);
+
+/* Create a detector on CUDA device `device`.
+ *   keys_blob/key_lens : the n_keys monitored field names, concatenated (R-tok keys:
+ *                        1..DM_MAX_KEYLEN bytes, none of ' ', '"', '\'', '=', '\n').
+ *                        Field k is the reference's monitor k
+ *                        (container/config/detector_config.yaml:6-9, header_variables pos).
+ *   max_batch_bytes    : largest message dm_process_lines will be given.
+ *   max_lines          : largest record count per message (0 = max_batch_bytes / 8).
+ *   table_log2_slots   : known-set table capacity = 2^table_log2_slots keys (10..28). */
+int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, const uint32_t* key_lens,
+              uint64_t max_batch_bytes, uint64_t max_lines, uint32_t table_log2_slots,
+              dm_handle** out);
+int dm_destroy(dm_handle* h);
+
+/* The hot path: one message of '\n'-terminated raw records (R-tok L1).
+ *   buf, nbytes      : the message; host memory (pageable or pinned) or, if buf_on_device,
+ *                      a 16-byte aligned device pointer with >= 16 readable bytes of slack
+ *                      after nbytes.
+ *   n_train_lines    : the first n_train_lines records of THIS message are training data
+ *                      (R-spec 1): their values are inserted, their flag/score are 0.  The
+ *                      rest are scored against the table as it stands after that insert.
+ *   flags_out/scores_out : one uint8 flag and one float32 score per record, capacity
+ *                      out_cap_lines; host memory, or device memory if out_on_device.
+ *                      Either may be NULL (results then stay in the handle's own buffers).
+ *   n_lines_out/n_anomalies_out : host pointers, may be NULL.  If both are NULL and no host
+ *                      output was requested the call only ENQUEUES work on `stream` and
+ *                      returns without synchronising (device-resident pipelines);
+ *                      otherwise it returns after the results are complete.
+ * Replaces: per-record CoreComponent.process calls made by core.py:201-203. */
+int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbytes, int buf_on_device,
+                     uint64_t n_train_lines,
+                     uint8_t* flags_out, float* scores_out, uint64_t out_cap_lines, int out_on_device,
+                     uint64_t* n_lines_out, uint64_t* n_anomalies_out, void* stream);
+
+/* Wait for everything enqueued on the handle and report the last batch's counts. */
+int dm_sync(dm_handle* h, uint64_t* n_lines_out, uint64_t* n_anomalies_out);
+
+/* The anomalous records of the last batch, sorted by record index (at most cap; *n_out is
+ * the total found, which may exceed cap and the handle's internal list). */
+int dm_get_anomalies(dm_handle* h, dm_anomaly_t* out, uint32_t cap, uint32_t* n_out);
+
+int dm_get_stats(dm_handle* h, dm_stats_t* out);
+
+/* Known-set persistence (the reference loses learned state on restart). */
+int dm_export_known(dm_handle* h, uint64_t* keys_out, uint64_t cap, uint64_t* n_out);
+int dm_import_known(dm_handle* h, const uint64_t* keys, uint64_t n);
+/* Forget everything learned and zero the statistics. */
+int dm_reset(dm_handle* h);
+
+/* Host-side helper: table key of (field k, value) = dm_fp64(value) ^ salt(k).  Pure
+ * function, no device needed -- lets a host seed/inspect the known set by value. */
+uint64_t dm_table_key(uint32_t field, const uint8_t* value, uint32_t len);
+
+/* Multi-GPU window exchange: ONE sum-all-reduce of `dm_window_words(world)` uint64 words
+ * per window carries the statistics delta and every rank's newly learned keys
+ * (rank r writes its keys only into segment r, so the sum is a concatenation).
+ *   export : pack this rank's delta since the previous window into dev_buf (device memory).
+ *   (caller all-reduces dev_buf with SUM over uint64 -- NCCL over NVLink via torch.distributed)
+ *   import : insert all ranks' keys into the local table, fold the global statistics. */
+uint64_t dm_window_words(dm_handle* h, uint32_t world, int with_keys);
+int dm_window_export(dm_handle* h, uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream);
+int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream);
+/* Statistics summed over all ranks as of the last dm_window_import. */
+int dm_get_global_stats(dm_handle* h, dm_stats_t* out);
+
+/* Measurement support (bench.py): when enabled, every dm_process_lines records a CUDA
+ * event pair on the launching stream around its dominant kernel (the tokenizer+detector
+ * kernel).  dm_profile_read synchronises and returns the summed kernel time of the
+ * launches timed since the last read, their count, and the total number of kernels this
+ * handle has launched since dm_create. */
+int dm_profile_enable(dm_handle* h, int on);
+int dm_profile_read(dm_handle* h, double* kernel_ms_sum, uint64_t* n_timed, uint64_t* kernels_launched_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMDETECT_H */
