@@ -224,8 +224,12 @@ def run_gpu(args):
     n_lines_msg = [m.count(b"\n") for m in msgs]
     det = DeviceDetector(MONITORED_KEYS, device=local_rank, max_batch_bytes=max(nbytes) + 4096,
                          max_lines=LINES_PER_MSG + 16, table_log2_slots=16)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the C ABI treats a NULL stream as "the handle's own
+    # stream", and torch's default stream IS NULL -- events must sit on the launching stream.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
 
     # device-resident copies (value) and pinned-host copies (e2e)
     d_msgs, h_msgs = [], []

@@ -1,0 +1,50 @@
+#!/bin/bash
+# One GPU-box visit: smoke, parity tests, bench, ncu launch list + full capture of the
+# dominant kernel.  Everything lands in gpurun_out/ (merged back by gpurun).
+# usage: scripts/gpu_round.sh <tag> [stages...]   stages: smoke tests bench ncu sanitize
+set -u
+TAG=${1:-r01}
+shift || true
+STAGES=${*:-smoke tests bench ncu}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > "$OUT/gpu.csv" 2>&1
+
+for S in $STAGES; do
+  case $S in
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1
+      echo "smoke rc=$?" | tee -a "$OUT/summary.txt" ;;
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > "$OUT/pytest_gpu.log" 2>&1
+      echo "pytest_gpu rc=$?" | tee -a "$OUT/summary.txt"
+      tail -5 "$OUT/pytest_gpu.log" ;;
+    tests_all)
+      timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > "$OUT/pytest_gpu.log" 2>&1
+      echo "pytest_gpu rc=$?" | tee -a "$OUT/summary.txt"
+      tail -15 "$OUT/pytest_gpu.log" ;;
+    bench)
+      for K in ${DM_KERNELS:-v1}; do
+        DM_KERNEL=$K timeout 900 python bench.py > "$OUT/bench_$K.json" 2> "$OUT/bench_$K.err"
+        echo "bench[$K] rc=$?" | tee -a "$OUT/summary.txt"
+        cat "$OUT/bench_$K.json"
+      done ;;
+    ncu)
+      for K in ${DM_KERNELS:-v1}; do
+        DM_KERNEL=$K timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+          --log-file "$OUT/launches_$K.csv" python bench.py --steps 6 --warmup 3 --no-cpu > "$OUT/ncu_list_$K.log" 2>&1
+        echo "ncu_list[$K] rc=$?" | tee -a "$OUT/summary.txt"
+        DM_KERNEL=$K timeout 1200 ncu --set full --clock-control none --import-source on \
+          -k regex:"${NCU_KERNEL:-dm_k_detect_lines|dm_k_tile}" -s 4 -c 3 -f -o "$OUT/prof_$K" \
+          python bench.py --steps 6 --warmup 3 --no-cpu > "$OUT/ncu_full_$K.log" 2>&1
+        echo "ncu_full[$K] rc=$?" | tee -a "$OUT/summary.txt"
+      done ;;
+    sanitize)
+      DM_KERNEL=${DM_KERNELS:-v1} timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
+        python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/sanitize.log" 2>&1
+      echo "sanitize rc=$?" | tee -a "$OUT/summary.txt"
+      tail -5 "$OUT/sanitize.log" ;;
+  esac
+done
+cat "$OUT/summary.txt"

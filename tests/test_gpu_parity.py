@@ -198,7 +198,9 @@ def test_device_resident_enqueue(variant):
         flags = torch.full((8192,), 7, dtype=torch.uint8, device="cuda")
         scores = torch.full((8192,), -1.0, dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
-        st = torch.cuda.current_stream().cuda_stream
+        stream = torch.cuda.Stream()
+        st = stream.cuda_stream
+        assert st != 0                      # NULL would mean "the handle's own stream"
         det.enqueue_device(t.data_ptr(), len(msg), 0, flags.data_ptr(), scores.data_ptr(), 8192, st)
         n_lines, n_anom = det.sync()
         assert n_lines == 8192 and n_anom == int(f_host.sum())
