@@ -1,6 +1,13 @@
 // dm_device.cuh -- device-side data structures and helpers shared by the kernels.
+//
+// Compiles with nvcc for sm_100a (the product) and, with -DDM_EMU, with g++ against
+// tests/emu/cuda_emu.h (CPU emulation used only by the test tier).
 #pragma once
+#ifdef DM_EMU
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/dmdetect.h"
@@ -14,7 +21,39 @@ struct DmKeys {
     uint32_t len[DM_MAX_KEYS];
     uint64_t salt[DM_MAX_KEYS];
     uint8_t bytes[DM_MAX_KEYS][DM_MAX_KEYLEN];
+    // fused-kernel key filter: the last min(len,4) key bytes as they sit in the 4 bytes
+    // before an '=' (byte q-1 in bits 24..31), and a 1024-bit filter over the hash of the
+    // last two bytes before an '=' (for 1-byte keys: delimiter + key byte).
+    uint32_t tailbits[DM_MAX_KEYS];
+    uint32_t tailmask[DM_MAX_KEYS];
+    uint32_t bitmap[32];
 };
+
+// hash of the two bytes before an '=' (x = byte[q-2] | byte[q-1] << 8) -> 10 bits
+DM_HD uint32_t dm_tail_hash(uint32_t x) { return (x * 0x9E3779B1u) >> 22; }
+
+static inline void dm_keys_finalize_host(DmKeys* k) {
+    for (int i = 0; i < 32; ++i) k->bitmap[i] = 0;
+    for (uint32_t i = 0; i < k->n; ++i) {
+        const uint32_t len = k->len[i];
+        const uint32_t tl = len < 4 ? len : 4;
+        uint32_t bits = 0;
+        for (uint32_t j = 0; j < tl; ++j) bits |= (uint32_t)k->bytes[i][len - 1 - j] << (8 * (3 - j));
+        k->tailbits[i] = bits;
+        k->tailmask[i] = tl == 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * (4 - tl)));
+        const uint32_t b0 = k->bytes[i][len - 1];
+        if (len >= 2) {
+            const uint32_t h = dm_tail_hash((uint32_t)k->bytes[i][len - 2] | (b0 << 8));
+            k->bitmap[h >> 5] |= 1u << (h & 31);
+        } else {
+            const uint32_t delims[3] = {0x20u, 0x27u, 0x0Au};
+            for (int d = 0; d < 3; ++d) {
+                const uint32_t h = dm_tail_hash(delims[d] | (b0 << 8));
+                k->bitmap[h >> 5] |= 1u << (h & 31);
+            }
+        }
+    }
+}
 
 // Per-batch header written by the kernels, read back by the host.
 struct DmBatchHeader {
@@ -44,10 +83,23 @@ __device__ __forceinline__ uint32_t dm_slot_of(uint64_t key, uint32_t mask) {
     return ((uint32_t)key ^ (uint32_t)(key >> 32)) & mask;
 }
 
+// Read-only probe (detection launches: the table does not change while they run).
 __device__ __forceinline__ bool dm_table_contains(const DmTable& t, uint64_t key) {
     uint32_t i = dm_slot_of(key, t.mask);
     for (uint32_t probes = 0; probes <= t.mask; ++probes) {
         unsigned long long v = __ldg(t.slots + i);
+        if (v == key) return true;
+        if (v == 0ull) return false;
+        i = (i + 1) & t.mask;
+    }
+    return false;
+}
+
+// Probe that tolerates concurrent inserts (training launches).
+__device__ __forceinline__ bool dm_table_contains_volatile(const DmTable& t, uint64_t key) {
+    uint32_t i = dm_slot_of(key, t.mask);
+    for (uint32_t probes = 0; probes <= t.mask; ++probes) {
+        unsigned long long v = *((volatile unsigned long long*)(t.slots + i));
         if (v == key) return true;
         if (v == 0ull) return false;
         i = (i + 1) & t.mask;
@@ -74,6 +126,7 @@ __device__ __forceinline__ bool dm_table_insert(const DmTable& t, uint64_t key, 
     return false;
 }
 
+#ifndef DM_EMU
 // 4-bit mask of the bytes of w equal to the replicated byte pattern pat (bit j = byte j).
 __device__ __forceinline__ uint32_t dm_nib_eq(uint32_t w, uint32_t pat) {
     uint32_t m = __vcmpeq4(w, pat) & 0x08040201u;
@@ -85,9 +138,30 @@ __device__ __forceinline__ uint32_t dm_mask16_eq(uint4 v, uint32_t pat) {
     return dm_nib_eq(v.x, pat) | (dm_nib_eq(v.y, pat) << 4) | (dm_nib_eq(v.z, pat) << 8) |
            (dm_nib_eq(v.w, pat) << 12);
 }
+#endif
 
 __device__ __forceinline__ uint32_t dm_lanemask_lt() {
+#ifdef DM_EMU
+    return (1u << (threadIdx.x & 31)) - 1u;
+#else
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+#endif
+}
+
+// Named barriers (PTX bar.sync / bar.arrive; counts are in threads).
+__device__ __forceinline__ void dm_bar_sync(int id, int count) {
+#ifdef DM_EMU
+    emu_bar_sync(id, (unsigned)count);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+__device__ __forceinline__ void dm_bar_arrive(int id, int count) {
+#ifdef DM_EMU
+    emu_bar_arrive(id, (unsigned)count);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
 }

@@ -54,7 +54,7 @@ struct dm_handle {
     uint64_t max_batch_bytes = 0, max_lines = 0;
     uint32_t table_log2 = 0;
     uint32_t n_keys = 0;
-    int kernel_variant = 0;              // 0 = v1 (line index + warp per record), 1 = fused tile kernel
+    int kernel_variant = 1;              // 0 = v1 (line index + warp per record), 1 = fused tile kernel
 
     DmKeys h_keys;
     DmKeys* d_keys = nullptr;
@@ -150,6 +150,7 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
         h->h_keys.salt[k] = dm_field_salt(k);
         off += len;
     }
+    dm_keys_finalize_host(&h->h_keys);
 
     DM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->last_stream = h->stream;
@@ -357,13 +358,20 @@ extern "C" int dm_get_anomalies(dm_handle* h, dm_anomaly_t* out, uint32_t cap, u
     int rc = dm_sync(h, nullptr, nullptr);
     if (rc != DM_OK) return rc;
     const uint32_t total = h->h_hdr->anomaly_list_count;
-    *n_out = total;
+    *n_out = std::min<uint64_t>(total, h->h_hdr->n_anomalies ? h->h_hdr->n_anomalies : total);
     const uint32_t have = std::min(total, h->anomaly_cap);
     if (!out || cap == 0 || have == 0) return DM_OK;
     std::vector<dm_anomaly_t> tmp(have);
     DM_CUDA(cudaMemcpy(tmp.data(), h->d_anoms, (uint64_t)have * sizeof(dm_anomaly_t), cudaMemcpyDeviceToHost));
     std::sort(tmp.begin(), tmp.end(), [](const dm_anomaly_t& a, const dm_anomaly_t& b) { return a.line < b.line; });
-    memcpy(out, tmp.data(), (uint64_t)std::min(have, cap) * sizeof(dm_anomaly_t));
+    // the fused kernel appends one entry per unknown field: merge the entries of a record
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < have; ++i) {
+        if (m && tmp[m - 1].line == tmp[i].line) { tmp[m - 1].mask |= tmp[i].mask; continue; }
+        tmp[m++] = tmp[i];
+    }
+    *n_out = m;
+    memcpy(out, tmp.data(), (uint64_t)std::min(m, cap) * sizeof(dm_anomaly_t));
     return DM_OK;
 }
 

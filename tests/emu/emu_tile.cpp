@@ -1,0 +1,143 @@
+// emu_tile.cpp -- runs the product's fused kernel source (dm_kernels_tile.cuh) on the CPU
+// emulator.  TEST INFRASTRUCTURE ONLY: built by tests/emu/build.py into tests/emu/_build/,
+// loaded by tests/test_emu_tile.py; never part of libdmdetect.so.
+#include "cuda_emu.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "dm_kernels_tile.cuh"
+
+thread_local emu_dim3 threadIdx;
+thread_local emu_dim3 blockIdx;
+emu_dim3 blockDim, gridDim;
+EmuBlock* g_emu_block = nullptr;
+
+void emu_launch(unsigned threads, const std::function<void()>& body) {
+    EmuBlock blk;
+    blk.warps = std::vector<EmuWarp>(threads / 32);
+    g_emu_block = &blk;
+    blockDim.x = threads;
+    gridDim.x = 1;
+    std::vector<std::thread> ts;
+    ts.reserve(threads);
+    for (unsigned t = 0; t < threads; ++t)
+        ts.emplace_back([t, &body] {
+            threadIdx.x = t;
+            blockIdx.x = 0;
+            body();
+        });
+    for (auto& t : ts) t.join();
+    g_emu_block = nullptr;
+}
+
+struct EmuHandle {
+    DmKeys keys;
+    DmTable table;
+    std::vector<unsigned long long> slots, novel;
+    unsigned long long counts[2] = {0, 0};
+    std::vector<unsigned long long> tile_state;
+    unsigned long long tile_ctr = 0, ctr_base = 0;
+    uint32_t epoch = 0;
+    unsigned long long stats[DM_STATS_WORDS] = {0};
+    DmBatchHeader hdr;
+    std::vector<dm_anomaly_t> anoms;
+    uint64_t max_lines = 0;
+};
+
+extern "C" EmuHandle* emu_create(uint32_t n_keys, const uint8_t* blob, const uint32_t* lens, uint32_t table_log2,
+                                 uint64_t max_tiles, uint64_t max_lines) {
+    EmuHandle* h = new EmuHandle();
+    memset(&h->keys, 0, sizeof(DmKeys));
+    h->keys.n = n_keys;
+    uint64_t off = 0;
+    for (uint32_t k = 0; k < n_keys; ++k) {
+        h->keys.len[k] = lens[k];
+        memcpy(h->keys.bytes[k], blob + off, lens[k]);
+        h->keys.salt[k] = dm_field_salt(k);
+        off += lens[k];
+    }
+    dm_keys_finalize_host(&h->keys);
+    const uint64_t cap = 1ull << table_log2;
+    h->slots.assign(cap, 0);
+    h->novel.assign(cap / 2, 0);
+    h->table.slots = h->slots.data();
+    h->table.mask = (uint32_t)(cap - 1);
+    h->table.limit = (uint32_t)(cap / 2);
+    h->table.count = &h->counts[0];
+    h->table.novel = h->novel.data();
+    h->table.novel_count = &h->counts[1];
+    h->table.novel_cap = (uint32_t)(cap / 2);
+    h->tile_state.assign(max_tiles + 1, 0);
+    h->anoms.resize(1 << 16);
+    h->max_lines = max_lines;
+    memset(&h->hdr, 0, sizeof(h->hdr));
+    return h;
+}
+
+extern "C" void emu_destroy(EmuHandle* h) { delete h; }
+
+// Mirrors dm_tile_launch (dm_kernels_tile.cuh): optional TRAIN launch, then the DETECT launch.
+extern "C" int emu_process(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                           float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    // 16-byte aligned copy with hostile slack bytes ('=' and '\n') after the message
+    uint8_t* buf = (uint8_t*)aligned_alloc(64, ((nbytes + 64 + 63) / 64) * 64 + 64);
+    memcpy(buf, msg, nbytes);
+    for (int i = 0; i < 64; ++i) buf[nbytes + i] = (i & 1) ? '\n' : '=';
+    memset(&h->hdr, 0, sizeof(h->hdr));
+    const uint32_t n_tiles = (uint32_t)((nbytes + DMT_TILE - 1) / DMT_TILE);
+    if (n_tiles >= h->tile_state.size()) { free(buf); return -4; }
+    if (n_tiles > 0) {
+        DmFusedArgs a;
+        a.buf = buf; a.nbytes = nbytes; a.n_tiles = n_tiles; a.keys = &h->keys; a.table = h->table;
+        a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data();
+        a.anomaly_cap = (uint32_t)h->anoms.size(); a.hdr = &h->hdr; a.stats = h->stats;
+        a.tile_state = h->tile_state.data(); a.tile_ctr = &h->tile_ctr; a.n_train_lines = n_train;
+        a.max_lines = h->max_lines;
+        if (n_train > 0) {
+            h->epoch = (h->epoch % 0x3FFFFFFEu) + 1u;
+            a.epoch = h->epoch; a.ctr_base = h->ctr_base;
+            a.line_lo = 0; a.line_hi = n_train; a.range_check = 1; a.zero_fill = 1; a.finalize = 0;
+            emu_launch(DMT_THREADS, [&] { dm_k_tile<true>(a); });
+            h->ctr_base += (unsigned long long)n_tiles + 1ull;
+        }
+        h->epoch = (h->epoch % 0x3FFFFFFEu) + 1u;
+        a.epoch = h->epoch; a.ctr_base = h->ctr_base;
+        a.line_lo = n_train; a.line_hi = ~0ull; a.range_check = n_train > 0 ? 1 : 0;
+        a.zero_fill = n_train > 0 ? 0 : 1; a.finalize = 1;
+        emu_launch(DMT_THREADS, [&] { dm_k_tile<false>(a); });
+        h->ctr_base += (unsigned long long)n_tiles + 1ull;
+    }
+    free(buf);
+    *n_lines = h->hdr.n_lines;
+    *n_anoms = h->hdr.n_anomalies;
+    *err = h->hdr.error;
+    return 0;
+}
+
+extern "C" uint32_t emu_get_anomalies(EmuHandle* h, dm_anomaly_t* out, uint32_t cap) {
+    uint32_t n = std::min<uint32_t>(h->hdr.anomaly_list_count, (uint32_t)h->anoms.size());
+    std::vector<dm_anomaly_t> v(h->anoms.begin(), h->anoms.begin() + n);
+    std::sort(v.begin(), v.end(), [](const dm_anomaly_t& a, const dm_anomaly_t& b) { return a.line < b.line; });
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (m && out[m - 1].line == v[i].line) { out[m - 1].mask |= v[i].mask; continue; }
+        if (m >= cap) break;
+        out[m++] = v[i];
+    }
+    return m;
+}
+
+extern "C" void emu_get_stats(EmuHandle* h, unsigned long long* out) {
+    for (int i = 0; i < DM_STATS_WORDS; ++i) out[i] = h->stats[i];
+    out[6] = h->counts[0];
+}
+
+extern "C" uint64_t emu_export_known(EmuHandle* h, unsigned long long* out, uint64_t cap) {
+    uint64_t n = std::min<uint64_t>(h->counts[1], h->novel.size());
+    std::vector<unsigned long long> v(h->novel.begin(), h->novel.begin() + n);
+    std::sort(v.begin(), v.end());
+    for (uint64_t i = 0; i < n && i < cap; ++i) out[i] = v[i];
+    return n;
+}
