@@ -88,6 +88,9 @@ SYMBOLS = {
     "dm_destroy": (C.c_int, [_P]),
     "dm_process_lines": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_uint64, _P, _P, C.c_uint64, C.c_int,
                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _P]),
+    "dm_process_values": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
+                                    _P, _P, _P, C.POINTER(C.c_uint64)]),
     "dm_sync": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dm_get_anomalies": (C.c_int, [_P, C.POINTER(Anomaly), C.c_uint32, C.POINTER(C.c_uint32)]),
     "dm_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),

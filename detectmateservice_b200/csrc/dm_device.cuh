@@ -21,37 +21,32 @@ struct DmKeys {
     uint32_t len[DM_MAX_KEYS];
     uint64_t salt[DM_MAX_KEYS];
     uint8_t bytes[DM_MAX_KEYS][DM_MAX_KEYLEN];
-    // fused-kernel key filter: the last min(len,4) key bytes as they sit in the 4 bytes
-    // before an '=' (byte q-1 in bits 24..31), and a 1024-bit filter over the hash of the
-    // last two bytes before an '=' (for 1-byte keys: delimiter + key byte).
+    // fused-kernel key identification.  With w_c = bytes q-4..q-1 and w_b = bytes q-8..q-5 in
+    // front of an '=' at q (later byte in the higher bits), key k matches its last
+    // min(len,8) bytes iff ((w_c ^ tailbits) & tailmask) | ((w_b ^ midbits) & midmask) == 0.
+    // The field-start delimiter (byte q-len-1) sits in word dsel (0 = w_c, 1 = w_b, 2 = w_a =
+    // bytes q-12..q-9) at bit offset dshift, for keys shorter than 12 bytes.
     uint32_t tailbits[DM_MAX_KEYS];
     uint32_t tailmask[DM_MAX_KEYS];
-    uint32_t bitmap[32];
+    uint32_t midbits[DM_MAX_KEYS];
+    uint32_t midmask[DM_MAX_KEYS];
+    uint32_t dsel[DM_MAX_KEYS];
+    uint32_t dshift[DM_MAX_KEYS];
 };
 
-// hash of the two bytes before an '=' (x = byte[q-2] | byte[q-1] << 8) -> 10 bits
-DM_HD uint32_t dm_tail_hash(uint32_t x) { return (x * 0x9E3779B1u) >> 22; }
-
 static inline void dm_keys_finalize_host(DmKeys* k) {
-    for (int i = 0; i < 32; ++i) k->bitmap[i] = 0;
     for (uint32_t i = 0; i < k->n; ++i) {
         const uint32_t len = k->len[i];
-        const uint32_t tl = len < 4 ? len : 4;
-        uint32_t bits = 0;
-        for (uint32_t j = 0; j < tl; ++j) bits |= (uint32_t)k->bytes[i][len - 1 - j] << (8 * (3 - j));
-        k->tailbits[i] = bits;
-        k->tailmask[i] = tl == 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * (4 - tl)));
-        const uint32_t b0 = k->bytes[i][len - 1];
-        if (len >= 2) {
-            const uint32_t h = dm_tail_hash((uint32_t)k->bytes[i][len - 2] | (b0 << 8));
-            k->bitmap[h >> 5] |= 1u << (h & 31);
-        } else {
-            const uint32_t delims[3] = {0x20u, 0x27u, 0x0Au};
-            for (int d = 0; d < 3; ++d) {
-                const uint32_t h = dm_tail_hash(delims[d] | (b0 << 8));
-                k->bitmap[h >> 5] |= 1u << (h & 31);
-            }
+        uint32_t tb = 0, tm = 0, mb = 0, mm = 0;
+        for (uint32_t d = 1; d <= len && d <= 8; ++d) {            // d = distance from the '='
+            const uint32_t byte = k->bytes[i][len - d];
+            if (d <= 4) { tb |= byte << (8 * (4 - d)); tm |= 0xFFu << (8 * (4 - d)); }
+            else { mb |= byte << (8 * (8 - d)); mm |= 0xFFu << (8 * (8 - d)); }
         }
+        k->tailbits[i] = tb; k->tailmask[i] = tm; k->midbits[i] = mb; k->midmask[i] = mm;
+        const uint32_t dd = len + 1;                                // distance of the delimiter
+        k->dsel[i] = dd <= 12 ? (dd - 1) / 4 : 3;                   // 3 = not in the 12-byte window
+        k->dshift[i] = dd <= 12 ? 8 * (4 * ((dd - 1) / 4 + 1) - dd) : 0;
     }
 }
 

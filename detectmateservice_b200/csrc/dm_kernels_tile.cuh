@@ -10,10 +10,11 @@
 //     tiles from an atomic counter (persistent, in order);
 //   * worker warp w owns the records that START inside its 4 KiB segment.  It reads 512-byte
 //     rows with one coalesced 16-byte load per lane.  Pass 1 counts its record starts (the
-//     rows stay in L1), pass 2 classifies '\n' and '=' bytes with SIMD-in-register compares,
-//     filters every '=' against the monitored keys by the bytes in front of it, and queues
-//     the matches; a full queue is drained one value per lane: dm_fp64 of the value, probe
-//     of the known-set table;
+//     rows stay in L1), pass 2 classifies '\n' and '=' bytes with SIMD-in-register compares
+//     and compacts every '=' into a per-warp queue.  The queues keep all 32 lanes busy in the
+//     expensive stages: stage 1 takes one '=' per lane and compares the 12 bytes in front of
+//     it against every monitored key (word-parallel), stage 2 takes one identified field per
+//     lane: dm_fp64 of its value, probe of the known-set table;
 //   * quote parity (R-tok L2-L4) and first-occurrence-wins (L6) are NOT tracked on that
 //     fast path.  They can only change the outcome for a value that is not in the table
 //     (an alert, or an insert while training), so exactly those -- rare -- candidates are
@@ -31,8 +32,9 @@
 #define DMT_SEG_ROWS 8u
 #define DMT_SEG (DMT_ROW * DMT_SEG_ROWS)
 #define DMT_TILE (DMT_SEG * DMT_WARPS)
-#define DMT_QCAP 64
-#define DMT_PCAP 64
+#define DMT_Q1CAP 128u     // '=' positions waiting for key identification (circular)
+#define DMT_Q2CAP 64u      // identified fields waiting for value hashing (circular)
+#define DMT_PCAP 64u       // alerts waiting for the record-index base (circular)
 
 #define DMT_ST_AGG 1ull
 #define DMT_ST_PREFIX 2ull
@@ -52,8 +54,8 @@ struct DmFusedArgs {
     unsigned long long* stats;
     unsigned long long* tile_state;   // one word per tile: epoch<<34 | status<<32 | value
     uint32_t epoch;
-    unsigned long long* tile_ctr;     // monotonically increasing across launches
-    unsigned long long ctr_base;      // value of *tile_ctr when this launch's tile 0 is taken
+    unsigned long long* tile_ctr;     // counts the dynamically fetched tiles, across launches
+    unsigned long long ctr_base;      // value of *tile_ctr when this launch starts
     uint64_t line_lo, line_hi;        // this launch handles records with index in [lo, hi)
     uint64_t n_train_lines;
     uint64_t max_lines;
@@ -62,7 +64,8 @@ struct DmFusedArgs {
     int finalize;                     // this launch writes the batch header and the statistics
 };
 
-struct DmQEntry { uint32_t vpos; int32_t ln; uint32_t k; };
+struct DmQ1Entry { uint32_t q; int32_t ln; };
+struct DmQ2Entry { uint32_t vpos; int32_t ln; uint32_t k; };
 struct DmPEntry { uint32_t ln; uint32_t k; uint32_t lstart; };
 
 // 0x80 in every byte of w that equals the byte replicated in pat (pat bytes < 0x80).
@@ -79,8 +82,9 @@ __device__ __forceinline__ uint32_t dm_ld32(const uint8_t* __restrict__ buf, uin
     return __ldg(reinterpret_cast<const uint32_t*>(buf + p_aligned));
 }
 
-// Does monitored key k end right before the '=' at q (bytes + field-start delimiter)?
-// Quote parity is deliberately not checked here (see file header).
+// Byte-wise check that key k ends right before the '=' at q and starts at a field start
+// (R-tok L4 delimiter; quote parity is re-checked later, see file header).  The last
+// `skip_tail` key bytes are known to match already.
 __device__ __forceinline__ bool dm_key_check(const uint8_t* __restrict__ buf, uint64_t q, uint32_t k, const DmKeys& sk,
                                              uint32_t skip_tail) {
     const uint32_t len = sk.len[k];
@@ -90,74 +94,95 @@ __device__ __forceinline__ bool dm_key_check(const uint8_t* __restrict__ buf, ui
         const uint32_t c = dm_ld8(buf, st - 1);
         if (c != 0x20u && c != 0x27u && c != 0x0Au) return false;
     }
-    const uint32_t n = len - skip_tail;     // the last skip_tail bytes were compared already
+    const uint32_t n = len - skip_tail;
     for (uint32_t i = 0; i < n; ++i)
         if (dm_ld8(buf, st + i) != sk.bytes[k][i]) return false;
     return true;
 }
 
-__device__ __forceinline__ int dm_key_filter(const uint8_t* __restrict__ buf, uint64_t q, const DmKeys& sk) {
-    if (q < 4) {
+// Which monitored key (if any) ends right before the '=' at q?  Word-parallel: the 12 bytes
+// in front of q are compared against every key's precomputed patterns.
+__device__ __forceinline__ int dm_key_identify(const uint8_t* __restrict__ buf, uint64_t q, const DmKeys& sk) {
+    if (q < 12) {
         for (uint32_t k = 0; k < sk.n; ++k)
             if (dm_key_check(buf, q, k, sk, 0)) return (int)k;
         return -1;
     }
-    const uint64_t a = (q - 4) & ~3ull;
-    const uint32_t w0 = dm_ld32(buf, a), w1 = dm_ld32(buf, a + 4);
-    const uint32_t t4 = __funnelshift_r(w0, w1, (uint32_t)((q - 4) & 3) * 8);   // bytes q-4 .. q-1
-    const uint32_t h = dm_tail_hash(t4 >> 16);
-    if (!((sk.bitmap[h >> 5] >> (h & 31)) & 1u)) return -1;
+    const uint64_t a0 = (q - 12) & ~3ull;
+    const uint32_t sh = (uint32_t)((q - 12) & 3) * 8;
+    const uint32_t x0 = dm_ld32(buf, a0), x1 = dm_ld32(buf, a0 + 4), x2 = dm_ld32(buf, a0 + 8), x3 = dm_ld32(buf, a0 + 12);
+    const uint32_t w_a = __funnelshift_r(x0, x1, sh);    // bytes q-12 .. q-9
+    const uint32_t w_b = __funnelshift_r(x1, x2, sh);    // bytes q-8 .. q-5
+    const uint32_t w_c = __funnelshift_r(x2, x3, sh);    // bytes q-4 .. q-1
+    int found = -1;
     for (uint32_t k = 0; k < sk.n; ++k) {
-        if (((t4 ^ sk.tailbits[k]) & sk.tailmask[k]) == 0) {
-            const uint32_t len = sk.len[k];
-            if (dm_key_check(buf, q, k, sk, len < 4 ? len : 4)) return (int)k;
+        const uint32_t diff = ((w_c ^ sk.tailbits[k]) & sk.tailmask[k]) | ((w_b ^ sk.midbits[k]) & sk.midmask[k]);
+        if (diff == 0 && found < 0) {
+            const uint32_t sel = sk.dsel[k];
+            bool ok;
+            if (sel < 3 && sk.len[k] <= 8) {
+                const uint32_t dw = sel == 0 ? w_c : (sel == 1 ? w_b : w_a);
+                const uint32_t d = (dw >> sk.dshift[k]) & 0xFFu;
+                ok = d == 0x20u || d == 0x27u || d == 0x0Au;
+            } else {
+                ok = dm_key_check(buf, q, k, sk, 8);      // long key: the rest byte by byte
+            }
+            if (ok) found = (int)k;
         }
     }
-    return -1;
+    return found;
 }
 
 // dm_fp64 of the value that starts at vpos: ends at the first space outside double quotes
 // (parity counted from the value start, R-tok L5), at '\n', or at the end of the message.
+// Works on 16-byte blocks; quote parity is carried with shift/xor prefix tricks, no branches
+// on the data inside a block.
 __device__ __forceinline__ uint64_t dm_hash_value(const uint8_t* __restrict__ buf, uint64_t nbytes, uint64_t vpos) {
     DmHashState st;
     dm_hash_init(st);
-    uint32_t n = 0, in_q = 0;
+    uint32_t n = 0, in_q = 0;                 // in_q: 0 or 0x80808080
     uint64_t a = vpos & ~3ull;
     const uint32_t sh = (uint32_t)(vpos & 3) * 8;
     uint32_t lo = (a < nbytes) ? dm_ld32(buf, a) : 0u;
     uint64_t pos = vpos;
     for (;;) {
-        a += 4;
-        const uint32_t hi = (a < nbytes) ? dm_ld32(buf, a) : 0u;
-        uint32_t w = __funnelshift_r(lo, hi, sh);
-        lo = hi;
-        // bytes at or beyond the end of the message terminate the value
-        const uint64_t rem = nbytes > pos ? nbytes - pos : 0;
-        uint32_t term;
-        const uint32_t dq = dm_eqflags(w, 0x22222222u);
-        if (dq == 0) {
-            const uint32_t nl = dm_eqflags(w, 0x0A0A0A0Au);
-            term = in_q ? nl : (nl | dm_eqflags(w, 0x20202020u));
-        } else {
-            term = 0;
+        const uint32_t x1 = (a + 4 < nbytes) ? dm_ld32(buf, a + 4) : 0u;
+        const uint32_t x2 = (a + 8 < nbytes) ? dm_ld32(buf, a + 8) : 0u;
+        const uint32_t x3 = (a + 12 < nbytes) ? dm_ld32(buf, a + 12) : 0u;
+        const uint32_t x4 = (a + 16 < nbytes) ? dm_ld32(buf, a + 16) : 0u;
+        uint32_t w[4];
+        w[0] = __funnelshift_r(lo, x1, sh); w[1] = __funnelshift_r(x1, x2, sh);
+        w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
+        lo = x4;
+        a += 16;
+        uint32_t nvtot = 16;
+        uint32_t q_state = in_q;
+        uint32_t term[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t c = (w >> (8 * b)) & 0xFFu;
-                if (term == 0) {
-                    if (c == 0x0Au || (c == 0x20u && !in_q)) term = 0x80u << (8 * b);
-                    else if (c == 0x22u) in_q ^= 1u;
-                }
-            }
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t nl = dm_eqflags(w[i], 0x0A0A0A0Au);
+            const uint32_t sp = dm_eqflags(w[i], 0x20202020u);
+            const uint32_t dq = dm_eqflags(w[i], 0x22222222u);
+            uint32_t incl = dq ^ (dq << 8);
+            incl ^= incl << 16;                                     // quote parity up to and including each byte
+            const uint32_t before = (incl << 8) ^ q_state;          // in-quote state in front of each byte
+            term[i] = nl | (sp & ~before);
+            q_state ^= (uint32_t)((int32_t)incl >> 31) & 0x80808080u;   // parity of the whole word
         }
-        uint32_t nv = term ? (uint32_t)(__ffs(term) - 1) >> 3 : 4u;
-        if (rem < nv) nv = (uint32_t)rem;
-        if (nv < 4) {
-            if (nv) { dm_hash_word(st, w & ((1u << (8 * nv)) - 1u)); n += nv; }
-            break;
+#pragma unroll
+        for (int i = 3; i >= 0; --i)
+            if (term[i]) nvtot = 4u * i + ((uint32_t)(__ffs(term[i]) - 1) >> 3);
+        const uint64_t rem = nbytes > pos ? nbytes - pos : 0;
+        if (rem < nvtot) nvtot = (uint32_t)rem;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (nvtot >= 4u * i + 4u) dm_hash_word(st, w[i]);
+            else if (nvtot > 4u * i) dm_hash_word(st, w[i] & ((1u << (8 * (nvtot - 4u * i))) - 1u));
         }
-        dm_hash_word(st, w);
-        n += 4;
-        pos += 4;
+        n += nvtot;
+        if (nvtot < 16) break;
+        in_q = q_state;
+        pos += 16;
     }
     return dm_hash_final(st, n);
 }
@@ -194,7 +219,8 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
     __shared__ uint32_t s_cnt[DMT_WARPS];
     __shared__ unsigned long long s_base[DMT_WARPS];
     __shared__ long long s_tile;
-    __shared__ DmQEntry s_queue[DMT_WARPS][DMT_QCAP];
+    __shared__ DmQ1Entry s_q1[DMT_WARPS][DMT_Q1CAP];
+    __shared__ DmQ2Entry s_q2[DMT_WARPS][DMT_Q2CAP];
     __shared__ DmPEntry s_pend[DMT_WARPS][DMT_PCAP];
 
     {
@@ -208,10 +234,12 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lt = dm_lanemask_lt();
 
+    // The first tile of a CTA is its block index (the host launches at most as many CTAs as
+    // are co-resident, and never more than there are tiles); further tiles come from the
+    // atomic counter.
+    long long tile = (long long)blockIdx.x;
+    __syncthreads();
     for (;;) {
-        if (threadIdx.x == DMT_WARPS * 32) s_tile = (long long)(atomicAdd(a.tile_ctr, 1ull) - a.ctr_base);
-        __syncthreads();
-        const long long tile = s_tile;
         if (tile >= (long long)a.n_tiles) break;
 
         if (warp == DMT_WARPS) {
@@ -266,6 +294,8 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
             }
             __threadfence_block();
             dm_bar_arrive(2, DMT_THREADS);                     // bases are in s_base
+            // fetch this CTA's next tile while the workers finish
+            if (lane == 0) s_tile = (long long)gridDim.x + (long long)(atomicAdd(a.tile_ctr, 1ull) - a.ctr_base);
         } else {
             // ------------------------------ worker warp -------------------------------
             const uint64_t seg_start = (uint64_t)tile * DMT_TILE + (uint64_t)warp * DMT_SEG;
@@ -308,11 +338,12 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
             unsigned long long base = 0;
             if (a.range_check) { dm_bar_sync(2, DMT_THREADS); have_base = true; base = s_base[warp]; }
 
-            uint32_t qn = 0, pn = 0;
-            DmQEntry* queue = s_queue[warp];
+            uint32_t q1h = 0, q1n = 0, q2h = 0, q2n = 0, ph = 0, pn = 0;   // circular queues: head, count
+            DmQ1Entry* q1 = s_q1[warp];
+            DmQ2Entry* q2 = s_q2[warp];
             DmPEntry* pend = s_pend[warp];
 
-            // apply the pending alerts (needs the global record index of this warp's records)
+            // apply up to 32 pending alerts (needs the global record index of this warp's records)
             auto flush = [&]() {
                 if (!have_base) { dm_bar_sync(2, DMT_THREADS); have_base = true; base = s_base[warp]; }
                 if (!zero_done) {
@@ -325,10 +356,11 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
                     zero_done = true;
                     __syncwarp();
                 }
-                if (pn) {
+                const uint32_t take = pn < 32u ? pn : 32u;
+                if (take) {
                     bool first = false;
-                    if (lane < pn) {
-                        const DmPEntry e = pend[lane];
+                    if (lane < take) {
+                        const DmPEntry e = pend[(ph + lane) & (DMT_PCAP - 1)];
                         const unsigned long long g = base + e.ln;
                         if (g < a.out_cap) {
                             const float old = atomicAdd(a.scores + g, 1.0f);
@@ -346,26 +378,21 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
                     const uint32_t nf = __popc(__ballot_sync(0xffffffffu, first));
                     if (lane == 0) {
                         if (nf) { atomicAdd(&a.hdr->n_anomalies, (unsigned long long)nf); atomicAdd(a.stats + 3, (unsigned long long)nf); }
-                        atomicAdd(a.stats + 4, (unsigned long long)(pn < 32u ? pn : 32u));
+                        atomicAdd(a.stats + 4, (unsigned long long)take);
                     }
-                    // entries beyond the first 32 move to the front
-                    DmPEntry mv;
-                    const bool has_mv = pn > 32u && lane < pn - 32u;
-                    if (has_mv) mv = pend[32 + lane];
-                    __syncwarp();
-                    if (has_mv) pend[lane] = mv;
-                    pn = pn > 32u ? pn - 32u : 0u;
+                    ph += take;
+                    pn -= take;
                     __syncwarp();
                 }
             };
 
-            // one queued value per lane: fingerprint, probe, and the exact re-check when unknown
-            auto drain = [&](uint32_t n) {
+            // stage 2: one identified field per lane -- fingerprint, probe, exact re-check when unknown
+            auto drain2 = [&](uint32_t n) {
                 bool unk = false;
                 DmPEntry pe;
                 pe.ln = 0; pe.k = 0; pe.lstart = 0;
                 if (lane < n) {
-                    const DmQEntry e = queue[lane];
+                    const DmQ2Entry e = q2[(q2h + lane) & (DMT_Q2CAP - 1)];
                     bool in_range = true;
                     if (a.range_check) {
                         const unsigned long long g = base + (unsigned long long)e.ln;
@@ -388,17 +415,12 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
                         }
                     }
                 }
-                // compact the queue
-                DmQEntry mv;
-                const bool has_mv = qn > n && lane < qn - n;
-                if (has_mv) mv = queue[n + lane];
-                __syncwarp();
-                if (has_mv) queue[lane] = mv;
-                qn -= n;
+                q2h += n;
+                q2n -= n;
                 if (!TRAIN) {
                     const uint32_t ub = __ballot_sync(0xffffffffu, unk);
                     if (ub) {
-                        if (unk) pend[pn + __popc(ub & lt)] = pe;
+                        if (unk) pend[(ph + pn + __popc(ub & lt)) & (DMT_PCAP - 1)] = pe;
                         pn += __popc(ub);
                         __syncwarp();
                         if (pn >= 32u) flush();
@@ -407,7 +429,31 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
                 __syncwarp();
             };
 
-            // ---- pass 2: classify, filter, queue ----
+            // stage 1: one '=' per lane -- which monitored key (if any) stands in front of it
+            auto drain1 = [&](uint32_t n) {
+                bool matched = false;
+                DmQ2Entry qe;
+                qe.vpos = 0; qe.ln = 0; qe.k = 0;
+                if (lane < n) {
+                    const DmQ1Entry e = q1[(q1h + lane) & (DMT_Q1CAP - 1)];
+                    if (e.ln >= 0 && e.ln < (int32_t)n_owned) {
+                        const int k = dm_key_identify(buf, (uint64_t)e.q, sk);
+                        if (k >= 0) { matched = true; qe.vpos = e.q + 1; qe.ln = e.ln; qe.k = (uint32_t)k; }
+                    }
+                }
+                q1h += n;
+                q1n -= n;
+                const uint32_t mb = __ballot_sync(0xffffffffu, matched);
+                if (mb) {
+                    if (matched) q2[(q2h + q2n + __popc(mb & lt)) & (DMT_Q2CAP - 1)] = qe;
+                    q2n += __popc(mb);
+                    __syncwarp();
+                    if (q2n >= 32u) drain2(32u);
+                }
+                __syncwarp();
+            };
+
+            // ---- pass 2: classify the rows, queue every '=' ----
             if (n_owned > 0) {
                 const int32_t ln_off = (int32_t)is_start0 - 1;
                 const uint32_t need_nl = n_owned - is_start0 + 1;   // newlines until the last owned record is closed
@@ -457,46 +503,77 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
                         }
                     }
                     const int32_t ln_chunk = ln_off + (int32_t)(nl_seen + pre);
-                    const int32_t limit = row >= in_seg_rows ? (int32_t)n_owned : 0x7fffffff;
 
-                    uint32_t m = eq16;
-                    while (__ballot_sync(0xffffffffu, m != 0)) {
-                        bool matched = false;
-                        DmQEntry qe;
-                        qe.vpos = 0; qe.ln = 0; qe.k = 0;
-                        if (m) {
-                            const uint32_t j = (uint32_t)__ffs(m) - 1;
-                            m &= m - 1;
-                            const uint64_t q = off + j;
-                            int32_t ln = ln_chunk;
-                            if (nl_any) {
-                                const uint32_t wj = j >> 2, bm = (1u << ((j & 3) * 8)) - 1u;
-                                ln += __popc(nlF0 & (wj > 0 ? 0xFFFFFFFFu : bm));
-                                ln += __popc(nlF1 & (wj > 1 ? 0xFFFFFFFFu : (wj == 1 ? bm : 0u)));
-                                ln += __popc(nlF2 & (wj > 2 ? 0xFFFFFFFFu : (wj == 2 ? bm : 0u)));
-                                ln += __popc(nlF3 & (wj == 3 ? bm : 0u));
+                    // every '=' of the row goes to queue 1, in position order
+                    const uint32_t my_eq = (uint32_t)__popc(eq16);
+                    uint32_t eincl = my_eq;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, eincl, d);
+                        if ((int)lane >= d) eincl += y;
+                    }
+                    const uint32_t row_eq = __shfl_sync(0xffffffffu, eincl, 31);
+                    if (row_eq) {
+                        uint32_t m = eq16;
+                        if (q1n + row_eq <= DMT_Q1CAP) {
+                            uint32_t slot = q1h + q1n + (eincl - my_eq);
+                            while (m) {
+                                const uint32_t j = (uint32_t)__ffs(m) - 1;
+                                m &= m - 1;
+                                int32_t ln = ln_chunk;
+                                if (nl_any) {
+                                    const uint32_t wj = j >> 2, bm = (1u << ((j & 3) * 8)) - 1u;
+                                    ln += __popc(nlF0 & (wj > 0 ? 0xFFFFFFFFu : bm));
+                                    ln += __popc(nlF1 & (wj > 1 ? 0xFFFFFFFFu : (wj == 1 ? bm : 0u)));
+                                    ln += __popc(nlF2 & (wj > 2 ? 0xFFFFFFFFu : (wj == 2 ? bm : 0u)));
+                                    ln += __popc(nlF3 & (wj == 3 ? bm : 0u));
+                                }
+                                DmQ1Entry e;
+                                e.q = (uint32_t)(off + j); e.ln = ln;
+                                q1[slot & (DMT_Q1CAP - 1)] = e;
+                                ++slot;
                             }
-                            if (ln >= 0 && ln < limit) {
-                                const int k = dm_key_filter(buf, q, sk);
-                                if (k >= 0) { matched = true; qe.vpos = (uint32_t)(q + 1); qe.ln = ln; qe.k = (uint32_t)k; }
-                            }
-                        }
-                        const uint32_t mb = __ballot_sync(0xffffffffu, matched);
-                        if (mb) {
-                            if (matched) queue[qn + __popc(mb & lt)] = qe;
-                            qn += __popc(mb);
+                            q1n += row_eq;
                             __syncwarp();
-                            if (qn >= 32u) drain(32u);
+                            while (q1n >= 32u) drain1(32u);
+                        } else {
+                            // a row dense in '=' (more than the queue holds): one per lane per round
+                            while (__ballot_sync(0xffffffffu, m != 0)) {
+                                bool has = false;
+                                DmQ1Entry e;
+                                e.q = 0; e.ln = 0;
+                                if (m) {
+                                    const uint32_t j = (uint32_t)__ffs(m) - 1;
+                                    m &= m - 1;
+                                    int32_t ln = ln_chunk;
+                                    if (nl_any) {
+                                        const uint32_t wj = j >> 2, bm = (1u << ((j & 3) * 8)) - 1u;
+                                        ln += __popc(nlF0 & (wj > 0 ? 0xFFFFFFFFu : bm));
+                                        ln += __popc(nlF1 & (wj > 1 ? 0xFFFFFFFFu : (wj == 1 ? bm : 0u)));
+                                        ln += __popc(nlF2 & (wj > 2 ? 0xFFFFFFFFu : (wj == 2 ? bm : 0u)));
+                                        ln += __popc(nlF3 & (wj == 3 ? bm : 0u));
+                                    }
+                                    has = true; e.q = (uint32_t)(off + j); e.ln = ln;
+                                }
+                                const uint32_t hb = __ballot_sync(0xffffffffu, has);
+                                if (has) q1[(q1h + q1n + __popc(hb & lt)) & (DMT_Q1CAP - 1)] = e;
+                                q1n += __popc(hb);
+                                __syncwarp();
+                                while (q1n >= 32u) drain1(32u);
+                            }
                         }
                     }
                     nl_seen += row_nl;
                     if (row + 1 >= in_seg_rows && nl_seen >= need_nl) break;
                 }
-                if (qn) drain(qn);
+                while (q1n) drain1(q1n < 32u ? q1n : 32u);
+                while (q2n) drain2(q2n < 32u ? q2n : 32u);
             }
-            if (pn > 32u) flush();
+            while (pn > 32u) flush();
             flush();
         }
+        __syncthreads();
+        tile = s_tile;
         __syncthreads();
     }
 }
@@ -555,7 +632,7 @@ static inline int dm_tile_launch(DmTileScratch* s, const uint8_t* d_buf, uint64_
         a.epoch = s->epoch; a.ctr_base = s->ctr_base;
         a.line_lo = 0; a.line_hi = n_train_lines; a.range_check = 1; a.zero_fill = 1; a.finalize = 0;
         dm_k_tile<true><<<grid, DMT_THREADS, 0, st>>>(a);
-        s->ctr_base += (unsigned long long)n_tiles + (unsigned long long)grid;
+        s->ctr_base += (unsigned long long)n_tiles;
         ++launched;
     }
     s->epoch = (s->epoch % 0x3FFFFFFEu) + 1u;
@@ -563,7 +640,7 @@ static inline int dm_tile_launch(DmTileScratch* s, const uint8_t* d_buf, uint64_
     a.line_lo = n_train_lines; a.line_hi = ~0ull; a.range_check = n_train_lines > 0 ? 1 : 0;
     a.zero_fill = n_train_lines > 0 ? 0 : 1; a.finalize = 1;
     dm_k_tile<false><<<grid, DMT_THREADS, 0, st>>>(a);
-    s->ctr_base += (unsigned long long)n_tiles + (unsigned long long)grid;
+    s->ctr_base += (unsigned long long)n_tiles;
     ++launched;
     if (cudaGetLastError() != cudaSuccess) return DM_ERR_CUDA;
     return launched;

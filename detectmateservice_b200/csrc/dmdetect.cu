@@ -14,6 +14,7 @@
 #include "dm_device.cuh"
 #include "dm_kernels_v1.cuh"
 #include "dm_kernels_tile.cuh"
+#include "dm_kernels_values.cuh"
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -76,6 +77,9 @@ struct dm_handle {
     uint64_t novel_exported = 0;         // novel keys already shipped in a window
     DmTileScratch tile;                  // fused-kernel scratch
     uint64_t last_nbytes = 0;
+    uint32_t* d_vals = nullptr;          // record mode: offsets / fields / record_of
+    uint64_t vals_cap = 0;
+    uint32_t* d_masks = nullptr;
     // measurement support
     bool profile = false;
     std::vector<cudaEvent_t> ev;         // pairs: ev[2i] start, ev[2i+1] stop
@@ -237,6 +241,7 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
     cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
+    cudaFree(h->d_vals); cudaFree(h->d_masks);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return DM_OK;
@@ -337,6 +342,81 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         if (scores_out && n_lines) DM_CUDA(cudaMemcpyAsync(scores_out, h->d_scores, n_lines * sizeof(float), cudaMemcpyDeviceToHost, st));
         DM_CUDA(cudaStreamSynchronize(st));
     }
+    return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// record mode
+// ---------------------------------------------------------------------------------------
+extern "C" int dm_process_values(dm_handle* h, const uint8_t* blob, uint64_t blob_bytes, const uint32_t* offsets,
+                                 const uint32_t* fields, const uint32_t* record_of, uint32_t n_values,
+                                 uint32_t n_records, uint32_t n_train_records, uint64_t record_bytes,
+                                 uint8_t* flags_out, float* scores_out, uint32_t* masks_out,
+                                 uint64_t* n_anomalies_out) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    if (n_values && (!blob && blob_bytes)) return dm_fail(DM_ERR_ARG, "blob is NULL");
+    if (n_values && (!offsets || !fields || !record_of)) return dm_fail(DM_ERR_ARG, "value arrays missing");
+    if (blob_bytes > h->max_batch_bytes) return dm_fail(DM_ERR_CAPACITY, "value blob of %llu bytes exceeds max_batch_bytes", (unsigned long long)blob_bytes);
+    if (n_records > h->max_lines) return dm_fail(DM_ERR_CAPACITY, "%u records exceed max_lines=%llu", n_records, (unsigned long long)h->max_lines);
+    for (uint32_t i = 0; i < n_values; ++i) {
+        if (fields[i] >= h->n_keys || record_of[i] >= n_records || offsets[i] > offsets[i + 1] || offsets[i + 1] > blob_bytes)
+            return dm_fail(DM_ERR_ARG, "value %u: field/record/offset out of range", i);
+    }
+    DM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    h->last_stream = st;
+    if (n_values > h->vals_cap) {
+        if (h->d_vals) DM_CUDA(cudaFree(h->d_vals));
+        h->vals_cap = std::max<uint64_t>(2ull * n_values, 4096);
+        DM_CUDA(cudaMalloc(&h->d_vals, (3 * h->vals_cap + 1) * sizeof(uint32_t)));
+    }
+    if (!h->d_masks) DM_CUDA(cudaMalloc(&h->d_masks, (h->max_lines + 4) * sizeof(uint32_t)));
+    uint32_t* d_off = h->d_vals;
+    uint32_t* d_fld = d_off + h->vals_cap + 1;
+    uint32_t* d_rec = d_fld + h->vals_cap;
+    DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
+    if (n_values) {
+        if (blob_bytes) DM_CUDA(cudaMemcpyAsync(h->d_in, blob, blob_bytes, cudaMemcpyHostToDevice, st));
+        DM_CUDA(cudaMemcpyAsync(d_off, offsets, (uint64_t)(n_values + 1) * 4, cudaMemcpyHostToDevice, st));
+        DM_CUDA(cudaMemcpyAsync(d_fld, fields, (uint64_t)n_values * 4, cudaMemcpyHostToDevice, st));
+        DM_CUDA(cudaMemcpyAsync(d_rec, record_of, (uint64_t)n_values * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (n_records) {
+        DM_CUDA(cudaMemsetAsync(h->d_flags, 0, n_records, st));
+        DM_CUDA(cudaMemsetAsync(h->d_scores, 0, (uint64_t)n_records * 4, st));
+        DM_CUDA(cudaMemsetAsync(h->d_masks, 0, (uint64_t)n_records * 4, st));
+    }
+    if (n_values) {
+        DmValuesArgs a;
+        a.blob = h->d_in; a.offsets = d_off; a.fields = d_fld; a.record_of = d_rec; a.n_values = n_values;
+        a.n_records = n_records; a.n_train_records = n_train_records; a.keys = h->d_keys; a.table = h->table;
+        a.flags = h->d_flags; a.scores = h->d_scores; a.masks = h->d_masks; a.hdr = h->d_hdr; a.stats = h->d_stats;
+        const int grid = (int)std::min<uint32_t>((n_values + 255) / 256, (uint32_t)h->sm_count * 8);
+        if (n_train_records > 0) { dm_k_values<<<grid, 256, 0, st>>>(a, 0); h->launches++; }
+        dm_k_values<<<grid, 256, 0, st>>>(a, 1);
+        h->launches++;
+        DM_CUDA(cudaGetLastError());
+    }
+    DM_CUDA(cudaMemcpyAsync(h->h_hdr, h->d_hdr, sizeof(DmBatchHeader), cudaMemcpyDeviceToHost, st));
+    if (flags_out && n_records) DM_CUDA(cudaMemcpyAsync(flags_out, h->d_flags, n_records, cudaMemcpyDeviceToHost, st));
+    if (scores_out && n_records) DM_CUDA(cudaMemcpyAsync(scores_out, h->d_scores, (uint64_t)n_records * 4, cudaMemcpyDeviceToHost, st));
+    if (masks_out && n_records) DM_CUDA(cudaMemcpyAsync(masks_out, h->d_masks, (uint64_t)n_records * 4, cudaMemcpyDeviceToHost, st));
+    DM_CUDA(cudaStreamSynchronize(st));
+    // statistics that do not need the device: record and byte counts
+    {
+        const unsigned long long tr = std::min<uint32_t>(n_train_records, n_records);
+        unsigned long long add[6] = {n_records, tr, n_records - tr, 0, 0, record_bytes};
+        unsigned long long cur[6];
+        DM_CUDA(cudaMemcpy(cur, h->d_stats, sizeof(cur), cudaMemcpyDeviceToHost));
+        cur[0] += add[0]; cur[1] += add[1]; cur[2] += add[2]; cur[5] += add[5];
+        unsigned long long upd[3] = {cur[0], cur[1], cur[2]};
+        DM_CUDA(cudaMemcpy(h->d_stats, upd, sizeof(upd), cudaMemcpyHostToDevice));
+        DM_CUDA(cudaMemcpy(h->d_stats + 5, &cur[5], sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    h->h_hdr->n_lines = n_records;
+    int rc = dm_check_device_errors(h);
+    if (rc != DM_OK) return rc;
+    if (n_anomalies_out) *n_anomalies_out = h->h_hdr->n_anomalies;
     return DM_OK;
 }
 

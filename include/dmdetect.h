@@ -100,6 +100,18 @@ int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbytes, int buf_
                      uint8_t* flags_out, float* scores_out, uint64_t out_cap_lines, int out_on_device,
                      uint64_t* n_lines_out, uint64_t* n_anomalies_out, void* stream);
 
+/* Record mode: the detector fed with already-extracted values, as when the upstream parser
+ * sends one ParserSchema per message (engine.py:163-187; the host decodes the protobuf
+ * framing, docs/interfaces.md:124-128).  Value i is blob[offsets[i], offsets[i+1]) and
+ * belongs to monitored field fields[i] of record record_of[i].  Records
+ * [0, n_train_records) are training data; the rest are scored: flags_out / scores_out /
+ * masks_out have n_records entries (host memory, any may be NULL).  Synchronous. */
+int dm_process_values(dm_handle* h, const uint8_t* blob, uint64_t blob_bytes, const uint32_t* offsets,
+                      const uint32_t* fields, const uint32_t* record_of, uint32_t n_values,
+                      uint32_t n_records, uint32_t n_train_records, uint64_t record_bytes,
+                      uint8_t* flags_out, float* scores_out, uint32_t* masks_out,
+                      uint64_t* n_anomalies_out);
+
 /* Wait for everything enqueued on the handle and report the last batch's counts. */
 int dm_sync(dm_handle* h, uint64_t* n_lines_out, uint64_t* n_anomalies_out);
 

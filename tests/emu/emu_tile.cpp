@@ -100,14 +100,14 @@ extern "C" int emu_process(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, ui
             a.epoch = h->epoch; a.ctr_base = h->ctr_base;
             a.line_lo = 0; a.line_hi = n_train; a.range_check = 1; a.zero_fill = 1; a.finalize = 0;
             emu_launch(DMT_THREADS, [&] { dm_k_tile<true>(a); });
-            h->ctr_base += (unsigned long long)n_tiles + 1ull;
+            h->ctr_base += (unsigned long long)n_tiles;
         }
         h->epoch = (h->epoch % 0x3FFFFFFEu) + 1u;
         a.epoch = h->epoch; a.ctr_base = h->ctr_base;
         a.line_lo = n_train; a.line_hi = ~0ull; a.range_check = n_train > 0 ? 1 : 0;
         a.zero_fill = n_train > 0 ? 0 : 1; a.finalize = 1;
         emu_launch(DMT_THREADS, [&] { dm_k_tile<false>(a); });
-        h->ctr_base += (unsigned long long)n_tiles + 1ull;
+        h->ctr_base += (unsigned long long)n_tiles;
     }
     free(buf);
     *n_lines = h->hdr.n_lines;

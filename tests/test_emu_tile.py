@@ -65,6 +65,7 @@ def test_emu_edge_cases():
         b"x" * 5000 + b" k=v\n", b"k=" + b"v" * 5000 + b"\n", b'q="a b k=1" k=2\n', b'q="unbalanced k=1\nk=1\n',
         b"longer_key_name_0123456789abcdef=1 xlonger_key_name_0123456789abcdef=2\n", b"a'k=5 b'type=Z\n",
         b" k=1\n  k=2\n", b"k=1\n" * 1000, (b"y" * 126 + b" k=edge\n") * 50, (b"y" * 123 + b" type=edge\n") * 50,
+        b" k=" * 600 + b"\n" + b"=" * 700 + b"\n" + b"k=2 " * 300 + b"\n",   # rows dense in '=' (queue overflow path)
         b"k=2",                                            # '=' at position 1 (q < 4), no newline
         b"k=9\n" + b"z" * 4090 + b"\nk=3\n",               # record starting exactly at a segment boundary
         b"z" * 4095 + b"\nk=4\n",                          # newline as the last byte of a segment

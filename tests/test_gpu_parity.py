@@ -141,6 +141,7 @@ def test_edge_cases(variant):
         b"k=1\n" * 1000,
         (b"y" * 126 + b" k=edge\n") * 50,                 # key straddling the 128-byte steps
         (b"y" * 123 + b" type=edge\n") * 50,
+        b" k=" * 600 + b"\n" + b"=" * 700 + b"\n" + b"k=2 " * 300 + b"\n",   # rows dense in '=' (queue overflow path)
     ]
     o = NativeOracle(keys)
     with _det(keys) as det:
