@@ -32,6 +32,11 @@ struct DmKeys {
     uint32_t midmask[DM_MAX_KEYS];
     uint32_t dsel[DM_MAX_KEYS];
     uint32_t dshift[DM_MAX_KEYS];
+    // the same patterns packed for one 16-byte shared-memory load per key, in the order the
+    // fused kernel tries the keys: longest first, so that a key that is a suffix of another
+    // ("res" / "xres") is only considered when the longer one does not match.
+    uint32_t order[DM_MAX_KEYS];
+    alignas(16) uint32_t pat[DM_MAX_KEYS][4];      // [slot] = {tailbits, tailmask, midbits, midmask} of key order[slot]
 };
 
 static inline void dm_keys_finalize_host(DmKeys* k) {
@@ -47,6 +52,18 @@ static inline void dm_keys_finalize_host(DmKeys* k) {
         const uint32_t dd = len + 1;                                // distance of the delimiter
         k->dsel[i] = dd <= 12 ? (dd - 1) / 4 : 3;                   // 3 = not in the 12-byte window
         k->dshift[i] = dd <= 12 ? 8 * (4 * ((dd - 1) / 4 + 1) - dd) : 0;
+    }
+    for (uint32_t i = 0; i < k->n; ++i) k->order[i] = i;
+    for (uint32_t i = 1; i < k->n; ++i) {                           // insertion sort, longest first, stable
+        const uint32_t v = k->order[i];
+        uint32_t j = i;
+        while (j > 0 && k->len[k->order[j - 1]] < k->len[v]) { k->order[j] = k->order[j - 1]; --j; }
+        k->order[j] = v;
+    }
+    for (uint32_t s = 0; s < k->n; ++s) {
+        const uint32_t i = k->order[s];
+        k->pat[s][0] = k->tailbits[i]; k->pat[s][1] = k->tailmask[i];
+        k->pat[s][2] = k->midbits[i]; k->pat[s][3] = k->midmask[i];
     }
 }
 

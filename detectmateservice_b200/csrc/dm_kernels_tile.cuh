@@ -26,7 +26,7 @@
 #pragma once
 #include "dm_device.cuh"
 
-#define DMT_WARPS 8
+#define DMT_WARPS 4
 #define DMT_THREADS (DMT_WARPS * 32 + 32)
 #define DMT_ROW 512u
 #define DMT_SEG_ROWS 8u
@@ -114,23 +114,31 @@ __device__ __forceinline__ int dm_key_identify(const uint8_t* __restrict__ buf, 
     const uint32_t w_a = __funnelshift_r(x0, x1, sh);    // bytes q-12 .. q-9
     const uint32_t w_b = __funnelshift_r(x1, x2, sh);    // bytes q-8 .. q-5
     const uint32_t w_c = __funnelshift_r(x2, x3, sh);    // bytes q-4 .. q-1
-    int found = -1;
-    for (uint32_t k = 0; k < sk.n; ++k) {
-        const uint32_t diff = ((w_c ^ sk.tailbits[k]) & sk.tailmask[k]) | ((w_b ^ sk.midbits[k]) & sk.midmask[k]);
-        if (diff == 0 && found < 0) {
-            const uint32_t sel = sk.dsel[k];
-            bool ok;
-            if (sel < 3 && sk.len[k] <= 8) {
-                const uint32_t dw = sel == 0 ? w_c : (sel == 1 ? w_b : w_a);
-                const uint32_t d = (dw >> sk.dshift[k]) & 0xFFu;
-                ok = d == 0x20u || d == 0x27u || d == 0x0Au;
-            } else {
-                ok = dm_key_check(buf, q, k, sk, 8);      // long key: the rest byte by byte
-            }
-            if (ok) found = (int)k;
-        }
+    // first (= longest) key whose last min(len,8) bytes stand in front of the '='
+    uint32_t slot = 0xFFFFFFFFu;
+    for (uint32_t s = 0; s < sk.n; ++s) {
+        const uint4 p = *reinterpret_cast<const uint4*>(sk.pat[s]);
+        const uint32_t diff = ((w_c ^ p.x) & p.y) | ((w_b ^ p.z) & p.w);
+        if (diff == 0 && slot == 0xFFFFFFFFu) slot = s;
     }
-    return found;
+    if (slot == 0xFFFFFFFFu) return -1;
+    const uint32_t k = sk.order[slot];
+    const uint32_t len = sk.len[k];
+    if (len <= 8) {
+        // field-start delimiter (R-tok L4); a shorter key that is a suffix of this one cannot
+        // be a field start here either, its delimiter position holds a byte of this key
+        const uint32_t sel = sk.dsel[k];
+        const uint32_t dw = sel == 0 ? w_c : (sel == 1 ? w_b : w_a);
+        const uint32_t d = (dw >> sk.dshift[k]) & 0xFFu;
+        return (d == 0x20u || d == 0x27u || d == 0x0Au) ? (int)k : -1;
+    }
+    // keys longer than the 8 compared bytes: finish byte by byte, then fall back to the others
+    if (dm_key_check(buf, q, k, sk, 8)) return (int)k;
+    for (uint32_t s = slot + 1; s < sk.n; ++s) {
+        const uint32_t k2 = sk.order[s];
+        if (dm_key_check(buf, q, k2, sk, 0)) return (int)k2;
+    }
+    return -1;
 }
 
 // dm_fp64 of the value that starts at vpos: ends at the first space outside double quotes
@@ -176,8 +184,10 @@ __device__ __forceinline__ uint64_t dm_hash_value(const uint8_t* __restrict__ bu
         if (rem < nvtot) nvtot = (uint32_t)rem;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (nvtot >= 4u * i + 4u) dm_hash_word(st, w[i]);
-            else if (nvtot > 4u * i) dm_hash_word(st, w[i] & ((1u << (8 * (nvtot - 4u * i))) - 1u));
+            if (nvtot > 4u * i) {
+                const uint32_t nb = nvtot - 4u * i;                 // valid bytes of this word (>= 1)
+                dm_hash_word(st, nb >= 4u ? w[i] : (w[i] & ((1u << (8 * nb)) - 1u)));
+            }
         }
         n += nvtot;
         if (nvtot < 16) break;
@@ -215,7 +225,7 @@ __device__ __forceinline__ bool dm_verify_field(const uint8_t* __restrict__ buf,
 // ---------------------------------------------------------------------------------------
 template <bool TRAIN>
 __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
-    __shared__ DmKeys sk;
+    __shared__ DmKeys sk;   // 16-byte aligned through its alignas(16) member
     __shared__ uint32_t s_cnt[DMT_WARPS];
     __shared__ unsigned long long s_base[DMT_WARPS];
     __shared__ long long s_tile;
@@ -223,11 +233,6 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
     __shared__ DmQ2Entry s_q2[DMT_WARPS][DMT_Q2CAP];
     __shared__ DmPEntry s_pend[DMT_WARPS][DMT_PCAP];
 
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.keys);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sk);
-        for (uint32_t i = threadIdx.x; i < sizeof(DmKeys) / 4; i += DMT_THREADS) dst[i] = src[i];
-    }
     const uint8_t* __restrict__ buf = a.buf;
     const uint64_t nbytes = a.nbytes;
     const uint32_t lane = threadIdx.x & 31;
@@ -238,13 +243,24 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
     // are co-resident, and never more than there are tiles); further tiles come from the
     // atomic counter.
     long long tile = (long long)blockIdx.x;
-    __syncthreads();
+    bool keys_ready = false;                                   // workers: sk is valid (barrier 3 passed)
+    if (warp == DMT_WARPS) {
+        // the scanner warp brings the key tables into shared memory while the workers are
+        // already counting record starts (pass 1 does not need them)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.keys);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sk);
+        for (uint32_t i = lane; i < sizeof(DmKeys) / 4; i += 32) dst[i] = __ldg(src + i);
+        __threadfence_block();
+        dm_bar_arrive(3, DMT_THREADS);
+    }
     for (;;) {
         if (tile >= (long long)a.n_tiles) break;
 
         if (warp == DMT_WARPS) {
             // ------------------------------ scanner warp ------------------------------
-            dm_bar_sync(1, DMT_THREADS);                       // the 8 record counts are in s_cnt
+            // fetch this CTA's next tile now; the answer is only needed after this tile
+            if (lane == 0) s_tile = (long long)gridDim.x + (long long)(atomicAdd(a.tile_ctr, 1ull) - a.ctr_base);
+            dm_bar_sync(1, DMT_THREADS);                       // the record counts are in s_cnt
             const uint32_t c = lane < DMT_WARPS ? s_cnt[lane] : 0u;
             uint32_t incl = c;
 #pragma unroll
@@ -294,8 +310,6 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
             }
             __threadfence_block();
             dm_bar_arrive(2, DMT_THREADS);                     // bases are in s_base
-            // fetch this CTA's next tile while the workers finish
-            if (lane == 0) s_tile = (long long)gridDim.x + (long long)(atomicAdd(a.tile_ctr, 1ull) - a.ctr_base);
         } else {
             // ------------------------------ worker warp -------------------------------
             const uint64_t seg_start = (uint64_t)tile * DMT_TILE + (uint64_t)warp * DMT_SEG;
@@ -334,6 +348,7 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
             __threadfence_block();
             dm_bar_arrive(1, DMT_THREADS);
 
+            if (!keys_ready) { dm_bar_sync(3, DMT_THREADS); keys_ready = true; }
             bool have_base = false, zero_done = false;
             unsigned long long base = 0;
             if (a.range_check) { dm_bar_sync(2, DMT_THREADS); have_base = true; base = s_base[warp]; }
