@@ -197,27 +197,76 @@ __device__ __forceinline__ uint64_t dm_hash_value(const uint8_t* __restrict__ bu
     return dm_hash_final(st, n);
 }
 
-// Slow, exact re-check of one candidate: is the '=' at q the FIRST true field (R-tok L2-L6)
-// with key k of its record?  Also returns the record's first byte.
-__device__ __forceinline__ bool dm_verify_field(const uint8_t* __restrict__ buf, uint64_t q, uint32_t k, const DmKeys& sk,
-                                                uint64_t* line_start) {
-    uint64_t s = q;
-    while (s > 0 && dm_ld8(buf, s - 1) != 0x0Au) --s;
+// 16-bit mask of the bytes of a 16-byte chunk equal to the byte replicated in pat
+__device__ __forceinline__ uint32_t dm_chunk_mask(const uint4& v, uint32_t pat) {
+    return dm_flags_to_nib(dm_eqflags(v.x, pat)) | (dm_flags_to_nib(dm_eqflags(v.y, pat)) << 4) |
+           (dm_flags_to_nib(dm_eqflags(v.z, pat)) << 8) | (dm_flags_to_nib(dm_eqflags(v.w, pat)) << 12);
+}
+
+// Exact re-check of one candidate, by the whole warp (all lanes pass the same q and k and get
+// the same answer): is the '=' at q the FIRST true field (R-tok L2-L6) with key k of its
+// record?  Also returns the record's first byte.  Each lane takes one 16-byte chunk of a
+// 512-byte window; quote parity is a ballot prefix, the first true field a warp minimum.
+__device__ __forceinline__ bool dm_verify_field_warp(const uint8_t* __restrict__ buf, uint32_t q, uint32_t k,
+                                                     const DmKeys& sk, uint32_t lane, uint32_t lt,
+                                                     uint32_t* line_start) {
+    // ---- the record's first byte: last '\n' before q ----
+    uint32_t s = 0;
+    for (long long cq = (long long)(q >> 4);; cq -= 32) {
+        const long long c = cq - 31 + (long long)lane;
+        uint32_t m = 0;
+        if (c >= 0) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(buf + c * 16));
+            m = dm_chunk_mask(v, 0x0A0A0A0Au);
+            if (c == (long long)(q >> 4)) m &= (1u << (q & 15u)) - 1u;       // only bytes in front of q
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, m != 0);
+        if (b) {
+            const uint32_t L = 31u - (uint32_t)__clz((int)b);
+            const uint32_t pos = (uint32_t)(c * 16) + (31u - (uint32_t)__clz((int)m)) + 1u;
+            s = __shfl_sync(0xffffffffu, pos, (int)L);
+            break;
+        }
+        if (cq - 31 <= 0) break;                                             // reached the start of the message
+    }
     *line_start = s;
+    // ---- first true field with key k in [s, q] ----
     const uint32_t len = sk.len[k];
-    uint32_t inq = 0, prev = 0x20u;
-    for (uint64_t p = s; p + len <= q; ++p) {
-        const uint32_t c = dm_ld8(buf, p);
-        if (!inq && (p == s || prev == 0x20u || prev == 0x27u)) {
-            if (dm_ld8(buf, p + len) == 0x3Du) {
-                bool eq = true;
-                for (uint32_t i = 0; i < len; ++i)
-                    if (dm_ld8(buf, p + i) != sk.bytes[k][i]) { eq = false; break; }
-                if (eq) return p + len == q;
+    uint32_t carry = 0;
+    for (uint32_t wbase = s & ~15u; wbase <= q; wbase += 512u) {
+        const uint32_t off = wbase + lane * 16u;
+        uint32_t dq16 = 0, eq16 = 0;
+        if (off <= q) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(buf + off));
+            uint32_t keep = 0xFFFFu;
+            if (off < s) keep &= ~((1u << (s - off)) - 1u);                  // bytes of the previous record
+            if (q - off < 15u) keep &= (2u << (q - off)) - 1u;                // bytes behind q
+            dq16 = dm_chunk_mask(v, 0x22222222u) & keep;
+            eq16 = dm_chunk_mask(v, 0x3D3D3D3Du) & keep;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, __popc(dq16) & 1);
+        const uint32_t inq_lane = carry ^ ((uint32_t)__popc(bal & lt) & 1u);
+        uint32_t best = 0xFFFFFFFFu;
+        uint32_t m = eq16;
+        while (m && best == 0xFFFFFFFFu) {
+            const uint32_t j = (uint32_t)__ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t p = off + j;
+            const uint32_t inq = inq_lane ^ ((uint32_t)__popc(dq16 & ((1u << j) - 1u)) & 1u);
+            if (!inq && p >= s + len) {
+                const uint32_t p0 = p - len;
+                bool ok = true;
+                if (p0 > s) {
+                    const uint32_t d = dm_ld8(buf, p0 - 1);
+                    ok = d == 0x20u || d == 0x27u;
+                }
+                for (uint32_t i = 0; ok && i < len; ++i) ok = dm_ld8(buf, p0 + i) == sk.bytes[k][i];
+                if (ok) best = p;
             }
         }
-        if (c == 0x22u) inq ^= 1u;
-        prev = c;
+        const uint32_t mn = __reduce_min_sync(0xffffffffu, best);
+        if (mn != 0xFFFFFFFFu) return mn == q;
+        carry ^= (uint32_t)__popc(bal) & 1u;
     }
     return false;
 }
@@ -273,27 +322,41 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
             unsigned long long excl = 0;
             if (tile > 0) {
                 if (lane == 0) atomicExch(a.tile_state + tile, tag | (DMT_ST_AGG << 32) | agg);
-                // decoupled look-back, 32 predecessors per step
+                // Decoupled look-back.  All tiles of a message are usually in flight at once, so
+                // hardly any predecessor has published a PREFIX yet: waiting for one would make
+                // tile t walk t/32 dependent round trips.  Instead 128 predecessors are loaded
+                // per step (4 independent loads per lane) and only their AGGREGATES are needed;
+                // a PREFIX, where one is found, just ends the walk early.
                 long long hi = tile - 1;
-                for (;;) {
-                    const long long idx = hi - (long long)lane;
-                    unsigned long long st = 0;
-                    if (idx >= 0) {
-                        st = *((volatile unsigned long long*)(a.tile_state + idx));
-                        if ((st >> 34) != a.epoch) st = 0;             // stale word of an earlier launch
+                bool done = false;
+                while (!done) {
+                    unsigned long long st[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const long long idx = hi - 32 * j - (long long)lane;
+                        st[j] = idx >= 0 ? *((volatile unsigned long long*)(a.tile_state + idx)) : 0ull;
                     }
-                    const uint32_t status = idx >= 0 ? (uint32_t)((st >> 32) & 3u) : (uint32_t)DMT_ST_PREFIX;
-                    const uint32_t not_ready = __ballot_sync(0xffffffffu, status == 0);
-                    const uint32_t is_pref = __ballot_sync(0xffffffffu, status == DMT_ST_PREFIX);
-                    // usable window: lanes up to (and including) the first prefix, none of them not-ready
-                    const uint32_t first_pref = is_pref ? (uint32_t)(__ffs(is_pref) - 1) : 32u;
-                    const uint32_t upto = first_pref < 32u ? first_pref : 31u;
-                    const uint32_t win = upto == 31u ? 0xffffffffu : ((2u << upto) - 1u);
-                    if (not_ready & win) { __nanosleep(40); continue; }
-                    const uint32_t val = (lane <= upto && idx >= 0) ? (uint32_t)st : 0u;
-                    excl += __reduce_add_sync(0xffffffffu, val);
-                    if (first_pref < 32u) break;
-                    hi -= 32;
+                    int consumed = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (done || consumed < j) continue;
+                        const long long idx = hi - 32 * j - (long long)lane;
+                        unsigned long long w = st[j];
+                        if (idx >= 0 && (w >> 34) != a.epoch) w = 0;       // stale word of an earlier launch
+                        const uint32_t status = idx >= 0 ? (uint32_t)((w >> 32) & 3u) : (uint32_t)DMT_ST_PREFIX;
+                        const uint32_t not_ready = __ballot_sync(0xffffffffu, status == 0);
+                        const uint32_t is_pref = __ballot_sync(0xffffffffu, status == DMT_ST_PREFIX);
+                        const uint32_t first_pref = is_pref ? (uint32_t)(__ffs(is_pref) - 1) : 32u;
+                        const uint32_t upto = first_pref < 32u ? first_pref : 31u;
+                        const uint32_t win = upto == 31u ? 0xffffffffu : ((2u << upto) - 1u);
+                        if (not_ready & win) continue;                      // retry from this window
+                        const uint32_t val = (lane <= upto && idx >= 0) ? (uint32_t)w : 0u;
+                        excl += __reduce_add_sync(0xffffffffu, val);
+                        consumed = j + 1;
+                        if (first_pref < 32u) done = true;
+                    }
+                    hi -= 32 * consumed;
+                    if (!done && consumed < 4) __nanosleep(20);
                 }
             }
             if (lane == 0) atomicExch(a.tile_state + tile, tag | (DMT_ST_PREFIX << 32) | (unsigned long long)((uint32_t)excl + agg));
@@ -403,7 +466,9 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
 
             // stage 2: one identified field per lane -- fingerprint, probe, exact re-check when unknown
             auto drain2 = [&](uint32_t n) {
-                bool unk = false;
+                bool unk = false, cand = false;
+                uint64_t ckey = 0;
+                uint32_t cq = 0, ck = 0, cln = 0;
                 DmPEntry pe;
                 pe.ln = 0; pe.k = 0; pe.lstart = 0;
                 if (lane < n) {
@@ -417,16 +482,33 @@ __global__ void __launch_bounds__(DMT_THREADS) dm_k_tile(DmFusedArgs a) {
                         const uint64_t fp = dm_hash_value(buf, nbytes, e.vpos);
                         const uint64_t key = dm_make_key(fp, sk.salt[e.k]);
                         const bool known = TRAIN ? dm_table_contains_volatile(a.table, key) : dm_table_contains(a.table, key);
-                        if (!known) {
-                            uint64_t ls;
-                            if (dm_verify_field(buf, (uint64_t)e.vpos - 1, e.k, sk, &ls)) {
-                                if (TRAIN) {
-                                    dm_table_insert(a.table, key, &a.hdr->error);
-                                } else {
-                                    unk = true;
-                                    pe.ln = (uint32_t)e.ln; pe.k = e.k; pe.lstart = (uint32_t)ls;
-                                }
-                            }
+                        cand = !known;
+                        ckey = key;
+                        cq = e.vpos - 1;
+                        ck = e.k;
+                        cln = (uint32_t)e.ln;
+                    }
+                }
+                // values that are not in the table: exact re-check, one candidate at a time, by the whole warp
+                uint32_t cb = __ballot_sync(0xffffffffu, cand);
+                while (cb) {
+                    const int L = __ffs(cb) - 1;
+                    cb &= cb - 1;
+                    const uint32_t vq = __shfl_sync(0xffffffffu, cq, L);
+                    const uint32_t vk = __shfl_sync(0xffffffffu, ck, L);
+                    if (TRAIN) {
+                        // another lane (or warp) may have inserted this very value meanwhile
+                        const int still_new = ((int)lane == L) ? (dm_table_contains_volatile(a.table, ckey) ? 0 : 1) : 0;
+                        if (!__shfl_sync(0xffffffffu, still_new, L)) continue;
+                    }
+                    uint32_t ls = 0;
+                    const bool ok = dm_verify_field_warp(buf, vq, vk, sk, lane, lt, &ls);
+                    if ((int)lane == L && ok) {
+                        if (TRAIN) {
+                            dm_table_insert(a.table, ckey, &a.hdr->error);
+                        } else {
+                            unk = true;
+                            pe.ln = cln; pe.k = ck; pe.lstart = ls;
                         }
                     }
                 }

@@ -109,11 +109,21 @@ static inline unsigned emu_reduce(unsigned v, int op) {
     return r;
 }
 static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return emu_reduce(v, 0); }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    EmuWarp& w = emu_warp();
+    w.slot[emu_lane()] = v;
+    w.bar.sync(32);
+    unsigned r = 0xFFFFFFFFu;
+    for (int i = 0; i < 32; ++i) r = (unsigned)w.slot[i] < r ? (unsigned)w.slot[i] : r;
+    w.bar.sync(32);
+    return r;
+}
 static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return emu_reduce(v, 1); }
 
 // ---- scalar intrinsics -------------------------------------------------------------------
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)(v >> (sh & 31));
