@@ -1,0 +1,456 @@
+// dm_kernels_rows.cuh -- the "rows" variant of the fused tokenizer + detector (sm_100a).
+//
+// Same rules and same device helpers as dm_kernels_tile.cuh (key identification, dm_fp64 of
+// a value, warp-cooperative exact re-check); different decomposition:
+//
+//   K_A  dm_k_rowindex   streams the message once from HBM (16-byte loads), counts the '\n'
+//        of every 512-byte row, turns the counts into a global exclusive prefix
+//        (row_prefix[r] = number of '\n' in front of row r; tiles of 128 rows, decoupled
+//        look-back with 128-wide windows), zero-fills flags / scores of the records that end
+//        in its tile and writes the batch header.  The record index of ANY byte is then
+//        row_prefix[row] + (number of '\n' in front of it inside its row): no ownership of
+//        records by warps, no extension rows.
+//   K_B  dm_k_rows       every warp fetches groups of rows from an atomic counter (the message
+//        is still in L2: 16 MiB << 126 MB) and treats each row on its own: classify '\n' / '=',
+//        compact the '=' into queue 1, identify keys (stage 1), hash + probe values (stage 2),
+//        re-check the rare unknown values exactly, apply alerts with atomics.  No block-level
+//        synchronisation after the key tables are loaded, so all warps of the grid finish
+//        within one row group of each other.
+#pragma once
+#include "dm_kernels_tile.cuh"
+
+#define DMR_ROW 512u
+#define DMR_TILE_ROWS 128u
+#define DMR_A_THREADS 256
+#define DMR_B_WARPS 8
+#define DMR_B_THREADS (DMR_B_WARPS * 32)
+#define DMR_GROUP 4u          // rows fetched per atomic
+#define DMR_Q1CAP 128u
+#define DMR_Q2CAP 64u
+
+struct DmRowsArgs {
+    const uint8_t* buf;
+    uint64_t nbytes;
+    uint32_t n_rows;
+    uint32_t n_tiles;
+    uint32_t* row_prefix;             // n_rows entries
+    unsigned long long* tile_state;   // look-back words of K_A
+    uint32_t epoch;
+    const DmKeys* keys;
+    DmTable table;
+    uint8_t* flags;
+    float* scores;
+    uint64_t out_cap;
+    dm_anomaly_t* anomalies;
+    uint32_t anomaly_cap;
+    DmBatchHeader* hdr;
+    unsigned long long* stats;
+    unsigned long long* row_ctr;      // monotonically increasing across launches
+    unsigned long long ctr_base;
+    uint64_t line_lo, line_hi;        // K_B handles records with index in [lo, hi)
+    uint64_t n_train_lines;
+    uint64_t max_lines;
+};
+
+// 16-bit '\n' mask of this lane's chunk of a row, slack bytes behind the message dropped
+__device__ __forceinline__ uint32_t dm_row_nl_mask(const uint4& v, uint64_t off, uint64_t nbytes) {
+    const uint32_t f0 = dm_eqflags(v.x, 0x0A0A0A0Au), f1 = dm_eqflags(v.y, 0x0A0A0A0Au);
+    const uint32_t f2 = dm_eqflags(v.z, 0x0A0A0A0Au), f3 = dm_eqflags(v.w, 0x0A0A0A0Au);
+    if ((f0 | f1 | f2 | f3) == 0) return 0;
+    uint32_t m = dm_flags_to_nib(f0) | (dm_flags_to_nib(f1) << 4) | (dm_flags_to_nib(f2) << 8) | (dm_flags_to_nib(f3) << 12);
+    if (off + 16 > nbytes) m &= (1u << (uint32_t)(nbytes - off)) - 1u;
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------
+// K_A: row index
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
+    __shared__ uint32_t s_rowcnt[DMR_TILE_ROWS];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_total;
+    const uint8_t* __restrict__ buf = a.buf;
+    const uint64_t nbytes = a.nbytes;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+
+    // newline count of each row of the tile: 8 warps x 16 rows, loads of 4 rows in flight per warp
+    for (uint32_t rr = warp * 4; rr < DMR_TILE_ROWS; rr += (DMR_A_THREADS / 32) * 4) {
+        uint4 v[4];
+        uint64_t off[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            off[i] = ((uint64_t)tile * DMR_TILE_ROWS + rr + i) * DMR_ROW + (uint64_t)lane * 16;
+            v[i] = make_uint4(0, 0, 0, 0);
+            if (off[i] < nbytes) v[i] = __ldg(reinterpret_cast<const uint4*>(buf + off[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t m = off[i] < nbytes ? dm_row_nl_mask(v[i], off[i], nbytes) : 0u;
+            const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
+            if (lane == 0) s_rowcnt[rr + i] = c;
+        }
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // exclusive prefix of the 128 row counts (4 per lane), then the tile's global base
+        uint32_t c[4], lane_sum = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { c[i] = s_rowcnt[lane * 4 + i]; lane_sum += c[i]; }
+        uint32_t incl = lane_sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += y;
+        }
+        const uint32_t agg = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned long long tag = (unsigned long long)a.epoch << 34;
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            if (lane == 0) atomicExch(a.tile_state + tile, tag | (DMT_ST_AGG << 32) | agg);
+            long long hi = (long long)tile - 1;
+            bool done = false;
+            while (!done) {
+                unsigned long long st[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long idx = hi - 32 * j - (long long)lane;
+                    st[j] = idx >= 0 ? *((volatile unsigned long long*)(a.tile_state + idx)) : 0ull;
+                }
+                int consumed = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (done || consumed < j) continue;
+                    const long long idx = hi - 32 * j - (long long)lane;
+                    unsigned long long w = st[j];
+                    if (idx >= 0 && (w >> 34) != a.epoch) w = 0;
+                    const uint32_t status = idx >= 0 ? (uint32_t)((w >> 32) & 3u) : (uint32_t)DMT_ST_PREFIX;
+                    const uint32_t not_ready = __ballot_sync(0xffffffffu, status == 0);
+                    const uint32_t is_pref = __ballot_sync(0xffffffffu, status == DMT_ST_PREFIX);
+                    const uint32_t first_pref = is_pref ? (uint32_t)(__ffs(is_pref) - 1) : 32u;
+                    const uint32_t upto = first_pref < 32u ? first_pref : 31u;
+                    const uint32_t win = upto == 31u ? 0xffffffffu : ((2u << upto) - 1u);
+                    if (not_ready & win) continue;
+                    const uint32_t val = (lane <= upto && idx >= 0) ? (uint32_t)w : 0u;
+                    excl += __reduce_add_sync(0xffffffffu, val);
+                    consumed = j + 1;
+                    if (first_pref < 32u) done = true;
+                }
+                hi -= 32 * consumed;
+                if (!done && consumed < 4) __nanosleep(20);
+            }
+        }
+        if (lane == 0) atomicExch(a.tile_state + tile, tag | (DMT_ST_PREFIX << 32) | (unsigned long long)((uint32_t)excl + agg));
+        uint32_t run = (uint32_t)excl + (incl - lane_sum);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t row = tile * DMR_TILE_ROWS + lane * 4 + i;
+            if (row < a.n_rows) a.row_prefix[row] = run;
+            run += c[i];
+        }
+        if (lane == 0) { s_base = excl; s_total = agg; }
+        if (tile == a.n_tiles - 1 && lane == 0) {
+            const unsigned long long nl = excl + agg;
+            const bool tail = nbytes > 0 && buf[nbytes - 1] != 0x0Au;
+            unsigned long long n_lines = nl + (tail ? 1ull : 0ull);
+            a.hdr->n_newlines = nl;
+            if (n_lines > a.max_lines || n_lines > a.out_cap) atomicOr(&a.hdr->error, DM_DEVERR_TOO_MANY_LINES);
+            a.hdr->n_lines = n_lines;
+            const unsigned long long tr = a.n_train_lines < n_lines ? a.n_train_lines : n_lines;
+            a.stats[0] += n_lines;
+            a.stats[1] += tr;
+            a.stats[2] += n_lines - tr;
+            a.stats[5] += nbytes;
+            if (tail) s_total = agg + 1;            // the unterminated last record is zero-filled here too
+        }
+    }
+    __syncthreads();
+    // zero-fill the outputs of the records that end in this tile
+    const unsigned long long base = s_base;
+    const uint32_t total = s_total;
+    for (uint32_t i = threadIdx.x; i < total; i += DMR_A_THREADS) {
+        const unsigned long long g = base + i;
+        if (g < a.out_cap) { a.flags[g] = 0; a.scores[g] = 0.0f; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K_B: rows
+// ---------------------------------------------------------------------------------------
+struct DmRQ1Entry { uint32_t q; uint32_t g; };
+struct DmRQ2Entry { uint32_t vpos; uint32_t g; uint32_t k; };
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
+    __shared__ DmKeys sk;   // 16-byte aligned through its alignas(16) member
+    __shared__ DmRQ1Entry s_q1[DMR_B_WARPS][DMR_Q1CAP];
+    __shared__ DmRQ2Entry s_q2[DMR_B_WARPS][DMR_Q2CAP];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.keys);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sk);
+        for (uint32_t i = threadIdx.x; i < sizeof(DmKeys) / 4; i += DMR_B_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const uint8_t* __restrict__ buf = a.buf;
+    const uint64_t nbytes = a.nbytes;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = dm_lanemask_lt();
+    DmRQ1Entry* q1 = s_q1[warp];
+    DmRQ2Entry* q2 = s_q2[warp];
+    uint32_t q1h = 0, q1n = 0, q2h = 0, q2n = 0;
+
+    // stage 2: one identified field per lane -- fingerprint, probe, exact re-check when unknown
+    auto drain2 = [&](uint32_t n) {
+        bool cand = false;
+        uint64_t ckey = 0;
+        uint32_t cq = 0, ck = 0, cg = 0;
+        if (lane < n) {
+            const DmRQ2Entry e = q2[(q2h + lane) & (DMR_Q2CAP - 1)];
+            const uint64_t fp = dm_hash_value(buf, nbytes, e.vpos);
+            const uint64_t key = dm_make_key(fp, sk.salt[e.k]);
+            const bool known = TRAIN ? dm_table_contains_volatile(a.table, key) : dm_table_contains(a.table, key);
+            cand = !known;
+            ckey = key; cq = e.vpos - 1; ck = e.k; cg = e.g;
+        }
+        q2h += n;
+        q2n -= n;
+        uint32_t cb = __ballot_sync(0xffffffffu, cand);
+        while (cb) {
+            const int L = __ffs(cb) - 1;
+            cb &= cb - 1;
+            const uint32_t vq = __shfl_sync(0xffffffffu, cq, L);
+            const uint32_t vk = __shfl_sync(0xffffffffu, ck, L);
+            if (TRAIN) {
+                const int still_new = ((int)lane == L) ? (dm_table_contains_volatile(a.table, ckey) ? 0 : 1) : 0;
+                if (!__shfl_sync(0xffffffffu, still_new, L)) continue;
+            }
+            uint32_t ls = 0;
+            const bool ok = dm_verify_field_warp(buf, vq, vk, sk, lane, lt, &ls);
+            if ((int)lane == L && ok) {
+                if (TRAIN) {
+                    dm_table_insert(a.table, ckey, &a.hdr->error);
+                } else {
+                    // an alert: unknown value in monitored field ck of record cg
+                    bool first = false;
+                    if (cg < a.out_cap) {
+                        const float old = atomicAdd(a.scores + cg, 1.0f);
+                        a.flags[cg] = 1;
+                        first = old == 0.0f;
+                    }
+                    atomicAdd(a.stats + 8 + ck, 1ull);
+                    atomicAdd(a.stats + 4, 1ull);
+                    if (first) { atomicAdd(&a.hdr->n_anomalies, 1ull); atomicAdd(a.stats + 3, 1ull); }
+                    const unsigned int idx = atomicAdd(&a.hdr->anomaly_list_count, 1u);
+                    if (idx < a.anomaly_cap) {
+                        dm_anomaly_t r;
+                        r.line = cg; r.mask = 1u << ck; r.offset = ls;
+                        a.anomalies[idx] = r;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    };
+
+    // stage 1: one '=' per lane -- which monitored key (if any) stands in front of it
+    auto drain1 = [&](uint32_t n) {
+        bool matched = false;
+        DmRQ2Entry qe;
+        qe.vpos = 0; qe.g = 0; qe.k = 0;
+        if (lane < n) {
+            const DmRQ1Entry e = q1[(q1h + lane) & (DMR_Q1CAP - 1)];
+            if (e.g != 0xFFFFFFFFu) {                      // 0xFFFFFFFF: record outside this launch's range
+                const int k = dm_key_identify(buf, (uint64_t)e.q, sk);
+                if (k >= 0) { matched = true; qe.vpos = e.q + 1; qe.g = e.g; qe.k = (uint32_t)k; }
+            }
+        }
+        q1h += n;
+        q1n -= n;
+        const uint32_t mb = __ballot_sync(0xffffffffu, matched);
+        if (mb) {
+            if (matched) q2[(q2h + q2n + __popc(mb & lt)) & (DMR_Q2CAP - 1)] = qe;
+            q2n += __popc(mb);
+            __syncwarp();
+            if (q2n >= 32u) drain2(32u);
+        }
+        __syncwarp();
+    };
+
+    for (;;) {
+        unsigned long long first_row = 0;
+        if (lane == 0) first_row = (atomicAdd(a.row_ctr, (unsigned long long)DMR_GROUP) - a.ctr_base);
+        first_row = __shfl_sync(0xffffffffu, first_row, 0);
+        if (first_row >= a.n_rows) break;
+        const uint32_t r_end = (uint32_t)(first_row + DMR_GROUP < a.n_rows ? first_row + DMR_GROUP : a.n_rows);
+        for (uint32_t row = (uint32_t)first_row; row < r_end; ++row) {
+            const uint64_t off = (uint64_t)row * DMR_ROW + (uint64_t)lane * 16;
+            uint32_t nl16 = 0, eq16 = 0;
+            if (off < nbytes) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(buf + off));
+                nl16 = dm_row_nl_mask(v, off, nbytes);
+                const uint32_t e0 = dm_eqflags(v.x, 0x3D3D3D3Du), e1 = dm_eqflags(v.y, 0x3D3D3D3Du);
+                const uint32_t e2 = dm_eqflags(v.z, 0x3D3D3D3Du), e3 = dm_eqflags(v.w, 0x3D3D3D3Du);
+                if (e0 | e1 | e2 | e3) {
+                    eq16 = dm_flags_to_nib(e0) | (dm_flags_to_nib(e1) << 4) | (dm_flags_to_nib(e2) << 8) | (dm_flags_to_nib(e3) << 12);
+                    if (off + 16 > nbytes) eq16 &= (1u << (uint32_t)(nbytes - off)) - 1u;
+                }
+            }
+            // record index in front of this lane's chunk
+            const uint32_t b_nl = __ballot_sync(0xffffffffu, nl16 != 0);
+            uint32_t pre = 0;
+            if (b_nl) {
+                const uint32_t my = (uint32_t)__popc(nl16);
+                const uint32_t b_multi = __ballot_sync(0xffffffffu, my > 1);
+                if (b_multi == 0) {
+                    pre = __popc(b_nl & lt);
+                } else {
+                    uint32_t incl = my;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                        if ((int)lane >= d) incl += y;
+                    }
+                    pre = incl - my;
+                }
+            }
+            const uint32_t g_chunk = a.row_prefix[row] + pre;
+
+            // every '=' of the row (whose record is in this launch's range) goes to queue 1
+            uint32_t m = eq16;
+            // drop the '=' whose record lies outside [line_lo, line_hi): cheap pre-filter per lane
+            if (m) {
+                const uint32_t g_lo = g_chunk, g_hi = g_chunk + (uint32_t)__popc(nl16);
+                if ((uint64_t)g_hi < a.line_lo || (uint64_t)g_lo >= a.line_hi) m = 0;
+            }
+            const uint32_t my_eq = (uint32_t)__popc(m);
+            uint32_t eincl = my_eq;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, eincl, d);
+                if ((int)lane >= d) eincl += y;
+            }
+            const uint32_t row_eq = __shfl_sync(0xffffffffu, eincl, 31);
+            if (row_eq == 0) continue;
+            if (q1n + row_eq <= DMR_Q1CAP) {
+                uint32_t slot = q1h + q1n + (eincl - my_eq);
+                while (m) {
+                    const uint32_t j = (uint32_t)__ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t g = g_chunk + (uint32_t)__popc(nl16 & ((1u << j) - 1u));
+                    DmRQ1Entry e;
+                    e.q = (uint32_t)off + j;
+                    e.g = ((uint64_t)g >= a.line_lo && (uint64_t)g < a.line_hi) ? g : 0xFFFFFFFFu;
+                    q1[slot & (DMR_Q1CAP - 1)] = e;
+                    ++slot;
+                }
+                q1n += row_eq;
+                __syncwarp();
+                while (q1n >= 32u) drain1(32u);
+            } else {
+                // a row dense in '=' (more than the queue holds): one per lane per round
+                while (__ballot_sync(0xffffffffu, m != 0)) {
+                    bool has = false;
+                    DmRQ1Entry e;
+                    e.q = 0; e.g = 0;
+                    if (m) {
+                        const uint32_t j = (uint32_t)__ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t g = g_chunk + (uint32_t)__popc(nl16 & ((1u << j) - 1u));
+                        has = true;
+                        e.q = (uint32_t)off + j;
+                        e.g = ((uint64_t)g >= a.line_lo && (uint64_t)g < a.line_hi) ? g : 0xFFFFFFFFu;
+                    }
+                    const uint32_t hb = __ballot_sync(0xffffffffu, has);
+                    if (has) q1[(q1h + q1n + __popc(hb & lt)) & (DMR_Q1CAP - 1)] = e;
+                    q1n += __popc(hb);
+                    __syncwarp();
+                    while (q1n >= 32u) drain1(32u);
+                }
+            }
+        }
+    }
+    while (q1n) drain1(q1n < 32u ? q1n : 32u);
+    while (q2n) drain2(q2n < 32u ? q2n : 32u);
+}
+
+#ifndef DM_EMU
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct DmRowsScratch {
+    uint32_t* d_row_prefix = nullptr;
+    unsigned long long* d_tile_state = nullptr;
+    unsigned long long* d_row_ctr = nullptr;
+    uint64_t max_rows = 0, max_tiles = 0;
+    unsigned long long ctr_base = 0;
+    uint32_t epoch = 0;
+    int grid_b = 0;
+};
+
+static inline int dm_rows_scratch_create(DmRowsScratch* s, uint64_t max_batch_bytes, int sm_count) {
+    s->max_rows = (max_batch_bytes + DMR_ROW - 1) / DMR_ROW + 1;
+    s->max_tiles = (s->max_rows + DMR_TILE_ROWS - 1) / DMR_TILE_ROWS + 1;
+    if (cudaMalloc(&s->d_row_prefix, s->max_rows * sizeof(uint32_t)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_tile_state, s->max_tiles * sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMemset(s->d_tile_state, 0, s->max_tiles * sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_row_ctr, sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMemset(s->d_row_ctr, 0, sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_rows<false>, DMR_B_THREADS, 0) != cudaSuccess) return DM_ERR_CUDA;
+    if (per_sm < 1) per_sm = 1;
+    s->grid_b = sm_count * per_sm;
+    return DM_OK;
+}
+
+static inline void dm_rows_scratch_destroy(DmRowsScratch* s) {
+    cudaFree(s->d_row_prefix);
+    cudaFree(s->d_tile_state);
+    cudaFree(s->d_row_ctr);
+    s->d_row_prefix = nullptr; s->d_tile_state = nullptr; s->d_row_ctr = nullptr;
+}
+
+// Enqueue K_A and K_B for one message.  Returns the number of kernels launched or < 0.
+static inline int dm_rows_launch(DmRowsScratch* s, const uint8_t* d_buf, uint64_t nbytes, uint64_t n_train_lines,
+                                 const DmKeys* d_keys, DmTable table, uint8_t* d_flags, float* d_scores,
+                                 uint64_t out_cap, dm_anomaly_t* d_anoms, uint32_t anomaly_cap, DmBatchHeader* d_hdr,
+                                 unsigned long long* d_stats, uint64_t max_lines, cudaStream_t st,
+                                 void (*mark)(void*, cudaStream_t, int), void* mark_ctx) {
+    const uint32_t n_rows = (uint32_t)((nbytes + DMR_ROW - 1) / DMR_ROW);
+    if (n_rows == 0) return 0;
+    if (n_rows > s->max_rows) return DM_ERR_CAPACITY;
+    DmRowsArgs a;
+    a.buf = d_buf; a.nbytes = nbytes; a.n_rows = n_rows;
+    a.n_tiles = (n_rows + DMR_TILE_ROWS - 1) / DMR_TILE_ROWS;
+    a.row_prefix = s->d_row_prefix; a.tile_state = s->d_tile_state;
+    s->epoch = (s->epoch % 0x3FFFFFFEu) + 1u;
+    a.epoch = s->epoch;
+    a.keys = d_keys; a.table = table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
+    a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap; a.hdr = d_hdr; a.stats = d_stats;
+    a.row_ctr = s->d_row_ctr; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
+    a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = s->ctr_base;
+    int launched = 0;
+    dm_k_rowindex<<<a.n_tiles, DMR_A_THREADS, 0, st>>>(a);
+    ++launched;
+    const uint32_t groups = (n_rows + DMR_GROUP - 1) / DMR_GROUP;
+    const int warps_needed = (int)((groups + 0) < 1 ? 1 : groups);
+    int grid = (warps_needed + DMR_B_WARPS - 1) / DMR_B_WARPS;
+    if (grid > s->grid_b) grid = s->grid_b;
+    // every warp of the grid ends with one failing fetch of DMR_GROUP rows
+    const unsigned long long per_launch = (unsigned long long)groups * DMR_GROUP + (unsigned long long)grid * DMR_B_WARPS * DMR_GROUP;
+    if (n_train_lines > 0) {
+        a.line_lo = 0; a.line_hi = n_train_lines; a.ctr_base = s->ctr_base;
+        dm_k_rows<true><<<grid, DMR_B_THREADS, 0, st>>>(a);
+        s->ctr_base += per_launch;
+        ++launched;
+    }
+    a.line_lo = n_train_lines; a.line_hi = ~0ull; a.ctr_base = s->ctr_base;
+    if (mark) mark(mark_ctx, st, 0);
+    dm_k_rows<false><<<grid, DMR_B_THREADS, 0, st>>>(a);
+    if (mark) mark(mark_ctx, st, 1);
+    s->ctr_base += per_launch;
+    ++launched;
+    if (cudaGetLastError() != cudaSuccess) return DM_ERR_CUDA;
+    return launched;
+}
+#endif  // DM_EMU

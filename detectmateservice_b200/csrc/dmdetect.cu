@@ -14,6 +14,7 @@
 #include "dm_device.cuh"
 #include "dm_kernels_v1.cuh"
 #include "dm_kernels_tile.cuh"
+#include "dm_kernels_rows.cuh"
 #include "dm_kernels_values.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -55,7 +56,7 @@ struct dm_handle {
     uint64_t max_batch_bytes = 0, max_lines = 0;
     uint32_t table_log2 = 0;
     uint32_t n_keys = 0;
-    int kernel_variant = 1;              // 0 = v1 (line index + warp per record), 1 = fused tile kernel
+    int kernel_variant = 2;              // 0 = v1 (line index + warp per record), 1 = fused tile kernel, 2 = rows (row index + independent rows)
 
     DmKeys h_keys;
     DmKeys* d_keys = nullptr;
@@ -76,6 +77,7 @@ struct dm_handle {
     DmTable table;
     uint64_t novel_exported = 0;         // novel keys already shipped in a window
     DmTileScratch tile;                  // fused-kernel scratch
+    DmRowsScratch rows;                  // rows-variant scratch
     uint64_t last_nbytes = 0;
     uint32_t* d_vals = nullptr;          // record mode: offsets / fields / record_of
     uint64_t vals_cap = 0;
@@ -96,6 +98,8 @@ static void dm_prof_mark(dm_handle* h, cudaStream_t st, int which) {
     cudaEventRecord(h->ev[h->ev_used], st);
     h->ev_used++;
 }
+
+static void dm_prof_mark_cb(void* ctx, cudaStream_t st, int which) { dm_prof_mark((dm_handle*)ctx, st, which); }
 
 static const uint32_t DM_WINDOW_KEYS = 1u << 16;    // keys one rank can ship per window
 
@@ -193,9 +197,12 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
 
     int rc = dm_tile_scratch_create(&h->tile, max_batch_bytes, h->sm_count);
     if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "tile scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    rc = dm_rows_scratch_create(&h->rows, max_batch_bytes, h->sm_count);
+    if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "rows scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     const char* env = getenv("DM_KERNEL");
     if (env && strcmp(env, "v1") == 0) h->kernel_variant = 0;
     if (env && strcmp(env, "tile") == 0) h->kernel_variant = 1;
+    if (env && strcmp(env, "rows") == 0) h->kernel_variant = 2;
     DM_CUDA(cudaDeviceSynchronize());
     *out = h;
     return DM_OK;
@@ -237,6 +244,7 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaDeviceSynchronize();
     for (auto& e : h->ev) cudaEventDestroy(e);
     dm_tile_scratch_destroy(&h->tile);
+    dm_rows_scratch_destroy(&h->rows);
     cudaFree(h->d_keys); cudaFree(h->d_in); cudaFree(h->d_tile_counts); cudaFree(h->d_tile_base);
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
@@ -315,6 +323,12 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         dm_k_detect_lines<false><<<grid, 256, 0, st>>>(a);
         dm_prof_mark(h, st, 1);
         h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
+    } else if (h->kernel_variant == 2) {
+        const int rc = dm_rows_launch(&h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,
+                                      out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st,
+                                      dm_prof_mark_cb, h);
+        if (rc < 0) return dm_fail(DM_ERR_CUDA, "rows kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->launches += (uint64_t)rc;
     } else {
         dm_prof_mark(h, st, 0);
         const int rc = dm_tile_launch(&h->tile, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,

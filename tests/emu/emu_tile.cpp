@@ -8,29 +8,36 @@
 #include <cstdlib>
 
 #include "dm_kernels_tile.cuh"
+#include "dm_kernels_rows.cuh"
 
 thread_local emu_dim3 threadIdx;
 thread_local emu_dim3 blockIdx;
 emu_dim3 blockDim, gridDim;
 EmuBlock* g_emu_block = nullptr;
 
-void emu_launch(unsigned threads, const std::function<void()>& body) {
-    EmuBlock blk;
-    blk.warps = std::vector<EmuWarp>(threads / 32);
-    g_emu_block = &blk;
+// Runs the blocks of a grid ONE AFTER THE OTHER (block b sees blocks < b complete, which
+// satisfies the look-back dependencies of the kernels under test).
+void emu_launch_grid(unsigned blocks, unsigned threads, const std::function<void()>& body) {
     blockDim.x = threads;
-    gridDim.x = 1;
-    std::vector<std::thread> ts;
-    ts.reserve(threads);
-    for (unsigned t = 0; t < threads; ++t)
-        ts.emplace_back([t, &body] {
-            threadIdx.x = t;
-            blockIdx.x = 0;
-            body();
-        });
-    for (auto& t : ts) t.join();
-    g_emu_block = nullptr;
+    gridDim.x = blocks;
+    for (unsigned b = 0; b < blocks; ++b) {
+        EmuBlock blk;
+        blk.warps = std::vector<EmuWarp>(threads / 32);
+        g_emu_block = &blk;
+        std::vector<std::thread> ts;
+        ts.reserve(threads);
+        for (unsigned t = 0; t < threads; ++t)
+            ts.emplace_back([t, b, &body] {
+                threadIdx.x = t;
+                blockIdx.x = b;
+                body();
+            });
+        for (auto& t : ts) t.join();
+        g_emu_block = nullptr;
+    }
 }
+
+void emu_launch(unsigned threads, const std::function<void()>& body) { emu_launch_grid(1, threads, body); }
 
 struct EmuHandle {
     DmKeys keys;
@@ -44,6 +51,11 @@ struct EmuHandle {
     DmBatchHeader hdr;
     std::vector<dm_anomaly_t> anoms;
     uint64_t max_lines = 0;
+    // rows variant
+    std::vector<uint32_t> row_prefix;
+    std::vector<unsigned long long> rows_tile_state;
+    unsigned long long row_ctr = 0, row_ctr_base = 0;
+    uint32_t rows_epoch = 0;
 };
 
 extern "C" EmuHandle* emu_create(uint32_t n_keys, const uint8_t* blob, const uint32_t* lens, uint32_t table_log2,
@@ -108,6 +120,45 @@ extern "C" int emu_process(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, ui
         a.zero_fill = n_train > 0 ? 0 : 1; a.finalize = 1;
         emu_launch(DMT_THREADS, [&] { dm_k_tile<false>(a); });
         h->ctr_base += (unsigned long long)n_tiles;
+    }
+    free(buf);
+    *n_lines = h->hdr.n_lines;
+    *n_anoms = h->hdr.n_anomalies;
+    *err = h->hdr.error;
+    return 0;
+}
+
+// Mirrors dm_rows_launch (dm_kernels_rows.cuh): K_A, optional K_B<train>, K_B<detect>.
+extern "C" int emu_process_rows(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    uint8_t* buf = (uint8_t*)aligned_alloc(64, ((nbytes + 64 + 63) / 64) * 64 + 64);
+    memcpy(buf, msg, nbytes);
+    for (int i = 0; i < 64; ++i) buf[nbytes + i] = (i & 1) ? '\n' : '=';
+    memset(&h->hdr, 0, sizeof(h->hdr));
+    const uint32_t n_rows = (uint32_t)((nbytes + DMR_ROW - 1) / DMR_ROW);
+    if (n_rows > 0) {
+        DmRowsArgs a;
+        a.buf = buf; a.nbytes = nbytes; a.n_rows = n_rows; a.n_tiles = (n_rows + DMR_TILE_ROWS - 1) / DMR_TILE_ROWS;
+        h->row_prefix.assign(n_rows + 1, 0xDEADBEEFu);
+        if (h->rows_tile_state.size() < a.n_tiles + 1) h->rows_tile_state.resize(a.n_tiles + 1, 0);
+        a.row_prefix = h->row_prefix.data(); a.tile_state = h->rows_tile_state.data();
+        h->rows_epoch = (h->rows_epoch % 0x3FFFFFFEu) + 1u;
+        a.epoch = h->rows_epoch;
+        a.keys = &h->keys; a.table = h->table; a.flags = flags; a.scores = scores; a.out_cap = cap;
+        a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size(); a.hdr = &h->hdr; a.stats = h->stats;
+        a.row_ctr = &h->row_ctr; a.n_train_lines = n_train; a.max_lines = h->max_lines;
+        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base;
+        emu_launch_grid(a.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(a); });
+        const uint32_t groups = (n_rows + DMR_GROUP - 1) / DMR_GROUP;
+        const unsigned long long per_launch = (unsigned long long)groups * DMR_GROUP + (unsigned long long)DMR_B_WARPS * DMR_GROUP;
+        if (n_train > 0) {
+            a.line_lo = 0; a.line_hi = n_train; a.ctr_base = h->row_ctr_base;
+            emu_launch(DMR_B_THREADS, [&] { dm_k_rows<true>(a); });
+            h->row_ctr_base += per_launch;
+        }
+        a.line_lo = n_train; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base;
+        emu_launch(DMR_B_THREADS, [&] { dm_k_rows<false>(a); });
+        h->row_ctr_base += per_launch;
     }
     free(buf);
     *n_lines = h->hdr.n_lines;

@@ -35,9 +35,12 @@ class Anomaly(C.Structure):
 
 
 class EmuDetector:
-    def __init__(self, keys, table_log2=12, max_bytes=4 << 20, max_lines=1 << 20):
+    def __init__(self, keys, table_log2=12, max_bytes=4 << 20, max_lines=1 << 20, variant="rows"):
         self.lib = C.CDLL(build())
+        self.variant = variant
         L = self.lib
+        L.emu_process_rows.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.c_uint32, C.c_char_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint64, C.c_uint64]
         L.emu_destroy.argtypes = [C.c_void_p]
@@ -64,7 +67,8 @@ class EmuDetector:
         flags = np.full(cap, 7, dtype=np.uint8)
         scores = np.full(cap, -1, dtype=np.float32)
         n_lines, n_anom, err = C.c_uint64(), C.c_uint64(), C.c_uint32()
-        rc = self.lib.emu_process(self.h, msg, len(msg), n_train, flags.ctypes.data, scores.ctypes.data, cap,
+        fn = self.lib.emu_process_rows if self.variant == "rows" else self.lib.emu_process
+        rc = fn(self.h, msg, len(msg), n_train, flags.ctypes.data, scores.ctypes.data, cap,
                                   C.byref(n_lines), C.byref(n_anom), C.byref(err))
         assert rc == 0 and err.value == 0, (rc, err.value)
         self.last_n_anomalies = n_anom.value

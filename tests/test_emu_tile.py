@@ -9,10 +9,25 @@ import os
 import numpy as np
 import pytest
 
-from emu_harness import EmuDetector
+import emu_harness
 from oracle import fingerprint
 from oracle.native import NativeOracle
 from util import FUZZ_KEYS, fuzz_lines
+
+
+@pytest.fixture(params=["rows", "tile"], autouse=True)
+def emu_variant(request):
+    """Every test runs against both device decompositions (DM_KERNEL=rows / tile)."""
+    global VARIANT
+    VARIANT = request.param
+    return request.param
+
+
+VARIANT = "rows"
+
+
+def EmuDetector(keys, **kw):
+    return emu_harness.EmuDetector(keys, variant=VARIANT, **kw)
 
 
 def _check(det, oracle, msg, n_train):
