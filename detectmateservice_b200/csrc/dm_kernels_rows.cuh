@@ -20,7 +20,7 @@
 #include "dm_kernels_tile.cuh"
 
 #define DMR_ROW 512u
-#define DMR_TILE_ROWS 128u
+#define DMR_TILE_ROWS 64u
 #define DMR_A_THREADS 256
 #define DMR_B_WARPS 8
 #define DMR_B_THREADS (DMR_B_WARPS * 32)
@@ -74,18 +74,25 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x;
 
-    // newline count of each row of the tile: 8 warps x 16 rows, loads of 4 rows in flight per warp
-    for (uint32_t rr = warp * 4; rr < DMR_TILE_ROWS; rr += (DMR_A_THREADS / 32) * 4) {
-        uint4 v[4];
-        uint64_t off[4];
+    // tile 0 also clears the per-batch counters (ordered before its look-back word is published,
+    // which every later tile -- and K_B -- depends on)
+    if (tile == 0 && threadIdx.x == 0) {
+        a.hdr->n_anomalies = 0; a.hdr->anomaly_list_count = 0; a.hdr->error = 0; a.hdr->n_lines = 0; a.hdr->n_newlines = 0;
+        __threadfence();
+    }
+    // newline count of each row of the tile: 8 warps x 8 rows, all 8 loads of a warp in flight
+    {
+        const uint32_t rr = warp * 8;
+        uint4 v[8];
+        uint64_t off[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             off[i] = ((uint64_t)tile * DMR_TILE_ROWS + rr + i) * DMR_ROW + (uint64_t)lane * 16;
             v[i] = make_uint4(0, 0, 0, 0);
             if (off[i] < nbytes) v[i] = __ldg(reinterpret_cast<const uint4*>(buf + off[i]));
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const uint32_t m = off[i] < nbytes ? dm_row_nl_mask(v[i], off[i], nbytes) : 0u;
             const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
             if (lane == 0) s_rowcnt[rr + i] = c;
@@ -94,10 +101,10 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
     __syncthreads();
 
     if (warp == 0) {
-        // exclusive prefix of the 128 row counts (4 per lane), then the tile's global base
-        uint32_t c[4], lane_sum = 0;
+        // exclusive prefix of the 64 row counts (2 per lane), then the tile's global base
+        uint32_t c[2], lane_sum = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { c[i] = s_rowcnt[lane * 4 + i]; lane_sum += c[i]; }
+        for (int i = 0; i < 2; ++i) { c[i] = s_rowcnt[lane * 2 + i]; lane_sum += c[i]; }
         uint32_t incl = lane_sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -144,8 +151,8 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
         if (lane == 0) atomicExch(a.tile_state + tile, tag | (DMT_ST_PREFIX << 32) | (unsigned long long)((uint32_t)excl + agg));
         uint32_t run = (uint32_t)excl + (incl - lane_sum);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t row = tile * DMR_TILE_ROWS + lane * 4 + i;
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t row = tile * DMR_TILE_ROWS + lane * 2 + i;
             if (row < a.n_rows) a.row_prefix[row] = run;
             run += c[i];
         }
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
 struct DmRQ1Entry { uint32_t q; uint32_t g; };
 struct DmRQ2Entry { uint32_t vpos; uint32_t g; uint32_t k; };
 
-template <bool TRAIN>
+template <bool TRAIN, bool RANGE>
 __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
     __shared__ DmKeys sk;   // 16-byte aligned through its alignas(16) member
     __shared__ DmRQ1Entry s_q1[DMR_B_WARPS][DMR_Q1CAP];
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
         qe.vpos = 0; qe.g = 0; qe.k = 0;
         if (lane < n) {
             const DmRQ1Entry e = q1[(q1h + lane) & (DMR_Q1CAP - 1)];
-            if (e.g != 0xFFFFFFFFu) {                      // 0xFFFFFFFF: record outside this launch's range
+            if (!RANGE || e.g != 0xFFFFFFFFu) {            // 0xFFFFFFFF: record outside this launch's range
                 const int k = dm_key_identify(buf, (uint64_t)e.q, sk);
                 if (k >= 0) { matched = true; qe.vpos = e.q + 1; qe.g = e.g; qe.k = (uint32_t)k; }
             }
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
             // every '=' of the row (whose record is in this launch's range) goes to queue 1
             uint32_t m = eq16;
             // drop the '=' whose record lies outside [line_lo, line_hi): cheap pre-filter per lane
-            if (m) {
+            if (RANGE && m) {
                 const uint32_t g_lo = g_chunk, g_hi = g_chunk + (uint32_t)__popc(nl16);
                 if ((uint64_t)g_hi < a.line_lo || (uint64_t)g_lo >= a.line_hi) m = 0;
             }
@@ -340,7 +347,7 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
                     const uint32_t g = g_chunk + (uint32_t)__popc(nl16 & ((1u << j) - 1u));
                     DmRQ1Entry e;
                     e.q = (uint32_t)off + j;
-                    e.g = ((uint64_t)g >= a.line_lo && (uint64_t)g < a.line_hi) ? g : 0xFFFFFFFFu;
+                    e.g = (!RANGE || ((uint64_t)g >= a.line_lo && (uint64_t)g < a.line_hi)) ? g : 0xFFFFFFFFu;
                     q1[slot & (DMR_Q1CAP - 1)] = e;
                     ++slot;
                 }
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
                         const uint32_t g = g_chunk + (uint32_t)__popc(nl16 & ((1u << j) - 1u));
                         has = true;
                         e.q = (uint32_t)off + j;
-                        e.g = ((uint64_t)g >= a.line_lo && (uint64_t)g < a.line_hi) ? g : 0xFFFFFFFFu;
+                        e.g = (!RANGE || ((uint64_t)g >= a.line_lo && (uint64_t)g < a.line_hi)) ? g : 0xFFFFFFFFu;
                     }
                     const uint32_t hb = __ballot_sync(0xffffffffu, has);
                     if (has) q1[(q1h + q1n + __popc(hb & lt)) & (DMR_Q1CAP - 1)] = e;
@@ -397,7 +404,7 @@ static inline int dm_rows_scratch_create(DmRowsScratch* s, uint64_t max_batch_by
     if (cudaMalloc(&s->d_row_ctr, sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
     if (cudaMemset(s->d_row_ctr, 0, sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_rows<false>, DMR_B_THREADS, 0) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_rows<false, false>, DMR_B_THREADS, 0) != cudaSuccess) return DM_ERR_CUDA;
     if (per_sm < 1) per_sm = 1;
     s->grid_b = sm_count * per_sm;
     return DM_OK;
@@ -440,13 +447,14 @@ static inline int dm_rows_launch(DmRowsScratch* s, const uint8_t* d_buf, uint64_
     const unsigned long long per_launch = (unsigned long long)groups * DMR_GROUP + (unsigned long long)grid * DMR_B_WARPS * DMR_GROUP;
     if (n_train_lines > 0) {
         a.line_lo = 0; a.line_hi = n_train_lines; a.ctr_base = s->ctr_base;
-        dm_k_rows<true><<<grid, DMR_B_THREADS, 0, st>>>(a);
+        dm_k_rows<true, true><<<grid, DMR_B_THREADS, 0, st>>>(a);
         s->ctr_base += per_launch;
         ++launched;
     }
     a.line_lo = n_train_lines; a.line_hi = ~0ull; a.ctr_base = s->ctr_base;
     if (mark) mark(mark_ctx, st, 0);
-    dm_k_rows<false><<<grid, DMR_B_THREADS, 0, st>>>(a);
+    if (n_train_lines > 0) dm_k_rows<false, true><<<grid, DMR_B_THREADS, 0, st>>>(a);
+    else dm_k_rows<false, false><<<grid, DMR_B_THREADS, 0, st>>>(a);
     if (mark) mark(mark_ctx, st, 1);
     s->ctr_base += per_launch;
     ++launched;

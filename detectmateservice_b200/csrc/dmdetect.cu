@@ -298,7 +298,8 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
     const uint64_t out_cap = std::min(cap_flags, cap_scores);
     (void)dev_cap;
 
-    DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
+    // (the rows variant clears the per-batch header in its first kernel)
+    if (h->kernel_variant != 2 || nbytes == 0) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
     h->last_nbytes = nbytes;
 
     if (h->kernel_variant == 0) {

@@ -35,7 +35,7 @@ for S in $STAGES; do
         DM_KERNEL=$K timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
           --log-file "$OUT/launches_$K.csv" python bench.py --steps 6 --warmup 3 --no-cpu > "$OUT/ncu_list_$K.log" 2>&1
         echo "ncu_list[$K] rc=$?" | tee -a "$OUT/summary.txt"
-        DM_KERNEL=$K timeout 1200 ncu --set full --clock-control none --import-source on \
+        DM_KERNEL=$K timeout 1200 ncu --set full --clock-control none ${NCU_EXTRA:-} --import-source on \
           -k regex:"${NCU_KERNEL:-dm_k_detect_lines|dm_k_tile|dm_k_rows}" -s 4 -c 3 -f -o "$OUT/prof_$K" \
           python bench.py --steps 6 --warmup 3 --no-cpu > "$OUT/ncu_full_$K.log" 2>&1
         echo "ncu_full[$K] rc=$?" | tee -a "$OUT/summary.txt"

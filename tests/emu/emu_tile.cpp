@@ -153,11 +153,12 @@ extern "C" int emu_process_rows(EmuHandle* h, const uint8_t* msg, uint64_t nbyte
         const unsigned long long per_launch = (unsigned long long)groups * DMR_GROUP + (unsigned long long)DMR_B_WARPS * DMR_GROUP;
         if (n_train > 0) {
             a.line_lo = 0; a.line_hi = n_train; a.ctr_base = h->row_ctr_base;
-            emu_launch(DMR_B_THREADS, [&] { dm_k_rows<true>(a); });
+            emu_launch(DMR_B_THREADS, [&] { dm_k_rows<true, true>(a); });
             h->row_ctr_base += per_launch;
         }
         a.line_lo = n_train; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base;
-        emu_launch(DMR_B_THREADS, [&] { dm_k_rows<false>(a); });
+        if (n_train > 0) emu_launch(DMR_B_THREADS, [&] { dm_k_rows<false, true>(a); });
+        else emu_launch(DMR_B_THREADS, [&] { dm_k_rows<false, false>(a); });
         h->row_ctr_base += per_launch;
     }
     free(buf);
