@@ -244,16 +244,11 @@ def run_gpu(args):
     d_flags = torch.zeros(LINES_PER_MSG + 16, dtype=torch.uint8, device=dev)
     d_scores = torch.zeros(LINES_PER_MSG + 16, dtype=torch.float32, device=dev)
     cap = LINES_PER_MSG + 16
-    win_words = det.window_words(world, True)
-    d_win = torch.zeros(win_words, dtype=torch.int64, device=dev)
-    d_win_stats = d_win[:det.window_words(world, False)]
+    from detectmateservice_b200.window import DeviceWindow
+    dwin = DeviceWindow(det, rank, world, dev)
 
     def window(with_keys: bool):
-        buf = d_win if with_keys else d_win_stats
-        det.window_export(buf.data_ptr(), rank, world, with_keys, sp)
-        if world > 1:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-        det.window_import(buf.data_ptr(), rank, world, with_keys, sp)
+        dwin.exchange(with_keys, sp)
 
     # training window (untimed): every rank learns its message 0, then one exchange with keys
     det.enqueue_device(d_msgs[0].data_ptr(), nbytes[0], n_lines_msg[0], d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)

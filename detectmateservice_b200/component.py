@@ -1,0 +1,259 @@
+"""B200NewValueDetector -- the reference's detector plugin surface on top of libdmdetect.
+
+Drop-in for ``detectmatelibrary.detectors.new_value_detector.NewValueDetector`` behind the
+UNMODIFIED reference service:
+
+  settings YAML   component_type: detectmateservice_b200.component.B200NewValueDetector
+                  (the loader imports dotted paths as-is first,
+                   /root/reference/src/service/features/component_loader.py:34-43,
+                   calls ``cls(config=<ServiceConfig dump>)`` :47-50 and checks
+                   ``isinstance(..., CoreComponent)`` :52-55)
+  process()       ``process(data: bytes) -> bytes | None`` (docs/interfaces.md:23-35), called
+                  from the single EngineLoop thread (features/engine.py:187)
+  config YAML     the reference's own detector config (container/config/detector_config.yaml,
+                  tests/config/detector_config.yaml): ``detectors: {<name>: {method_type,
+                  data_use_training, auto_config, global: {...}, events: {...}, params: {...}}}``;
+                  GPU options live under ``params`` (settings.py has extra="forbid").
+
+Two input formats, told apart per message (``params.input_format``: auto | raw_lines |
+parser_schema):
+
+  record mode   one serialized ParserSchema per message -- what the upstream parser stage
+                sends today.  The host decodes the protobuf framing, the monitored values go
+                to the GPU (dm_process_values); an anomalous record yields ONE DetectorSchema
+                (what container/fluentout/fluent.conf:4-17 parses), anything else None.
+  raw mode      N '\\n'-terminated raw log records per message (the fused path: tokenizer +
+                detector in one pass on the GPU, R-tok rules in DESIGN.md).  Output per
+                ``params.output_format``: ``alerts`` = DetectorSchema messages of the anomalous
+                records (a single bare message when the input held one record, else
+                varint-length-delimited), None when there are none; ``compact`` =
+                ``<u32 n><n x u8 flag><n x f32 score>`` for pipelines that want every score.
+
+All detection decisions are taken on the device; there is no CPU path (DeviceDetector
+raises without a GPU).
+"""
+from __future__ import annotations
+
+import struct
+import time
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import alerts as _alerts
+from . import wire
+from .compat import install_shims
+
+install_shims()
+from detectmatelibrary.common.core import CoreComponent, CoreConfig  # noqa: E402
+
+_FORBIDDEN = (0x20, 0x22, 0x27, 0x3D, 0x0A)
+
+
+class B200NewValueDetectorConfig(CoreConfig):
+    """Schema of the detector's config entry (found by the resolver as <Class>Config in the
+    same module, features/component_resolver.py:98-123)."""
+    method_type: str = "new_value_detector"
+    data_use_training: Optional[int] = None
+    auto_config: bool = False
+
+
+class Monitor:
+    __slots__ = ("event_id", "source", "pos", "label", "key")
+
+    def __init__(self, event_id: Optional[int], source: str, pos: Any, label: str):
+        self.event_id, self.source, self.pos, self.label = event_id, source, pos, label
+        self.key = b""
+
+    @property
+    def alert_key(self) -> str:
+        return f"Global - {self.label}" if self.event_id is None else f"EventID {self.event_id} - {self.label}"
+
+
+def select_component_config(config: Optional[dict], name: str) -> dict:
+    """Pick this component's entry out of the ServiceConfig dump the loader passes
+    (src/service/core.py:127-133,144-148) and flatten ``params`` (docs/interfaces.md:74-84)."""
+    cfg = dict(config or {})
+    if isinstance(cfg.get("detectors"), dict):
+        dets = cfg["detectors"]
+        pick = dets.get(name) or dets.get("NewValueDetector") or (next(iter(dets.values())) if dets else {})
+        cfg = dict(pick or {})
+    params = cfg.pop("params", None) or {}
+    for k, v in params.items():
+        cfg[k[4:] if k.startswith("all_") else k] = v
+    return cfg
+
+
+def parse_monitors(cfg: dict) -> List[Monitor]:
+    mons: List[Monitor] = []
+
+    def instances(scope: dict, event_id: Optional[int]) -> None:
+        for _name, inst in (scope or {}).items():
+            inst = inst or {}
+            for hv in inst.get("header_variables") or []:
+                mons.append(Monitor(event_id, "header", str(hv["pos"]), str(hv["pos"])))
+            for var in inst.get("variables") or []:
+                pos = int(var["pos"])
+                mons.append(Monitor(event_id, "variable", pos, str(var.get("name", pos))))
+
+    instances(cfg.get("global") or {}, None)
+    for eid, scope in (cfg.get("events") or {}).items():
+        instances(scope or {}, int(eid))
+    if len(mons) > 32:
+        raise ValueError(f"{len(mons)} monitored fields configured, the device table addresses at most 32")
+    # device key of each monitor: global header variables are matched by name in raw records;
+    # everything else only exists in record mode and gets a name no log can contain.
+    used = set()
+    for i, m in enumerate(mons):
+        raw_ok = m.event_id is None and m.source == "header"
+        kb = m.pos.encode("utf-8") if raw_ok else b""
+        if not raw_ok or not kb or len(kb) > 32 or any(c in _FORBIDDEN for c in kb) or kb in used:
+            kb = b"\x01m%d" % i
+        used.add(kb)
+        m.key = kb
+    return mons
+
+
+class B200NewValueDetector(CoreComponent):
+    def __init__(self, name: str = "B200NewValueDetector", config: Optional[Any] = None) -> None:
+        raw_cfg = config.model_dump() if hasattr(config, "model_dump") else config
+        cfg = select_component_config(raw_cfg, name)
+        super().__init__(name=name, config=B200NewValueDetectorConfig(
+            method_type=cfg.get("method_type", "new_value_detector"),
+            data_use_training=cfg.get("data_use_training"), auto_config=bool(cfg.get("auto_config", False))))
+        if cfg.get("auto_config"):
+            raise ValueError("auto_config: true (a configure phase) is not supported by the B200 detector; "
+                             "list the monitored fields under global/events")
+        self.detector_id = cfg.get("detector_id", "NewValueDetector" if name.startswith("B200") else name)
+        self.method_type = cfg.get("method_type", "new_value_detector")
+        self.data_use_training = int(cfg.get("data_use_training") or 0)
+        self.start_id = int(cfg.get("start_id", 10))
+        self.input_format = cfg.get("input_format", "auto")
+        self.output_format = cfg.get("output_format", "alerts")
+        if self.input_format not in ("auto", "raw_lines", "parser_schema"):
+            raise ValueError(f"input_format {self.input_format!r} not in auto|raw_lines|parser_schema")
+        if self.output_format not in ("alerts", "compact"):
+            raise ValueError(f"output_format {self.output_format!r} not in alerts|compact")
+        self.monitors = parse_monitors(cfg)
+        self.device = int(cfg.get("device", 0))
+        self.max_batch_bytes = int(cfg.get("max_batch_bytes", 64 << 20))
+        self.table_log2_slots = int(cfg.get("table_log2_slots", 20))
+        self._det = None                       # created on first use, on the EngineLoop thread
+        self.n_seen = 0
+        self.n_alerts = 0
+        self.clock = time.time
+
+    # ------------------------------------------------------------------ device handle
+    @property
+    def det(self):
+        if self._det is None:
+            from .detector import DeviceDetector
+            self._det = DeviceDetector([m.key for m in self.monitors], device=self.device,
+                                       max_batch_bytes=self.max_batch_bytes,
+                                       table_log2_slots=self.table_log2_slots)
+        return self._det
+
+    def close(self) -> None:
+        if self._det is not None:
+            self._det.close()
+            self._det = None
+
+    # ------------------------------------------------------------------ the plugin entry point
+    def process(self, data: bytes) -> Optional[bytes]:
+        if not data:
+            return None
+        fmt = self.input_format
+        if fmt == "auto":
+            fmt = "parser_schema" if wire.looks_like_parser_schema(data) else "raw_lines"
+        if fmt == "parser_schema":
+            return self._process_record(data)
+        return self._process_lines(data)
+
+    # ------------------------------------------------------------------ record mode
+    def _record_values(self, rec: Dict) -> List[Tuple[int, bytes]]:
+        out = []
+        eid, lfv, var = rec.get("EventID"), rec.get("logFormatVariables") or {}, rec.get("variables") or []
+        for i, m in enumerate(self.monitors):
+            if m.event_id is not None and m.event_id != eid:
+                continue
+            v = lfv.get(m.pos) if m.source == "header" else (var[m.pos] if 0 <= m.pos < len(var) else None)
+            if v is not None:
+                out.append((i, v.encode("utf-8") if isinstance(v, str) else bytes(v)))
+        return out
+
+    def _process_record(self, data: bytes) -> Optional[bytes]:
+        rec = wire.decode_parser_schema(data, strict=False)
+        vals = self._record_values(rec)
+        train = self.n_seen < self.data_use_training
+        self.n_seen += 1
+        flags, scores, masks = self.det.process_values([[v for v in vals]], n_train_records=1 if train else 0,
+                                                       record_bytes=len(data))
+        if train or not flags[0]:
+            return None
+        mask = int(masks[0])
+        by_field = dict(vals)
+        alerts = {self.monitors[i].alert_key: _alerts.alert_text(by_field[i])
+                  for i in range(len(self.monitors)) if mask >> i & 1}
+        t = (rec.get("logFormatVariables") or {}).get("Time")
+        return self._detector_schema(rec.get("logID", ""), float(scores[0]), alerts, t)
+
+    # ------------------------------------------------------------------ raw mode
+    def _process_lines(self, data: bytes) -> Optional[bytes]:
+        remaining = max(0, self.data_use_training - self.n_seen)
+        flags, scores = self.det.process_lines(data, n_train_lines=remaining, copy=False)
+        n = int(flags.size)
+        base = self.n_seen
+        self.n_seen += n
+        if self.output_format == "compact":
+            return struct.pack("<I", n) + flags.tobytes() + scores.tobytes()
+        if self.det.last_n_anomalies == 0:
+            return None
+        out = []
+        raw_keys = [m.key for m in self.monitors]
+        for line_idx, mask, offset in self.det.anomalies():
+            rec = _alerts.record_at(data, offset)
+            wanted = [raw_keys[i] for i in range(len(raw_keys)) if mask >> i & 1]
+            vals = _alerts.record_fields(rec, wanted)
+            alerts = {self.monitors[i].alert_key: _alerts.alert_text(vals.get(raw_keys[i], b""))
+                      for i in range(len(raw_keys)) if mask >> i & 1}
+            out.append(self._detector_schema(str(base + line_idx), float(scores[line_idx]), alerts,
+                                             _alerts.record_time(rec)))
+        if not out:
+            return None
+        return out[0] if n == 1 else wire.frame_delimited(out)
+
+    # ------------------------------------------------------------------ output
+    def _detector_schema(self, log_id: str, score: float, alerts: Dict[str, str], time_value) -> bytes:
+        now = int(self.clock())
+        try:
+            ts = int(float(time_value))
+        except (TypeError, ValueError):
+            ts = now
+        alert_id = str(self.start_id + self.n_alerts)
+        self.n_alerts += 1
+        return wire.encode_detector_schema(
+            detector_id=self.detector_id, detector_type=self.method_type, alert_id=alert_id, detection_ts=now,
+            log_ids=[log_id], score=score, extracted_ts=[ts],
+            description=f"{self.detector_id} detects values not encountered in training as anomalies.",
+            received_ts=now, alerts=alerts)
+
+    # ------------------------------------------------------------------ state
+    def stats(self) -> dict:
+        return self.det.stats()
+
+    def export_state(self) -> dict:
+        """Learnt keys + counters (the reference loses detector state on restart)."""
+        return {"known": self.det.export_known().tolist(), "n_seen": self.n_seen, "n_alerts": self.n_alerts}
+
+    def import_state(self, state: dict) -> None:
+        self.det.import_known(np.array(state.get("known", []), dtype=np.uint64))
+        self.n_seen = int(state.get("n_seen", 0))
+        self.n_alerts = int(state.get("n_alerts", 0))
+
+
+def decode_compact(blob: bytes) -> Tuple[np.ndarray, np.ndarray]:
+    """Inverse of the ``compact`` output format."""
+    (n,) = struct.unpack_from("<I", blob, 0)
+    flags = np.frombuffer(blob, dtype=np.uint8, count=n, offset=4)
+    scores = np.frombuffer(blob, dtype=np.float32, count=n, offset=4 + n)
+    return flags, scores

@@ -122,6 +122,35 @@ class DeviceDetector:
                                               flags_ptr or None, scores_ptr or None, int(out_cap_lines), 1,
                                               None, None, stream or None))
 
+    # ------------------------------------------------------------------ record mode
+    def process_values(self, records, n_train_records: int = 0, record_bytes: int = 0
+                       ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """records: one list of (monitored-field index, value bytes) per record (the values a
+        ParserSchema holds for the configured monitors).  The first n_train_records records
+        are training data.  Returns (flags u8, scores f32, unknown-field masks u32)."""
+        n_rec = len(records)
+        blob = bytearray()
+        offsets, fields, rec_of = [0], [], []
+        for r, vals in enumerate(records):
+            for f, v in vals:
+                blob += v
+                offsets.append(len(blob))
+                fields.append(int(f))
+                rec_of.append(r)
+        n_val = len(fields)
+        off_a = (C.c_uint32 * (n_val + 1))(*offsets)
+        fld_a = (C.c_uint32 * max(1, n_val))(*fields)
+        rec_a = (C.c_uint32 * max(1, n_val))(*rec_of)
+        flags = np.zeros(max(1, n_rec), dtype=np.uint8)
+        scores = np.zeros(max(1, n_rec), dtype=np.float32)
+        masks = np.zeros(max(1, n_rec), dtype=np.uint32)
+        n_anom = C.c_uint64()
+        _lib.check(self._lib.dm_process_values(self._h, bytes(blob), len(blob), off_a, fld_a, rec_a, n_val, n_rec,
+                                               int(n_train_records), int(record_bytes), flags.ctypes.data,
+                                               scores.ctypes.data, masks.ctypes.data, C.byref(n_anom)))
+        self.last_n_anomalies = n_anom.value
+        return flags[:n_rec], scores[:n_rec], masks[:n_rec]
+
     def sync(self) -> Tuple[int, int]:
         n_lines = C.c_uint64()
         n_anom = C.c_uint64()

@@ -242,3 +242,55 @@ def test_capacity_errors_are_loud(variant):
         with pytest.raises(_lib.DmError) as e:
             det.process_lines(many, 2000)
         assert e.value.code == _lib.DM_ERR_TABLE_FULL
+
+
+def test_window_exchange_two_ranks_on_one_gpu(variant):
+    """dm_window_export / dm_window_import with two handles standing in for two ranks: the SUM
+    of their buffers (what the NCCL all-reduce computes) teaches each rank the other's keys and
+    yields the global statistics."""
+    import torch
+    from detectmateservice_b200 import window
+    from detectmateservice_b200.synth import AuditSynth, MONITORED_KEYS
+    g = AuditSynth(seed=21)
+    train, _ = g.batch(6000, inject=False)
+    detect, _ = g.batch(6000, inject=True)
+    cuts = window.shard_bounds(train, 2)
+    dcuts = window.shard_bounds(detect, 2)
+    keys = [k.encode() for k in MONITORED_KEYS]
+    one = NativeOracle(keys)
+    one.process(train, 6000)
+    wf, ws, _ = one.process(detect, 0)
+    with _det(MONITORED_KEYS) as d0, _det(MONITORED_KEYS) as d1:
+        dets = [d0, d1]
+        bufs = []
+        for r, d in enumerate(dets):
+            shard = train[cuts[r]:cuts[r + 1]]
+            d.process_lines(shard, shard.count(b"\n"))
+            b = torch.zeros(d.window_words(2, True), dtype=torch.int64, device="cuda")
+            d.window_export(b.data_ptr(), r, 2, True)
+            d.sync()
+            bufs.append(b)
+        total = bufs[0] + bufs[1]                               # the all-reduce
+        torch.cuda.synchronize()
+        for r, d in enumerate(dets):
+            d.window_import(total.data_ptr(), r, 2, True)
+            d.sync()
+        assert d0.export_known().tolist() == d1.export_known().tolist()
+        got = []
+        for r, d in enumerate(dets):
+            f, s = d.process_lines(detect[dcuts[r]:dcuts[r + 1]], 0)
+            got.append((f, s))
+        assert np.concatenate([g_[0] for g_ in got]).tolist() == wf.tolist()
+        assert np.concatenate([g_[1] for g_ in got]).tolist() == ws.tolist()
+        # statistics-only window: global = sum over ranks
+        sb = [torch.zeros(d.window_words(2, False), dtype=torch.int64, device="cuda") for d in dets]
+        for r, d in enumerate(dets):
+            d.window_export(sb[r].data_ptr(), r, 2, False)
+            d.sync()
+        tot = sb[0] + sb[1]
+        torch.cuda.synchronize()
+        for r, d in enumerate(dets):
+            d.window_import(tot.data_ptr(), r, 2, False)
+        gs = d0.global_stats()
+        assert gs["lines"] == 12000 and gs["train_lines"] == 6000 and gs["anomalies"] == int(wf.sum())
+        assert gs["score_sum"] == int(ws.sum()) and gs == d1.global_stats()
