@@ -216,6 +216,9 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO prints a banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("DM_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -247,8 +250,19 @@ def run_gpu(args):
     from detectmateservice_b200.window import DeviceWindow
     dwin = DeviceWindow(det, rank, world, dev)
 
+    # the per-window exchange runs on a side stream: in steady state it carries statistics
+    # only and gates nothing, so it overlaps the next message's kernels
+    side = torch.cuda.Stream(device=dev)
+    win_ev = torch.cuda.Event()
+
     def window(with_keys: bool):
-        dwin.exchange(with_keys, sp)
+        if with_keys:
+            dwin.exchange(True, sp)                 # training window: detection must wait for it
+            return
+        win_ev.record(stream)
+        side.wait_event(win_ev)
+        with torch.cuda.stream(side):
+            dwin.exchange(False, side.cuda_stream)
 
     # training window (untimed): every rank learns its message 0, then one exchange with keys
     det.enqueue_device(d_msgs[0].data_ptr(), nbytes[0], n_lines_msg[0], d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
@@ -280,6 +294,7 @@ def run_gpu(args):
     e0.record(stream)
     for i in range(args.steps):
         lines_timed += n_lines_msg[step(i)]
+    stream.wait_stream(side)                         # the last windows' all-reduces are part of the job
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -317,19 +332,37 @@ def run_gpu(args):
                 "algorithmic_bytes_per_launch": alg_bytes / max(k_n, 1),
                 "kernel": os.environ.get("DM_KERNEL", "default")}
 
-    # ---- e2e: C-ABI call with pinned HOST buffers, H2D + D2H inside the timed region --------
-    e2e_steps = max(4, min(args.steps, 48))
-    for i in range(3):
-        det.process_lines(h_msgs[1 + i].numpy(), 0, copy=False)
+    # ---- e2e: C-ABI calls with pinned HOST buffers, H2D + D2H inside the timed region --------
+    # dm_submit_lines / dm_collect (two slots): message i+1 crosses PCIe while message i runs;
+    # every step's flags and scores are read back into host memory.
+    torch.cuda.synchronize()
+    e2e_steps = max(4, min(args.steps, 60))
+    pipelined = os.environ.get("DM_KERNEL", "rows") == "rows"
+
+    def e2e_loop(n_steps: int) -> int:
+        lines = 0
+        if pipelined:
+            for i in range(n_steps):
+                slot = i & 1
+                if i >= 2:
+                    f, s = det.collect(slot)
+                    lines += f.size
+                det.submit(h_msgs[1 + (i % (N_MSGS - 1))].numpy(), 0, slot)
+            for i in range(max(0, n_steps - 2), n_steps):
+                f, s = det.collect(i & 1)
+                lines += f.size
+        else:
+            for i in range(n_steps):
+                f, s = det.process_lines(h_msgs[1 + (i % (N_MSGS - 1))].numpy(), 0, copy=False)
+                lines += f.size
+        return lines
+
+    e2e_loop(4)
     barrier()
     t0 = time.perf_counter()
-    e2e_lines = 0
-    for i in range(e2e_steps):
-        j = 1 + (i % (N_MSGS - 1))
-        f, s = det.process_lines(h_msgs[j].numpy(), 0, copy=False)
-        e2e_lines += f.size
-        if world > 1:
-            window(False)
+    e2e_lines = e2e_loop(e2e_steps)
+    if world > 1:
+        window(False)
     barrier()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -338,9 +371,18 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     e2e_value = float(tot.item()) / float(t.item())
+    # plain H2D bandwidth of the same pinned buffers, for context
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(8):
+        d_msgs[1 + i][:nbytes[1 + i]].copy_(h_msgs[1 + i], non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = sum(nbytes[1:9]) / (time.perf_counter() - t0) / 1e9
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes[1],
            "d2h_bytes_per_step": 5 * n_lines_msg[1] + 32, "steps": e2e_steps,
-           "api": "dm_process_lines(host pinned buffer) via DeviceDetector.process_lines"}
+           "api": ("dm_submit_lines/dm_collect (2 slots, pinned host buffers)" if pipelined else
+                   "dm_process_lines(host pinned buffer)") + " via DeviceDetector",
+           "ms_per_step": 1e3 * float(t.item()) / e2e_steps, "h2d_gbs_pinned": h2d_gbs}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None

@@ -82,6 +82,17 @@ struct dm_handle {
     uint32_t* d_vals = nullptr;          // record mode: offsets / fields / record_of
     uint64_t vals_cap = 0;
     uint32_t* d_masks = nullptr;
+    // pipelined host path: two slots
+    struct Slot {
+        uint8_t* d_in = nullptr; uint8_t* d_flags = nullptr; float* d_scores = nullptr;
+        DmBatchHeader* d_hdr = nullptr; DmBatchHeader* h_hdr = nullptr; dm_anomaly_t* d_anoms = nullptr;
+        uint8_t* h_flags = nullptr; float* h_scores = nullptr;
+        cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_hdr = nullptr;
+        cudaStream_t st_out = nullptr;
+        bool busy = false;
+    } slots[2];
+    cudaStream_t st_in = nullptr;
+    bool slots_ready = false;
     // measurement support
     bool profile = false;
     std::vector<cudaEvent_t> ev;         // pairs: ev[2i] start, ev[2i+1] stop
@@ -250,6 +261,15 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
     cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
     cudaFree(h->d_vals); cudaFree(h->d_masks);
+    for (auto& sl : h->slots) {
+        cudaFree(sl.d_in); cudaFree(sl.d_flags); cudaFree(sl.d_scores); cudaFree(sl.d_hdr); cudaFree(sl.d_anoms);
+        cudaFreeHost(sl.h_hdr); cudaFreeHost(sl.h_flags); cudaFreeHost(sl.h_scores);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
+        if (sl.ev_hdr) cudaEventDestroy(sl.ev_hdr);
+        if (sl.st_out) cudaStreamDestroy(sl.st_out);
+    }
+    if (h->st_in) cudaStreamDestroy(h->st_in);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return DM_OK;
@@ -433,6 +453,114 @@ extern "C" int dm_process_values(dm_handle* h, const uint8_t* blob, uint64_t blo
     if (rc != DM_OK) return rc;
     if (n_anomalies_out) *n_anomalies_out = h->h_hdr->n_anomalies;
     return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// pipelined host path
+// ---------------------------------------------------------------------------------------
+static int dm_slots_init(dm_handle* h) {
+    if (h->slots_ready) return DM_OK;
+    DM_CUDA(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+    for (auto& sl : h->slots) {
+        DM_CUDA(cudaMalloc(&sl.d_in, h->max_batch_bytes + 256));
+        DM_CUDA(cudaMemset(sl.d_in, 0, h->max_batch_bytes + 256));
+        DM_CUDA(cudaMalloc(&sl.d_flags, h->max_lines + 16));
+        DM_CUDA(cudaMalloc(&sl.d_scores, (h->max_lines + 4) * sizeof(float)));
+        DM_CUDA(cudaMalloc(&sl.d_hdr, sizeof(DmBatchHeader)));
+        DM_CUDA(cudaMemset(sl.d_hdr, 0, sizeof(DmBatchHeader)));
+        DM_CUDA(cudaMalloc(&sl.d_anoms, (uint64_t)h->anomaly_cap * sizeof(dm_anomaly_t)));
+        DM_CUDA(cudaHostAlloc(&sl.h_hdr, sizeof(DmBatchHeader), cudaHostAllocDefault));
+        DM_CUDA(cudaHostAlloc(&sl.h_flags, h->max_lines + 16, cudaHostAllocDefault));
+        DM_CUDA(cudaHostAlloc(&sl.h_scores, (h->max_lines + 4) * sizeof(float), cudaHostAllocDefault));
+        DM_CUDA(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+        DM_CUDA(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
+        DM_CUDA(cudaEventCreateWithFlags(&sl.ev_hdr, cudaEventDisableTiming));
+        DM_CUDA(cudaStreamCreateWithFlags(&sl.st_out, cudaStreamNonBlocking));
+    }
+    h->slots_ready = true;
+    return DM_OK;
+}
+
+extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t nbytes, uint64_t n_train_lines, uint32_t slot) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    if (slot > 1) return dm_fail(DM_ERR_ARG, "slot must be 0 or 1");
+    if (nbytes > h->max_batch_bytes)
+        return dm_fail(DM_ERR_CAPACITY, "message of %llu bytes exceeds max_batch_bytes=%llu", (unsigned long long)nbytes, (unsigned long long)h->max_batch_bytes);
+    if (nbytes && !host_buf) return dm_fail(DM_ERR_ARG, "host_buf is NULL");
+    if (h->kernel_variant != 2) return dm_fail(DM_ERR_STATE, "the pipelined path needs the rows kernels (DM_KERNEL=rows)");
+    DM_CUDA(cudaSetDevice(h->device));
+    int rc = dm_slots_init(h);
+    if (rc != DM_OK) return rc;
+    dm_handle::Slot& sl = h->slots[slot];
+    if (sl.busy) return dm_fail(DM_ERR_STATE, "slot %u was submitted and not collected yet", slot);
+    if (nbytes) DM_CUDA(cudaMemcpyAsync(sl.d_in, host_buf, nbytes, cudaMemcpyHostToDevice, h->st_in));
+    DM_CUDA(cudaMemsetAsync(sl.d_in + nbytes, 0, 64, h->st_in));
+    DM_CUDA(cudaEventRecord(sl.ev_in, h->st_in));
+    cudaStream_t st = h->stream;                       // ONE compute stream: submission order = processing order
+    h->last_stream = st;
+    DM_CUDA(cudaStreamWaitEvent(st, sl.ev_in, 0));
+    if (nbytes == 0) DM_CUDA(cudaMemsetAsync(sl.d_hdr, 0, sizeof(DmBatchHeader), st));
+    const int launched = dm_rows_launch(&h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
+                                        h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st,
+                                        dm_prof_mark_cb, h);
+    if (launched < 0) return dm_fail(DM_ERR_CUDA, "rows kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += (uint64_t)launched;
+    DM_CUDA(cudaEventRecord(sl.ev_comp, st));
+    DM_CUDA(cudaStreamWaitEvent(sl.st_out, sl.ev_comp, 0));
+    DM_CUDA(cudaMemcpyAsync(sl.h_hdr, sl.d_hdr, sizeof(DmBatchHeader), cudaMemcpyDeviceToHost, sl.st_out));
+    DM_CUDA(cudaEventRecord(sl.ev_hdr, sl.st_out));
+    sl.busy = true;
+    return DM_OK;
+}
+
+extern "C" int dm_collect(dm_handle* h, uint32_t slot, const uint8_t** flags_out, const float** scores_out,
+                          uint64_t* n_lines_out, uint64_t* n_anomalies_out) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    if (slot > 1 || !h->slots_ready || !h->slots[slot].busy) return dm_fail(DM_ERR_STATE, "slot %u has nothing to collect", slot);
+    DM_CUDA(cudaSetDevice(h->device));
+    dm_handle::Slot& sl = h->slots[slot];
+    DM_CUDA(cudaEventSynchronize(sl.ev_hdr));
+    sl.busy = false;
+    *h->h_hdr = *sl.h_hdr;
+    int rc = dm_check_device_errors(h);
+    if (rc != DM_OK) return rc;
+    const uint64_t n = sl.h_hdr->n_lines;
+    if (n && (flags_out || scores_out)) {
+        if (flags_out) DM_CUDA(cudaMemcpyAsync(sl.h_flags, sl.d_flags, n, cudaMemcpyDeviceToHost, sl.st_out));
+        if (scores_out) DM_CUDA(cudaMemcpyAsync(sl.h_scores, sl.d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, sl.st_out));
+        DM_CUDA(cudaStreamSynchronize(sl.st_out));
+    }
+    if (flags_out) *flags_out = sl.h_flags;
+    if (scores_out) *scores_out = sl.h_scores;
+    if (n_lines_out) *n_lines_out = n;
+    if (n_anomalies_out) *n_anomalies_out = sl.h_hdr->n_anomalies;
+    return DM_OK;
+}
+
+static int dm_fetch_anomalies(dm_handle* h, const dm_anomaly_t* d_list, uint32_t total, dm_anomaly_t* out, uint32_t cap, uint32_t* n_out) {
+    const uint32_t have = std::min(total, h->anomaly_cap);
+    *n_out = 0;
+    if (have == 0) return DM_OK;
+    std::vector<dm_anomaly_t> tmp(have);
+    DM_CUDA(cudaMemcpy(tmp.data(), d_list, (uint64_t)have * sizeof(dm_anomaly_t), cudaMemcpyDeviceToHost));
+    std::sort(tmp.begin(), tmp.end(), [](const dm_anomaly_t& a, const dm_anomaly_t& b) { return a.line < b.line; });
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < have; ++i) {
+        if (m && tmp[m - 1].line == tmp[i].line) { tmp[m - 1].mask |= tmp[i].mask; continue; }
+        tmp[m++] = tmp[i];
+    }
+    *n_out = m;
+    if (out && cap) memcpy(out, tmp.data(), (uint64_t)std::min(m, cap) * sizeof(dm_anomaly_t));
+    return DM_OK;
+}
+
+extern "C" int dm_collect_anomalies(dm_handle* h, uint32_t slot, dm_anomaly_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!h || !n_out) return dm_fail(DM_ERR_ARG, "NULL argument");
+    if (slot > 1 || !h->slots_ready) return dm_fail(DM_ERR_STATE, "slot %u was never used", slot);
+    DM_CUDA(cudaSetDevice(h->device));
+    dm_handle::Slot& sl = h->slots[slot];
+    if (sl.busy) return dm_fail(DM_ERR_STATE, "slot %u is still in flight: dm_collect it first", slot);
+    return dm_fetch_anomalies(h, sl.d_anoms, sl.h_hdr->anomaly_list_count, out, cap, n_out);
 }
 
 extern "C" int dm_sync(dm_handle* h, uint64_t* n_lines_out, uint64_t* n_anomalies_out) {

@@ -122,6 +122,43 @@ class DeviceDetector:
                                               flags_ptr or None, scores_ptr or None, int(out_cap_lines), 1,
                                               None, None, stream or None))
 
+    # ------------------------------------------------------------------ pipelined host path
+    def submit(self, buf: BytesLike, n_train_lines: int = 0, slot: int = 0) -> None:
+        """Enqueue one host message on `slot` (0 or 1) without waiting: H2D copy, kernels and
+        the header copy back overlap with the other slot's work.  `buf` must stay alive and
+        unchanged until collect(slot); pinned memory (stage_pinned / torch pin_memory) gives
+        real copy/compute overlap."""
+        ptr, n, keep = self._host_ptr(buf)
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[slot] = keep
+        _lib.check(self._lib.dm_submit_lines(self._h, ptr, n, int(n_train_lines), int(slot)))
+
+    def collect(self, slot: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """Wait for `slot`; returns (flags, scores) as views of the handle's pinned result
+        buffers (valid until the slot is submitted again)."""
+        pf, ps = C.c_void_p(), C.c_void_p()
+        n_lines, n_anom = C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.dm_collect(self._h, int(slot), C.byref(pf), C.byref(ps), C.byref(n_lines), C.byref(n_anom)))
+        self._inflight.pop(slot, None)
+        k = n_lines.value
+        self.last_n_anomalies = n_anom.value
+        if k == 0:
+            return np.zeros(0, np.uint8), np.zeros(0, np.float32)
+        f = np.ctypeslib.as_array(C.cast(pf, C.POINTER(C.c_uint8)), shape=(k,))
+        s = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_float)), shape=(k,))
+        return f, s
+
+    def collect_anomalies(self, slot: int = 0, cap: int = 1 << 20) -> List[Tuple[int, int, int]]:
+        n = C.c_uint32()
+        _lib.check(self._lib.dm_collect_anomalies(self._h, int(slot), None, 0, C.byref(n)))
+        k = min(n.value, cap)
+        if k == 0:
+            return []
+        arr = (_lib.Anomaly * k)()
+        _lib.check(self._lib.dm_collect_anomalies(self._h, int(slot), arr, k, C.byref(n)))
+        return [(arr[i].line, arr[i].mask, arr[i].offset) for i in range(min(k, n.value))]
+
     # ------------------------------------------------------------------ record mode
     def process_values(self, records, n_train_records: int = 0, record_bytes: int = 0
                        ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

@@ -112,6 +112,20 @@ int dm_process_values(dm_handle* h, const uint8_t* blob, uint64_t blob_bytes, co
                       uint8_t* flags_out, float* scores_out, uint32_t* masks_out,
                       uint64_t* n_anomalies_out);
 
+/* Pipelined host path (two slots): dm_submit_lines enqueues, without waiting, the copy of a
+ * HOST message (pinned memory gives real overlap) to the device, the kernels and the copy
+ * of the batch header back; dm_collect waits for that slot, copies the slot's flags and
+ * scores into pinned buffers owned by the handle and returns pointers to them (valid until
+ * the slot is submitted again).  While slot 1's message is crossing PCIe, slot 0's kernels
+ * run and its results travel back.  Messages are processed in submission order (training
+ * before detection is preserved).  Raw-mode equivalent of calling dm_process_lines per
+ * message; replaces the same per-record calls of core.py:201-203. */
+int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t nbytes, uint64_t n_train_lines, uint32_t slot);
+int dm_collect(dm_handle* h, uint32_t slot, const uint8_t** flags_out, const float** scores_out,
+               uint64_t* n_lines_out, uint64_t* n_anomalies_out);
+/* Anomalous records of the batch last collected from `slot` (same format as dm_get_anomalies). */
+int dm_collect_anomalies(dm_handle* h, uint32_t slot, dm_anomaly_t* out, uint32_t cap, uint32_t* n_out);
+
 /* Wait for everything enqueued on the handle and report the last batch's counts. */
 int dm_sync(dm_handle* h, uint64_t* n_lines_out, uint64_t* n_anomalies_out);
 

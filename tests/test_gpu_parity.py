@@ -294,3 +294,47 @@ def test_window_exchange_two_ranks_on_one_gpu(variant):
         gs = d0.global_stats()
         assert gs["lines"] == 12000 and gs["train_lines"] == 6000 and gs["anomalies"] == int(wf.sum())
         assert gs["score_sum"] == int(ws.sum()) and gs == d1.global_stats()
+
+
+def test_pipelined_submit_collect(monkeypatch):
+    """dm_submit_lines / dm_collect (two slots in flight) give the same flags, scores and
+    anomaly lists as the synchronous call, in submission order, training included."""
+    import torch
+    from detectmateservice_b200.synth import AuditSynth, MONITORED_KEYS
+    monkeypatch.setenv("DM_KERNEL", "rows")
+    g = AuditSynth(seed=31)
+    msgs = [g.batch(5000, inject=False)[0]] + [g.batch(5000, inject=True)[0] for _ in range(6)] + [b"", b"type=A\n"]
+    n_train = [3000] + [0] * (len(msgs) - 1)
+    keys = [k.encode() for k in MONITORED_KEYS]
+    o = NativeOracle(keys)
+    want = [o.process(m, t, want_masks=True) for m, t in zip(msgs, n_train)]
+    pinned = []
+    for m in msgs:
+        t = torch.empty(max(len(m), 1), dtype=torch.uint8, pin_memory=True)
+        t[:len(m)].copy_(torch.frombuffer(bytearray(m), dtype=torch.uint8)) if m else None
+        pinned.append(t.numpy()[:len(m)])
+    with _det(keys) as det:
+        got = {}
+        for i in range(len(msgs)):
+            slot = i & 1
+            if i >= 2:
+                f, s = det.collect(slot)
+                got[i - 2] = (f.copy(), s.copy(), det.collect_anomalies(slot))
+            det.submit(pinned[i], n_train[i], slot)
+        for i in range(len(msgs) - 2, len(msgs)):
+            f, s = det.collect(i & 1)
+            got[i] = (f.copy(), s.copy(), det.collect_anomalies(i & 1))
+        for i, (wf, ws, wm) in enumerate(want):
+            f, s, an = got[i]
+            assert f.tolist() == wf.tolist() and s.tolist() == ws.tolist(), i
+            idx = np.nonzero(wf)[0]
+            assert [a[0] for a in an] == idx.tolist() and [a[1] for a in an] == wm[idx].tolist()
+        from detectmateservice_b200 import _lib
+        with pytest.raises(_lib.DmError):
+            det.collect(0)                                   # nothing in flight
+        det.submit(pinned[1], 0, 0)
+        with pytest.raises(_lib.DmError):
+            det.submit(pinned[2], 0, 0)                      # slot busy
+        det.collect(0)
+        st = det.stats()
+        assert st["lines"] == sum(w[0].size for w in want) + 5000 and st["train_lines"] == 3000
