@@ -406,6 +406,8 @@ static inline int dm_rows_scratch_create(DmRowsScratch* s, uint64_t max_batch_by
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_rows<false, false>, DMR_B_THREADS, 0) != cudaSuccess) return DM_ERR_CUDA;
     if (per_sm < 1) per_sm = 1;
+    const char* cap = getenv("DM_ROWS_CTAS_PER_SM");       // tuning knob: fewer, longer-lived warps
+    if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
     s->grid_b = sm_count * per_sm;
     return DM_OK;
 }
