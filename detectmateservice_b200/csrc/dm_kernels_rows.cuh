@@ -50,6 +50,7 @@ struct DmRowsArgs {
     uint64_t line_lo, line_hi;        // K_B handles records with index in [lo, hi)
     uint64_t n_train_lines;
     uint64_t max_lines;
+    unsigned int* aux_counts;         // staged variant: list counters cleared by K_A (else NULL)
 };
 
 // 16-bit '\n' mask of this lane's chunk of a row, slack bytes behind the message dropped
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
     // which every later tile -- and K_B -- depends on)
     if (tile == 0 && threadIdx.x == 0) {
         a.hdr->n_anomalies = 0; a.hdr->anomaly_list_count = 0; a.hdr->error = 0; a.hdr->n_lines = 0; a.hdr->n_newlines = 0;
+        if (a.aux_counts) { a.aux_counts[0] = 0; a.aux_counts[1] = 0; a.aux_counts[2] = 0; }
         __threadfence();
     }
     // newline count of each row of the tile: 8 warps x 8 rows, all 8 loads of a warp in flight
@@ -437,7 +439,7 @@ static inline int dm_rows_launch(DmRowsScratch* s, const uint8_t* d_buf, uint64_
     a.keys = d_keys; a.table = table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
     a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap; a.hdr = d_hdr; a.stats = d_stats;
     a.row_ctr = s->d_row_ctr; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
-    a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = s->ctr_base;
+    a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = s->ctr_base; a.aux_counts = nullptr;
     int launched = 0;
     dm_k_rowindex<<<a.n_tiles, DMR_A_THREADS, 0, st>>>(a);
     ++launched;

@@ -15,6 +15,7 @@
 #include "dm_kernels_v1.cuh"
 #include "dm_kernels_tile.cuh"
 #include "dm_kernels_rows.cuh"
+#include "dm_kernels_staged.cuh"
 #include "dm_kernels_values.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -78,6 +79,7 @@ struct dm_handle {
     uint64_t novel_exported = 0;         // novel keys already shipped in a window
     DmTileScratch tile;                  // fused-kernel scratch
     DmRowsScratch rows;                  // rows-variant scratch
+    DmStagedScratch staged;              // staged-variant scratch (candidate / field lists)
     uint64_t last_nbytes = 0;
     uint32_t* d_vals = nullptr;          // record mode: offsets / fields / record_of
     uint64_t vals_cap = 0;
@@ -214,6 +216,11 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
     if (env && strcmp(env, "v1") == 0) h->kernel_variant = 0;
     if (env && strcmp(env, "tile") == 0) h->kernel_variant = 1;
     if (env && strcmp(env, "rows") == 0) h->kernel_variant = 2;
+    if (env && strcmp(env, "staged") == 0) h->kernel_variant = 3;
+    if (h->kernel_variant == 3) {
+        rc = dm_staged_scratch_create(&h->staged, max_batch_bytes, h->sm_count);
+        if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "staged scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    }
     DM_CUDA(cudaDeviceSynchronize());
     *out = h;
     return DM_OK;
@@ -256,6 +263,7 @@ extern "C" int dm_destroy(dm_handle* h) {
     for (auto& e : h->ev) cudaEventDestroy(e);
     dm_tile_scratch_destroy(&h->tile);
     dm_rows_scratch_destroy(&h->rows);
+    dm_staged_scratch_destroy(&h->staged);
     cudaFree(h->d_keys); cudaFree(h->d_in); cudaFree(h->d_tile_counts); cudaFree(h->d_tile_base);
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
@@ -319,7 +327,7 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
     (void)dev_cap;
 
     // (the rows variant clears the per-batch header in its first kernel)
-    if (h->kernel_variant != 2 || nbytes == 0) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
+    if (h->kernel_variant < 2 || nbytes == 0) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
     h->last_nbytes = nbytes;
 
     if (h->kernel_variant == 0) {
@@ -344,6 +352,12 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         dm_k_detect_lines<false><<<grid, 256, 0, st>>>(a);
         dm_prof_mark(h, st, 1);
         h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
+    } else if (h->kernel_variant == 3) {
+        const int rc = dm_staged_launch(&h->staged, &h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags,
+                                        d_scores, out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines,
+                                        st, dm_prof_mark_cb, h);
+        if (rc < 0) return dm_fail(DM_ERR_CUDA, "staged kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->launches += (uint64_t)rc;
     } else if (h->kernel_variant == 2) {
         const int rc = dm_rows_launch(&h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,
                                       out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st,
@@ -487,7 +501,7 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     if (nbytes > h->max_batch_bytes)
         return dm_fail(DM_ERR_CAPACITY, "message of %llu bytes exceeds max_batch_bytes=%llu", (unsigned long long)nbytes, (unsigned long long)h->max_batch_bytes);
     if (nbytes && !host_buf) return dm_fail(DM_ERR_ARG, "host_buf is NULL");
-    if (h->kernel_variant != 2) return dm_fail(DM_ERR_STATE, "the pipelined path needs the rows kernels (DM_KERNEL=rows)");
+    if (h->kernel_variant < 2) return dm_fail(DM_ERR_STATE, "the pipelined path needs the rows or staged kernels");
     DM_CUDA(cudaSetDevice(h->device));
     int rc = dm_slots_init(h);
     if (rc != DM_OK) return rc;
@@ -500,9 +514,11 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     h->last_stream = st;
     DM_CUDA(cudaStreamWaitEvent(st, sl.ev_in, 0));
     if (nbytes == 0) DM_CUDA(cudaMemsetAsync(sl.d_hdr, 0, sizeof(DmBatchHeader), st));
-    const int launched = dm_rows_launch(&h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
-                                        h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st,
-                                        dm_prof_mark_cb, h);
+    const int launched = h->kernel_variant == 3
+        ? dm_staged_launch(&h->staged, &h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
+                           h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, dm_prof_mark_cb, h)
+        : dm_rows_launch(&h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
+                         h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, dm_prof_mark_cb, h);
     if (launched < 0) return dm_fail(DM_ERR_CUDA, "rows kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += (uint64_t)launched;
     DM_CUDA(cudaEventRecord(sl.ev_comp, st));

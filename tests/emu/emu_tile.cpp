@@ -9,6 +9,7 @@
 
 #include "dm_kernels_tile.cuh"
 #include "dm_kernels_rows.cuh"
+#include "dm_kernels_staged.cuh"
 
 thread_local emu_dim3 threadIdx;
 thread_local emu_dim3 blockIdx;
@@ -129,8 +130,21 @@ extern "C" int emu_process(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, ui
 }
 
 // Mirrors dm_rows_launch (dm_kernels_rows.cuh): K_A, optional K_B<train>, K_B<detect>.
+static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                 float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err, bool staged);
+
 extern "C" int emu_process_rows(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
                                 float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    return emu_process_rows_impl(h, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err, false);
+}
+
+extern "C" int emu_process_staged(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                  float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    return emu_process_rows_impl(h, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err, true);
+}
+
+static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                 float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err, bool staged) {
     uint8_t* buf = (uint8_t*)aligned_alloc(64, ((nbytes + 64 + 63) / 64) * 64 + 64);
     memcpy(buf, msg, nbytes);
     for (int i = 0; i < 64; ++i) buf[nbytes + i] = (i & 1) ? '\n' : '=';
@@ -147,7 +161,32 @@ extern "C" int emu_process_rows(EmuHandle* h, const uint8_t* msg, uint64_t nbyte
         a.keys = &h->keys; a.table = h->table; a.flags = flags; a.scores = scores; a.out_cap = cap;
         a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size(); a.hdr = &h->hdr; a.stats = h->stats;
         a.row_ctr = &h->row_ctr; a.n_train_lines = n_train; a.max_lines = h->max_lines;
-        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base;
+        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base; a.aux_counts = nullptr;
+        if (staged) {
+            static std::vector<DmCand> cand;
+            static std::vector<DmField> fields;
+            static unsigned int counts[4];
+            cand.assign(nbytes + 1024, DmCand{0, 0});
+            fields.assign(nbytes / 2 + 1024, DmField{0, 0, 0});
+            counts[0] = 77; counts[1] = 88; counts[2] = 99;          // K_A must clear them
+            DmStagedArgs sa;
+            sa.r = a; sa.r.aux_counts = counts;
+            sa.cand = cand.data(); sa.fields = fields.data(); sa.counts = counts;
+            sa.cand_cap = (uint32_t)cand.size(); sa.field_cap = (uint32_t)fields.size();
+            emu_launch_grid(a.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(sa.r); });
+            const uint32_t tiles1 = (n_rows + DMS_ROWS_PER_CTA - 1) / DMS_ROWS_PER_CTA;
+            emu_launch_grid(tiles1 < 3 ? tiles1 : 3, DMS_THREADS, [&] { dm_k_stage1(sa); });
+            emu_launch(DMS_THREADS, [&] { dm_k_stage2(sa); });
+            if (n_train > 0) {
+                sa.r.line_lo = 0; sa.r.line_hi = n_train;
+                emu_launch(DMS_THREADS, [&] { dm_k_stage3<true>(sa); });
+            }
+            sa.r.line_lo = n_train; sa.r.line_hi = ~0ull;
+            emu_launch(DMS_THREADS, [&] { dm_k_stage3<false>(sa); });
+            free(buf);
+            *n_lines = h->hdr.n_lines; *n_anoms = h->hdr.n_anomalies; *err = h->hdr.error;
+            return 0;
+        }
         emu_launch_grid(a.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(a); });
         const uint32_t groups = (n_rows + DMR_GROUP - 1) / DMR_GROUP;
         const unsigned long long per_launch = (unsigned long long)groups * DMR_GROUP + (unsigned long long)DMR_B_WARPS * DMR_GROUP;

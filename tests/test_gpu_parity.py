@@ -16,7 +16,7 @@ from util import FUZZ_KEYS, fuzz_lines
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["v1", "tile", "rows"]
+VARIANTS = ["v1", "tile", "rows", "staged"]
 SCORE_TOL = 1e-5
 
 
