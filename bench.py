@@ -63,7 +63,7 @@ def _make_messages(seed_offset: int, n_msgs: int = N_MSGS, lines: int = LINES_PE
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
 
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -115,17 +115,24 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle's C restatement, threads over shards of the same workload
 # ------------------------------------------------------------------------------------------
-def _cpu_throughput(msgs, sample_lines: int, threads: int, repeats: int = 1):
-    """Detect `sample_lines` records per thread with `threads` threads (each owns a trained
-    oracle instance).  Returns (lines/s, seconds)."""
+def _cpu_oracles(msgs, threads: int):
+    """One trained C-oracle instance per thread (training window = message 0, untimed)."""
     from detectmateservice_b200.synth import MONITORED_KEYS
     from oracle.native import NativeOracle
     keys = [k.encode() for k in MONITORED_KEYS]
     oracles = []
     for _ in range(threads):
         o = NativeOracle(keys)
-        o.process(msgs[0], LINES_PER_MSG)            # training window, untimed
+        o.process(msgs[0], LINES_PER_MSG)
         oracles.append(o)
+    return oracles
+
+
+def _cpu_throughput(msgs, sample_lines: int, threads: int, repeats: int = 1, oracles=None):
+    """Detect `sample_lines` records per thread with `threads` threads (each owns a trained
+    oracle instance).  Returns (lines/s, seconds)."""
+    if oracles is None:
+        oracles = _cpu_oracles(msgs, threads)
     nbytes = sample_lines * LINE_BYTES
     shards = [np.frombuffer(msgs[1 + (t % (len(msgs) - 1))], dtype=np.uint8)[:nbytes] for t in range(threads)]
     barrier = threading.Barrier(threads + 1)
@@ -174,11 +181,12 @@ def run_reference(args):
     msgs = _make_messages(0, n_msgs=4)
     # bounded sample per step: 8192 records per thread (about 2 MiB each)
     sample = 8192
-    for _ in range(max(args.warmup, 1)):
-        _cpu_throughput(msgs, sample, threads)
+    oracles = _cpu_oracles(msgs, threads)
+    for _ in range(max(min(args.warmup, 5), 1)):
+        _cpu_throughput(msgs, sample, threads, oracles=oracles)
     t_total, lines_total = 0.0, 0
     for _ in range(args.steps):
-        rate, dt = _cpu_throughput(msgs, sample, threads)
+        rate, dt = _cpu_throughput(msgs, sample, threads, oracles=oracles)
         t_total += dt
         lines_total += sample * threads
     value = lines_total / t_total
@@ -424,8 +432,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=150)
-    ap.add_argument("--warmup", type=int, default=15)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()

@@ -199,6 +199,32 @@ class B200NewValueDetector(CoreComponent):
 
     # ------------------------------------------------------------------ raw mode
     def _process_lines(self, data: bytes) -> Optional[bytes]:
+        if len(data) > self.max_batch_bytes:
+            return self._process_lines_chunked(data)
+        return self._process_lines_one(data)
+
+    def _process_lines_chunked(self, data: bytes) -> Optional[bytes]:
+        """A message larger than the device batch: cut at record boundaries, process the pieces
+        in order (training counter and record numbering carry over), merge the outputs."""
+        outs, pos, n = [], 0, len(data)
+        while pos < n:
+            end = min(pos + self.max_batch_bytes, n)
+            if end < n:
+                cut = data.rfind(b"\n", pos, end)
+                if cut < 0:
+                    raise ValueError(f"a single record exceeds max_batch_bytes={self.max_batch_bytes}")
+                end = cut + 1
+            outs.append(self._process_lines_one(data[pos:end], force_delimited=True))
+            pos = end
+        if self.output_format == "compact":
+            parts = [decode_compact(o) for o in outs]
+            flags = np.concatenate([p[0] for p in parts])
+            scores = np.concatenate([p[1] for p in parts])
+            return struct.pack("<I", flags.size) + flags.tobytes() + scores.tobytes()
+        merged = b"".join(o for o in outs if o)
+        return merged or None
+
+    def _process_lines_one(self, data: bytes, force_delimited: bool = False) -> Optional[bytes]:
         remaining = max(0, self.data_use_training - self.n_seen)
         flags, scores = self.det.process_lines(data, n_train_lines=remaining, copy=False)
         n = int(flags.size)
@@ -220,7 +246,7 @@ class B200NewValueDetector(CoreComponent):
                                              _alerts.record_time(rec)))
         if not out:
             return None
-        return out[0] if n == 1 else wire.frame_delimited(out)
+        return out[0] if (n == 1 and not force_delimited) else wire.frame_delimited(out)
 
     # ------------------------------------------------------------------ output
     def _detector_schema(self, log_id: str, score: float, alerts: Dict[str, str], time_value) -> bytes:

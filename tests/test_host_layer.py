@@ -380,3 +380,21 @@ def test_reference_service_loads_b200_component(tmp_path, monkeypatch, golden_di
         svc.stop()
     inst = ComponentLoader.load_component("detectmateservice_b200.component.B200NewValueDetector", {})
     assert isinstance(inst, comp_mod.B200NewValueDetector)
+
+
+def test_component_chunks_messages_larger_than_the_device_batch(golden_dir):
+    from detectmateservice_b200.component import decode_compact
+    exp = json.load(open(os.path.join(golden_dir, "audit_sample.expected.json")))
+    buf = open(os.path.join(golden_dir, "audit_sample.log"), "rb").read()
+    base = {"method_type": "new_value_detector", "data_use_training": exp["n_train"], "auto_config": False,
+            "global": {"g": {"header_variables": [{"pos": k} for k in exp["keys"]]}}}
+    whole = _component({"detectors": {"B200NewValueDetector": base}})
+    small = _component({"detectors": {"B200NewValueDetector": dict(base, params={"max_batch_bytes": 5000})}})
+    a = [wire.decode_detector_schema(b) for b in wire.split_delimited(whole.process(buf))]
+    b = [wire.decode_detector_schema(x) for x in wire.split_delimited(small.process(buf))]
+    assert [(x["logIDs"], x["alertID"], x["alertsObtain"]) for x in a] == [(x["logIDs"], x["alertID"], x["alertsObtain"]) for x in b]
+    comp = _component({"detectors": {"B200NewValueDetector": dict(base, params={"max_batch_bytes": 3000, "output_format": "compact"})}})
+    f, s = decode_compact(comp.process(buf))
+    assert f.tolist() == exp["flags"] and s.tolist() == exp["scores"]
+    with pytest.raises(ValueError):
+        _component({"detectors": {"B200NewValueDetector": dict(base, params={"max_batch_bytes": 100})}}).process(buf)
