@@ -74,6 +74,11 @@ class Stats(C.Structure):
                 "known_keys": self.known_keys, "unknown_per_key": list(self.unknown_per_key)[:n_keys]}
 
 
+class Monitor(C.Structure):
+    _fields_ = [("event_id", C.c_int32), ("has_event", C.c_uint32), ("source", C.c_uint32), ("var_index", C.c_uint32),
+                ("key_len", C.c_uint32), ("key", C.c_uint8 * 64)]
+
+
 class Anomaly(C.Structure):
     _fields_ = [("line", C.c_uint32), ("mask", C.c_uint32), ("offset", C.c_uint64)]
 
@@ -91,6 +96,9 @@ SYMBOLS = {
     "dm_process_values": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                     _P, _P, _P, C.POINTER(C.c_uint64)]),
+    "dm_set_monitors": (C.c_int, [_P, C.c_uint32, C.POINTER(Monitor)]),
+    "dm_process_records": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64,
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dm_submit_lines": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint32]),
     "dm_collect": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dm_collect_anomalies": (C.c_int, [_P, C.c_uint32, C.POINTER(Anomaly), C.c_uint32, C.POINTER(C.c_uint32)]),

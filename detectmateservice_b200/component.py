@@ -130,8 +130,8 @@ class B200NewValueDetector(CoreComponent):
         self.start_id = int(cfg.get("start_id", 10))
         self.input_format = cfg.get("input_format", "auto")
         self.output_format = cfg.get("output_format", "alerts")
-        if self.input_format not in ("auto", "raw_lines", "parser_schema"):
-            raise ValueError(f"input_format {self.input_format!r} not in auto|raw_lines|parser_schema")
+        if self.input_format not in ("auto", "raw_lines", "parser_schema", "parser_schema_batch"):
+            raise ValueError(f"input_format {self.input_format!r} not in auto|raw_lines|parser_schema|parser_schema_batch")
         if self.output_format not in ("alerts", "compact"):
             raise ValueError(f"output_format {self.output_format!r} not in alerts|compact")
         self.monitors = parse_monitors(cfg)
@@ -151,6 +151,7 @@ class B200NewValueDetector(CoreComponent):
             self._det = DeviceDetector([m.key for m in self.monitors], device=self.device,
                                        max_batch_bytes=self.max_batch_bytes,
                                        table_log2_slots=self.table_log2_slots)
+            self._det.set_monitors([{"event_id": m.event_id, "source": m.source, "pos": m.pos} for m in self.monitors])
         return self._det
 
     def close(self) -> None:
@@ -164,9 +165,16 @@ class B200NewValueDetector(CoreComponent):
             return None
         fmt = self.input_format
         if fmt == "auto":
-            fmt = "parser_schema" if wire.looks_like_parser_schema(data) else "raw_lines"
+            if wire.looks_like_parser_schema(data):
+                fmt = "parser_schema"
+            elif wire.looks_like_delimited_parser_schemas(data):
+                fmt = "parser_schema_batch"
+            else:
+                fmt = "raw_lines"
         if fmt == "parser_schema":
             return self._process_record(data)
+        if fmt == "parser_schema_batch":
+            return self._process_record_batch(data)
         return self._process_lines(data)
 
     # ------------------------------------------------------------------ record mode
@@ -196,6 +204,30 @@ class B200NewValueDetector(CoreComponent):
                   for i in range(len(self.monitors)) if mask >> i & 1}
         t = (rec.get("logFormatVariables") or {}).get("Time")
         return self._detector_schema(rec.get("logID", ""), float(scores[0]), alerts, t)
+
+    def _process_record_batch(self, data: bytes) -> Optional[bytes]:
+        """A message holding many length-delimited ParserSchema records: field walk, monitor
+        matching, hashing and scoring happen on the device; the host only decodes the (rare)
+        anomalous records to word their alerts."""
+        remaining = max(0, self.data_use_training - self.n_seen)
+        flags, scores, masks = self.det.process_records(data, n_train_records=remaining)
+        n = int(flags.size)
+        self.n_seen += n
+        if self.output_format == "compact":
+            return struct.pack("<I", n) + flags.tobytes() + scores.tobytes()
+        if self.det.last_n_anomalies == 0:
+            return None
+        frames = wire.split_delimited(data)
+        out = []
+        for idx in np.flatnonzero(flags):
+            rec = wire.decode_parser_schema(frames[int(idx)], strict=False)
+            by_field = dict(self._record_values(rec))
+            mask = int(masks[idx])
+            alerts = {self.monitors[i].alert_key: _alerts.alert_text(by_field.get(i, b""))
+                      for i in range(len(self.monitors)) if mask >> i & 1}
+            t = (rec.get("logFormatVariables") or {}).get("Time")
+            out.append(self._detector_schema(rec.get("logID", ""), float(scores[idx]), alerts, t))
+        return wire.frame_delimited(out) if out else None
 
     # ------------------------------------------------------------------ raw mode
     def _process_lines(self, data: bytes) -> Optional[bytes]:

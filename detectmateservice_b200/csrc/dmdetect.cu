@@ -17,6 +17,7 @@
 #include "dm_kernels_rows.cuh"
 #include "dm_kernels_staged.cuh"
 #include "dm_kernels_values.cuh"
+#include "dm_kernels_records.cuh"
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -84,6 +85,8 @@ struct dm_handle {
     uint32_t* d_vals = nullptr;          // record mode: offsets / fields / record_of
     uint64_t vals_cap = 0;
     uint32_t* d_masks = nullptr;
+    DmMonitors* d_mons = nullptr;        // record mode on the device
+    bool mons_set = false;
     // pipelined host path: two slots
     struct Slot {
         uint8_t* d_in = nullptr; uint8_t* d_flags = nullptr; float* d_scores = nullptr;
@@ -268,7 +271,7 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
     cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
-    cudaFree(h->d_vals); cudaFree(h->d_masks);
+    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons);
     for (auto& sl : h->slots) {
         cudaFree(sl.d_in); cudaFree(sl.d_flags); cudaFree(sl.d_scores); cudaFree(sl.d_hdr); cudaFree(sl.d_anoms);
         cudaFreeHost(sl.h_hdr); cudaFreeHost(sl.h_flags); cudaFreeHost(sl.h_scores);
@@ -465,6 +468,107 @@ extern "C" int dm_process_values(dm_handle* h, const uint8_t* blob, uint64_t blo
     h->h_hdr->n_lines = n_records;
     int rc = dm_check_device_errors(h);
     if (rc != DM_OK) return rc;
+    if (n_anomalies_out) *n_anomalies_out = h->h_hdr->n_anomalies;
+    return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// record mode on the device (batches of length-delimited ParserSchema records)
+// ---------------------------------------------------------------------------------------
+static_assert(sizeof(dm_monitor_t) == sizeof(DmMonitor), "dm_monitor_t and DmMonitor must have the same layout");
+
+extern "C" int dm_set_monitors(dm_handle* h, uint32_t n_monitors, const dm_monitor_t* monitors) {
+    if (!h || (n_monitors && !monitors)) return dm_fail(DM_ERR_ARG, "NULL argument");
+    if (n_monitors != h->n_keys) return dm_fail(DM_ERR_ARG, "%u monitors given, the handle was created with %u fields", n_monitors, h->n_keys);
+    DmMonitors hm;
+    memset(&hm, 0, sizeof(hm));
+    hm.n = n_monitors;
+    for (uint32_t i = 0; i < n_monitors; ++i) {
+        if (monitors[i].source > 1) return dm_fail(DM_ERR_ARG, "monitor %u: source must be 0 (header) or 1 (variable)", i);
+        if (monitors[i].source == 0 && (monitors[i].key_len == 0 || monitors[i].key_len > 64))
+            return dm_fail(DM_ERR_ARG, "monitor %u: header key length %u not in 1..64", i, monitors[i].key_len);
+        memcpy(&hm.m[i], &monitors[i], sizeof(DmMonitor));
+    }
+    DM_CUDA(cudaSetDevice(h->device));
+    if (!h->d_mons) DM_CUDA(cudaMalloc(&h->d_mons, sizeof(DmMonitors)));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    DM_CUDA(cudaMemcpy(h->d_mons, &hm, sizeof(DmMonitors), cudaMemcpyHostToDevice));
+    h->mons_set = true;
+    return DM_OK;
+}
+
+extern "C" int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nbytes, uint32_t n_train_records,
+                                  uint8_t* flags_out, float* scores_out, uint32_t* masks_out, uint64_t out_cap,
+                                  uint64_t* n_records_out, uint64_t* n_anomalies_out) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    if (!h->mons_set) return dm_fail(DM_ERR_STATE, "dm_set_monitors has not been called");
+    if (nbytes && !buf) return dm_fail(DM_ERR_ARG, "buf is NULL");
+    if (nbytes > h->max_batch_bytes) return dm_fail(DM_ERR_CAPACITY, "message of %llu bytes exceeds max_batch_bytes=%llu", (unsigned long long)nbytes, (unsigned long long)h->max_batch_bytes);
+    // framing: varint length, payload, varint length, payload ...
+    std::vector<uint32_t> off, len;
+    uint64_t pos = 0;
+    while (pos < nbytes) {
+        uint64_t l = 0;
+        int shift = 0;
+        for (;;) {
+            if (pos >= nbytes || shift > 63) return dm_fail(DM_ERR_ARG, "truncated length prefix at byte %llu", (unsigned long long)pos);
+            const uint8_t b = buf[pos++];
+            l |= (uint64_t)(b & 0x7F) << shift;
+            if (!(b & 0x80)) break;
+            shift += 7;
+        }
+        if (l > nbytes - pos) return dm_fail(DM_ERR_ARG, "record of %llu bytes at byte %llu runs past the end of the message", (unsigned long long)l, (unsigned long long)pos);
+        off.push_back((uint32_t)pos);
+        len.push_back((uint32_t)l);
+        pos += l;
+    }
+    const uint32_t n_records = (uint32_t)off.size();
+    if (n_records > h->max_lines) return dm_fail(DM_ERR_CAPACITY, "%u records exceed max_lines=%llu", n_records, (unsigned long long)h->max_lines);
+    if ((flags_out || scores_out || masks_out) && n_records > out_cap)
+        return dm_fail(DM_ERR_CAPACITY, "batch holds %u records, output capacity is %llu", n_records, (unsigned long long)out_cap);
+    DM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    h->last_stream = st;
+    if (2ull * n_records > 3ull * h->vals_cap) {
+        if (h->d_vals) DM_CUDA(cudaFree(h->d_vals));
+        h->vals_cap = std::max<uint64_t>(2ull * n_records, 4096);
+        DM_CUDA(cudaMalloc(&h->d_vals, (3 * h->vals_cap + 1) * sizeof(uint32_t)));
+    }
+    if (!h->d_masks) DM_CUDA(cudaMalloc(&h->d_masks, (h->max_lines + 4) * sizeof(uint32_t)));
+    uint32_t* d_off = h->d_vals;
+    uint32_t* d_len = h->d_vals + n_records;
+    DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
+    if (n_records) {
+        DM_CUDA(cudaMemcpyAsync(h->d_in, buf, nbytes, cudaMemcpyHostToDevice, st));
+        DM_CUDA(cudaMemcpyAsync(d_off, off.data(), (uint64_t)n_records * 4, cudaMemcpyHostToDevice, st));
+        DM_CUDA(cudaMemcpyAsync(d_len, len.data(), (uint64_t)n_records * 4, cudaMemcpyHostToDevice, st));
+        DmRecordsArgs a;
+        a.buf = h->d_in; a.rec_off = d_off; a.rec_len = d_len; a.n_records = n_records; a.n_train_records = n_train_records;
+        a.mons = h->d_mons; a.table = h->table; a.flags = h->d_flags; a.scores = h->d_scores; a.masks = h->d_masks;
+        a.hdr = h->d_hdr; a.stats = h->d_stats;
+        const int grid = (int)std::min<uint32_t>((n_records + 127) / 128, (uint32_t)h->sm_count * 16);
+        if (n_train_records > 0) { dm_k_records<<<grid, 128, 0, st>>>(a, 0); h->launches++; }
+        if (n_train_records < n_records) { dm_k_records<<<grid, 128, 0, st>>>(a, 1); h->launches++; }
+        DM_CUDA(cudaGetLastError());
+    }
+    DM_CUDA(cudaMemcpyAsync(h->h_hdr, h->d_hdr, sizeof(DmBatchHeader), cudaMemcpyDeviceToHost, st));
+    if (flags_out && n_records) DM_CUDA(cudaMemcpyAsync(flags_out, h->d_flags, n_records, cudaMemcpyDeviceToHost, st));
+    if (scores_out && n_records) DM_CUDA(cudaMemcpyAsync(scores_out, h->d_scores, (uint64_t)n_records * 4, cudaMemcpyDeviceToHost, st));
+    if (masks_out && n_records) DM_CUDA(cudaMemcpyAsync(masks_out, h->d_masks, (uint64_t)n_records * 4, cudaMemcpyDeviceToHost, st));
+    DM_CUDA(cudaStreamSynchronize(st));
+    {
+        const unsigned long long tr = std::min<uint32_t>(n_train_records, n_records);
+        unsigned long long cur[6];
+        DM_CUDA(cudaMemcpy(cur, h->d_stats, sizeof(cur), cudaMemcpyDeviceToHost));
+        unsigned long long upd[3] = {cur[0] + n_records, cur[1] + tr, cur[2] + (n_records - tr)};
+        const unsigned long long nb = cur[5] + nbytes;
+        DM_CUDA(cudaMemcpy(h->d_stats, upd, sizeof(upd), cudaMemcpyHostToDevice));
+        DM_CUDA(cudaMemcpy(h->d_stats + 5, &nb, sizeof(nb), cudaMemcpyHostToDevice));
+    }
+    h->h_hdr->n_lines = n_records;
+    int rc = dm_check_device_errors(h);
+    if (rc != DM_OK) return rc;
+    if (n_records_out) *n_records_out = n_records;
     if (n_anomalies_out) *n_anomalies_out = h->h_hdr->n_anomalies;
     return DM_OK;
 }

@@ -188,6 +188,39 @@ class DeviceDetector:
         self.last_n_anomalies = n_anom.value
         return flags[:n_rec], scores[:n_rec], masks[:n_rec]
 
+    # ------------------------------------------------------------------ record mode on the device
+    def set_monitors(self, monitors) -> None:
+        """monitors: one dict per monitored field, in field order:
+        {"event_id": int|None, "source": "header"|"variable", "pos": key str/bytes | index}."""
+        arr = (_lib.Monitor * max(1, len(monitors)))()
+        for i, m in enumerate(monitors):
+            arr[i].event_id = int(m["event_id"]) if m.get("event_id") is not None else 0
+            arr[i].has_event = 0 if m.get("event_id") is None else 1
+            if m["source"] == "header":
+                kb = m["pos"] if isinstance(m["pos"], bytes) else str(m["pos"]).encode("utf-8")
+                if not 0 < len(kb) <= 64:
+                    raise ValueError(f"header key {kb!r}: length not in 1..64")
+                arr[i].source, arr[i].var_index, arr[i].key_len = 0, 0, len(kb)
+                for j, c in enumerate(kb):
+                    arr[i].key[j] = c
+            else:
+                arr[i].source, arr[i].var_index, arr[i].key_len = 1, int(m["pos"]), 0
+        _lib.check(self._lib.dm_set_monitors(self._h, len(monitors), arr))
+
+    def process_records(self, buf: bytes, n_train_records: int = 0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """A batch of varint-length-delimited ParserSchema records, decoded and scored on the
+        device.  Returns (flags u8, scores f32, unknown-field masks u32), one entry per record."""
+        cap = max(1, len(buf) // 2 + 1)
+        flags = np.zeros(cap, dtype=np.uint8)
+        scores = np.zeros(cap, dtype=np.float32)
+        masks = np.zeros(cap, dtype=np.uint32)
+        n_rec, n_anom = C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.dm_process_records(self._h, bytes(buf), len(buf), int(n_train_records), flags.ctypes.data,
+                                                scores.ctypes.data, masks.ctypes.data, cap, C.byref(n_rec), C.byref(n_anom)))
+        self.last_n_anomalies = n_anom.value
+        k = n_rec.value
+        return flags[:k], scores[:k], masks[:k]
+
     def sync(self) -> Tuple[int, int]:
         n_lines = C.c_uint64()
         n_anom = C.c_uint64()

@@ -151,6 +151,18 @@ def looks_like_parser_schema(buf: bytes) -> bool:
         return False
 
 
+def looks_like_delimited_parser_schemas(buf: bytes) -> bool:
+    """varint length + a clean ParserSchema of exactly that length, at least for the first
+    record (the batch framing of record mode)."""
+    try:
+        ln, pos = _read_varint(buf, 0)
+    except (WireError, IndexError):
+        return False
+    if ln == 0 or pos + ln > len(buf):
+        return False
+    return looks_like_parser_schema(buf[pos:pos + ln])
+
+
 def encode_parser_schema(rec: Dict) -> bytes:
     """dict -> ParserSchema bytes (used by tests and by the in-process demo pipeline)."""
     out = bytearray()

@@ -112,6 +112,27 @@ int dm_process_values(dm_handle* h, const uint8_t* blob, uint64_t blob_bytes, co
                       uint8_t* flags_out, float* scores_out, uint32_t* masks_out,
                       uint64_t* n_anomalies_out);
 
+/* Record mode on the device: a message holding a BATCH of serialized ParserSchema records,
+ * each preceded by its varint length (protobuf "delimited" framing; a message that holds a
+ * single bare record is the reference's native case and goes through dm_process_values).
+ * The host only walks the length prefixes; the protobuf field walk, the monitor matching
+ * (dm_set_monitors), dm_fp64, the table probe and the scoring run in one kernel, one thread
+ * per record.  Records [0, n_train_records) are training data.  Host output buffers of
+ * out_cap entries (any may be NULL).  Synchronous.  Replaces per-record
+ * ParserSchema.deserialize + NewValueDetector.train/detect behind core.py:201-203. */
+typedef struct {
+    int32_t event_id;     /* records with this EventID only ...                          */
+    uint32_t has_event;   /* ... if non-zero; 0 = global scope (every record)            */
+    uint32_t source;      /* 0 = header variable logFormatVariables[key], 1 = variables[var_index] */
+    uint32_t var_index;
+    uint32_t key_len;
+    uint8_t key[64];
+} dm_monitor_t;
+int dm_set_monitors(dm_handle* h, uint32_t n_monitors, const dm_monitor_t* monitors);
+int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nbytes, uint32_t n_train_records,
+                       uint8_t* flags_out, float* scores_out, uint32_t* masks_out, uint64_t out_cap,
+                       uint64_t* n_records_out, uint64_t* n_anomalies_out);
+
 /* Pipelined host path (two slots): dm_submit_lines enqueues, without waiting, the copy of a
  * HOST message (pinned memory gives real overlap) to the device, the kernels and the copy
  * of the batch header back; dm_collect waits for that slot, copies the slot's flags and

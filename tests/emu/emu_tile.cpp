@@ -10,6 +10,7 @@
 #include "dm_kernels_tile.cuh"
 #include "dm_kernels_rows.cuh"
 #include "dm_kernels_staged.cuh"
+#include "dm_kernels_records.cuh"
 
 thread_local emu_dim3 threadIdx;
 thread_local emu_dim3 blockIdx;
@@ -204,6 +205,45 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
     *n_lines = h->hdr.n_lines;
     *n_anoms = h->hdr.n_anomalies;
     *err = h->hdr.error;
+    return 0;
+}
+
+// Record mode on the device: mirrors dm_process_records (framing walk on the host, then
+// dm_k_records train pass + detect pass).  `mons` uses the dm_monitor_t layout.
+extern "C" int emu_process_records(EmuHandle* h, const DmMonitor* mons, uint32_t n_mons, const uint8_t* msg,
+                                   uint64_t nbytes, uint32_t n_train, uint8_t* flags, float* scores, uint32_t* masks,
+                                   uint64_t cap, uint64_t* n_records, uint64_t* n_anoms) {
+    static DmMonitors hm;
+    memset(&hm, 0, sizeof(hm));
+    hm.n = n_mons;
+    for (uint32_t i = 0; i < n_mons; ++i) hm.m[i] = mons[i];
+    std::vector<uint32_t> off, len;
+    uint64_t pos = 0;
+    while (pos < nbytes) {
+        uint64_t l = 0; int shift = 0;
+        for (;;) {
+            if (pos >= nbytes) return -1;
+            const uint8_t b = msg[pos++];
+            l |= (uint64_t)(b & 0x7F) << shift;
+            if (!(b & 0x80)) break;
+            shift += 7;
+        }
+        if (l > nbytes - pos) return -1;
+        off.push_back((uint32_t)pos); len.push_back((uint32_t)l);
+        pos += l;
+    }
+    const uint32_t n = (uint32_t)off.size();
+    if (n > cap) return -4;
+    memset(&h->hdr, 0, sizeof(h->hdr));
+    DmRecordsArgs a;
+    a.buf = msg; a.rec_off = off.data(); a.rec_len = len.data(); a.n_records = n; a.n_train_records = n_train;
+    a.mons = &hm; a.table = h->table; a.flags = flags; a.scores = scores; a.masks = masks; a.hdr = &h->hdr; a.stats = h->stats;
+    if (n) {
+        if (n_train > 0) emu_launch(128, [&] { dm_k_records(a, 0); });
+        if (n_train < n) emu_launch(128, [&] { dm_k_records(a, 1); });
+    }
+    *n_records = n;
+    *n_anoms = h->hdr.n_anomalies;
     return 0;
 }
 
