@@ -16,6 +16,7 @@
 #include "dm_kernels_tile.cuh"
 #include "dm_kernels_rows.cuh"
 #include "dm_kernels_staged.cuh"
+#include "dm_kernels_cta.cuh"
 #include "dm_kernels_values.cuh"
 #include "dm_kernels_records.cuh"
 
@@ -81,6 +82,7 @@ struct dm_handle {
     DmTileScratch tile;                  // fused-kernel scratch
     DmRowsScratch rows;                  // rows-variant scratch
     DmStagedScratch staged;              // staged-variant scratch (candidate / field lists)
+    DmCtaScratch cta;                    // cta-variant launch geometry
     uint64_t last_nbytes = 0;
     uint32_t* d_vals = nullptr;          // record mode: offsets / fields / record_of
     uint64_t vals_cap = 0;
@@ -220,6 +222,11 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
     if (env && strcmp(env, "tile") == 0) h->kernel_variant = 1;
     if (env && strcmp(env, "rows") == 0) h->kernel_variant = 2;
     if (env && strcmp(env, "staged") == 0) h->kernel_variant = 3;
+    if (env && strcmp(env, "cta") == 0) h->kernel_variant = 4;
+    if (h->kernel_variant == 4) {
+        rc = dm_cta_scratch_create(&h->cta, h->sm_count);
+        if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "cta occupancy query failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    }
     if (h->kernel_variant == 3) {
         rc = dm_staged_scratch_create(&h->staged, max_batch_bytes, h->sm_count);
         if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "staged scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -355,6 +362,12 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         dm_k_detect_lines<false><<<grid, 256, 0, st>>>(a);
         dm_prof_mark(h, st, 1);
         h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
+    } else if (h->kernel_variant == 4) {
+        const int rc = dm_cta_launch(&h->cta, &h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,
+                                     out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st,
+                                     dm_prof_mark_cb, h);
+        if (rc < 0) return dm_fail(DM_ERR_CUDA, "cta kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->launches += (uint64_t)rc;
     } else if (h->kernel_variant == 3) {
         const int rc = dm_staged_launch(&h->staged, &h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags,
                                         d_scores, out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines,
@@ -618,7 +631,10 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     h->last_stream = st;
     DM_CUDA(cudaStreamWaitEvent(st, sl.ev_in, 0));
     if (nbytes == 0) DM_CUDA(cudaMemsetAsync(sl.d_hdr, 0, sizeof(DmBatchHeader), st));
-    const int launched = h->kernel_variant == 3
+    const int launched = h->kernel_variant == 4
+        ? dm_cta_launch(&h->cta, &h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
+                        h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, dm_prof_mark_cb, h)
+        : h->kernel_variant == 3
         ? dm_staged_launch(&h->staged, &h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
                            h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, dm_prof_mark_cb, h)
         : dm_rows_launch(&h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,

@@ -64,6 +64,20 @@ static inline unsigned emu_lane() { return threadIdx.x & 31; }
 
 static inline void __syncthreads() { g_emu_block->block_bar.sync(blockDim.x); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp().bar.sync(32); }
+extern std::atomic<int> g_emu_or_flag[2];
+static inline int __syncthreads_or(int pred) {
+    // two flags used alternately so that a fast thread's next call cannot clobber this one
+    static thread_local int phase = 0;
+    const int p = phase;
+    phase ^= 1;
+    if (pred) g_emu_or_flag[p].store(1);
+    g_emu_block->block_bar.sync(blockDim.x);
+    const int r = g_emu_or_flag[p].load();
+    g_emu_block->block_bar.sync(blockDim.x);
+    if (threadIdx.x == 0) g_emu_or_flag[p].store(0);
+    g_emu_block->block_bar.sync(blockDim.x);
+    return r;
+}
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }

@@ -11,11 +11,13 @@
 #include "dm_kernels_rows.cuh"
 #include "dm_kernels_staged.cuh"
 #include "dm_kernels_records.cuh"
+#include "dm_kernels_cta.cuh"
 
 thread_local emu_dim3 threadIdx;
 thread_local emu_dim3 blockIdx;
 emu_dim3 blockDim, gridDim;
 EmuBlock* g_emu_block = nullptr;
+std::atomic<int> g_emu_or_flag[2];
 
 // Runs the blocks of a grid ONE AFTER THE OTHER (block b sees blocks < b complete, which
 // satisfies the look-back dependencies of the kernels under test).
@@ -130,6 +132,8 @@ extern "C" int emu_process(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, ui
     return 0;
 }
 
+static bool g_emu_cta = false;
+
 // Mirrors dm_rows_launch (dm_kernels_rows.cuh): K_A, optional K_B<train>, K_B<detect>.
 static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
                                  float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err, bool staged);
@@ -137,6 +141,14 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
 extern "C" int emu_process_rows(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
                                 float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
     return emu_process_rows_impl(h, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err, false);
+}
+
+extern "C" int emu_process_cta(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                               float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    g_emu_cta = true;
+    const int rc = emu_process_rows_impl(h, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err, false);
+    g_emu_cta = false;
+    return rc;
 }
 
 extern "C" int emu_process_staged(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
@@ -189,6 +201,22 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
             return 0;
         }
         emu_launch_grid(a.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(a); });
+        if (g_emu_cta) {
+            const uint32_t rounds = (n_rows + DMC_WARPS - 1) / DMC_WARPS;
+            const unsigned long long per = (unsigned long long)rounds * DMC_WARPS + DMC_WARPS;     // grid = 1
+            if (n_train > 0) {
+                a.line_lo = 0; a.line_hi = n_train; a.ctr_base = h->row_ctr_base;
+                emu_launch(DMC_THREADS, [&] { dm_k_cta<true, true>(a); });
+                h->row_ctr_base += per;
+            }
+            a.line_lo = n_train; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base;
+            if (n_train > 0) emu_launch(DMC_THREADS, [&] { dm_k_cta<false, true>(a); });
+            else emu_launch(DMC_THREADS, [&] { dm_k_cta<false, false>(a); });
+            h->row_ctr_base += per;
+            free(buf);
+            *n_lines = h->hdr.n_lines; *n_anoms = h->hdr.n_anomalies; *err = h->hdr.error;
+            return 0;
+        }
         const uint32_t groups = (n_rows + DMR_GROUP - 1) / DMR_GROUP;
         const unsigned long long per_launch = (unsigned long long)groups * DMR_GROUP + (unsigned long long)DMR_B_WARPS * DMR_GROUP;
         if (n_train > 0) {

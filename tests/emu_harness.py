@@ -39,6 +39,8 @@ class EmuDetector:
         self.lib = C.CDLL(build())
         self.variant = variant
         L = self.lib
+        L.emu_process_cta.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_process_staged.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_process_rows.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -69,7 +71,7 @@ class EmuDetector:
         flags = np.full(cap, 7, dtype=np.uint8)
         scores = np.full(cap, -1, dtype=np.float32)
         n_lines, n_anom, err = C.c_uint64(), C.c_uint64(), C.c_uint32()
-        fn = {"rows": self.lib.emu_process_rows, "staged": self.lib.emu_process_staged}.get(self.variant, self.lib.emu_process)
+        fn = {"rows": self.lib.emu_process_rows, "staged": self.lib.emu_process_staged, "cta": self.lib.emu_process_cta}.get(self.variant, self.lib.emu_process)
         rc = fn(self.h, msg, len(msg), n_train, flags.ctypes.data, scores.ctypes.data, cap,
                                   C.byref(n_lines), C.byref(n_anom), C.byref(err))
         assert rc == 0 and err.value == 0, (rc, err.value)

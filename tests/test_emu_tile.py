@@ -15,7 +15,7 @@ from oracle.native import NativeOracle
 from util import FUZZ_KEYS, fuzz_lines
 
 
-@pytest.fixture(params=["staged", "rows", "tile"], autouse=True)
+@pytest.fixture(params=["cta", "staged", "rows", "tile"], autouse=True)
 def emu_variant(request):
     """Every test runs against both device decompositions (DM_KERNEL=rows / tile)."""
     global VARIANT

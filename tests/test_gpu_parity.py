@@ -16,7 +16,7 @@ from util import FUZZ_KEYS, fuzz_lines
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["v1", "tile", "rows", "staged"]
+VARIANTS = ["v1", "tile", "rows", "staged", "cta"]
 SCORE_TOL = 1e-5
 
 
