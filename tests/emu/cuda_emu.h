@@ -142,6 +142,10 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)(v >> (sh & 31));
 }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) {
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)((v << (sh & 31)) >> 32);
+}
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline uint4 __ldg(const uint4* p) { uint4 r; std::memcpy(&r, p, 16); return r; }
 

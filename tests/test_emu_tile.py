@@ -12,7 +12,7 @@ import pytest
 import emu_harness
 from oracle import fingerprint
 from oracle.native import NativeOracle
-from util import FUZZ_KEYS, fuzz_lines
+from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines
 
 
 @pytest.fixture(params=["cta", "staged", "rows", "tile"], autouse=True)
@@ -70,9 +70,10 @@ def test_emu_audit_sample_golden(golden_dir):
     det.close()
 
 
-@pytest.mark.parametrize("seed", [1, 2])
-def test_emu_fuzz_tokenizer(seed):
+@pytest.mark.parametrize("seed,keys", [(1, FUZZ_KEYS), (2, FUZZ_KEYS_FEW)])
+def test_emu_fuzz_tokenizer(seed, keys):
     _default_variant_only()
+    FUZZ_KEYS = keys
     o = NativeOracle(FUZZ_KEYS)
     det = EmuDetector(FUZZ_KEYS)
     _check(det, o, fuzz_lines(seed, 1500), 600)

@@ -12,7 +12,7 @@ import pytest
 
 from oracle import fingerprint
 from oracle.native import NativeOracle
-from util import FUZZ_KEYS, fuzz_lines
+from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines
 
 pytestmark = pytest.mark.gpu
 
@@ -108,6 +108,15 @@ def test_train_detect_split_inside_one_message(variant):
     with _det(keys) as det:
         _check(det, o, a + b, 3000)
         _check(det, o, b, 100)         # more training on top, then detect
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz_tokenizer_prefilter_on(variant, seed):
+    """Same fuzz with keys that share 3 last bytes: the row phase's candidate pre-filter is active."""
+    o = NativeOracle(FUZZ_KEYS_FEW)
+    with _det(FUZZ_KEYS_FEW) as det:
+        _check(det, o, fuzz_lines(seed + 7, 4000), 1500)
+        _check(det, o, fuzz_lines(seed + 107, 4000), 0)
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])

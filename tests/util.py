@@ -3,7 +3,8 @@ import numpy as np
 
 from oracle.native import NativeOracle
 
-FUZZ_KEYS = [b"a", b"ab", b"type", b"res", b"k1"]
+FUZZ_KEYS = [b"a", b"ab", b"type", b"res", b"k1"]          # 5 distinct last bytes: candidate pre-filter off
+FUZZ_KEYS_FEW = [b"a", b"ab", b"type", b"sa", b"ra"]        # 3 distinct last bytes: pre-filter on
 
 
 def fuzz_lines(seed: int, n_lines: int, max_len: int = 600, alphabet: bytes = b"ab=  '\"typeresk1xq") -> bytes:
