@@ -37,14 +37,7 @@ struct DmKeys {
     // ("res" / "xres") is only considered when the longer one does not match.
     uint32_t order[DM_MAX_KEYS];
     alignas(16) uint32_t pat[DM_MAX_KEYS][4];      // [slot] = {tailbits, tailmask, midbits, midmask} of key order[slot]
-    // candidate pre-filter of the row phase: the distinct LAST bytes of the keys (replicated into
-    // a word each).  An '=' can only belong to a monitored key if the byte in front of it is one
-    // of them; with few distinct bytes that test is cheaper in registers than queueing the '='.
-    // n_last == 0 switches the pre-filter off (more than DM_MAX_LAST distinct bytes).
-    uint32_t n_last;
-    uint32_t lastpat[4];
 };
-#define DM_MAX_LAST 4
 
 static inline void dm_keys_finalize_host(DmKeys* k) {
     for (uint32_t i = 0; i < k->n; ++i) {
@@ -71,16 +64,6 @@ static inline void dm_keys_finalize_host(DmKeys* k) {
         const uint32_t i = k->order[s];
         k->pat[s][0] = k->tailbits[i]; k->pat[s][1] = k->tailmask[i];
         k->pat[s][2] = k->midbits[i]; k->pat[s][3] = k->midmask[i];
-    }
-    k->n_last = 0;
-    for (uint32_t i = 0; i < k->n; ++i) {
-        const uint32_t b = k->bytes[i][k->len[i] - 1];
-        const uint32_t pat = b * 0x01010101u;
-        bool seen = false;
-        for (uint32_t j = 0; j < k->n_last && j < 4; ++j) seen = seen || k->lastpat[j] == pat;
-        if (seen) continue;
-        if (k->n_last == 4 || b >= 0x80u) { k->n_last = 0; break; }     // too many / not a dm_eqflags pattern: off
-        k->lastpat[k->n_last++] = pat;
     }
 }
 

@@ -208,10 +208,6 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
     DmRQ1Entry* q1 = s_q1[warp];
     DmRQ2Entry* q2 = s_q2[warp];
     uint32_t q1h = 0, q1n = 0, q2h = 0, q2n = 0;
-    const uint32_t n_last = sk.n_last;
-    uint32_t lastpat[DM_MAX_LAST];
-#pragma unroll
-    for (uint32_t c = 0; c < DM_MAX_LAST; ++c) lastpat[c] = sk.lastpat[c];
 
     // stage 2: one identified field per lane -- fingerprint, probe, exact re-check when unknown
     auto drain2 = [&](uint32_t n) {
@@ -299,34 +295,15 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
         for (uint32_t row = (uint32_t)first_row; row < r_end; ++row) {
             const uint64_t off = (uint64_t)row * DMR_ROW + (uint64_t)lane * 16;
             uint32_t nl16 = 0, eq16 = 0;
-            uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, l0 = 0, l1 = 0, l2 = 0, l3 = 0;
             if (off < nbytes) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(buf + off));
                 nl16 = dm_row_nl_mask(v, off, nbytes);
-                e0 = dm_eqflags(v.x, 0x3D3D3D3Du); e1 = dm_eqflags(v.y, 0x3D3D3D3Du);
-                e2 = dm_eqflags(v.z, 0x3D3D3D3Du); e3 = dm_eqflags(v.w, 0x3D3D3D3Du);
-                if (n_last) {
-                    // flags of the bytes that can END a monitored key
-#pragma unroll
-                    for (uint32_t c = 0; c < DM_MAX_LAST; ++c) {
-                        if (c < n_last) {
-                            l0 |= dm_eqflags(v.x, lastpat[c]); l1 |= dm_eqflags(v.y, lastpat[c]);
-                            l2 |= dm_eqflags(v.z, lastpat[c]); l3 |= dm_eqflags(v.w, lastpat[c]);
-                        }
-                    }
+                const uint32_t e0 = dm_eqflags(v.x, 0x3D3D3D3Du), e1 = dm_eqflags(v.y, 0x3D3D3D3Du);
+                const uint32_t e2 = dm_eqflags(v.z, 0x3D3D3D3Du), e3 = dm_eqflags(v.w, 0x3D3D3D3Du);
+                if (e0 | e1 | e2 | e3) {
+                    eq16 = dm_flags_to_nib(e0) | (dm_flags_to_nib(e1) << 4) | (dm_flags_to_nib(e2) << 8) | (dm_flags_to_nib(e3) << 12);
+                    if (off + 16 > nbytes) eq16 &= (1u << (uint32_t)(nbytes - off)) - 1u;
                 }
-            }
-            if (n_last) {
-                // keep an '=' only if the byte in front of it is such a byte (the one in front of
-                // this lane's chunk sits in the previous lane; unknown for lane 0: keep)
-                uint32_t prev3 = __shfl_up_sync(0xffffffffu, l3, 1);
-                if (lane == 0) prev3 = 0x80000000u;
-                e0 &= __funnelshift_l(prev3, l0, 8); e1 &= __funnelshift_l(l0, l1, 8);
-                e2 &= __funnelshift_l(l1, l2, 8);    e3 &= __funnelshift_l(l2, l3, 8);
-            }
-            if (e0 | e1 | e2 | e3) {
-                eq16 = dm_flags_to_nib(e0) | (dm_flags_to_nib(e1) << 4) | (dm_flags_to_nib(e2) << 8) | (dm_flags_to_nib(e3) << 12);
-                if (off + 16 > nbytes) eq16 &= (1u << (uint32_t)(nbytes - off)) - 1u;
             }
             // record index in front of this lane's chunk
             const uint32_t b_nl = __ballot_sync(0xffffffffu, nl16 != 0);
