@@ -398,3 +398,76 @@ def test_component_chunks_messages_larger_than_the_device_batch(golden_dir):
     assert f.tolist() == exp["flags"] and s.tolist() == exp["scores"]
     with pytest.raises(ValueError):
         _component({"detectors": {"B200NewValueDetector": dict(base, params={"max_batch_bytes": 100})}}).process(buf)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE config 1: reader -> parser -> detector over the sample audit log, one process,
+# chained over the transport exactly like docker-compose.yml:16-40 chains the services
+# (out_addr of one stage = engine_addr of the next).  No GPU: the detector's device is the
+# oracle-backed double; reader and parser are minimal stand-ins for the library's
+# LogFileReader / MatcherParser (not on the hot path) that speak the real wire schemas.
+# ------------------------------------------------------------------------------------------
+class _ReaderStage:
+    """`read` request -> next log line as LogSchema-like ParserSchema input (one per message)."""
+
+    def __init__(self, lines):
+        self.lines, self.i = lines, 0
+
+    def process(self, raw):
+        if self.i >= len(self.lines):
+            return None
+        line = self.lines[self.i]
+        self.i += 1
+        return b"%d\t" % self.i + line                       # logID \t raw line
+
+
+class _ParserStage:
+    """raw line -> ParserSchema whose logFormatVariables hold every key=value field (R-tok)."""
+
+    def process(self, raw):
+        from oracle import rtok
+        log_id, line = raw.split(b"\t", 1)
+        fields = {k.decode("latin-1"): v.decode("latin-1") for k, v in rtok.tokenize_line(line).items()}
+        t = rtok.line_time(line)
+        if t is not None:
+            fields["Time"] = t.decode()
+        return wire.encode_parser_schema({"EventID": 0, "logID": log_id.decode(), "log": line.decode("latin-1"),
+                                          "logFormatVariables": fields})
+
+
+def test_config1_reader_parser_detector_pipeline(tmp_path, golden_dir):
+    from detectmateservice_b200.service import DetectorEngine
+    exp = json.load(open(os.path.join(golden_dir, "audit_sample.expected.json")))
+    lines = open(os.path.join(golden_dir, "audit_sample.log"), "rb").read().split(b"\n")[:-1]
+    cfg = {"detectors": {"B200NewValueDetector": {
+        "method_type": "new_value_detector", "data_use_training": exp["n_train"], "auto_config": False,
+        "global": {"g": {"header_variables": [{"pos": k} for k in exp["keys"]]}}}}}
+    det = _component(cfg)
+    a_reader, a_parser, a_det, a_out = (f"ipc://{tmp_path}/{n}.ipc" for n in ("reader", "parser", "detector", "out"))
+    sink = pynng.Pair0(listen=a_out, recv_timeout=300)
+    with DetectorEngine(det, a_det, out_addr=[a_out]) as e_det, \
+            DetectorEngine(_ParserStage(), a_parser, out_addr=[a_det]), \
+            DetectorEngine(_ReaderStage(lines), a_reader, out_addr=[a_parser]):
+        time.sleep(0.4)                                       # background dials connect
+        alerts = []
+        with pynng.Pair0(dial=a_reader) as trigger:
+            for i in range(len(lines)):
+                trigger.send(b"read")
+                # the engines drop on a full output queue (engine.py:233-241), like the
+                # reference: pace the source on the last stage's message counter
+                t_end = time.monotonic() + 5
+                while e_det.counters["messages"] <= i and time.monotonic() < t_end:
+                    time.sleep(0.0005)
+                assert e_det.counters["messages"] == i + 1
+                if exp["flags"][i]:
+                    alerts.append(wire.decode_detector_schema(sink.recv()))
+            with pytest.raises(pynng.Timeout):
+                sink.recv()                                   # nothing else was sent
+    sink.close()
+    want = [i for i, f in enumerate(exp["flags"]) if f]
+    assert [int(a["logIDs"][0]) - 1 for a in alerts] == want
+    assert [a["score"] for a in alerts] == [exp["scores"][i] for i in want]
+    keys = exp["keys"]
+    for a, i in zip(alerts, want):
+        assert sorted(a["alertsObtain"]) == sorted(f"Global - {keys[b]}" for b in range(len(keys)) if exp["masks"][i] >> b & 1)
+        assert a["extractedTimestamps"][0] > 1600000000
