@@ -115,6 +115,8 @@ def parse_monitors(cfg: dict) -> List[Monitor]:
 
 
 class B200NewValueDetector(CoreComponent):
+    accepts_bytes_like = True      # process() takes bytes, bytearray or memoryview (see service.py)
+
     def __init__(self, name: str = "B200NewValueDetector", config: Optional[Any] = None) -> None:
         raw_cfg = config.model_dump() if hasattr(config, "model_dump") else config
         cfg = select_component_config(raw_cfg, name)

@@ -99,6 +99,22 @@ def _recv_exact(sock: socket.socket, n: int) -> Optional[bytes]:
     return b"".join(chunks)
 
 
+def _recv_into_new(sock: socket.socket, n: int) -> Optional[bytearray]:
+    """Large frames: one allocation, filled in place (no per-chunk objects, no join copy)."""
+    buf = bytearray(n)
+    mv = memoryview(buf)
+    got = 0
+    while got < n:
+        try:
+            k = sock.recv_into(mv[got:], n - got)
+        except OSError:
+            return None
+        if k == 0:
+            return None
+        got += k
+    return buf
+
+
 class _Pipe:
     """One established connection (after the SP handshake)."""
 
@@ -121,7 +137,10 @@ class _Pipe:
             if h is None:
                 break
             (ln,) = struct.unpack(">Q", h)
-            body = _recv_exact(s, ln) if ln else b""
+            if ln >= 65536 and getattr(self.owner, "large_frames_as_bytearray", False):
+                body = _recv_into_new(s, ln)       # opt-in (shim only): bytes-like, not bytes
+            else:
+                body = _recv_exact(s, ln) if ln else b""
             if body is None:
                 break
             self.owner._deliver(body)
@@ -208,6 +227,11 @@ class Socket:
 
     # ------------------------------------------------------------------ internals
     def _deliver(self, body: bytes) -> None:
+        # NNG holds at most recv_buffer_size messages per socket; beyond that the pipe's reader
+        # stalls and the transport (TCP / unix socket buffers) pushes back on the sender.
+        cap = max(1, int(self.recv_buffer_size or 0))
+        while self._rx.qsize() >= cap and not self._closed:
+            time.sleep(0.0002)
         self._rx.put(body)
 
     def _adopt(self, pipe: _Pipe) -> bool:

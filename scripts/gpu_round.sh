@@ -40,6 +40,22 @@ for S in $STAGES; do
           python bench.py --steps 6 --warmup 3 --no-cpu > "$OUT/ncu_full_$K.log" 2>&1
         echo "ncu_full[$K] rc=$?" | tee -a "$OUT/summary.txt"
       done ;;
+    pipeline)
+      for T in ipc tcp; do
+        timeout 600 python scripts/pipeline_bench.py --transport $T --messages 48 > "$OUT/pipeline_$T.json" 2> "$OUT/pipeline_$T.err"
+        echo "pipeline[$T] rc=$?" | tee -a "$OUT/summary.txt"
+        cat "$OUT/pipeline_$T.json"
+      done
+      timeout 600 python scripts/pipeline_bench.py --transport ipc --messages 48 --output-format alerts > "$OUT/pipeline_ipc_alerts.json" 2> "$OUT/pipeline_ipc_alerts.err"
+      echo "pipeline[ipc,alerts] rc=$?" | tee -a "$OUT/summary.txt"
+      cat "$OUT/pipeline_ipc_alerts.json"
+      timeout 600 python scripts/pipeline_bench.py --transport ipc --messages 48 --transport-only > "$OUT/pipeline_transport_only.json" 2>&1
+      cat "$OUT/pipeline_transport_only.json" ;;
+    racecheck)
+      DM_KERNEL=${DM_KERNELS:-rows} timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 \
+        python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/racecheck.log" 2>&1
+      echo "racecheck rc=$?" | tee -a "$OUT/summary.txt"
+      tail -5 "$OUT/racecheck.log" ;;
     sanitize)
       DM_KERNEL=${DM_KERNELS:-v1} timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
         python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/sanitize.log" 2>&1
