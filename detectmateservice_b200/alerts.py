@@ -60,7 +60,7 @@ def record_time(line: bytes) -> Optional[int]:
 
 def record_at(msg: bytes, offset: int) -> bytes:
     end = msg.find(b"\n", offset)
-    return msg[offset:] if end < 0 else msg[offset:end]
+    return bytes(msg[offset:] if end < 0 else msg[offset:end])      # msg may be any bytes-like
 
 
 def alert_text(value: bytes) -> str:

@@ -56,10 +56,10 @@ class _Timed:
 
     def process(self, raw):
         t0 = time.perf_counter()
-        if self.t_first is None:
-            self.t_first = t0
         out = self.inner.process(raw)
         t1 = time.perf_counter()
+        if self.t_first is None:
+            self.t_first = t1                               # clock starts after message 0 (lazy CUDA init + training)
         self.n_seen = getattr(self.inner, "n_seen", self.n_seen + 1)
         if self.n > 0:                                      # message 0 = training + lazy init
             self.t_proc += t1 - t0
@@ -78,6 +78,7 @@ def main() -> None:
     ap.add_argument("--transport", default="ipc", choices=["ipc", "tcp"])
     ap.add_argument("--output-format", default="compact", choices=["compact", "alerts"])
     ap.add_argument("--transport-only", action="store_true")
+    ap.add_argument("--diag", action="store_true", help="time the shim's receive pieces (alloc vs socket reads)")
     a = ap.parse_args()
     if a.role == "sender":
         run_sender(a.addr, a.messages, a.lines, a.pool)
@@ -88,6 +89,28 @@ def main() -> None:
     import pynng
     from detectmateservice_b200.service import DetectorEngine
     from detectmateservice_b200.synth import MONITORED_KEYS
+
+    diag = {"alloc_s": 0.0, "recv_s": 0.0, "frames": 0, "recv_calls": 0}
+    if a.diag:
+        shim = sys.modules["pynng"]
+
+        def timed_recv_into_new(sock, n):
+            t0 = time.perf_counter()
+            buf = bytearray(n)
+            mv = memoryview(buf)
+            t1 = time.perf_counter()
+            got = 0
+            while got < n:
+                k = sock.recv_into(mv[got:], n - got)
+                if k == 0:
+                    return None
+                got += k
+                diag["recv_calls"] += 1
+            diag["alloc_s"] += t1 - t0
+            diag["recv_s"] += time.perf_counter() - t1
+            diag["frames"] += 1
+            return buf
+        shim._recv_into_new = timed_recv_into_new
 
     tag = f"{os.getpid()}"
     if a.transport == "ipc":
@@ -139,7 +162,6 @@ def main() -> None:
     sink.close()
     n_timed = proc.n - 1
     wall = (proc.t_last - proc.t_first) if proc.n > 1 else float("nan")
-    # wall spans message 0's process() too; subtract nothing, report both views
     res = {
         "what": "transport-only" if a.transport_only else "detector stage in the service plumbing",
         "transport": a.transport, "messages": proc.n, "lines_per_message": a.lines,
@@ -149,6 +171,10 @@ def main() -> None:
         "ms_per_message_in_process": round(1e3 * proc.t_proc / max(1, n_timed), 3),
         "replies": got["n"], "reply_bytes": got["bytes"], "engine": c,
     }
+    if a.diag and diag["frames"]:
+        res["diag_ms_per_frame"] = {"alloc": round(1e3 * diag["alloc_s"] / diag["frames"], 3),
+                                    "socket_reads": round(1e3 * diag["recv_s"] / diag["frames"], 3),
+                                    "recv_calls": diag["recv_calls"] // diag["frames"]}
     print(json.dumps(res))
 
 
