@@ -35,6 +35,7 @@ raises without a GPU).
 from __future__ import annotations
 
 import struct
+import threading
 import time
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -141,6 +142,8 @@ class B200NewValueDetector(CoreComponent):
         self.max_batch_bytes = int(cfg.get("max_batch_bytes", 64 << 20))
         self.table_log2_slots = int(cfg.get("table_log2_slots", 20))
         self._det = None                       # created on first use, on the EngineLoop thread
+        self._frames = None                    # pinned receive slots, created on first alloc_frame()
+        self._frame_lock = threading.Condition()
         self.n_seen = 0
         self.n_alerts = 0
         self.clock = time.time
@@ -156,6 +159,52 @@ class B200NewValueDetector(CoreComponent):
             self._det.set_monitors([{"event_id": m.event_id, "source": m.source, "pos": m.pos} for m in self.monitors])
         return self._det
 
+    # ------------------------------------------------------------------ receive buffers (lent to the transport)
+    FRAME_SLOTS = 4
+
+    def alloc_frame(self, nbytes: int):
+        """Lend the transport a receive buffer for one large message: a slot of pinned host
+        memory, so the message is DMA-able where it lands (no staging copy, no per-message
+        allocation).  Returns a writable memoryview, or None when no slot is free / the
+        message does not fit / there is no CUDA device (the transport then allocates itself).
+        Called on the transport's reader thread; slots come back through release_frame()."""
+        if nbytes > self.max_batch_bytes:
+            return None
+        with self._frame_lock:
+            if self._frames is None:
+                import torch
+                if not torch.cuda.is_available():
+                    self._frames = []
+                else:
+                    self._frames = []
+                    for _ in range(self.FRAME_SLOTS):
+                        t = torch.empty(self.max_batch_bytes + 64, dtype=torch.uint8, pin_memory=True)
+                        self._frames.append([t, memoryview(t.numpy()), False])
+            deadline = time.monotonic() + 0.2
+            while self._frames:
+                for slot in self._frames:
+                    if not slot[2]:
+                        slot[2] = True
+                        return slot[1][:nbytes]
+                # every slot is queued or being processed: stall the reader (back-pressure on
+                # the sender) rather than allocate; give up after 200 ms
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    break
+                self._frame_lock.wait(left)
+        return None
+
+    def release_frame(self, frame) -> None:
+        if not isinstance(frame, memoryview) or not self._frames:
+            return
+        base = frame.obj
+        with self._frame_lock:
+            for slot in self._frames:
+                if slot[1].obj is base:
+                    slot[2] = False
+                    self._frame_lock.notify()
+                    return
+
     def close(self) -> None:
         if self._det is not None:
             self._det.close()
@@ -166,6 +215,13 @@ class B200NewValueDetector(CoreComponent):
         if not data:
             return None
         fmt = self.input_format
+        if isinstance(data, memoryview) and fmt != "raw_lines":
+            # a lent receive buffer: raw lines are used in place; protobuf inputs (rare as
+            # large frames) are decoded from a bytes copy
+            if fmt == "auto" and data[0] == 0x74:                # 't' of "type=": cannot start a ParserSchema
+                fmt = "raw_lines"
+            else:
+                data = bytes(data)
         if fmt == "auto":
             if wire.looks_like_parser_schema(data):
                 fmt = "parser_schema"
@@ -304,6 +360,12 @@ class B200NewValueDetector(CoreComponent):
     def export_state(self) -> dict:
         """Learnt keys + counters (the reference loses detector state on restart)."""
         return {"known": self.det.export_known().tolist(), "n_seen": self.n_seen, "n_alerts": self.n_alerts}
+
+    def reset_state(self) -> None:
+        """Forget everything learnt and restart the training window."""
+        self.det.reset()
+        self.n_seen = 0
+        self.n_alerts = 0
 
     def import_state(self, state: dict) -> None:
         self.det.import_known(np.array(state.get("known", []), dtype=np.uint64))

@@ -46,6 +46,11 @@ class DetectorEngine:
         # shim-only hint (ignored by real pynng): hand big frames over as a bytearray filled in
         # place; the component takes any bytes-like object, and this halves the receive cost
         self._sock.large_frames_as_bytearray = bool(getattr(processor, "accepts_bytes_like", False))
+        # a processor may lend receive buffers (alloc_frame / release_frame): the component hands
+        # out pinned host memory, so a frame lands where the GPU can DMA it from (no extra copy)
+        self._release = getattr(processor, "release_frame", None)
+        if self._release is not None and hasattr(processor, "alloc_frame"):
+            self._sock.frame_allocator = processor.alloc_frame
         self._sock.listen(engine_addr)
         self._outs: List[Any] = []
         for addr in out_addr:
@@ -95,6 +100,9 @@ class DetectorEngine:
                 c["errors"] += 1
                 self.log.exception("engine error during process: %s", e)
                 continue
+            finally:
+                if self._release is not None:
+                    self._release(raw)                           # the frame buffer may be reused now
             if out is None:
                 continue
             if self._outs:

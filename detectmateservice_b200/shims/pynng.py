@@ -99,6 +99,19 @@ def _recv_exact(sock: socket.socket, n: int) -> Optional[bytes]:
     return b"".join(chunks)
 
 
+def _recv_into(sock: socket.socket, mv: memoryview) -> Optional[memoryview]:
+    n, got = len(mv), 0
+    while got < n:
+        try:
+            k = sock.recv_into(mv[got:], n - got)
+        except OSError:
+            return None
+        if k == 0:
+            return None
+        got += k
+    return mv
+
+
 def _recv_into_new(sock: socket.socket, n: int) -> Optional[bytearray]:
     """Large frames: one allocation, filled in place (no per-chunk objects, no join copy)."""
     buf = bytearray(n)
@@ -137,7 +150,13 @@ class _Pipe:
             if h is None:
                 break
             (ln,) = struct.unpack(">Q", h)
-            if ln >= 65536 and getattr(self.owner, "large_frames_as_bytearray", False):
+            alloc = getattr(self.owner, "frame_allocator", None)
+            frame = alloc(ln) if (alloc is not None and ln >= 65536) else None
+            if frame is not None:
+                # opt-in (shim only): the consumer lends receive buffers (e.g. pinned host memory
+                # the GPU can DMA from); the frame is delivered as a memoryview into that buffer
+                body = _recv_into(s, memoryview(frame)[:ln])
+            elif ln >= 65536 and getattr(self.owner, "large_frames_as_bytearray", False):
                 body = _recv_into_new(s, ln)       # opt-in (shim only): bytes-like, not bytes
             else:
                 body = _recv_exact(s, ln) if ln else b""

@@ -118,5 +118,18 @@ def test_engine_pipeline_raw_messages(tmp_path):
                 f, s = decode_compact(sink.recv())
                 assert (f == wf).all() and (s == ws).all()
         assert eng.counters["errors"] == 0 and eng.counters["processed_lines"] == 6 * 8192
+        # the frames were received straight into the component's pinned slots, all returned
+        assert comp._frames and len(comp._frames) == comp.FRAME_SLOTS and not any(b for _, _, b in comp._frames)
+        assert all(t.is_pinned() for t, _, _ in comp._frames)
+        # burst: more messages in flight than slots -> the reader stalls on a slot, nothing is lost
+        comp.reset_state()
+        with pynng.Pair0(dial=eng_addr) as tx:
+            time.sleep(0.2)
+            for m in msgs:
+                tx.send(m)
+            for wf, ws, _ in want:
+                f, s = decode_compact(sink.recv())
+                assert (f == wf).all() and (s == ws).all()
+        assert eng.counters["errors"] == 0 and not any(b for _, _, b in comp._frames)
     sink.close()
     comp.close()

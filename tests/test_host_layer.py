@@ -471,3 +471,58 @@ def test_config1_reader_parser_detector_pipeline(tmp_path, golden_dir):
     for a, i in zip(alerts, want):
         assert sorted(a["alertsObtain"]) == sorted(f"Global - {keys[b]}" for b in range(len(keys)) if exp["masks"][i] >> b & 1)
         assert a["extractedTimestamps"][0] > 1600000000
+
+
+def test_engine_lends_receive_frames(tmp_path, golden_dir):
+    """alloc_frame / release_frame: the engine hands the transport the processor's receive
+    buffers for large messages and gives each one back after process() (also on errors)."""
+    from detectmateservice_b200.service import DetectorEngine
+
+    class Lender:
+        accepts_bytes_like = True
+
+        def __init__(self):
+            self.slots = [bytearray(1 << 20) for _ in range(2)]
+            self.busy = [False, False]
+            self.n_seen = 0
+            self.seen, self.kinds, self.lent, self.released = [], [], 0, 0
+
+        def alloc_frame(self, n):
+            for i, b in enumerate(self.busy):
+                if not b and n <= len(self.slots[i]):
+                    self.busy[i] = True
+                    self.lent += 1
+                    return memoryview(self.slots[i])[:n]
+            return None
+
+        def release_frame(self, frame):
+            if isinstance(frame, memoryview):
+                i = [j for j, s in enumerate(self.slots) if frame.obj is s][0]
+                self.busy[i] = False
+                self.released += 1
+
+        def process(self, raw):
+            self.n_seen += 1
+            self.kinds.append(type(raw).__name__)
+            self.seen.append(bytes(raw[:8]) + bytes(raw[-8:]))
+            if bytes(raw[:4]) == b"boom":
+                raise RuntimeError("boom")
+            return None
+
+    p = Lender()
+    addr = f"ipc://{tmp_path}/lend.ipc"
+    msgs = [bytes([65 + i]) * (200000 + i) for i in range(6)] + [b"boom" * 50000, b"small", b"Z" * (2 << 20)]
+    with DetectorEngine(p, addr) as e, pynng.Pair0(dial=addr) as s:
+        time.sleep(0.2)
+        for i, m in enumerate(msgs):
+            s.send(m)
+            t_end = time.monotonic() + 5                      # paced: a free slot for every frame
+            while e.counters["messages"] <= i and time.monotonic() < t_end:
+                time.sleep(0.002)
+        time.sleep(0.05)
+        assert e.counters["messages"] == len(msgs) and e.counters["errors"] == 1
+    assert p.seen == [m[:8] + m[-8:] for m in msgs]              # content and order intact
+    assert p.kinds[:7] == ["memoryview"] * 7                      # large frames landed in lent slots
+    assert p.kinds[7] == "bytes"                                  # small frames are plain bytes
+    assert p.kinds[8] == "bytearray"                              # too large for a slot -> transport allocates
+    assert p.lent == 7 and p.released == 7 and p.busy == [False, False]
