@@ -59,8 +59,17 @@ def record_time(line: bytes) -> Optional[int]:
 
 
 def record_at(msg: bytes, offset: int) -> bytes:
+    if isinstance(msg, memoryview):                  # a lent receive buffer: look in 4 KiB windows
+        pos, n = offset, len(msg)
+        while pos < n:
+            win = bytes(msg[pos:pos + 4096])
+            k = win.find(b"\n")
+            if k >= 0:
+                return bytes(msg[offset:pos + k])
+            pos += len(win)
+        return bytes(msg[offset:])
     end = msg.find(b"\n", offset)
-    return bytes(msg[offset:] if end < 0 else msg[offset:end])      # msg may be any bytes-like
+    return bytes(msg[offset:] if end < 0 else msg[offset:end])      # bytes or bytearray
 
 
 def alert_text(value: bytes) -> str:

@@ -54,6 +54,11 @@ class _Timed:
         self.n_seen = 0
         self.t_first = self.t_last = None
 
+    def __getattr__(self, name):                            # alloc_frame / release_frame of the component
+        if name in ("alloc_frame", "release_frame"):
+            return getattr(self.inner, name)
+        raise AttributeError(name)
+
     def process(self, raw):
         t0 = time.perf_counter()
         out = self.inner.process(raw)

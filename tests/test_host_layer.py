@@ -300,8 +300,10 @@ def test_component_raw_mode_alerts_and_compact(golden_dir):
     comp = _component({"detectors": {"B200NewValueDetector": base}})
     half = buf[:buf.index(b"\n", len(buf) // 2) + 1]
     out1 = comp.process(half)                                   # training window + some detection
-    out2 = comp.process(bytearray(buf[len(half):]))             # any bytes-like message is accepted
-    alerts = [wire.decode_detector_schema(b) for o in (out1, out2) if o for b in wire.split_delimited(o)]
+    rest = bytearray(buf[len(half):])
+    out2 = comp.process(memoryview(rest)[:len(rest) // 2 + 1 + rest[len(rest) // 2:].index(b"\n")])
+    out2b = comp.process(rest[len(rest) // 2 + 1 + rest[len(rest) // 2:].index(b"\n"):])   # any bytes-like is accepted
+    alerts = [wire.decode_detector_schema(b) for o in (out1, out2, out2b) if o for b in wire.split_delimited(o)]
     want_idx = [i for i, fl in enumerate(exp["flags"]) if fl]
     assert [int(a["logIDs"][0]) for a in alerts] == want_idx
     assert [a["score"] for a in alerts] == [exp["scores"][i] for i in want_idx]
