@@ -97,6 +97,7 @@ SYMBOLS = {
                                     C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                     _P, _P, _P, C.POINTER(C.c_uint64)]),
     "dm_set_monitors": (C.c_int, [_P, C.c_uint32, C.POINTER(Monitor)]),
+    "dm_set_combos": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]),
     "dm_process_records": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64,
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dm_submit_lines": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint32]),

@@ -71,13 +71,13 @@ class Monitor:
         return f"Global - {self.label}" if self.event_id is None else f"EventID {self.event_id} - {self.label}"
 
 
-def select_component_config(config: Optional[dict], name: str) -> dict:
+def select_component_config(config: Optional[dict], name: str, fallback: str = "NewValueDetector") -> dict:
     """Pick this component's entry out of the ServiceConfig dump the loader passes
     (src/service/core.py:127-133,144-148) and flatten ``params`` (docs/interfaces.md:74-84)."""
     cfg = dict(config or {})
     if isinstance(cfg.get("detectors"), dict):
         dets = cfg["detectors"]
-        pick = dets.get(name) or dets.get("NewValueDetector") or (next(iter(dets.values())) if dets else {})
+        pick = dets.get(name) or dets.get(fallback) or (next(iter(dets.values())) if dets else {})
         cfg = dict(pick or {})
     params = cfg.pop("params", None) or {}
     for k, v in params.items():
@@ -263,6 +263,12 @@ class B200NewValueDetector(CoreComponent):
         t = (rec.get("logFormatVariables") or {}).get("Time")
         return self._detector_schema(rec.get("logID", ""), float(scores[0]), alerts, t)
 
+    def _record_alerts(self, rec: Dict, mask: int) -> Dict[str, str]:
+        """alertsObtain of one anomalous record from the device's unknown-field mask."""
+        by_field = dict(self._record_values(rec))
+        return {self.monitors[i].alert_key: _alerts.alert_text(by_field.get(i, b""))
+                for i in range(len(self.monitors)) if mask >> i & 1}
+
     def _process_record_batch(self, data: bytes) -> Optional[bytes]:
         """A message holding many length-delimited ParserSchema records: field walk, monitor
         matching, hashing and scoring happen on the device; the host only decodes the (rare)
@@ -279,10 +285,7 @@ class B200NewValueDetector(CoreComponent):
         out = []
         for idx in np.flatnonzero(flags):
             rec = wire.decode_parser_schema(frames[int(idx)], strict=False)
-            by_field = dict(self._record_values(rec))
-            mask = int(masks[idx])
-            alerts = {self.monitors[i].alert_key: _alerts.alert_text(by_field.get(i, b""))
-                      for i in range(len(self.monitors)) if mask >> i & 1}
+            alerts = self._record_alerts(rec, int(masks[idx]))
             t = (rec.get("logFormatVariables") or {}).get("Time")
             out.append(self._detector_schema(rec.get("logID", ""), float(scores[idx]), alerts, t))
         return wire.frame_delimited(out) if out else None
@@ -339,6 +342,9 @@ class B200NewValueDetector(CoreComponent):
         return out[0] if (n == 1 and not force_delimited) else wire.frame_delimited(out)
 
     # ------------------------------------------------------------------ output
+    def _description(self) -> str:
+        return f"{self.detector_id} detects values not encountered in training as anomalies."
+
     def _detector_schema(self, log_id: str, score: float, alerts: Dict[str, str], time_value) -> bytes:
         now = int(self.clock())
         try:
@@ -350,7 +356,7 @@ class B200NewValueDetector(CoreComponent):
         return wire.encode_detector_schema(
             detector_id=self.detector_id, detector_type=self.method_type, alert_id=alert_id, detection_ts=now,
             log_ids=[log_id], score=score, extracted_ts=[ts],
-            description=f"{self.detector_id} detects values not encountered in training as anomalies.",
+            description=self._description(),
             received_ts=now, alerts=alerts)
 
     # ------------------------------------------------------------------ state
@@ -371,6 +377,89 @@ class B200NewValueDetector(CoreComponent):
         self.det.import_known(np.array(state.get("known", []), dtype=np.uint64))
         self.n_seen = int(state.get("n_seen", 0))
         self.n_alerts = int(state.get("n_alerts", 0))
+
+
+class B200NewValueComboDetectorConfig(B200NewValueDetectorConfig):
+    method_type: str = "new_value_combo_detector"
+
+
+def parse_combos(cfg: dict) -> Tuple[List[Monitor], List[List[int]]]:
+    """NewValueComboDetector config (same tree as NewValueDetector,
+    tests/test_reconfigure_params.py:149-169): every instance is one combination = the
+    ordered tuple of its fields, header_variables first, then variables."""
+    mons = parse_monitors(cfg)                    # same instance / field order as below
+    combos: List[List[int]] = []
+    k = 0
+
+    def instances(scope: dict) -> None:
+        nonlocal k
+        for _name, inst in (scope or {}).items():
+            inst = inst or {}
+            n = len(inst.get("header_variables") or []) + len(inst.get("variables") or [])
+            if n:
+                combos.append(list(range(k, k + n)))
+            k += n
+
+    instances(cfg.get("global") or {})
+    for _eid, scope in (cfg.get("events") or {}).items():
+        instances(scope or {})
+    assert k == len(mons)
+    if len(mons) + len(combos) > 32:
+        raise ValueError(f"{len(mons)} fields + {len(combos)} combinations configured, the device mask holds 32")
+    if len(mons) > 64:
+        raise ValueError("at most 64 combination members in total")
+    return mons, combos
+
+
+class B200NewValueComboDetector(B200NewValueDetector):
+    """NewValueComboDetector on the device (semantics R-combo in DESIGN.md /
+    oracle/nvcd.py): tuples of field values instead of single values.  The member
+    fingerprints are folded in order into one 64-bit key and learnt / probed in the same
+    table (`dm_set_combos`).  Input is ParserSchema (one per message or a delimited batch)."""
+
+    def __init__(self, name: str = "B200NewValueComboDetector", config: Optional[Any] = None) -> None:
+        raw_cfg = config.model_dump() if hasattr(config, "model_dump") else config
+        cfg = select_component_config(raw_cfg, name, fallback="NewValueComboDetector")
+        cfg.setdefault("method_type", "new_value_combo_detector")
+        cfg.setdefault("detector_id", "NewValueComboDetector" if name.startswith("B200") else name)
+        if cfg.get("input_format", "auto") == "raw_lines":
+            raise ValueError("combination monitors work on ParserSchema input (input_format auto | parser_schema | "
+                             "parser_schema_batch), not on raw lines")
+        super().__init__(name=name, config={"detectors": {name: cfg}})
+        self.monitors, self.combos = parse_combos(cfg)
+
+    @property
+    def det(self):
+        fresh = self._det is None
+        d = B200NewValueDetector.det.fget(self)
+        if fresh:
+            d.set_combos(self.combos, member_only_mask=(1 << len(self.monitors)) - 1)
+        return d
+
+    def _description(self) -> str:
+        return f"{self.detector_id} detects value combinations not encountered in training as anomalies."
+
+    def _record_alerts(self, rec: Dict, mask: int) -> Dict[str, str]:
+        by_field = dict(self._record_values(rec))
+        n = len(self.monitors)
+        out = {}
+        for c, members in enumerate(self.combos):
+            if mask >> (n + c) & 1:
+                m0 = self.monitors[members[0]]
+                scope = "Global" if m0.event_id is None else f"EventID {m0.event_id}"
+                key = "%s - (%s)" % (scope, ", ".join(self.monitors[i].label for i in members))
+                out[key] = "Unknown value combination: (%s)" % ", ".join(
+                    "'%s'" % by_field.get(i, b"").decode("utf-8", "replace") for i in members)
+        return out
+
+    def _process_record(self, data: bytes) -> Optional[bytes]:
+        out = self._process_record_batch(wire.frame_delimited([data]))     # the device walks the record
+        if out is None or self.output_format == "compact":
+            return out
+        return wire.split_delimited(out)[0]                                 # one record in, one bare alert out
+
+    def _process_lines(self, data: bytes) -> Optional[bytes]:
+        raise ValueError("combination monitors work on ParserSchema input, this message is not one")
 
 
 def decode_compact(blob: bytes) -> Tuple[np.ndarray, np.ndarray]:

@@ -24,10 +24,25 @@ struct DmMonitor {
     uint8_t key[64];
 };
 
+// Combination monitors (NewValueComboDetector, DESIGN.md R-combo): combo c is the ordered
+// tuple of the values of monitors combo_members[combo_off[c] .. combo_off[c+1]); its table
+// field (salt) and output-mask bit are n + c.  A monitor whose member_only bit is set does
+// not alert on its own.
+#define DM_MAX_COMBO_MEMBERS 64
 struct DmMonitors {
     uint32_t n;
+    uint32_t n_combos;
+    uint32_t member_only;
+    uint32_t pad_;
+    uint32_t combo_off[DM_MAX_KEYS + 1];
+    uint8_t combo_members[DM_MAX_COMBO_MEMBERS];
+    uint32_t pad2_[3];
     DmMonitor m[DM_MAX_KEYS];
 };
+
+// Fingerprint of an ordered tuple of value fingerprints (order-sensitive fold).
+DM_HD uint64_t dm_combo_fold(uint64_t acc, uint64_t fp) { return dm_splitmix64(acc ^ fp); }
+DM_HD uint64_t dm_combo_seed(uint32_t n_members) { return 0xC0B0C0B0ull + 0x9E3779B97F4A7C15ull * (uint64_t)n_members; }
 
 struct DmRecordsArgs {
     const uint8_t* buf;
@@ -123,13 +138,32 @@ __global__ void __launch_bounds__(128) dm_k_records(DmRecordsArgs a, int phase) 
             }
         }
         if (!ok) { atomicAdd(a.stats + 7, 1ull); continue; }     // malformed record: counted, not scored
-        uint32_t unknown = 0;
+        uint32_t unknown = 0, have = 0;
+        uint64_t fpv[DM_MAX_KEYS];
         for (uint32_t k = 0; k < sm.n; ++k) {
             if (!((present >> k) & 1u)) continue;
             if (sm.m[k].has_event && !(has_eid && eid == sm.m[k].event_id)) continue;
-            const uint64_t key = dm_make_key(dm_fp64_bytes(buf + vp[k], vl[k]), dm_field_salt(k));
+            const uint64_t fp = dm_fp64_bytes(buf + vp[k], vl[k]);
+            fpv[k] = fp;
+            have |= 1u << k;
+            if ((sm.member_only >> k) & 1u) continue;
+            const uint64_t key = dm_make_key(fp, dm_field_salt(k));
             if (train) dm_table_insert(a.table, key, &a.hdr->error);
             else if (!dm_table_contains(a.table, key)) unknown |= 1u << k;
+        }
+        for (uint32_t c = 0; c < sm.n_combos; ++c) {
+            const uint32_t lo = sm.combo_off[c], hi = sm.combo_off[c + 1];
+            uint64_t acc = dm_combo_seed(hi - lo);
+            bool all = true;
+            for (uint32_t j = lo; j < hi; ++j) {
+                const uint32_t k = sm.combo_members[j];
+                if (!((have >> k) & 1u)) { all = false; break; }
+                acc = dm_combo_fold(acc, fpv[k]);
+            }
+            if (!all) continue;                                   // a missing member skips the combination
+            const uint64_t key = dm_make_key(acc ? acc : 1ull, dm_field_salt(sm.n + c));
+            if (train) dm_table_insert(a.table, key, &a.hdr->error);
+            else if (!dm_table_contains(a.table, key)) unknown |= 1u << (sm.n + c);
         }
         if (!train) {
             const uint32_t cnt = (uint32_t)__popc(unknown);

@@ -89,6 +89,7 @@ struct dm_handle {
     uint32_t* d_masks = nullptr;
     DmMonitors* d_mons = nullptr;        // record mode on the device
     bool mons_set = false;
+    DmMonitors h_mons;             // host copy (dm_set_monitors + dm_set_combos)
     // pipelined host path: two slots
     struct Slot {
         uint8_t* d_in = nullptr; uint8_t* d_flags = nullptr; float* d_scores = nullptr;
@@ -493,7 +494,7 @@ static_assert(sizeof(dm_monitor_t) == sizeof(DmMonitor), "dm_monitor_t and DmMon
 extern "C" int dm_set_monitors(dm_handle* h, uint32_t n_monitors, const dm_monitor_t* monitors) {
     if (!h || (n_monitors && !monitors)) return dm_fail(DM_ERR_ARG, "NULL argument");
     if (n_monitors != h->n_keys) return dm_fail(DM_ERR_ARG, "%u monitors given, the handle was created with %u fields", n_monitors, h->n_keys);
-    DmMonitors hm;
+    DmMonitors& hm = h->h_mons;
     memset(&hm, 0, sizeof(hm));
     hm.n = n_monitors;
     for (uint32_t i = 0; i < n_monitors; ++i) {
@@ -507,6 +508,35 @@ extern "C" int dm_set_monitors(dm_handle* h, uint32_t n_monitors, const dm_monit
     DM_CUDA(cudaStreamSynchronize(h->last_stream));
     DM_CUDA(cudaMemcpy(h->d_mons, &hm, sizeof(DmMonitors), cudaMemcpyHostToDevice));
     h->mons_set = true;
+    return DM_OK;
+}
+
+extern "C" int dm_set_combos(dm_handle* h, uint32_t n_combos, const uint32_t* member_off, const uint32_t* members,
+                             uint32_t member_only_mask) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    if (!h->mons_set) return dm_fail(DM_ERR_STATE, "dm_set_monitors has not been called");
+    if (n_combos && (!member_off || !members)) return dm_fail(DM_ERR_ARG, "NULL argument");
+    DmMonitors& hm = h->h_mons;
+    if (hm.n + n_combos > DM_MAX_KEYS)
+        return dm_fail(DM_ERR_ARG, "%u monitors + %u combinations exceed the %d output-mask bits", hm.n, n_combos, DM_MAX_KEYS);
+    if (n_combos && member_off[0] != 0) return dm_fail(DM_ERR_ARG, "member_off[0] must be 0");
+    if (n_combos && member_off[n_combos] > DM_MAX_COMBO_MEMBERS)
+        return dm_fail(DM_ERR_ARG, "%u combination members in total, at most %d", member_off[n_combos], DM_MAX_COMBO_MEMBERS);
+    for (uint32_t c = 0; c < n_combos; ++c) {
+        if (member_off[c + 1] <= member_off[c]) return dm_fail(DM_ERR_ARG, "combination %u is empty or member_off is not increasing", c);
+        for (uint32_t j = member_off[c]; j < member_off[c + 1]; ++j)
+            if (members[j] >= hm.n) return dm_fail(DM_ERR_ARG, "combination %u: member %u is not a monitor index (< %u)", c, members[j], hm.n);
+    }
+    if (hm.n < 32 && (member_only_mask >> hm.n)) return dm_fail(DM_ERR_ARG, "member_only_mask has bits beyond the %u monitors", hm.n);
+    hm.n_combos = n_combos;
+    hm.member_only = member_only_mask;
+    memset(hm.combo_off, 0, sizeof(hm.combo_off));
+    memset(hm.combo_members, 0, sizeof(hm.combo_members));
+    for (uint32_t c = 0; c <= n_combos && n_combos; ++c) hm.combo_off[c] = member_off[c];
+    for (uint32_t j = 0; n_combos && j < member_off[n_combos]; ++j) hm.combo_members[j] = (uint8_t)members[j];
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    DM_CUDA(cudaMemcpy(h->d_mons, &hm, sizeof(DmMonitors), cudaMemcpyHostToDevice));
     return DM_OK;
 }
 

@@ -207,6 +207,17 @@ class DeviceDetector:
                 arr[i].source, arr[i].var_index, arr[i].key_len = 1, int(m["pos"]), 0
         _lib.check(self._lib.dm_set_monitors(self._h, len(monitors), arr))
 
+    def set_combos(self, combos, member_only_mask: int = 0) -> None:
+        """combos: lists of monitor indices (ordered tuples of fields, NewValueComboDetector);
+        combination c reports in mask bit n_monitors + c.  Call after set_monitors."""
+        off, flat = [0], []
+        for members in combos:
+            flat.extend(int(i) for i in members)
+            off.append(len(flat))
+        a_off = (C.c_uint32 * len(off))(*off)
+        a_mem = (C.c_uint32 * max(1, len(flat)))(*flat)
+        _lib.check(self._lib.dm_set_combos(self._h, len(combos), a_off, a_mem, int(member_only_mask)))
+
     def process_records(self, buf: bytes, n_train_records: int = 0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """A batch of varint-length-delimited ParserSchema records, decoded and scored on the
         device.  Returns (flags u8, scores f32, unknown-field masks u32), one entry per record."""

@@ -129,6 +129,17 @@ typedef struct {
     uint8_t key[64];
 } dm_monitor_t;
 int dm_set_monitors(dm_handle* h, uint32_t n_monitors, const dm_monitor_t* monitors);
+/* Combination monitors -- NewValueComboDetector (named at
+ * src/service/features/component_resolver.py:15,39-40; config shape
+ * tests/test_reconfigure_params.py:149-169): combination c is the ordered tuple of the
+ * values of monitors members[member_off[c] .. member_off[c+1]); a record yields it when all
+ * of them are present (and in scope).  It is learnt / looked up in the same table under
+ * field n_monitors + c and reported in bit n_monitors + c of the masks of
+ * dm_process_records (n_monitors + n_combos <= 32).  Monitors whose bit is set in
+ * member_only_mask do not alert on their own.  Call after dm_set_monitors (which clears the
+ * combinations); applies to dm_process_records. */
+int dm_set_combos(dm_handle* h, uint32_t n_combos, const uint32_t* member_off, const uint32_t* members,
+                  uint32_t member_only_mask);
 int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nbytes, uint32_t n_train_records,
                        uint8_t* flags_out, float* scores_out, uint32_t* masks_out, uint64_t out_cap,
                        uint64_t* n_records_out, uint64_t* n_anomalies_out);

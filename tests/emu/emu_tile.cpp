@@ -238,6 +238,16 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
 
 // Record mode on the device: mirrors dm_process_records (framing walk on the host, then
 // dm_k_records train pass + detect pass).  `mons` uses the dm_monitor_t layout.
+static uint32_t g_n_combos = 0, g_member_only = 0;
+static std::vector<uint32_t> g_combo_off, g_combo_members;
+// mirrors dm_set_combos; applies to the following emu_process_records calls (0 combos = off)
+extern "C" void emu_set_combos(uint32_t n_combos, const uint32_t* member_off, const uint32_t* members, uint32_t member_only) {
+    g_n_combos = n_combos;
+    g_member_only = member_only;
+    g_combo_off.assign(member_off, member_off + (n_combos ? n_combos + 1 : 0));
+    g_combo_members.assign(members, members + (n_combos ? member_off[n_combos] : 0));
+}
+
 extern "C" int emu_process_records(EmuHandle* h, const DmMonitor* mons, uint32_t n_mons, const uint8_t* msg,
                                    uint64_t nbytes, uint32_t n_train, uint8_t* flags, float* scores, uint32_t* masks,
                                    uint64_t cap, uint64_t* n_records, uint64_t* n_anoms) {
@@ -245,6 +255,10 @@ extern "C" int emu_process_records(EmuHandle* h, const DmMonitor* mons, uint32_t
     memset(&hm, 0, sizeof(hm));
     hm.n = n_mons;
     for (uint32_t i = 0; i < n_mons; ++i) hm.m[i] = mons[i];
+    hm.n_combos = g_n_combos;
+    hm.member_only = g_member_only;
+    for (size_t i = 0; i < g_combo_off.size(); ++i) hm.combo_off[i] = g_combo_off[i];
+    for (size_t i = 0; i < g_combo_members.size(); ++i) hm.combo_members[i] = (uint8_t)g_combo_members[i];
     std::vector<uint32_t> off, len;
     uint64_t pos = 0;
     while (pos < nbytes) {
