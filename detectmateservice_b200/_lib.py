@@ -66,12 +66,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 class Stats(C.Structure):
     _fields_ = [("lines", C.c_uint64), ("train_lines", C.c_uint64), ("detect_lines", C.c_uint64),
                 ("anomalies", C.c_uint64), ("score_sum", C.c_uint64), ("bytes", C.c_uint64),
-                ("known_keys", C.c_uint64), ("unknown_per_key", C.c_uint64 * DM_MAX_KEYS)]
+                ("known_keys", C.c_uint64), ("bad_records", C.c_uint64), ("unknown_per_key", C.c_uint64 * DM_MAX_KEYS)]
 
     def as_dict(self, n_keys: int = DM_MAX_KEYS) -> dict:
         return {"lines": self.lines, "train_lines": self.train_lines, "detect_lines": self.detect_lines,
                 "anomalies": self.anomalies, "score_sum": self.score_sum, "bytes": self.bytes,
-                "known_keys": self.known_keys, "unknown_per_key": list(self.unknown_per_key)[:n_keys]}
+                "known_keys": self.known_keys, "bad_records": self.bad_records, "unknown_per_key": list(self.unknown_per_key)[:n_keys]}
 
 
 class Monitor(C.Structure):
@@ -98,6 +98,7 @@ SYMBOLS = {
                                     _P, _P, _P, C.POINTER(C.c_uint64)]),
     "dm_set_monitors": (C.c_int, [_P, C.c_uint32, C.POINTER(Monitor)]),
     "dm_set_combos": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]),
+    "dm_set_format": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p)]),
     "dm_process_records": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64,
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dm_submit_lines": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint32]),
@@ -134,8 +135,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.dm_abi_version() != 1:
-        raise RuntimeError(f"libdmdetect ABI version {lib.dm_abi_version()} != 1")
+    if lib.dm_abi_version() != 2:
+        raise RuntimeError(f"libdmdetect ABI version {lib.dm_abi_version()} != 2")
     _lib = lib
     return lib
 

@@ -138,6 +138,20 @@ class B200NewValueDetector(CoreComponent):
         if self.output_format not in ("alerts", "compact"):
             raise ValueError(f"output_format {self.output_format!r} not in alerts|compact")
         self.monitors = parse_monitors(cfg)
+        # MatcherParser fused in front of the detector (raw-line input): params.log_format
+        # (+ params.templates: list, or params.path_templates: file, matched against the
+        # capture params.content_name = "Content") -- the parser config of
+        # tests/library_integration/test_pipe_filereader_matcher_nvd.py:74-88 moved here
+        self.logformat = None
+        if cfg.get("log_format"):
+            from .logformat import LogFormat, load_templates
+            templates = list(cfg.get("templates") or [])
+            if cfg.get("path_templates"):
+                templates += load_templates(str(cfg["path_templates"]))
+            for k in ("remove_spaces", "remove_punctuation", "lowercase"):
+                if cfg.get(k):
+                    raise ValueError(f"{k}: true is not supported by the fused matcher (templates are matched verbatim)")
+            self.logformat = LogFormat(cfg["log_format"], templates, str(cfg.get("content_name", "Content")))
         self.device = int(cfg.get("device", 0))
         self.max_batch_bytes = int(cfg.get("max_batch_bytes", 64 << 20))
         self.table_log2_slots = int(cfg.get("table_log2_slots", 20))
@@ -157,6 +171,9 @@ class B200NewValueDetector(CoreComponent):
                                        max_batch_bytes=self.max_batch_bytes,
                                        table_log2_slots=self.table_log2_slots)
             self._det.set_monitors([{"event_id": m.event_id, "source": m.source, "pos": m.pos} for m in self.monitors])
+            if self.logformat is not None:
+                lf = self.logformat
+                self._det.set_format(lf.source, lf.template_sources, lf.content_name)
         return self._det
 
     # ------------------------------------------------------------------ receive buffers (lent to the transport)
@@ -215,6 +232,8 @@ class B200NewValueDetector(CoreComponent):
         if not data:
             return None
         fmt = self.input_format
+        if fmt == "auto" and self.logformat is not None:
+            fmt = "raw_lines"                                    # a log_format is configured: the input is log text
         if isinstance(data, memoryview) and fmt != "raw_lines":
             # a lent receive buffer: raw lines are used in place; protobuf inputs (rare as
             # large frames) are decoded from a bytes copy
@@ -331,6 +350,15 @@ class B200NewValueDetector(CoreComponent):
         raw_keys = [m.key for m in self.monitors]
         for line_idx, mask, offset in self.det.anomalies():
             rec = _alerts.record_at(data, offset)
+            if self.logformat is not None:
+                _eid, variables, lfv = self.logformat.parse(rec) or (-1, [], {})
+                alerts = {}
+                for i, m in enumerate(self.monitors):
+                    if mask >> i & 1:
+                        v = lfv.get(m.pos, b"") if m.source == "header" else (variables[m.pos] if m.pos < len(variables) else b"")
+                        alerts[m.alert_key] = _alerts.alert_text(v)
+                out.append(self._detector_schema(str(base + line_idx), float(scores[line_idx]), alerts, lfv.get("Time")))
+                continue
             wanted = [raw_keys[i] for i in range(len(raw_keys)) if mask >> i & 1]
             vals = _alerts.record_fields(rec, wanted)
             alerts = {self.monitors[i].alert_key: _alerts.alert_text(vals.get(raw_keys[i], b""))

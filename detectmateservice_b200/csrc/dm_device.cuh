@@ -177,3 +177,21 @@ __device__ __forceinline__ void dm_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 #endif
 }
+
+// Arguments of the warp-per-record kernels (dm_kernels_v1.cuh, dm_kernels_format.cuh).
+struct DmKeys;
+struct DmDetectArgs {
+    const uint8_t* buf;
+    const uint32_t* line_start;
+    const DmBatchHeader* hdr_in;      // n_lines
+    DmBatchHeader* hdr;
+    const DmKeys* keys;
+    DmTable table;
+    uint8_t* flags;
+    float* scores;
+    uint64_t out_cap;
+    dm_anomaly_t* anomalies;
+    uint32_t anomaly_cap;
+    unsigned long long* stats;
+    uint64_t line_lo, line_hi;        // records [line_lo, min(line_hi, n_lines)) are processed
+};

@@ -1,0 +1,197 @@
+// dm_kernels_format.cuh -- the MatcherParser step fused in front of the detector
+// (SURVEY.md section 8a8 / 8f-3): `log_format` header extraction and `<*>` template matching on
+// the device, one warp per record, feeding the same known-set table.
+//
+// What it replaces: detectmatelibrary.parsers.template_matcher.MatcherParser (un-vendored;
+// configured at /root/reference/tests/library_integration/test_pipe_filereader_matcher_nvd.py:74-88
+// and docs/getting_started.md:395-415) followed by NewValueDetector behind
+// /root/reference/src/service/core.py:201-203.  Rules: DESIGN.md R-fmt / R-match.
+//
+//   chain     L0 C0 L1 C1 ... L(n-1) [C(n-1)]     literals L, captures C
+//   match     L0 anchored at the start; every later literal at its EARLIEST occurrence at or
+//             after the current position (captures are non-greedy); a chain that ends with a
+//             literal anchors that literal at the END of the text; a chain that ends with a
+//             capture lets it run to the end.  Equivalent to the regular expression
+//             ^L0(.*?)L1(.*?)...$ with the literals escaped (checked against Python's `re`
+//             in tests/test_format_matcher.py).
+//   chain 0   the log_format: captures are the header variables (logFormatVariables)
+//   chain 1+  the templates, matched in file order against the capture named Content;
+//             the first match gives EventID (0-based template index; -1 = none) and its
+//             captures are variables[0..].
+#pragma once
+#include "dm_device.cuh"
+
+#define DM_FMT_MAX_CHAINS 64          // log_format + 63 templates
+#define DM_FMT_MAX_LITS 512           // literals over all chains
+#define DM_FMT_MAX_CHAIN_LITS 32      // literals (and captures) per chain: one capture per lane
+#define DM_FMT_POOL_BYTES 4096        // literal bytes over all chains
+#define DM_FMT_NONE 0xFFu
+
+struct DmFormat {
+    uint32_t n_chains;
+    uint32_t content_capture;                         // header capture the templates apply to, DM_FMT_NONE = none
+    uint32_t n_mons;
+    uint32_t pad_;
+    uint16_t chain_first[DM_FMT_MAX_CHAINS + 2];      // first literal of chain c in lit_off (c+1: one past)
+    uint8_t chain_endcap[DM_FMT_MAX_CHAINS];          // 1: the chain ends with a capture
+    uint16_t lit_off[DM_FMT_MAX_LITS + 2];            // literal i = pool[lit_off[i] .. lit_off[i+1])
+    uint8_t pool[DM_FMT_POOL_BYTES];
+    // monitors bound to the format: header capture index or variable index
+    int32_t mon_event[DM_MAX_KEYS];
+    uint8_t mon_has_event[DM_MAX_KEYS];
+    uint8_t mon_source[DM_MAX_KEYS];                  // 0 = header capture, 1 = template variable
+    uint8_t mon_index[DM_MAX_KEYS];                   // capture / variable index, DM_FMT_NONE = never present
+};
+
+// all lanes: does text[q, q+len) equal the literal?  (warp-uniform result)
+__device__ __forceinline__ bool dm_fmt_match_at(const uint8_t* __restrict__ buf, uint64_t q, const uint8_t* lit,
+                                                uint32_t len, uint32_t lane) {
+    bool ok = true;
+    for (uint32_t j = lane; j < len; j += 32) ok = ok && (buf[q + j] == lit[j]);
+    return __all_sync(0xffffffffu, ok);
+}
+
+// all lanes: earliest q in [pos, e - len] with text[q, q+len) == literal, or ~0ull
+__device__ __forceinline__ uint64_t dm_fmt_find(const uint8_t* __restrict__ buf, uint64_t pos, uint64_t e,
+                                                const uint8_t* lit, uint32_t len, uint32_t lane) {
+    if (e < pos + len) return ~0ull;
+    const uint64_t last = e - len;                    // last admissible start
+    const uint8_t c0 = lit[0];
+    for (uint64_t base = pos; base <= last; base += 32) {
+        const uint64_t p = base + lane;
+        bool m = false;
+        if (p <= last && buf[p] == c0) {
+            m = true;
+            for (uint32_t j = 1; j < len; ++j)
+                if (buf[p + j] != lit[j]) { m = false; break; }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, m);
+        if (b) return base + (uint32_t)(__ffs(b) - 1);
+    }
+    return ~0ull;
+}
+
+// Match chain `c` against text [s, e).  Warp-uniform result; on success lane i holds capture i
+// in (cap_s, cap_l) for i < number of captures (other lanes: cap_l = 0, cap_s = e).
+__device__ bool dm_fmt_match_chain(const DmFormat& f, uint32_t c, const uint8_t* __restrict__ buf, uint64_t s,
+                                   uint64_t e, uint32_t lane, uint64_t& cap_s, uint32_t& cap_l, uint32_t& n_caps) {
+    const uint32_t first = f.chain_first[c];
+    const uint32_t n = (uint32_t)f.chain_first[c + 1] - first;
+    const bool endcap = f.chain_endcap[c] != 0;
+    uint64_t pos = s;
+    cap_s = e;
+    cap_l = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t lo = f.lit_off[first + i];
+        const uint32_t len = (uint32_t)f.lit_off[first + i + 1] - lo;
+        const uint8_t* lit = f.pool + lo;
+        uint64_t q;
+        if (i == 0) {                                             // anchored at the start
+            if (e < pos + len || !dm_fmt_match_at(buf, pos, lit, len, lane)) return false;
+            q = pos;
+        } else if (i == n - 1 && !endcap) {                       // anchored at the end
+            if (e < pos + len) return false;
+            q = e - len;
+            if (!dm_fmt_match_at(buf, q, lit, len, lane)) return false;
+        } else {
+            q = dm_fmt_find(buf, pos, e, lit, len, lane);
+            if (q == ~0ull) return false;
+        }
+        if (i > 0 && lane == i - 1) { cap_s = pos; cap_l = (uint32_t)(q - pos); }
+        pos = q + len;
+    }
+    if (endcap) {
+        if (n == 0) { if (lane == 0) { cap_s = s; cap_l = (uint32_t)(e - s); } }   // the chain is one capture
+        else if (lane == n - 1) { cap_s = pos; cap_l = (uint32_t)(e - pos); }
+        n_caps = n ? n : 1;
+    } else {
+        if (pos != e) return false;                              // (n == 1: the literal is the whole text)
+        n_caps = n ? n - 1 : 0;
+    }
+    return true;
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256) dm_k_format_lines(DmDetectArgs a, const DmFormat* __restrict__ gfmt) {
+    __shared__ DmFormat sf;
+    __shared__ unsigned int s_unk[DM_MAX_KEYS];
+    __shared__ unsigned long long s_anom, s_score;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(gfmt);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sf);
+        for (uint32_t i = threadIdx.x; i < sizeof(DmFormat) / 4; i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x < DM_MAX_KEYS) s_unk[threadIdx.x] = 0;
+        if (threadIdx.x == 0) { s_anom = 0; s_score = 0; }
+    }
+    __syncthreads();
+
+    const uint8_t* __restrict__ buf = a.buf;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t warp_id = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t n_lines = a.hdr_in->n_lines;
+    const uint64_t hi = a.line_hi < n_lines ? a.line_hi : n_lines;
+
+    for (uint64_t line = a.line_lo + warp_id; line < hi; line += warps_total) {
+        const uint64_t s = a.line_start[line];
+        const uint64_t e = (uint64_t)a.line_start[line + 1] - 1;     // the '\n' (or nbytes)
+        uint64_t hs, vs = e;
+        uint32_t hl, vl = 0, n_hcaps = 0, n_vars = 0;
+        const bool hok = dm_fmt_match_chain(sf, 0, buf, s, e, lane, hs, hl, n_hcaps);
+        int32_t eid = -1;
+        if (hok && sf.content_capture != DM_FMT_NONE && sf.n_chains > 1) {
+            const uint64_t cs = __shfl_sync(0xffffffffu, hs, sf.content_capture);
+            const uint64_t ce = cs + __shfl_sync(0xffffffffu, hl, sf.content_capture);
+            for (uint32_t t = 1; t < sf.n_chains; ++t) {
+                if (dm_fmt_match_chain(sf, t, buf, cs, ce, lane, vs, vl, n_vars)) { eid = (int32_t)t - 1; break; }
+            }
+            if (eid < 0) { vl = 0; n_vars = 0; }
+        }
+        // lane k serves monitor k: fetch its value from the lane that holds the capture
+        const uint32_t k = lane;
+        const bool mon = k < sf.n_mons;
+        const uint32_t src = mon ? sf.mon_source[k] : 0u;
+        const uint32_t idx = mon ? sf.mon_index[k] : DM_FMT_NONE;
+        const uint32_t from = idx & 31u;
+        const uint64_t xs = src ? __shfl_sync(0xffffffffu, vs, from) : __shfl_sync(0xffffffffu, hs, from);
+        const uint32_t xl = src ? __shfl_sync(0xffffffffu, vl, from) : __shfl_sync(0xffffffffu, hl, from);
+        bool present = hok && mon && idx != DM_FMT_NONE && idx < (src ? n_vars : n_hcaps);
+        if (present && sf.mon_has_event[k] && eid != sf.mon_event[k]) present = false;
+        bool unk = false;
+        if (present) {
+            const uint64_t key = dm_make_key(dm_fp64_bytes(buf + xs, xl), dm_field_salt(k));
+            if (TRAIN) dm_table_insert(a.table, key, &a.hdr->error);
+            else unk = !dm_table_contains(a.table, key);
+        }
+        const uint32_t unknown = __ballot_sync(0xffffffffu, unk);
+        if (lane == 0) {
+            const uint32_t cnt = __popc(unknown);
+            if (line < a.out_cap) {
+                if (a.flags) a.flags[line] = cnt ? 1 : 0;
+                if (a.scores) a.scores[line] = (float)cnt;
+            }
+            if (!hok) atomicAdd(a.stats + 7, 1ull);                 // record the log_format does not match: counted, not scored
+            if (cnt) {
+                atomicAdd(&s_anom, 1ull);
+                atomicAdd(&s_score, (unsigned long long)cnt);
+                uint32_t m = unknown;
+                while (m) { int b = __ffs(m) - 1; m &= m - 1; atomicAdd(&s_unk[b], 1u); }
+                unsigned int at = atomicAdd(&a.hdr->anomaly_list_count, 1u);
+                if (at < a.anomaly_cap) {
+                    dm_anomaly_t r; r.line = (uint32_t)line; r.mask = unknown; r.offset = s;
+                    a.anomalies[at] = r;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!TRAIN) {
+        if (threadIdx.x == 0 && s_anom) {
+            atomicAdd(&a.hdr->n_anomalies, s_anom);
+            atomicAdd(&a.stats[3], s_anom);
+            atomicAdd(&a.stats[4], s_score);
+        }
+        if (threadIdx.x < DM_MAX_KEYS && s_unk[threadIdx.x])
+            atomicAdd(&a.stats[8 + threadIdx.x], (unsigned long long)s_unk[threadIdx.x]);
+    }
+}

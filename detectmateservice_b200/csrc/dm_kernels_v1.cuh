@@ -175,21 +175,7 @@ __device__ __forceinline__ uint64_t dm_hash_value_g(const uint8_t* __restrict__ 
     return dm_hash_final(st, n);
 }
 
-struct DmDetectArgs {
-    const uint8_t* buf;
-    const uint32_t* line_start;
-    const DmBatchHeader* hdr_in;      // n_lines
-    DmBatchHeader* hdr;
-    const DmKeys* keys;
-    DmTable table;
-    uint8_t* flags;
-    float* scores;
-    uint64_t out_cap;
-    dm_anomaly_t* anomalies;
-    uint32_t anomaly_cap;
-    unsigned long long* stats;
-    uint64_t line_lo, line_hi;        // records [line_lo, min(line_hi, n_lines)) are processed
-};
+// (DmDetectArgs lives in dm_device.cuh: shared with dm_kernels_format.cuh)
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(256) dm_k_detect_lines(DmDetectArgs a) {

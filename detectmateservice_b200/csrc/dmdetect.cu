@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "dm_device.cuh"
@@ -19,6 +20,8 @@
 #include "dm_kernels_cta.cuh"
 #include "dm_kernels_values.cuh"
 #include "dm_kernels_records.cuh"
+#include "dm_kernels_format.cuh"
+#include "dm_format_host.h"
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -90,6 +93,8 @@ struct dm_handle {
     DmMonitors* d_mons = nullptr;        // record mode on the device
     bool mons_set = false;
     DmMonitors h_mons;             // host copy (dm_set_monitors + dm_set_combos)
+    DmFormat* d_fmt = nullptr;     // log_format + templates (dm_set_format)
+    bool fmt_set = false;
     // pipelined host path: two slots
     struct Slot {
         uint8_t* d_in = nullptr; uint8_t* d_flags = nullptr; float* d_scores = nullptr;
@@ -279,7 +284,7 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
     cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
-    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons);
+    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons); cudaFree(h->d_fmt);
     for (auto& sl : h->slots) {
         cudaFree(sl.d_in); cudaFree(sl.d_flags); cudaFree(sl.d_scores); cudaFree(sl.d_hdr); cudaFree(sl.d_anoms);
         cudaFreeHost(sl.h_hdr); cudaFreeHost(sl.h_flags); cudaFreeHost(sl.h_scores);
@@ -338,10 +343,33 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
     (void)dev_cap;
 
     // (the rows variant clears the per-batch header in its first kernel)
-    if (h->kernel_variant < 2 || nbytes == 0) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
+    if (h->kernel_variant < 2 || nbytes == 0 || h->fmt_set) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
     h->last_nbytes = nbytes;
 
-    if (h->kernel_variant == 0) {
+    if (h->fmt_set) {
+        // log_format / template mode: line index, then one warp per record (dm_kernels_format.cuh)
+        const uint32_t n_tiles = (uint32_t)((nbytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES);
+        const int grid_tiles = std::max(1, std::min<int>((int)n_tiles, h->sm_count * 8));
+        dm_k_count_newlines<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts);
+        dm_k_scan_tiles<<<1, 1024, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts, h->d_tile_base,
+                                             h->d_line_start, h->max_lines, n_train_lines, h->d_hdr, h->d_stats);
+        dm_k_line_starts<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_base,
+                                                                  h->d_line_start, h->max_lines);
+        DmDetectArgs a;
+        a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
+        a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
+        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats;
+        const int grid = h->sm_count * 8;
+        if (n_train_lines > 0) {
+            a.line_lo = 0; a.line_hi = n_train_lines;
+            dm_k_format_lines<true><<<grid, 256, 0, st>>>(a, h->d_fmt);
+        }
+        a.line_lo = n_train_lines; a.line_hi = ~0ull;
+        dm_prof_mark(h, st, 0);
+        dm_k_format_lines<false><<<grid, 256, 0, st>>>(a, h->d_fmt);
+        dm_prof_mark(h, st, 1);
+        h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
+    } else if (h->kernel_variant == 0) {
         const uint32_t n_tiles = (uint32_t)((nbytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES);
         const int grid_tiles = std::max(1, std::min<int>((int)n_tiles, h->sm_count * 8));
         dm_k_count_newlines<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts);
@@ -540,6 +568,37 @@ extern "C" int dm_set_combos(dm_handle* h, uint32_t n_combos, const uint32_t* me
     return DM_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// log_format + templates (MatcherParser fused in front of the detector)
+// ---------------------------------------------------------------------------------------
+
+extern "C" int dm_set_format(dm_handle* h, const char* log_format, const char* content_name, uint32_t n_templates,
+                             const char* const* templates) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    if (!log_format) {                                             // back to key=value tokenisation
+        h->fmt_set = false;
+        return DM_OK;
+    }
+    if (!h->mons_set) return dm_fail(DM_ERR_STATE, "dm_set_monitors has not been called");
+    if (n_templates && !templates) return dm_fail(DM_ERR_ARG, "templates is NULL");
+    DmFormat* f = new (std::nothrow) DmFormat;
+    if (!f) return dm_fail(DM_ERR_CUDA, "out of host memory");
+    std::string err;
+    int rc = DM_OK;
+    if (!dm_format_build(log_format, content_name, n_templates, templates, h->h_mons, f, &err)) {
+        rc = dm_fail(DM_ERR_ARG, "%s", err.c_str());
+    } else {
+        cudaError_t e = cudaSetDevice(h->device);
+        if (e == cudaSuccess && !h->d_fmt) e = cudaMalloc(&h->d_fmt, sizeof(DmFormat));
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->last_stream);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_fmt, f, sizeof(DmFormat), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = dm_fail(DM_ERR_CUDA, "dm_set_format: %s", cudaGetErrorString(e));
+        else h->fmt_set = true;
+    }
+    delete f;
+    return rc;
+}
+
 extern "C" int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nbytes, uint32_t n_train_records,
                                   uint8_t* flags_out, float* scores_out, uint32_t* masks_out, uint64_t out_cap,
                                   uint64_t* n_records_out, uint64_t* n_anomalies_out) {
@@ -649,6 +708,7 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
         return dm_fail(DM_ERR_CAPACITY, "message of %llu bytes exceeds max_batch_bytes=%llu", (unsigned long long)nbytes, (unsigned long long)h->max_batch_bytes);
     if (nbytes && !host_buf) return dm_fail(DM_ERR_ARG, "host_buf is NULL");
     if (h->kernel_variant < 2) return dm_fail(DM_ERR_STATE, "the pipelined path needs the rows or staged kernels");
+    if (h->fmt_set) return dm_fail(DM_ERR_STATE, "the pipelined path tokenises key=value records; with a log_format use dm_process_lines");
     DM_CUDA(cudaSetDevice(h->device));
     int rc = dm_slots_init(h);
     if (rc != DM_OK) return rc;
@@ -766,7 +826,7 @@ extern "C" int dm_get_anomalies(dm_handle* h, dm_anomaly_t* out, uint32_t cap, u
 
 static void dm_words_to_stats(const unsigned long long* w, dm_stats_t* out) {
     out->lines = w[0]; out->train_lines = w[1]; out->detect_lines = w[2]; out->anomalies = w[3];
-    out->score_sum = w[4]; out->bytes = w[5]; out->known_keys = w[6];
+    out->score_sum = w[4]; out->bytes = w[5]; out->known_keys = w[6]; out->bad_records = w[7];
     for (int k = 0; k < DM_MAX_KEYS; ++k) out->unknown_per_key[k] = w[8 + k];
 }
 

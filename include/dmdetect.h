@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 1
+#define DM_ABI_VERSION 2
 #define DM_MAX_KEYS 32      /* monitored fields per detector                         */
 #define DM_MAX_KEYLEN 32    /* bytes per monitored key                                */
 
@@ -54,6 +54,8 @@ typedef struct {
     uint64_t score_sum;      /* sum of scores (scores are small integers)             */
     uint64_t bytes;          /* input bytes consumed                                  */
     uint64_t known_keys;     /* entries in the known-set table                        */
+    uint64_t bad_records;    /* records that could not be parsed (malformed protobuf,
+                                log_format mismatch): counted, never scored           */
     uint64_t unknown_per_key[DM_MAX_KEYS]; /* alerts per monitored field             */
 } dm_stats_t;
 
@@ -140,6 +142,25 @@ int dm_set_monitors(dm_handle* h, uint32_t n_monitors, const dm_monitor_t* monit
  * combinations); applies to dm_process_records. */
 int dm_set_combos(dm_handle* h, uint32_t n_combos, const uint32_t* member_off, const uint32_t* members,
                   uint32_t member_only_mask);
+/* MatcherParser fused in front of the detector.  Replaces
+ * detectmatelibrary.parsers.template_matcher.MatcherParser as configured at
+ * tests/library_integration/test_pipe_filereader_matcher_nvd.py:74-88 and
+ * docs/getting_started.md:395-415, i.e. the parser service upstream of core.py:201-203.
+ *   log_format   literal text with <Name> captures, e.g.
+ *                `<IP> - - [<Time>] "<Method> <URL> <Protocol>" <Status> <Bytes> "<Referer>" "<UserAgent>"`
+ *                or `type=<type> msg=audit(<Time>): <Content>`; captures are the record's header
+ *                variables (logFormatVariables).  Semantics = ^L0(.*?)L1(.*?)...$ with escaped
+ *                literals (non-greedy captures, last one to the end).
+ *   templates    `<*>` wildcard templates matched in order against the capture named
+ *                content_name (NULL = "Content"); the first match sets EventID = its index
+ *                (0-based, -1 = no match) and variables[i] = its i-th wildcard.
+ * The monitors of dm_set_monitors are bound to it: header monitors by capture name, variable
+ * monitors by wildcard index, event scope by EventID.  After this call dm_process_lines
+ * tokenises with the log_format instead of key=value fields (one warp per record); records
+ * the log_format does not match are counted (dm_stats_t.bad_records) and never alert.
+ * log_format = NULL switches back.  At most 63 templates, 32 captures per chain. */
+int dm_set_format(dm_handle* h, const char* log_format, const char* content_name, uint32_t n_templates,
+                  const char* const* templates);
 int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nbytes, uint32_t n_train_records,
                        uint8_t* flags_out, float* scores_out, uint32_t* masks_out, uint64_t out_cap,
                        uint64_t* n_records_out, uint64_t* n_anomalies_out);

@@ -113,6 +113,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 static inline unsigned emu_reduce(unsigned v, int op) {
     EmuWarp& w = emu_warp();
     w.slot[emu_lane()] = v;

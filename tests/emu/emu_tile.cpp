@@ -12,6 +12,8 @@
 #include "dm_kernels_staged.cuh"
 #include "dm_kernels_records.cuh"
 #include "dm_kernels_cta.cuh"
+#include "dm_kernels_format.cuh"
+#include "dm_format_host.h"
 
 thread_local emu_dim3 threadIdx;
 thread_local emu_dim3 blockIdx;
@@ -285,6 +287,48 @@ extern "C" int emu_process_records(EmuHandle* h, const DmMonitor* mons, uint32_t
         if (n_train < n) emu_launch(128, [&] { dm_k_records(a, 1); });
     }
     *n_records = n;
+    *n_anoms = h->hdr.n_anomalies;
+    return 0;
+}
+
+// log_format / template mode: mirrors dm_set_format + the fmt branch of dm_process_lines (line
+// starts are computed here on the host; the device's index kernels are the v1 ones, GPU-tested).
+static DmFormat g_fmt;
+static bool g_fmt_set = false;
+static char g_fmt_err[256];
+extern "C" const char* emu_set_format(const DmMonitor* mons, uint32_t n_mons, const char* log_format, const char* content_name,
+                                      uint32_t n_templates, const char* const* templates) {
+    static DmMonitors hm;
+    memset(&hm, 0, sizeof(hm));
+    hm.n = n_mons;
+    for (uint32_t i = 0; i < n_mons; ++i) hm.m[i] = mons[i];
+    std::string err;
+    g_fmt_set = dm_format_build(log_format, content_name, n_templates, templates, hm, &g_fmt, &err);
+    snprintf(g_fmt_err, sizeof(g_fmt_err), "%s", err.c_str());
+    return g_fmt_set ? nullptr : g_fmt_err;
+}
+
+extern "C" int emu_process_format(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                  float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms) {
+    if (!g_fmt_set) return -6;
+    std::vector<uint32_t> ls;
+    ls.push_back(0);
+    for (uint64_t i = 0; i < nbytes; ++i)
+        if (msg[i] == '\n') ls.push_back((uint32_t)(i + 1));
+    uint64_t n = ls.size() - 1;
+    if (nbytes && msg[nbytes - 1] != '\n') { ls.push_back((uint32_t)(nbytes + 1)); ++n; }   // unterminated last record
+    if (n > cap) return -4;
+    memset(&h->hdr, 0, sizeof(h->hdr));
+    h->hdr.n_lines = n;
+    h->anoms.assign(std::max<size_t>(h->anoms.size(), 4096), dm_anomaly_t{});
+    DmDetectArgs a;
+    a.buf = msg; a.line_start = ls.data(); a.hdr_in = &h->hdr; a.hdr = &h->hdr; a.keys = &h->keys; a.table = h->table;
+    a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
+    a.stats = h->stats;
+    const uint64_t nt = std::min<uint64_t>(n_train, n);
+    if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch(256, [&] { dm_k_format_lines<true>(a, &g_fmt); }); }
+    if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch(256, [&] { dm_k_format_lines<false>(a, &g_fmt); }); }
+    *n_lines = n;
     *n_anoms = h->hdr.n_anomalies;
     return 0;
 }
