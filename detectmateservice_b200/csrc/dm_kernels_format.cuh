@@ -153,8 +153,11 @@ __global__ void __launch_bounds__(256) dm_k_format_lines(DmDetectArgs a, const D
         const uint32_t src = mon ? sf.mon_source[k] : 0u;
         const uint32_t idx = mon ? sf.mon_index[k] : DM_FMT_NONE;
         const uint32_t from = idx & 31u;
-        const uint64_t xs = src ? __shfl_sync(0xffffffffu, vs, from) : __shfl_sync(0xffffffffu, hs, from);
-        const uint32_t xl = src ? __shfl_sync(0xffffffffu, vl, from) : __shfl_sync(0xffffffffu, hl, from);
+        // (every lane executes all four shuffles: the source register differs per lane)
+        const uint64_t xs_h = __shfl_sync(0xffffffffu, hs, from), xs_v = __shfl_sync(0xffffffffu, vs, from);
+        const uint32_t xl_h = __shfl_sync(0xffffffffu, hl, from), xl_v = __shfl_sync(0xffffffffu, vl, from);
+        const uint64_t xs = src ? xs_v : xs_h;
+        const uint32_t xl = src ? xl_v : xl_h;
         bool present = hok && mon && idx != DM_FMT_NONE && idx < (src ? n_vars : n_hcaps);
         if (present && sf.mon_has_event[k] && eid != sf.mon_event[k]) present = false;
         bool unk = false;

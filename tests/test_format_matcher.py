@@ -243,6 +243,36 @@ def test_emu_kernel_fuzz_formats():
     assert checked > 100
 
 
+SYNTH_TMPL = "pid=<*> uid=<*> auid=<*> ses=<*> msg='op=<*> acct=<*> exe=<*> hostname=<*> addr=<*> terminal=<*> res=<*>' pad=<*>"
+SYNTH_CFG = {"detectors": {"NewValueDetector": {"method_type": "new_value_detector", "data_use_training": 2000,
+             "global": {"g": {"header_variables": [{"pos": "type"}]}},
+             "events": {0: {"pam": {"variables": [{"pos": 5, "name": "acct"}, {"pos": 6, "name": "exe"},
+                                                  {"pos": 9, "name": "terminal"}, {"pos": 10, "name": "res"}]}}}}}}
+
+
+def test_emu_kernel_synthetic_header_and_variable_monitors():
+    """Header-capture and template-variable monitors side by side (different source lanes), on
+    the config-2 synthetic records with their injected anomalies."""
+    from detectmateservice_b200.synth import AuditSynth
+    g = AuditSynth(seed=99)
+    train, _ = g.batch(2000, inject=False)
+    big, truth = g.batch(24000, inject=True)
+    lines = big.split(b"\n")[:-1]
+    sel = []
+    for i in np.flatnonzero(truth):
+        sel += lines[max(0, i - 1):i + 1]
+    test = b"\n".join(sel) + b"\n"
+    orc = FormatOracle(SYNTH_CFG, AUDIT, [SYNTH_TMPL])
+    orc.process_lines(train)
+    wf, ws, wa, bad = orc.process_lines(test)
+    emu = EmuFormat(SYNTH_CFG, AUDIT, [SYNTH_TMPL])
+    emu.process(train, 2000)
+    f, s, masks = emu.process(test, 0)
+    assert bad == 0 and f == wf and s == ws and sum(wf) >= 15
+    assert masks == {i: _mask_of(a, emu.mons) for i, a in enumerate(wa) if a}
+    assert len({m for m in masks.values()}) >= 3                  # several different monitors fired
+
+
 def test_emu_set_format_errors():
     with pytest.raises(ValueError, match="nothing between"):
         EmuFormat(NGINX_CFG, "<A><B>")
@@ -366,11 +396,7 @@ def test_gpu_format_mode_full_size_message():
     from detectmateservice_b200.detector import DeviceDetector
     from detectmateservice_b200.component import parse_monitors, select_component_config
     from detectmateservice_b200.synth import AuditSynth
-    tmpl = ("pid=<*> uid=<*> auid=<*> ses=<*> msg='op=<*> acct=<*> exe=<*> hostname=<*> addr=<*> terminal=<*> res=<*>' pad=<*>")
-    cfg = {"detectors": {"NewValueDetector": {"method_type": "new_value_detector", "data_use_training": 65536,
-           "global": {"g": {"header_variables": [{"pos": "type"}]}},
-           "events": {0: {"pam": {"variables": [{"pos": 5, "name": "acct"}, {"pos": 6, "name": "exe"},
-                                                {"pos": 9, "name": "terminal"}, {"pos": 10, "name": "res"}]}}}}}}
+    tmpl, cfg = SYNTH_TMPL, SYNTH_CFG
     mons = parse_monitors(select_component_config(cfg, "NewValueDetector"))
     g = AuditSynth(seed=99)
     train, _ = g.batch(65536, inject=False)
