@@ -16,12 +16,15 @@ struct FmtBuilder {
 
     bool add_literal(const std::string& lit) {
         if (n_lits >= DM_FMT_MAX_LITS) { err = "too many literals over the log_format and the templates"; return false; }
-        if (pool_used + lit.size() > DM_FMT_POOL_BYTES) { err = "the literal text of log_format + templates exceeds 4096 bytes"; return false; }
+        if (lit.size() > DM_FMT_MAX_LIT_LEN) { err = "a literal between two captures is longer than 255 bytes"; return false; }
+        const uint32_t words = (uint32_t)(lit.size() + 3) / 4;
+        if (pool_used + words > DM_FMT_POOL_WORDS) { err = "the literal text of log_format + templates exceeds 4096 bytes"; return false; }
         f.lit_off[n_lits] = (uint16_t)pool_used;
-        memcpy(f.pool + pool_used, lit.data(), lit.size());
-        pool_used += (uint32_t)lit.size();
+        f.lit_len[n_lits] = (uint8_t)lit.size();
+        for (size_t i = 0; i < lit.size(); ++i)
+            f.pool[pool_used + i / 4] |= (uint32_t)(uint8_t)lit[i] << (8 * (i % 4));
+        pool_used += words;
         ++n_lits;
-        f.lit_off[n_lits] = (uint16_t)pool_used;
         return true;
     }
 

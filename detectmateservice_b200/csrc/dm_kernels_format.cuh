@@ -24,18 +24,21 @@
 #define DM_FMT_MAX_CHAINS 64          // log_format + 63 templates
 #define DM_FMT_MAX_LITS 512           // literals over all chains
 #define DM_FMT_MAX_CHAIN_LITS 32      // literals (and captures) per chain: one capture per lane
-#define DM_FMT_POOL_BYTES 4096        // literal bytes over all chains
+#define DM_FMT_POOL_WORDS 1024        // literal text over all chains, each literal padded to 4-byte words
+#define DM_FMT_MAX_LIT_LEN 255
 #define DM_FMT_NONE 0xFFu
+#define DM_FMT_NOT_FOUND 0xFFFFFFFFu
 
 struct DmFormat {
     uint32_t n_chains;
     uint32_t content_capture;                         // header capture the templates apply to, DM_FMT_NONE = none
     uint32_t n_mons;
     uint32_t pad_;
-    uint16_t chain_first[DM_FMT_MAX_CHAINS + 2];      // first literal of chain c in lit_off (c+1: one past)
+    uint16_t chain_first[DM_FMT_MAX_CHAINS + 2];      // first literal of chain c (c+1: one past)
     uint8_t chain_endcap[DM_FMT_MAX_CHAINS];          // 1: the chain ends with a capture
-    uint16_t lit_off[DM_FMT_MAX_LITS + 2];            // literal i = pool[lit_off[i] .. lit_off[i+1])
-    uint8_t pool[DM_FMT_POOL_BYTES];
+    uint16_t lit_off[DM_FMT_MAX_LITS];                // literal i starts at pool[lit_off[i]] (word index)
+    uint8_t lit_len[DM_FMT_MAX_LITS];                 // its length in bytes
+    uint32_t pool[DM_FMT_POOL_WORDS];                 // little-endian words, zero padded per literal
     // monitors bound to the format: header capture index or variable index
     int32_t mon_event[DM_MAX_KEYS];
     uint8_t mon_has_event[DM_MAX_KEYS];
@@ -43,49 +46,78 @@ struct DmFormat {
     uint8_t mon_index[DM_MAX_KEYS];                   // capture / variable index, DM_FMT_NONE = never present
 };
 
-// all lanes: does text[q, q+len) equal the literal?  (warp-uniform result)
-__device__ __forceinline__ bool dm_fmt_match_at(const uint8_t* __restrict__ buf, uint64_t q, const uint8_t* lit,
+// 4 text bytes starting at any byte offset (little endian).  Reads the two aligned words
+// around it: up to 7 bytes past `p`, covered by the slack every message buffer carries.
+__device__ __forceinline__ uint32_t dm_fmt_load4(const uint8_t* __restrict__ buf, uint32_t p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(buf) + p;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint32_t dm_fmt_tail_mask(uint32_t nbytes) {     // nbytes in 1..4
+    return 0xFFFFFFFFu >> (8u * (4u - nbytes));
+}
+
+// dm_fp64 of text[p, p+n) with word loads
+__device__ __forceinline__ uint64_t dm_fmt_fp64(const uint8_t* __restrict__ buf, uint32_t p, uint32_t n) {
+    DmHashState st;
+    dm_hash_init(st);
+    for (uint32_t i = 0; i < n; i += 4) {
+        uint32_t w = dm_fmt_load4(buf, p + i);
+        if (n - i < 4) w &= dm_fmt_tail_mask(n - i);
+        dm_hash_word(st, w);
+    }
+    return dm_hash_final(st, n);
+}
+
+// all lanes: does text[q, q+len) equal the literal?  (warp-uniform result; lane j checks word j)
+__device__ __forceinline__ bool dm_fmt_match_at(const uint8_t* __restrict__ buf, uint32_t q, const uint32_t* lit,
                                                 uint32_t len, uint32_t lane) {
     bool ok = true;
-    for (uint32_t j = lane; j < len; j += 32) ok = ok && (buf[q + j] == lit[j]);
+    for (uint32_t j = lane * 4; j < len; j += 128) {
+        const uint32_t m = len - j >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len - j);
+        ok = ok && (((dm_fmt_load4(buf, q + j) ^ lit[j >> 2]) & m) == 0);
+    }
     return __all_sync(0xffffffffu, ok);
 }
 
-// all lanes: earliest q in [pos, e - len] with text[q, q+len) == literal, or ~0ull
-__device__ __forceinline__ uint64_t dm_fmt_find(const uint8_t* __restrict__ buf, uint64_t pos, uint64_t e,
-                                                const uint8_t* lit, uint32_t len, uint32_t lane) {
-    if (e < pos + len) return ~0ull;
-    const uint64_t last = e - len;                    // last admissible start
-    const uint8_t c0 = lit[0];
-    for (uint64_t base = pos; base <= last; base += 32) {
-        const uint64_t p = base + lane;
+// all lanes: earliest q in [pos, e - len] with text[q, q+len) == literal, or DM_FMT_NOT_FOUND (len >= 1)
+__device__ __forceinline__ uint32_t dm_fmt_find(const uint8_t* __restrict__ buf, uint32_t pos, uint32_t e,
+                                                const uint32_t* lit, uint32_t len, uint32_t lane) {
+    if (e < pos + len) return DM_FMT_NOT_FOUND;
+    const uint32_t last = e - len;                    // last admissible start
+    const uint32_t w0 = lit[0];
+    const uint32_t m0 = len >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len);
+    for (uint32_t base = pos; base <= last; base += 32) {
+        const uint32_t p = base + lane;
         bool m = false;
-        if (p <= last && buf[p] == c0) {
+        if (p <= last && ((dm_fmt_load4(buf, p) ^ w0) & m0) == 0) {
             m = true;
-            for (uint32_t j = 1; j < len; ++j)
-                if (buf[p + j] != lit[j]) { m = false; break; }
+            for (uint32_t j = 4; j < len; j += 4) {     // the few lanes whose first word matched
+                const uint32_t lm = len - j >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len - j);
+                if (((dm_fmt_load4(buf, p + j) ^ lit[j >> 2]) & lm) != 0) { m = false; break; }
+            }
         }
         const uint32_t b = __ballot_sync(0xffffffffu, m);
         if (b) return base + (uint32_t)(__ffs(b) - 1);
     }
-    return ~0ull;
+    return DM_FMT_NOT_FOUND;
 }
 
-// Match chain `c` against text [s, e).  Warp-uniform result; on success lane i holds capture i
-// in (cap_s, cap_l) for i < number of captures (other lanes: cap_l = 0, cap_s = e).
-__device__ bool dm_fmt_match_chain(const DmFormat& f, uint32_t c, const uint8_t* __restrict__ buf, uint64_t s,
-                                   uint64_t e, uint32_t lane, uint64_t& cap_s, uint32_t& cap_l, uint32_t& n_caps) {
+// Match chain `c` against text [s, e) (byte offsets into buf).  Warp-uniform result; on success
+// lane i holds capture i in (cap_s, cap_l) for i < n_caps (other lanes: cap_l = 0).
+__device__ bool dm_fmt_match_chain(const DmFormat& f, uint32_t c, const uint8_t* __restrict__ buf, uint32_t s,
+                                   uint32_t e, uint32_t lane, uint32_t& cap_s, uint32_t& cap_l, uint32_t& n_caps) {
     const uint32_t first = f.chain_first[c];
     const uint32_t n = (uint32_t)f.chain_first[c + 1] - first;
     const bool endcap = f.chain_endcap[c] != 0;
-    uint64_t pos = s;
+    uint32_t pos = s;
     cap_s = e;
     cap_l = 0;
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t lo = f.lit_off[first + i];
-        const uint32_t len = (uint32_t)f.lit_off[first + i + 1] - lo;
-        const uint8_t* lit = f.pool + lo;
-        uint64_t q;
+        const uint32_t len = f.lit_len[first + i];
+        const uint32_t* lit = f.pool + f.lit_off[first + i];
+        uint32_t q;
         if (i == 0) {                                             // anchored at the start
             if (e < pos + len || !dm_fmt_match_at(buf, pos, lit, len, lane)) return false;
             q = pos;
@@ -95,14 +127,14 @@ __device__ bool dm_fmt_match_chain(const DmFormat& f, uint32_t c, const uint8_t*
             if (!dm_fmt_match_at(buf, q, lit, len, lane)) return false;
         } else {
             q = dm_fmt_find(buf, pos, e, lit, len, lane);
-            if (q == ~0ull) return false;
+            if (q == DM_FMT_NOT_FOUND) return false;
         }
-        if (i > 0 && lane == i - 1) { cap_s = pos; cap_l = (uint32_t)(q - pos); }
+        if (i > 0 && lane == i - 1) { cap_s = pos; cap_l = q - pos; }
         pos = q + len;
     }
     if (endcap) {
-        if (n == 0) { if (lane == 0) { cap_s = s; cap_l = (uint32_t)(e - s); } }   // the chain is one capture
-        else if (lane == n - 1) { cap_s = pos; cap_l = (uint32_t)(e - pos); }
+        if (n == 0) { if (lane == 0) { cap_s = s; cap_l = e - s; } }   // the chain is one capture
+        else if (lane == n - 1) { cap_s = pos; cap_l = e - pos; }
         n_caps = n ? n : 1;
     } else {
         if (pos != e) return false;                              // (n == 1: the literal is the whole text)
@@ -133,15 +165,15 @@ __global__ void __launch_bounds__(256) dm_k_format_lines(DmDetectArgs a, const D
     const uint64_t hi = a.line_hi < n_lines ? a.line_hi : n_lines;
 
     for (uint64_t line = a.line_lo + warp_id; line < hi; line += warps_total) {
-        const uint64_t s = a.line_start[line];
-        const uint64_t e = (uint64_t)a.line_start[line + 1] - 1;     // the '\n' (or nbytes)
-        uint64_t hs, vs = e;
+        const uint32_t s = a.line_start[line];
+        const uint32_t e = a.line_start[line + 1] - 1;               // the '\n' (or nbytes)
+        uint32_t hs, vs = e;
         uint32_t hl, vl = 0, n_hcaps = 0, n_vars = 0;
         const bool hok = dm_fmt_match_chain(sf, 0, buf, s, e, lane, hs, hl, n_hcaps);
         int32_t eid = -1;
         if (hok && sf.content_capture != DM_FMT_NONE && sf.n_chains > 1) {
-            const uint64_t cs = __shfl_sync(0xffffffffu, hs, sf.content_capture);
-            const uint64_t ce = cs + __shfl_sync(0xffffffffu, hl, sf.content_capture);
+            const uint32_t cs = __shfl_sync(0xffffffffu, hs, sf.content_capture);
+            const uint32_t ce = cs + __shfl_sync(0xffffffffu, hl, sf.content_capture);
             for (uint32_t t = 1; t < sf.n_chains; ++t) {
                 if (dm_fmt_match_chain(sf, t, buf, cs, ce, lane, vs, vl, n_vars)) { eid = (int32_t)t - 1; break; }
             }
@@ -154,15 +186,15 @@ __global__ void __launch_bounds__(256) dm_k_format_lines(DmDetectArgs a, const D
         const uint32_t idx = mon ? sf.mon_index[k] : DM_FMT_NONE;
         const uint32_t from = idx & 31u;
         // (every lane executes all four shuffles: the source register differs per lane)
-        const uint64_t xs_h = __shfl_sync(0xffffffffu, hs, from), xs_v = __shfl_sync(0xffffffffu, vs, from);
+        const uint32_t xs_h = __shfl_sync(0xffffffffu, hs, from), xs_v = __shfl_sync(0xffffffffu, vs, from);
         const uint32_t xl_h = __shfl_sync(0xffffffffu, hl, from), xl_v = __shfl_sync(0xffffffffu, vl, from);
-        const uint64_t xs = src ? xs_v : xs_h;
+        const uint32_t xs = src ? xs_v : xs_h;
         const uint32_t xl = src ? xl_v : xl_h;
         bool present = hok && mon && idx != DM_FMT_NONE && idx < (src ? n_vars : n_hcaps);
         if (present && sf.mon_has_event[k] && eid != sf.mon_event[k]) present = false;
         bool unk = false;
         if (present) {
-            const uint64_t key = dm_make_key(dm_fp64_bytes(buf + xs, xl), dm_field_salt(k));
+            const uint64_t key = dm_make_key(dm_fmt_fp64(buf, xs, xl), dm_field_salt(k));
             if (TRAIN) dm_table_insert(a.table, key, &a.hdr->error);
             else unk = !dm_table_contains(a.table, key);
         }

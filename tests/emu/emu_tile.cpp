@@ -311,6 +311,9 @@ extern "C" const char* emu_set_format(const DmMonitor* mons, uint32_t n_mons, co
 extern "C" int emu_process_format(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
                                   float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms) {
     if (!g_fmt_set) return -6;
+    std::vector<uint8_t> padded(nbytes + 64, 0);                 // the device buffer's zeroed slack
+    memcpy(padded.data(), msg, nbytes);
+    msg = padded.data();
     std::vector<uint32_t> ls;
     ls.push_back(0);
     for (uint64_t i = 0; i < nbytes; ++i)
