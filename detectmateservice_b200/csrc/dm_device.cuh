@@ -194,4 +194,5 @@ struct DmDetectArgs {
     uint32_t anomaly_cap;
     unsigned long long* stats;
     uint64_t line_lo, line_hi;        // records [line_lo, min(line_hi, n_lines)) are processed
+    uint64_t nbytes;                  // message size
 };

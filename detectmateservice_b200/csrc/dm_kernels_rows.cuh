@@ -51,6 +51,8 @@ struct DmRowsArgs {
     uint64_t n_train_lines;
     uint64_t max_lines;
     unsigned int* aux_counts;         // staged variant: list counters cleared by K_A (else NULL)
+    uint32_t* line_start;             // lanes variant: K_A also writes the record index (else NULL):
+                                      // line_start[g] = first byte of record g, line_start[n] = end sentinel
 };
 
 // 16-bit '\n' mask of this lane's chunk of a row, slack bytes behind the message dropped
@@ -68,6 +70,7 @@ __device__ __forceinline__ uint32_t dm_row_nl_mask(const uint4& v, uint64_t off,
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
     __shared__ uint32_t s_rowcnt[DMR_TILE_ROWS];
+    __shared__ uint32_t s_rowpre[DMR_TILE_ROWS];      // '\n' in front of each row, inside the tile
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_total;
     const uint8_t* __restrict__ buf = a.buf;
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
         __threadfence();
     }
     // newline count of each row of the tile: 8 warps x 8 rows, all 8 loads of a warp in flight
+    uint32_t nlm[8];                                  // this lane's '\n' masks (kept for the record index)
     {
         const uint32_t rr = warp * 8;
         uint4 v[8];
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const uint32_t m = off[i] < nbytes ? dm_row_nl_mask(v[i], off[i], nbytes) : 0u;
+            nlm[i] = m;
             const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
             if (lane == 0) s_rowcnt[rr + i] = c;
         }
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
         for (int i = 0; i < 2; ++i) {
             const uint32_t row = tile * DMR_TILE_ROWS + lane * 2 + i;
             if (row < a.n_rows) a.row_prefix[row] = run;
+            s_rowpre[lane * 2 + i] = run - (uint32_t)excl;
             run += c[i];
         }
         if (lane == 0) { s_base = excl; s_total = agg; }
@@ -175,8 +181,41 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
         }
     }
     __syncthreads();
-    // zero-fill the outputs of the records that end in this tile
     const unsigned long long base = s_base;
+    if (a.line_start) {
+        // lanes variant: the record index.  The '\n' at byte x with k '\n' in front of it ends
+        // record k, so record k+1 starts at x+1.  (Every record's outputs are written by its own
+        // lane there, no zero-fill.)
+        if (tile == 0 && threadIdx.x == 0) a.line_start[0] = 0;
+        if (tile == a.n_tiles - 1 && threadIdx.x == 0 && nbytes > 0 && buf[nbytes - 1] != 0x0Au) {
+            const unsigned long long n_lines = base + s_total;          // s_total counts the unterminated record
+            if (n_lines <= a.max_lines) a.line_start[n_lines] = (uint32_t)(nbytes + 1);
+        }
+        const uint32_t rr = warp * 8;
+        const uint32_t lt = dm_lanemask_lt();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t m = nlm[i];
+            // records in front of this lane's chunk: tile base + row prefix + lower lanes of the row
+            uint32_t incl = (uint32_t)__popc(m);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += y;
+            }
+            (void)lt;
+            unsigned long long k = base + s_rowpre[rr + i] + (incl - (uint32_t)__popc(m));
+            const uint64_t off = ((uint64_t)tile * DMR_TILE_ROWS + rr + i) * DMR_ROW + (uint64_t)lane * 16;
+            while (m) {
+                const uint32_t b = (uint32_t)__ffs(m) - 1u;
+                m &= m - 1;
+                ++k;
+                if (k <= a.max_lines) a.line_start[k] = (uint32_t)(off + b + 1);
+            }
+        }
+        return;
+    }
+    // zero-fill the outputs of the records that end in this tile
     const uint32_t total = s_total;
     for (uint32_t i = threadIdx.x; i < total; i += DMR_A_THREADS) {
         const unsigned long long g = base + i;
@@ -439,7 +478,7 @@ static inline int dm_rows_launch(DmRowsScratch* s, const uint8_t* d_buf, uint64_
     a.keys = d_keys; a.table = table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
     a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap; a.hdr = d_hdr; a.stats = d_stats;
     a.row_ctr = s->d_row_ctr; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
-    a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = s->ctr_base; a.aux_counts = nullptr;
+    a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = s->ctr_base; a.aux_counts = nullptr; a.line_start = nullptr;
     int launched = 0;
     dm_k_rowindex<<<a.n_tiles, DMR_A_THREADS, 0, st>>>(a);
     ++launched;

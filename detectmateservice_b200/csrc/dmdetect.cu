@@ -21,6 +21,7 @@
 #include "dm_kernels_values.cuh"
 #include "dm_kernels_records.cuh"
 #include "dm_kernels_format.cuh"
+#include "dm_kernels_lanes.cuh"
 #include "dm_format_host.h"
 
 // ---------------------------------------------------------------------------------------
@@ -229,6 +230,7 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
     if (env && strcmp(env, "rows") == 0) h->kernel_variant = 2;
     if (env && strcmp(env, "staged") == 0) h->kernel_variant = 3;
     if (env && strcmp(env, "cta") == 0) h->kernel_variant = 4;
+    if (env && strcmp(env, "lanes") == 0) h->kernel_variant = 5;
     if (h->kernel_variant == 4) {
         rc = dm_cta_scratch_create(&h->cta, h->sm_count);
         if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "cta occupancy query failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -358,7 +360,7 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         DmDetectArgs a;
         a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
         a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
-        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats;
+        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes;
         const int grid = h->sm_count * 8;
         if (n_train_lines > 0) {
             a.line_lo = 0; a.line_hi = n_train_lines;
@@ -369,6 +371,12 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         dm_k_format_lines<false><<<grid, 256, 0, st>>>(a, h->d_fmt);
         dm_prof_mark(h, st, 1);
         h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
+    } else if (h->kernel_variant == 5) {
+        const int rc = dm_lanes_launch(&h->rows, h->d_line_start, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags,
+                                       d_scores, out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines,
+                                       h->sm_count, st, dm_prof_mark_cb, h);
+        if (rc < 0) return dm_fail(DM_ERR_CUDA, "lanes kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->launches += (uint64_t)rc;
     } else if (h->kernel_variant == 0) {
         const uint32_t n_tiles = (uint32_t)((nbytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES);
         const int grid_tiles = std::max(1, std::min<int>((int)n_tiles, h->sm_count * 8));
@@ -380,7 +388,7 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         DmDetectArgs a;
         a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
         a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
-        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats;
+        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes;
         const int grid = h->sm_count * 8;
         if (n_train_lines > 0) {
             a.line_lo = 0; a.line_hi = n_train_lines;
@@ -707,7 +715,7 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     if (nbytes > h->max_batch_bytes)
         return dm_fail(DM_ERR_CAPACITY, "message of %llu bytes exceeds max_batch_bytes=%llu", (unsigned long long)nbytes, (unsigned long long)h->max_batch_bytes);
     if (nbytes && !host_buf) return dm_fail(DM_ERR_ARG, "host_buf is NULL");
-    if (h->kernel_variant < 2) return dm_fail(DM_ERR_STATE, "the pipelined path needs the rows or staged kernels");
+    if (h->kernel_variant < 2 || h->kernel_variant == 5) return dm_fail(DM_ERR_STATE, "the pipelined path needs the rows or staged kernels");
     if (h->fmt_set) return dm_fail(DM_ERR_STATE, "the pipelined path tokenises key=value records; with a log_format use dm_process_lines");
     DM_CUDA(cudaSetDevice(h->device));
     int rc = dm_slots_init(h);

@@ -13,6 +13,7 @@
 #include "dm_kernels_records.cuh"
 #include "dm_kernels_cta.cuh"
 #include "dm_kernels_format.cuh"
+#include "dm_kernels_lanes.cuh"
 #include "dm_format_host.h"
 
 thread_local emu_dim3 threadIdx;
@@ -176,7 +177,7 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
         a.keys = &h->keys; a.table = h->table; a.flags = flags; a.scores = scores; a.out_cap = cap;
         a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size(); a.hdr = &h->hdr; a.stats = h->stats;
         a.row_ctr = &h->row_ctr; a.n_train_lines = n_train; a.max_lines = h->max_lines;
-        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base; a.aux_counts = nullptr;
+        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base; a.aux_counts = nullptr; a.line_start = nullptr;
         if (staged) {
             static std::vector<DmCand> cand;
             static std::vector<DmField> fields;
@@ -333,6 +334,48 @@ extern "C" int emu_process_format(EmuHandle* h, const uint8_t* msg, uint64_t nby
     if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch(256, [&] { dm_k_format_lines<false>(a, &g_fmt); }); }
     *n_lines = n;
     *n_anoms = h->hdr.n_anomalies;
+    return 0;
+}
+
+// one thread per record (dm_kernels_lanes.cuh): K_A writes the record index, as in dm_lanes_launch
+extern "C" int emu_process_lanes(EmuHandle* h, const uint8_t* msg_in, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                 float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    uint8_t* buf = (uint8_t*)aligned_alloc(64, ((nbytes + 64 + 63) / 64) * 64 + 64);
+    memcpy(buf, msg_in, nbytes);
+    for (int i = 0; i < 64; ++i) buf[nbytes + i] = (i & 1) ? '\n' : '=';      // hostile slack
+    memset(&h->hdr, 0, sizeof(h->hdr));
+    *n_lines = 0; *n_anoms = 0; *err = 0;
+    const uint32_t n_rows = (uint32_t)((nbytes + DMR_ROW - 1) / DMR_ROW);
+    if (n_rows == 0) { free(buf); return 0; }
+    DmRowsArgs ra;
+    ra.buf = buf; ra.nbytes = nbytes; ra.n_rows = n_rows; ra.n_tiles = (n_rows + DMR_TILE_ROWS - 1) / DMR_TILE_ROWS;
+    h->row_prefix.assign(n_rows + 1, 0xDEADBEEFu);
+    if (h->rows_tile_state.size() < ra.n_tiles + 1) h->rows_tile_state.resize(ra.n_tiles + 1, 0);
+    ra.row_prefix = h->row_prefix.data(); ra.tile_state = h->rows_tile_state.data();
+    h->rows_epoch = (h->rows_epoch % 0x3FFFFFFEu) + 1u;
+    ra.epoch = h->rows_epoch;
+    ra.keys = &h->keys; ra.table = h->table; ra.flags = flags; ra.scores = scores; ra.out_cap = cap;
+    ra.anomalies = h->anoms.data(); ra.anomaly_cap = (uint32_t)h->anoms.size(); ra.hdr = &h->hdr; ra.stats = h->stats;
+    ra.row_ctr = &h->row_ctr; ra.n_train_lines = n_train; ra.max_lines = h->max_lines;
+    ra.line_lo = 0; ra.line_hi = ~0ull; ra.ctr_base = h->row_ctr_base; ra.aux_counts = nullptr;
+    std::vector<uint32_t> ls(h->max_lines + 2, 0xDEADBEEFu);
+    ra.line_start = ls.data();
+    emu_launch_grid(ra.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(ra); });
+    const uint64_t n = h->hdr.n_lines;
+    if (h->hdr.error == 0 && n <= cap) {
+        DmDetectArgs a;
+        a.buf = buf; a.line_start = ls.data(); a.hdr_in = &h->hdr; a.hdr = &h->hdr; a.keys = &h->keys; a.table = h->table;
+        a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
+        a.stats = h->stats; a.nbytes = nbytes;
+        const uint64_t nt = std::min<uint64_t>(n_train, n);
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + DM_LANES_THREADS - 1) / DM_LANES_THREADS, 5));
+        if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch_grid(blocks, DM_LANES_THREADS, [&] { dm_k_lanes<true>(a); }); }
+        if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch_grid(blocks, DM_LANES_THREADS, [&] { dm_k_lanes<false>(a); }); }
+    }
+    free(buf);
+    *n_lines = h->hdr.n_lines;
+    *n_anoms = h->hdr.n_anomalies;
+    *err = h->hdr.error;
     return 0;
 }
 

@@ -16,7 +16,7 @@ from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["v1", "tile", "rows", "staged", "cta"]
+VARIANTS = ["v1", "tile", "rows", "staged", "cta", "lanes"]
 SCORE_TOL = 1e-5
 
 
