@@ -159,7 +159,7 @@ static inline int dm_lanes_launch(DmRowsScratch* s, uint32_t* d_line_start, cons
     ra.anomalies = d_anoms; ra.anomaly_cap = anomaly_cap; ra.hdr = d_hdr; ra.stats = d_stats;
     ra.row_ctr = s->d_row_ctr; ra.n_train_lines = n_train_lines; ra.max_lines = max_lines;
     ra.line_lo = 0; ra.line_hi = ~0ull; ra.ctr_base = s->ctr_base; ra.aux_counts = nullptr;
-    ra.line_start = d_line_start;
+    ra.line_start = d_line_start; ra.group = DMR_GROUP;
     int launched = 0;
     dm_k_rowindex<<<ra.n_tiles, DMR_A_THREADS, 0, st>>>(ra);
     ++launched;

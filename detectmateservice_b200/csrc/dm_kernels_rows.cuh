@@ -51,6 +51,7 @@ struct DmRowsArgs {
     uint64_t n_train_lines;
     uint64_t max_lines;
     unsigned int* aux_counts;         // staged variant: list counters cleared by K_A (else NULL)
+    uint32_t group;                   // rows fetched per atomic by a K_B warp
     uint32_t* line_start;             // lanes variant: K_A also writes the record index (else NULL):
                                       // line_start[g] = first byte of record g, line_start[n] = end sentinel
 };
@@ -327,10 +328,10 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
 
     for (;;) {
         unsigned long long first_row = 0;
-        if (lane == 0) first_row = (atomicAdd(a.row_ctr, (unsigned long long)DMR_GROUP) - a.ctr_base);
+        if (lane == 0) first_row = (atomicAdd(a.row_ctr, (unsigned long long)a.group) - a.ctr_base);
         first_row = __shfl_sync(0xffffffffu, first_row, 0);
         if (first_row >= a.n_rows) break;
-        const uint32_t r_end = (uint32_t)(first_row + DMR_GROUP < a.n_rows ? first_row + DMR_GROUP : a.n_rows);
+        const uint32_t r_end = (uint32_t)(first_row + a.group < a.n_rows ? first_row + a.group : a.n_rows);
         for (uint32_t row = (uint32_t)first_row; row < r_end; ++row) {
             const uint64_t off = (uint64_t)row * DMR_ROW + (uint64_t)lane * 16;
             uint32_t nl16 = 0, eq16 = 0;
@@ -434,6 +435,7 @@ struct DmRowsScratch {
     unsigned long long ctr_base = 0;
     uint32_t epoch = 0;
     int grid_b = 0;
+    uint32_t group = DMR_GROUP;       // DM_ROWS_GROUP
 };
 
 static inline int dm_rows_scratch_create(DmRowsScratch* s, uint64_t max_batch_bytes, int sm_count) {
@@ -447,6 +449,8 @@ static inline int dm_rows_scratch_create(DmRowsScratch* s, uint64_t max_batch_by
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_rows<false, false>, DMR_B_THREADS, 0) != cudaSuccess) return DM_ERR_CUDA;
     if (per_sm < 1) per_sm = 1;
+    const char* grp = getenv("DM_ROWS_GROUP");             // tuning knob: rows per atomic fetch
+    if (grp && atoi(grp) >= 1 && atoi(grp) <= 64) s->group = (uint32_t)atoi(grp);
     const char* cap = getenv("DM_ROWS_CTAS_PER_SM");       // tuning knob: fewer, longer-lived warps
     if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
     s->grid_b = sm_count * per_sm;
@@ -482,12 +486,14 @@ static inline int dm_rows_launch(DmRowsScratch* s, const uint8_t* d_buf, uint64_
     int launched = 0;
     dm_k_rowindex<<<a.n_tiles, DMR_A_THREADS, 0, st>>>(a);
     ++launched;
-    const uint32_t groups = (n_rows + DMR_GROUP - 1) / DMR_GROUP;
+    const uint32_t G = s->group;
+    a.group = G;
+    const uint32_t groups = (n_rows + G - 1) / G;
     const int warps_needed = (int)((groups + 0) < 1 ? 1 : groups);
     int grid = (warps_needed + DMR_B_WARPS - 1) / DMR_B_WARPS;
     if (grid > s->grid_b) grid = s->grid_b;
     // every warp of the grid ends with one failing fetch of DMR_GROUP rows
-    const unsigned long long per_launch = (unsigned long long)groups * DMR_GROUP + (unsigned long long)grid * DMR_B_WARPS * DMR_GROUP;
+    const unsigned long long per_launch = (unsigned long long)groups * G + (unsigned long long)grid * DMR_B_WARPS * G;
     if (n_train_lines > 0) {
         a.line_lo = 0; a.line_hi = n_train_lines; a.ctr_base = s->ctr_base;
         dm_k_rows<true, true><<<grid, DMR_B_THREADS, 0, st>>>(a);

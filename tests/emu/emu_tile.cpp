@@ -177,7 +177,7 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
         a.keys = &h->keys; a.table = h->table; a.flags = flags; a.scores = scores; a.out_cap = cap;
         a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size(); a.hdr = &h->hdr; a.stats = h->stats;
         a.row_ctr = &h->row_ctr; a.n_train_lines = n_train; a.max_lines = h->max_lines;
-        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base; a.aux_counts = nullptr; a.line_start = nullptr;
+        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base; a.aux_counts = nullptr; a.line_start = nullptr; a.group = DMR_GROUP;
         if (staged) {
             static std::vector<DmCand> cand;
             static std::vector<DmField> fields;
@@ -359,7 +359,7 @@ extern "C" int emu_process_lanes(EmuHandle* h, const uint8_t* msg_in, uint64_t n
     ra.row_ctr = &h->row_ctr; ra.n_train_lines = n_train; ra.max_lines = h->max_lines;
     ra.line_lo = 0; ra.line_hi = ~0ull; ra.ctr_base = h->row_ctr_base; ra.aux_counts = nullptr;
     std::vector<uint32_t> ls(h->max_lines + 2, 0xDEADBEEFu);
-    ra.line_start = ls.data();
+    ra.line_start = ls.data(); ra.group = DMR_GROUP;
     emu_launch_grid(ra.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(ra); });
     const uint64_t n = h->hdr.n_lines;
     if (h->hdr.error == 0 && n <= cap) {
