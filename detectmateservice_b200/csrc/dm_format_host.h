@@ -105,6 +105,23 @@ inline bool dm_format_build(const char* log_format, const char* content_name, ui
             b.f.mon_index[k] = (uint8_t)hm.m[k].var_index;
         }
     }
+    // captures each chain has to keep for the thread-per-record kernel
+    {
+        DmFormat& f = b.f;
+        if (f.content_capture != DM_FMT_NONE && f.n_chains > 1) f.chain_need[0] |= 1u << f.content_capture;
+        for (uint32_t k = 0; k < hm.n; ++k) {
+            const uint32_t idx = f.mon_index[k];
+            if (idx == DM_FMT_NONE) continue;
+            if (f.mon_source[k] == 0) { f.chain_need[0] |= 1u << idx; continue; }
+            for (uint32_t c = 1; c < f.n_chains; ++c)
+                if (!f.mon_has_event[k] || f.mon_event[k] == (int32_t)c - 1) f.chain_need[c] |= 1u << idx;
+        }
+        f.max_slots = 1;
+        for (uint32_t c = 0; c < f.n_chains; ++c) {
+            const uint32_t n = (uint32_t)__builtin_popcount(f.chain_need[c]);
+            if (n > f.max_slots) f.max_slots = n;
+        }
+    }
     *out = b.f;
     return true;
 }

@@ -96,6 +96,8 @@ struct dm_handle {
     DmMonitors h_mons;             // host copy (dm_set_monitors + dm_set_combos)
     DmFormat* d_fmt = nullptr;     // log_format + templates (dm_set_format)
     bool fmt_set = false;
+    uint32_t fmt_slots = 1;        // DmFormat.max_slots (dynamic shared memory of the thread-per-record kernel)
+    bool fmt_warp_kernel = false;  // DM_FORMAT_KERNEL=warp: one warp per record (the first implementation)
     // pipelined host path: two slots
     struct Slot {
         uint8_t* d_in = nullptr; uint8_t* d_flags = nullptr; float* d_scores = nullptr;
@@ -348,8 +350,43 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
     if (h->kernel_variant < 2 || nbytes == 0 || h->fmt_set) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
     h->last_nbytes = nbytes;
 
-    if (h->fmt_set) {
-        // log_format / template mode: line index, then one warp per record (dm_kernels_format.cuh)
+    if (h->fmt_set && !h->fmt_warp_kernel) {
+        // log_format / template mode: K_A writes the record index, then one THREAD per record
+        const uint32_t n_rows = (uint32_t)((nbytes + DMR_ROW - 1) / DMR_ROW);
+        if (n_rows > h->rows.max_rows) return dm_fail(DM_ERR_CAPACITY, "message too large for the row index");
+        if (n_rows > 0) {
+            DmRowsArgs ra;
+            ra.buf = d_buf; ra.nbytes = nbytes; ra.n_rows = n_rows;
+            ra.n_tiles = (n_rows + DMR_TILE_ROWS - 1) / DMR_TILE_ROWS;
+            ra.row_prefix = h->rows.d_row_prefix; ra.tile_state = h->rows.d_tile_state;
+            h->rows.epoch = (h->rows.epoch % 0x3FFFFFFEu) + 1u;
+            ra.epoch = h->rows.epoch;
+            ra.keys = h->d_keys; ra.table = h->table; ra.flags = d_flags; ra.scores = d_scores; ra.out_cap = out_cap;
+            ra.anomalies = h->d_anoms; ra.anomaly_cap = h->anomaly_cap; ra.hdr = h->d_hdr; ra.stats = h->d_stats;
+            ra.row_ctr = h->rows.d_row_ctr; ra.n_train_lines = n_train_lines; ra.max_lines = h->max_lines;
+            ra.line_lo = 0; ra.line_hi = ~0ull; ra.ctr_base = h->rows.ctr_base; ra.aux_counts = nullptr;
+            ra.line_start = h->d_line_start; ra.group = DMR_GROUP;
+            dm_k_rowindex<<<ra.n_tiles, DMR_A_THREADS, 0, st>>>(ra);
+            DmDetectArgs a;
+            a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
+            a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
+            a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes;
+            const uint64_t max_recs = std::min<uint64_t>(nbytes / 2 + 1, h->max_lines);
+            const uint64_t want = (max_recs + DM_FMTL_THREADS - 1) / DM_FMTL_THREADS;
+            const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * 32));
+            const size_t smem = (size_t)2 * h->fmt_slots * DM_FMTL_THREADS * sizeof(uint2);
+            if (n_train_lines > 0) {
+                a.line_lo = 0; a.line_hi = n_train_lines;
+                dm_k_format_lanes<true><<<grid, DM_FMTL_THREADS, smem, st>>>(a, h->d_fmt);
+            }
+            a.line_lo = n_train_lines; a.line_hi = ~0ull;
+            dm_prof_mark(h, st, 0);
+            dm_k_format_lanes<false><<<grid, DM_FMTL_THREADS, smem, st>>>(a, h->d_fmt);
+            dm_prof_mark(h, st, 1);
+            h->launches += 2 + (n_train_lines > 0 ? 1 : 0);
+        }
+    } else if (h->fmt_set) {
+        // log_format / template mode, first implementation: line index, then one warp per record
         const uint32_t n_tiles = (uint32_t)((nbytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES);
         const int grid_tiles = std::max(1, std::min<int>((int)n_tiles, h->sm_count * 8));
         dm_k_count_newlines<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts);
@@ -601,7 +638,12 @@ extern "C" int dm_set_format(dm_handle* h, const char* log_format, const char* c
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->last_stream);
         if (e == cudaSuccess) e = cudaMemcpy(h->d_fmt, f, sizeof(DmFormat), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = dm_fail(DM_ERR_CUDA, "dm_set_format: %s", cudaGetErrorString(e));
-        else h->fmt_set = true;
+        else {
+            h->fmt_set = true;
+            h->fmt_slots = f->max_slots;
+            const char* fk = getenv("DM_FORMAT_KERNEL");
+            h->fmt_warp_kernel = fk && strcmp(fk, "warp") == 0;
+        }
     }
     delete f;
     return rc;

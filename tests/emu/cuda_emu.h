@@ -28,6 +28,9 @@
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }
+extern std::vector<uint8_t> g_emu_dyn_smem;           // stands in for `extern __shared__` (blocks run one at a time)
 static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
 
 extern thread_local emu_dim3 threadIdx;

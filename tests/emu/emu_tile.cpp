@@ -21,6 +21,7 @@ thread_local emu_dim3 blockIdx;
 emu_dim3 blockDim, gridDim;
 EmuBlock* g_emu_block = nullptr;
 std::atomic<int> g_emu_or_flag[2];
+std::vector<uint8_t> g_emu_dyn_smem;
 
 // Runs the blocks of a grid ONE AFTER THE OTHER (block b sees blocks < b complete, which
 // satisfies the look-back dependencies of the kernels under test).
@@ -296,6 +297,8 @@ extern "C" int emu_process_records(EmuHandle* h, const DmMonitor* mons, uint32_t
 // starts are computed here on the host; the device's index kernels are the v1 ones, GPU-tested).
 static DmFormat g_fmt;
 static bool g_fmt_set = false;
+static bool g_fmt_lanes = true;                       // which of the two format kernels emu_process_format runs
+extern "C" void emu_format_kernel(int lanes) { g_fmt_lanes = lanes != 0; }
 static char g_fmt_err[256];
 extern "C" const char* emu_set_format(const DmMonitor* mons, uint32_t n_mons, const char* log_format, const char* content_name,
                                       uint32_t n_templates, const char* const* templates) {
@@ -330,8 +333,14 @@ extern "C" int emu_process_format(EmuHandle* h, const uint8_t* msg, uint64_t nby
     a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
     a.stats = h->stats;
     const uint64_t nt = std::min<uint64_t>(n_train, n);
-    if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch(256, [&] { dm_k_format_lines<true>(a, &g_fmt); }); }
-    if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch(256, [&] { dm_k_format_lines<false>(a, &g_fmt); }); }
+    if (g_fmt_lanes) {
+        g_emu_dyn_smem.assign((size_t)2 * g_fmt.max_slots * DM_FMTL_THREADS * sizeof(uint2), 0);
+        if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<true>(a, &g_fmt); }); }
+        if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<false>(a, &g_fmt); }); }
+    } else {
+        if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch(256, [&] { dm_k_format_lines<true>(a, &g_fmt); }); }
+        if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch(256, [&] { dm_k_format_lines<false>(a, &g_fmt); }); }
+    }
     *n_lines = n;
     *n_anoms = h->hdr.n_anomalies;
     return 0;

@@ -153,6 +153,18 @@ def _monitor_array(mons):
     return arr
 
 
+EMU_KERNEL = "lanes"
+
+
+@pytest.fixture(params=["lanes", "warp"])
+def emu_kernel(request):
+    """Both device decompositions of the matcher: one thread per record (default) / one warp per record."""
+    global EMU_KERNEL
+    EMU_KERNEL = request.param
+    yield request.param
+    EMU_KERNEL = "lanes"
+
+
 class EmuFormat:
     def __init__(self, cfg, log_format, templates=(), name="NewValueDetector"):
         import emu_harness
@@ -161,6 +173,7 @@ class EmuFormat:
         self.lib = C.CDLL(emu_harness.build())
         self.det = emu_harness.EmuDetector([m.key for m in self.mons], table_log2=12)
         L = self.lib
+        L.emu_format_kernel(1 if EMU_KERNEL == "lanes" else 0)
         L.emu_set_format.restype = C.c_char_p
         L.emu_set_format.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p)]
         L.emu_process_format.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -187,7 +200,7 @@ def _mask_of(alerts, mons):
     return sum(1 << i for i, m in enumerate(mons) if m.alert_key in alerts)
 
 
-def test_emu_kernel_docs_nginx_golden():
+def test_emu_kernel_docs_nginx_golden(emu_kernel):
     buf = b"\n".join(nginx_line(u) for u in ("/hello", "/world", "/foobar", "/hello", "/x y")) + b"\n"
     emu = EmuFormat(NGINX_CFG, NGINX)
     f, s, masks = emu.process(buf, 2)
@@ -204,7 +217,7 @@ AUDIT_CFG = {"detectors": {"NewValueDetector": {
                40: {"never": {"variables": [{"pos": 0}]}}}}}}
 
 
-def test_emu_kernel_audit_templates(golden_dir):
+def test_emu_kernel_audit_templates(golden_dir, emu_kernel):
     tm = audit_templates(golden_dir)
     buf = open(os.path.join(golden_dir, "audit_sample.log"), "rb").read()
     buf += b"type=WEIRD msg=audit(1.0:1): totally unlike=any template\nnot an audit line at all\n\n"
@@ -222,7 +235,7 @@ def test_emu_kernel_audit_templates(golden_dir):
     assert stats[7] == bad
 
 
-def test_emu_kernel_fuzz_formats():
+def test_emu_kernel_fuzz_formats(emu_kernel):
     r = np.random.Generator(np.random.PCG64(17))
     checked = 0
     for lits, ends in fuzz_formats(r, 25):
@@ -250,7 +263,7 @@ SYNTH_CFG = {"detectors": {"NewValueDetector": {"method_type": "new_value_detect
                                                   {"pos": 9, "name": "terminal"}, {"pos": 10, "name": "res"}]}}}}}}
 
 
-def test_emu_kernel_synthetic_header_and_variable_monitors():
+def test_emu_kernel_synthetic_header_and_variable_monitors(emu_kernel):
     """Header-capture and template-variable monitors side by side (different source lanes), on
     the config-2 synthetic records with their injected anomalies."""
     from detectmateservice_b200.synth import AuditSynth
