@@ -257,6 +257,7 @@ __device__ __forceinline__ uint32_t dm_fmtl_find(const uint8_t* __restrict__ buf
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0);
     uint32_t sh = (uint32_t)((reinterpret_cast<uintptr_t>(buf) + pos) & 3u) * 8u;
     uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
+    uint32_t found = DM_FMT_NOT_FOUND;
     for (uint32_t q = pos; q <= last; ++q) {
         const uint32_t x = __funnelshift_r(lo, hi, sh);
         if (((x ^ w0) & m0) == 0) {
@@ -265,12 +266,12 @@ __device__ __forceinline__ uint32_t dm_fmtl_find(const uint8_t* __restrict__ buf
                 const uint32_t lm = len - j >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len - j);
                 if (((dm_fmt_load4(buf, q + j) ^ lit[j >> 2]) & lm) != 0) { ok = false; break; }
             }
-            if (ok) return q;
+            if (ok) { found = q; break; }
         }
         sh += 8;
         if (sh == 32) { sh = 0; lo = hi; ++wp; hi = __ldg(wp + 1); }
     }
-    return DM_FMT_NOT_FOUND;
+    return found;
 }
 
 __device__ __forceinline__ bool dm_fmtl_match_at(const uint8_t* __restrict__ buf, uint32_t q, const uint32_t* lit, uint32_t len) {
@@ -283,32 +284,41 @@ __device__ __forceinline__ bool dm_fmtl_match_at(const uint8_t* __restrict__ buf
 
 // One lane matches chain c against text [s, e); needed captures go to caps[slot * DM_FMTL_THREADS]
 // (the caller passes its own column).  Returns the number of captures, or 0xFFFFFFFF on mismatch.
+// EVERY lane of the warp calls this with the same chain and runs the same number of steps (a lane
+// that is inactive or has already failed just idles): the __syncwarp() after each literal is
+// what keeps the 32 records of a warp in lockstep -- without it the lanes drift apart through
+// the data-dependent search loops and the warp degenerates to 3 active threads per instruction.
 __device__ uint32_t dm_fmtl_match_chain(const DmFormat& f, uint32_t c, const uint8_t* __restrict__ buf, uint32_t s,
-                                        uint32_t e, uint2* caps) {
+                                        uint32_t e, uint2* caps, bool active) {
     const uint32_t first = f.chain_first[c];
     const uint32_t n = (uint32_t)f.chain_first[c + 1] - first;
     const bool endcap = f.chain_endcap[c] != 0;
     const uint32_t need = f.chain_need[c];
     uint32_t pos = s;
+    bool ok = active;
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t len = f.lit_len[first + i];
-        const uint32_t* lit = f.pool + f.lit_off[first + i];
-        uint32_t q;
-        if (i == 0) {
-            if (e < pos + len || !dm_fmtl_match_at(buf, pos, lit, len)) return 0xFFFFFFFFu;
-            q = pos;
-        } else if (i == n - 1 && !endcap) {
-            if (e < pos + len) return 0xFFFFFFFFu;
-            q = e - len;
-            if (!dm_fmtl_match_at(buf, q, lit, len)) return 0xFFFFFFFFu;
-        } else {
-            q = dm_fmtl_find(buf, pos, e, lit, len);
-            if (q == DM_FMT_NOT_FOUND) return 0xFFFFFFFFu;
+        if (ok) {
+            const uint32_t len = f.lit_len[first + i];
+            const uint32_t* lit = f.pool + f.lit_off[first + i];
+            uint32_t q = DM_FMT_NOT_FOUND;
+            if (i == 0) {
+                if (e >= pos + len && dm_fmtl_match_at(buf, pos, lit, len)) q = pos;
+            } else if (i == n - 1 && !endcap) {
+                if (e >= pos + len && dm_fmtl_match_at(buf, e - len, lit, len)) q = e - len;
+            } else {
+                q = dm_fmtl_find(buf, pos, e, lit, len);
+            }
+            if (q == DM_FMT_NOT_FOUND) {
+                ok = false;
+            } else {
+                if (i > 0 && ((need >> (i - 1)) & 1u))
+                    caps[(uint32_t)__popc(need & ((1u << (i - 1)) - 1u)) * DM_FMTL_THREADS] = make_uint2(pos, q - pos);
+                pos = q + len;
+            }
         }
-        if (i > 0 && ((need >> (i - 1)) & 1u))
-            caps[(uint32_t)__popc(need & ((1u << (i - 1)) - 1u)) * DM_FMTL_THREADS] = make_uint2(pos, q - pos);
-        pos = q + len;
+        __syncwarp();
     }
+    if (!ok) return 0xFFFFFFFFu;
     if (endcap) {
         const uint32_t ci = n ? n - 1 : 0;
         const uint32_t cs = n ? pos : s;
@@ -347,41 +357,49 @@ __global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArg
     const uint64_t hi = a.line_hi < n_lines ? a.line_hi : n_lines;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 
-    for (uint64_t line = a.line_lo + (uint64_t)blockIdx.x * blockDim.x + tid; line < hi; line += stride) {
-        const uint32_t s = a.line_start[line];
-        const uint32_t e = a.line_start[line + 1] - 1;
-        const uint32_t n_hcaps = dm_fmtl_match_chain(sf, 0, buf, s, e, hcap);
+    // the warps iterate a warp-uniform number of times; a lane without a record idles through the
+    // same steps (see dm_fmtl_match_chain)
+    const uint64_t warp_first = a.line_lo + (uint64_t)blockIdx.x * blockDim.x + (tid & ~31u);
+    for (uint64_t wbase = warp_first; wbase < hi; wbase += stride) {
+        const uint64_t line = wbase + (tid & 31u);
+        const bool act = line < hi;
+        const uint32_t s = act ? a.line_start[line] : 0u;
+        const uint32_t e = act ? a.line_start[line + 1] - 1 : 0u;
+        const uint32_t n_hcaps = dm_fmtl_match_chain(sf, 0, buf, s, e, hcap, act);
         const bool hok = n_hcaps != 0xFFFFFFFFu;
         int32_t eid = -1;
         uint32_t n_vars = 0;
-        if (hok && sf.content_capture != DM_FMT_NONE && sf.n_chains > 1) {
-            const uint2 cc = hcap[(uint32_t)__popc(sf.chain_need[0] & ((1u << sf.content_capture) - 1u)) * DM_FMTL_THREADS];
+        if (sf.content_capture != DM_FMT_NONE) {
+            uint2 cc = make_uint2(0, 0);
+            if (hok) cc = hcap[(uint32_t)__popc(sf.chain_need[0] & ((1u << sf.content_capture) - 1u)) * DM_FMTL_THREADS];
             for (uint32_t t = 1; t < sf.n_chains; ++t) {
-                const uint32_t nv = dm_fmtl_match_chain(sf, t, buf, cc.x, cc.x + cc.y, vcap);
-                if (nv != 0xFFFFFFFFu) { eid = (int32_t)t - 1; n_vars = nv; break; }
+                const uint32_t nv = dm_fmtl_match_chain(sf, t, buf, cc.x, cc.x + cc.y, vcap, hok && eid < 0);
+                if (nv != 0xFFFFFFFFu) { eid = (int32_t)t - 1; n_vars = nv; }
             }
         }
         uint32_t unknown = 0;
-        if (hok) {
-            for (uint32_t k = 0; k < sf.n_mons; ++k) {
-                const uint32_t idx = sf.mon_index[k];
-                if (idx == DM_FMT_NONE) continue;
-                if (sf.mon_has_event[k] && eid != sf.mon_event[k]) continue;
-                uint2 cap;
+        for (uint32_t k = 0; k < sf.n_mons; ++k) {
+            const uint32_t idx = sf.mon_index[k];
+            bool use = hok && idx != DM_FMT_NONE && !(sf.mon_has_event[k] && eid != sf.mon_event[k]);
+            uint2 cap = make_uint2(0, 0);
+            if (use) {
                 if (sf.mon_source[k]) {
-                    if (eid < 0 || idx >= n_vars) continue;
-                    cap = vcap[(uint32_t)__popc(sf.chain_need[eid + 1] & ((1u << idx) - 1u)) * DM_FMTL_THREADS];
+                    use = eid >= 0 && idx < n_vars;
+                    if (use) cap = vcap[(uint32_t)__popc(sf.chain_need[eid + 1] & ((1u << idx) - 1u)) * DM_FMTL_THREADS];
                 } else {
-                    if (idx >= n_hcaps) continue;
-                    cap = hcap[(uint32_t)__popc(sf.chain_need[0] & ((1u << idx) - 1u)) * DM_FMTL_THREADS];
+                    use = idx < n_hcaps;
+                    if (use) cap = hcap[(uint32_t)__popc(sf.chain_need[0] & ((1u << idx) - 1u)) * DM_FMTL_THREADS];
                 }
+            }
+            if (use) {
                 const uint64_t key = dm_make_key(dm_fmt_fp64(buf, cap.x, cap.y), dm_field_salt(k));
                 if (TRAIN) dm_table_insert(a.table, key, &a.hdr->error);
                 else if (!dm_table_contains(a.table, key)) unknown |= 1u << k;
             }
-        } else {
-            atomicAdd(&s_bad, 1ull);
+            __syncwarp();
         }
+        if (!act) continue;
+        if (!hok) atomicAdd(&s_bad, 1ull);
         const uint32_t cnt = (uint32_t)__popc(unknown);
         if (line < a.out_cap) {
             if (a.flags) a.flags[line] = cnt ? 1 : 0;
