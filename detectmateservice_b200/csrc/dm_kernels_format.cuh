@@ -246,21 +246,30 @@ __global__ void __launch_bounds__(256) dm_k_format_lines(DmDetectArgs a, const D
 // =========================================================================================
 #define DM_FMTL_THREADS 64
 
-// earliest q in [pos, e - len] with text[q, q+len) == literal (len >= 1), else DM_FMT_NOT_FOUND
+// earliest q in [pos, e - len] with text[q, q+len) == literal (len >= 1), else DM_FMT_NOT_FOUND.
+// Four start positions per step (one aligned word): the four compares are independent, which
+// matters because a lane is one long dependent chain and only ~14 warps per SM hide latency.
 __device__ __forceinline__ uint32_t dm_fmtl_find(const uint8_t* __restrict__ buf, uint32_t pos, uint32_t e,
                                                  const uint32_t* lit, uint32_t len) {
     if (e < pos + len) return DM_FMT_NOT_FOUND;
     const uint32_t last = e - len;
     const uint32_t w0 = lit[0];
     const uint32_t m0 = len >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len);
-    const uintptr_t a0 = (reinterpret_cast<uintptr_t>(buf) + pos) & ~(uintptr_t)3;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0);
-    uint32_t sh = (uint32_t)((reinterpret_cast<uintptr_t>(buf) + pos) & 3u) * 8u;
-    uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
+    const uintptr_t base_addr = reinterpret_cast<uintptr_t>(buf);
+    const uint32_t mis = (uint32_t)(base_addr & 3u);               // buf is word aligned in the product (mis == 0)
+    uint32_t q0 = ((pos + mis) & ~3u) - mis;                       // position of the aligned word that holds pos (may be pos-3..pos)
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(base_addr + q0);
+    uint32_t lo = __ldg(wp), hi = __ldg(wp + 1), nx = __ldg(wp + 2);
     uint32_t found = DM_FMT_NOT_FOUND;
-    for (uint32_t q = pos; q <= last; ++q) {
-        const uint32_t x = __funnelshift_r(lo, hi, sh);
-        if (((x ^ w0) & m0) == 0) {
+    for (;;) {
+        const uint32_t x1 = __funnelshift_r(lo, hi, 8), x2 = __funnelshift_r(lo, hi, 16), x3 = __funnelshift_r(lo, hi, 24);
+        uint32_t h = (((lo ^ w0) & m0) == 0 ? 1u : 0u) | (((x1 ^ w0) & m0) == 0 ? 2u : 0u) |
+                     (((x2 ^ w0) & m0) == 0 ? 4u : 0u) | (((x3 ^ w0) & m0) == 0 ? 8u : 0u);
+        if (q0 < pos) h &= 0xFu << (pos - q0);                                    // positions in front of pos (first word only)
+        if (q0 + 3u > last) h &= (last >= q0) ? (0xFu >> (3u - (last - q0))) : 0u;   // positions behind last
+        while (h) {
+            const uint32_t q = q0 + (uint32_t)__ffs(h) - 1u;
+            h &= h - 1;
             bool ok = true;
             for (uint32_t j = 4; j < len; j += 4) {
                 const uint32_t lm = len - j >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len - j);
@@ -268,8 +277,9 @@ __device__ __forceinline__ uint32_t dm_fmtl_find(const uint8_t* __restrict__ buf
             }
             if (ok) { found = q; break; }
         }
-        sh += 8;
-        if (sh == 32) { sh = 0; lo = hi; ++wp; hi = __ldg(wp + 1); }
+        if (found != DM_FMT_NOT_FOUND || q0 + 4u > last) break;
+        q0 += 4;
+        lo = hi; hi = nx; ++wp; nx = __ldg(wp + 2);
     }
     return found;
 }
@@ -340,6 +350,13 @@ __global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArg
     __shared__ DmFormat sf;
     __shared__ unsigned int s_unk[DM_MAX_KEYS];
     __shared__ unsigned long long s_anom, s_score, s_bad;
+    {
+        // the grid is sized for the worst case (the record count is only known on the device):
+        // CTAs without records leave before touching anything
+        const uint64_t n_lines0 = a.hdr_in->n_lines;
+        const uint64_t hi0 = a.line_hi < n_lines0 ? a.line_hi : n_lines0;
+        if (a.hdr_in->error || a.line_lo + (uint64_t)blockIdx.x * blockDim.x >= hi0) return;
+    }
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(gfmt);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sf);

@@ -50,6 +50,12 @@ __global__ void __launch_bounds__(DM_LANES_THREADS) dm_k_lanes(DmDetectArgs a) {
     __shared__ unsigned int s_unk[DM_MAX_KEYS];
     __shared__ unsigned long long s_anom, s_score;
     {
+        // CTAs without records (the grid is sized for the worst case) leave before touching anything
+        const uint64_t n_lines0 = a.hdr_in->n_lines;
+        const uint64_t hi0 = a.line_hi < n_lines0 ? a.line_hi : n_lines0;
+        if (a.hdr_in->error || a.line_lo + (uint64_t)blockIdx.x * blockDim.x >= hi0) return;
+    }
+    {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.keys);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sk);
         for (uint32_t i = threadIdx.x; i < sizeof(DmKeys) / 4; i += blockDim.x) dst[i] = src[i];
