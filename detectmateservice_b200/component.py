@@ -359,15 +359,19 @@ class B200NewValueDetector(CoreComponent):
                         alerts[m.alert_key] = _alerts.alert_text(v)
                 out.append(self._detector_schema(str(base + line_idx), float(scores[line_idx]), alerts, lfv.get("Time")))
                 continue
-            wanted = [raw_keys[i] for i in range(len(raw_keys)) if mask >> i & 1]
-            vals = _alerts.record_fields(rec, wanted)
-            alerts = {self.monitors[i].alert_key: _alerts.alert_text(vals.get(raw_keys[i], b""))
-                      for i in range(len(raw_keys)) if mask >> i & 1}
+            alerts = self._line_alerts(rec, mask, raw_keys)
             out.append(self._detector_schema(str(base + line_idx), float(scores[line_idx]), alerts,
                                              _alerts.record_time(rec)))
         if not out:
             return None
         return out[0] if (n == 1 and not force_delimited) else wire.frame_delimited(out)
+
+    def _line_alerts(self, rec: bytes, mask: int, raw_keys: List[bytes]) -> Dict[str, str]:
+        """alertsObtain of one anomalous raw record from the device's unknown-field mask."""
+        wanted = [raw_keys[i] for i in range(len(raw_keys)) if mask >> i & 1]
+        vals = _alerts.record_fields(rec, wanted)
+        return {self.monitors[i].alert_key: _alerts.alert_text(vals.get(raw_keys[i], b""))
+                for i in range(len(raw_keys)) if mask >> i & 1}
 
     # ------------------------------------------------------------------ output
     def _description(self) -> str:
@@ -443,16 +447,17 @@ class B200NewValueComboDetector(B200NewValueDetector):
     """NewValueComboDetector on the device (semantics R-combo in DESIGN.md /
     oracle/nvcd.py): tuples of field values instead of single values.  The member
     fingerprints are folded in order into one 64-bit key and learnt / probed in the same
-    table (`dm_set_combos`).  Input is ParserSchema (one per message or a delimited batch)."""
+    table (`dm_set_combos`).  Input: ParserSchema (one per message or a delimited batch), or raw
+    key=value records for combinations of global header variables."""
 
     def __init__(self, name: str = "B200NewValueComboDetector", config: Optional[Any] = None) -> None:
         raw_cfg = config.model_dump() if hasattr(config, "model_dump") else config
         cfg = select_component_config(raw_cfg, name, fallback="NewValueComboDetector")
         cfg.setdefault("method_type", "new_value_combo_detector")
         cfg.setdefault("detector_id", "NewValueComboDetector" if name.startswith("B200") else name)
-        if cfg.get("input_format", "auto") == "raw_lines":
-            raise ValueError("combination monitors work on ParserSchema input (input_format auto | parser_schema | "
-                             "parser_schema_batch), not on raw lines")
+        if cfg.get("log_format"):
+            raise ValueError("combination monitors are not evaluated in log_format mode; feed key=value records "
+                             "or ParserSchema messages")
         super().__init__(name=name, config={"detectors": {name: cfg}})
         self.monitors, self.combos = parse_combos(cfg)
 
@@ -486,8 +491,20 @@ class B200NewValueComboDetector(B200NewValueDetector):
             return out
         return wire.split_delimited(out)[0]                                 # one record in, one bare alert out
 
-    def _process_lines(self, data: bytes) -> Optional[bytes]:
-        raise ValueError("combination monitors work on ParserSchema input, this message is not one")
+    def _line_alerts(self, rec: bytes, mask: int, raw_keys: List[bytes]) -> Dict[str, str]:
+        """Raw key=value records (one thread per record on the device, dm_kernels_lanes.cuh): a
+        combination of global header variables is the tuple of those fields of the record."""
+        n = len(self.monitors)
+        out = {}
+        for c, members in enumerate(self.combos):
+            if mask >> (n + c) & 1:
+                vals = _alerts.record_fields(rec, [raw_keys[i] for i in members])
+                m0 = self.monitors[members[0]]
+                scope = "Global" if m0.event_id is None else f"EventID {m0.event_id}"
+                key = "%s - (%s)" % (scope, ", ".join(self.monitors[i].label for i in members))
+                out[key] = "Unknown value combination: (%s)" % ", ".join(
+                    "'%s'" % vals.get(raw_keys[i], b"").decode("utf-8", "replace") for i in members)
+        return out
 
 
 def decode_compact(blob: bytes) -> Tuple[np.ndarray, np.ndarray]:

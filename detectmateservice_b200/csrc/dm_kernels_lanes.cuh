@@ -18,6 +18,7 @@
 #include "dm_device.cuh"
 #include "dm_kernels_tile.cuh"      // dm_eqflags, dm_key_identify, dm_hash_value
 #include "dm_kernels_rows.cuh"      // K_A (dm_k_rowindex) writes the record index
+#include "dm_kernels_records.cuh"   // DmMonitors: combination monitors (dm_set_combos)
 
 #define DM_LANES_THREADS 64         // small CTAs: a 64k-record message is only 2048 warps, spread them evenly
 #define DM_LANES_Q 20               // queued '=' per record before the queue is drained early
@@ -32,19 +33,31 @@ __device__ __forceinline__ uint32_t dm_lanes_cand(uint32_t w) {
     return dm_flags_to_nib(dm_zeroflags((w & 0xF8F8F8F8u) ^ 0x20202020u) | dm_eqflags(w, 0x3D3D3D3Du));
 }
 
-template <bool TRAIN>
+// COMBO: the record's value fingerprints are kept (fps[k * DM_LANES_THREADS], this lane's column) for
+// the combination monitors evaluated after the record; member-only fields do not alert themselves.
+template <bool TRAIN, bool COMBO>
 __device__ __forceinline__ void dm_lanes_event(const DmDetectArgs& a, const DmKeys& sk, uint32_t q, uint32_t& seen,
-                                               uint32_t& unknown) {
+                                               uint32_t& unknown, unsigned long long* fps, uint32_t member_only) {
     const int k = dm_key_identify(a.buf, q, sk);
     if (k < 0 || ((seen >> k) & 1u)) return;                       // not monitored / not the first occurrence (L6)
     seen |= 1u << k;
-    const uint64_t key = dm_make_key(dm_hash_value(a.buf, a.nbytes, (uint64_t)q + 1), sk.salt[k]);
+    const uint64_t fp = dm_hash_value(a.buf, a.nbytes, (uint64_t)q + 1);
+    if (COMBO) {
+        fps[(uint32_t)k * DM_LANES_THREADS] = fp;
+        if ((member_only >> k) & 1u) return;
+    }
+    const uint64_t key = dm_make_key(fp, sk.salt[k]);
     if (TRAIN) dm_table_insert(a.table, key, &a.hdr->error);
     else if (!dm_table_contains(a.table, key)) unknown |= 1u << k;
 }
 
-template <bool TRAIN>
+template <bool TRAIN, bool COMBO>
 __global__ void __launch_bounds__(DM_LANES_THREADS) dm_k_lanes(DmDetectArgs a) {
+#ifdef DM_EMU
+    unsigned long long* s_fp = reinterpret_cast<unsigned long long*>(g_emu_dyn_smem.data());
+#else
+    extern __shared__ unsigned long long s_fp[];                  // COMBO: [n_keys][DM_LANES_THREADS] value fingerprints
+#endif
     __shared__ DmKeys sk;
     __shared__ uint32_t s_q[DM_LANES_Q][DM_LANES_THREADS];
     __shared__ unsigned int s_unk[DM_MAX_KEYS];
@@ -69,6 +82,8 @@ __global__ void __launch_bounds__(DM_LANES_THREADS) dm_k_lanes(DmDetectArgs a) {
     if (a.hdr_in->error) return;                                  // K_A: more records than the index / outputs hold
     const uint8_t* __restrict__ buf = a.buf;
     const uint32_t tid = threadIdx.x;
+    const DmMonitors* __restrict__ cm = reinterpret_cast<const DmMonitors*>(a.combos);
+    const uint32_t member_only = COMBO ? cm->member_only : 0u;
     const uint64_t n_lines = a.hdr_in->n_lines;
     const uint64_t hi = a.line_hi < n_lines ? a.line_hi : n_lines;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -99,7 +114,7 @@ __global__ void __launch_bounds__(DM_LANES_THREADS) dm_k_lanes(DmDetectArgs a) {
                     const uint32_t klen = q - kstart;
                     if (kopen && klen >= 1u && klen <= DM_MAX_KEYLEN && ((lenmask >> klen) & 1ull)) {
                         if (cnt == DM_LANES_Q) {                   // rare: drain, keeping position order
-                            for (uint32_t j = 0; j < cnt; ++j) dm_lanes_event<TRAIN>(a, sk, s_q[j][tid], seen, unknown);
+                            for (uint32_t j = 0; j < cnt; ++j) dm_lanes_event<TRAIN, COMBO>(a, sk, s_q[j][tid], seen, unknown, s_fp + tid, member_only);
                             cnt = 0;
                         }
                         s_q[cnt++][tid] = q;
@@ -114,8 +129,26 @@ __global__ void __launch_bounds__(DM_LANES_THREADS) dm_k_lanes(DmDetectArgs a) {
                 }
             }
         }
-        for (uint32_t j = 0; j < cnt; ++j) dm_lanes_event<TRAIN>(a, sk, s_q[j][tid], seen, unknown);
+        for (uint32_t j = 0; j < cnt; ++j) dm_lanes_event<TRAIN, COMBO>(a, sk, s_q[j][tid], seen, unknown, s_fp + tid, member_only);
 
+        if (COMBO) {
+            // combination c = ordered tuple of the member fields' values; needs every member present
+            const uint32_t n_combos = cm->n_combos;
+            for (uint32_t c = 0; c < n_combos; ++c) {
+                const uint32_t lo = cm->combo_off[c], hi_m = cm->combo_off[c + 1];
+                uint64_t acc = dm_combo_seed(hi_m - lo);
+                bool all = true;
+                for (uint32_t j = lo; j < hi_m; ++j) {
+                    const uint32_t k = cm->combo_members[j];
+                    if (!((seen >> k) & 1u)) { all = false; break; }
+                    acc = dm_combo_fold(acc, s_fp[k * DM_LANES_THREADS + tid]);
+                }
+                if (!all) continue;
+                const uint64_t key = dm_make_key(acc ? acc : 1ull, dm_field_salt(sk.n + c));
+                if (TRAIN) dm_table_insert(a.table, key, &a.hdr->error);
+                else if (!dm_table_contains(a.table, key)) unknown |= 1u << (sk.n + c);
+            }
+        }
         const uint32_t n_unk = (uint32_t)__popc(unknown);
         if (line < a.out_cap) {
             if (a.flags) a.flags[line] = n_unk ? 1 : 0;
@@ -151,6 +184,7 @@ static inline int dm_lanes_launch(DmRowsScratch* s, uint32_t* d_line_start, cons
                                   uint64_t n_train_lines, const DmKeys* d_keys, DmTable table, uint8_t* d_flags,
                                   float* d_scores, uint64_t out_cap, dm_anomaly_t* d_anoms, uint32_t anomaly_cap,
                                   DmBatchHeader* d_hdr, unsigned long long* d_stats, uint64_t max_lines, int sm_count,
+                                  const void* d_combos, uint32_t n_keys,
                                   cudaStream_t st, void (*mark)(void*, cudaStream_t, int), void* mark_ctx) {
     const uint32_t n_rows = (uint32_t)((nbytes + DMR_ROW - 1) / DMR_ROW);
     if (n_rows == 0) return 0;
@@ -178,14 +212,18 @@ static inline int dm_lanes_launch(DmRowsScratch* s, uint32_t* d_line_start, cons
     const uint64_t max_recs = std::min<uint64_t>(nbytes / 2 + 1, max_lines);
     const uint64_t want = (max_recs + DM_LANES_THREADS - 1) / DM_LANES_THREADS;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)sm_count * 32));
+    a.combos = d_combos;
+    const size_t smem = d_combos ? (size_t)n_keys * DM_LANES_THREADS * sizeof(unsigned long long) : 0;
     if (n_train_lines > 0) {
         a.line_lo = 0; a.line_hi = n_train_lines;
-        dm_k_lanes<true><<<grid, DM_LANES_THREADS, 0, st>>>(a);
+        if (d_combos) dm_k_lanes<true, true><<<grid, DM_LANES_THREADS, smem, st>>>(a);
+        else dm_k_lanes<true, false><<<grid, DM_LANES_THREADS, 0, st>>>(a);
         ++launched;
     }
     a.line_lo = n_train_lines; a.line_hi = ~0ull;
     if (mark) mark(mark_ctx, st, 0);
-    dm_k_lanes<false><<<grid, DM_LANES_THREADS, 0, st>>>(a);
+    if (d_combos) dm_k_lanes<false, true><<<grid, DM_LANES_THREADS, smem, st>>>(a);
+    else dm_k_lanes<false, false><<<grid, DM_LANES_THREADS, 0, st>>>(a);
     if (mark) mark(mark_ctx, st, 1);
     ++launched;
     if (cudaGetLastError() != cudaSuccess) return DM_ERR_CUDA;

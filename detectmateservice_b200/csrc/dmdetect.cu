@@ -350,6 +350,8 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
     if (h->kernel_variant < 2 || nbytes == 0 || h->fmt_set) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
     h->last_nbytes = nbytes;
 
+    if (h->fmt_set && h->mons_set && h->h_mons.n_combos > 0)
+        return dm_fail(DM_ERR_STATE, "combination monitors are not evaluated in log_format mode (use key=value records or ParserSchema input)");
     if (h->fmt_set && !h->fmt_warp_kernel) {
         // log_format / template mode: K_A writes the record index, then one THREAD per record
         const uint32_t n_rows = (uint32_t)((nbytes + DMR_ROW - 1) / DMR_ROW);
@@ -370,7 +372,7 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
             DmDetectArgs a;
             a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
             a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
-            a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes;
+            a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes; a.combos = nullptr;
             const uint64_t max_recs = std::min<uint64_t>(nbytes / 2 + 1, h->max_lines);
             const uint64_t want = (max_recs + DM_FMTL_THREADS - 1) / DM_FMTL_THREADS;
             const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * 32));
@@ -397,7 +399,7 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         DmDetectArgs a;
         a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
         a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
-        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes;
+        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes; a.combos = nullptr;
         const int grid = h->sm_count * 8;
         if (n_train_lines > 0) {
             a.line_lo = 0; a.line_hi = n_train_lines;
@@ -408,10 +410,12 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         dm_k_format_lines<false><<<grid, 256, 0, st>>>(a, h->d_fmt);
         dm_prof_mark(h, st, 1);
         h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
-    } else if (h->kernel_variant == 5) {
+    } else if (h->kernel_variant == 5 || (h->mons_set && h->h_mons.n_combos > 0)) {
+        // one thread per record; the only raw-line kernel that evaluates combination monitors
+        const bool combos = h->mons_set && h->h_mons.n_combos > 0;
         const int rc = dm_lanes_launch(&h->rows, h->d_line_start, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags,
                                        d_scores, out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines,
-                                       h->sm_count, st, dm_prof_mark_cb, h);
+                                       h->sm_count, combos ? (const void*)h->d_mons : nullptr, h->n_keys, st, dm_prof_mark_cb, h);
         if (rc < 0) return dm_fail(DM_ERR_CUDA, "lanes kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         h->launches += (uint64_t)rc;
     } else if (h->kernel_variant == 0) {
@@ -425,7 +429,7 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         DmDetectArgs a;
         a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
         a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
-        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes;
+        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes; a.combos = nullptr;
         const int grid = h->sm_count * 8;
         if (n_train_lines > 0) {
             a.line_lo = 0; a.line_hi = n_train_lines;
@@ -759,6 +763,7 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     if (nbytes && !host_buf) return dm_fail(DM_ERR_ARG, "host_buf is NULL");
     if (h->kernel_variant < 2 || h->kernel_variant == 5) return dm_fail(DM_ERR_STATE, "the pipelined path needs the rows or staged kernels");
     if (h->fmt_set) return dm_fail(DM_ERR_STATE, "the pipelined path tokenises key=value records; with a log_format use dm_process_lines");
+    if (h->mons_set && h->h_mons.n_combos > 0) return dm_fail(DM_ERR_STATE, "combination monitors run in dm_process_lines / dm_process_records, not in the pipelined path");
     DM_CUDA(cudaSetDevice(h->device));
     int rc = dm_slots_init(h);
     if (rc != DM_OK) return rc;

@@ -331,7 +331,7 @@ extern "C" int emu_process_format(EmuHandle* h, const uint8_t* msg, uint64_t nby
     DmDetectArgs a;
     a.buf = msg; a.line_start = ls.data(); a.hdr_in = &h->hdr; a.hdr = &h->hdr; a.keys = &h->keys; a.table = h->table;
     a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
-    a.stats = h->stats;
+    a.stats = h->stats; a.combos = nullptr; a.nbytes = nbytes;
     const uint64_t nt = std::min<uint64_t>(n_train, n);
     if (g_fmt_lanes) {
         g_emu_dyn_smem.assign((size_t)2 * g_fmt.max_slots * DM_FMTL_THREADS * sizeof(uint2), 0);
@@ -378,8 +378,20 @@ extern "C" int emu_process_lanes(EmuHandle* h, const uint8_t* msg_in, uint64_t n
         a.stats = h->stats; a.nbytes = nbytes;
         const uint64_t nt = std::min<uint64_t>(n_train, n);
         const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + DM_LANES_THREADS - 1) / DM_LANES_THREADS, 5));
-        if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch_grid(blocks, DM_LANES_THREADS, [&] { dm_k_lanes<true>(a); }); }
-        if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch_grid(blocks, DM_LANES_THREADS, [&] { dm_k_lanes<false>(a); }); }
+        static DmMonitors cm;                                  // combination monitors (emu_set_combos), as dm_set_combos leaves them
+        memset(&cm, 0, sizeof(cm));
+        cm.n = h->keys.n; cm.n_combos = g_n_combos; cm.member_only = g_member_only;
+        for (size_t i = 0; i < g_combo_off.size(); ++i) cm.combo_off[i] = g_combo_off[i];
+        for (size_t i = 0; i < g_combo_members.size(); ++i) cm.combo_members[i] = (uint8_t)g_combo_members[i];
+        a.combos = g_n_combos ? &cm : nullptr;
+        g_emu_dyn_smem.assign((size_t)DM_MAX_KEYS * DM_LANES_THREADS * sizeof(unsigned long long), 0);
+        if (g_n_combos) {
+            if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch_grid(blocks, DM_LANES_THREADS, [&] { dm_k_lanes<true, true>(a); }); }
+            if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch_grid(blocks, DM_LANES_THREADS, [&] { dm_k_lanes<false, true>(a); }); }
+        } else {
+            if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch_grid(blocks, DM_LANES_THREADS, [&] { dm_k_lanes<true, false>(a); }); }
+            if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch_grid(blocks, DM_LANES_THREADS, [&] { dm_k_lanes<false, false>(a); }); }
+        }
     }
     free(buf);
     *n_lines = h->hdr.n_lines;

@@ -191,11 +191,9 @@ def test_component_wording_matches_oracle_cpu():
         out = comp.process(wire.encode_parser_schema(r))
         got += [out] if out else []
     _same_alerts(got, [o for o in outs if o is not None])
-    with pytest.raises(ValueError):
-        comp.process(b"type=X msg=audit(1.0:1): a=b\n")                          # raw lines are not supported here
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError):                                              # not together with a log_format
         B200NewValueComboDetector(config={"detectors": {"NewValueComboDetector": dict(
-            CFG["detectors"]["NewValueComboDetector"], params={"input_format": "raw_lines"})}})
+            CFG["detectors"]["NewValueComboDetector"], params={"log_format": "<A> <B>"})}})
 
 
 @pytest.mark.gpu
@@ -244,3 +242,136 @@ def test_gpu_set_combos_validation():
     # (a=x, v=y): combo0 (a,v)=(x,y) new, combo1 (v,a)=(y,x) new, monitor 1 (v=y) new; monitor 0 is member-only
     assert f.tolist() == [1] and s.tolist() == [3.0] and m.tolist() == [0b1110]
     det.close()
+
+
+# ------------------------------------------------------------------------------------------ raw key=value records
+RAW_CFG = {"detectors": {"NewValueComboDetector": {
+    "method_type": "new_value_combo_detector", "data_use_training": 1500, "auto_config": False,
+    "global": {"exe_acct": {"header_variables": [{"pos": "exe"}, {"pos": "acct"}]},
+               "type_res_term": {"header_variables": [{"pos": "type"}, {"pos": "res"}, {"pos": "terminal"}]},
+               "lonely": {"header_variables": [{"pos": "hostname"}]},
+               "never": {"header_variables": [{"pos": "nosuchkey"}, {"pos": "exe"}]}}}}}
+
+
+def raw_lines(n, seed):
+    """Synthetic audit records whose individual values are all seen in training, but whose
+    pairs are not: the detection half draws (exe, acct) and (type, res, terminal) independently."""
+    r = np.random.Generator(np.random.PCG64(seed))
+    exes, accts, types, terms = ["/bin/a", "/bin/b", "/usr/c"], ["root", "bob", "eve"], ["LOGIN", "USER_ACCT", "CRED"], ["tty1", "ssh", "cron"]
+    out = []
+    for i in range(n):
+        train = i < 1500
+        e = int(r.integers(0, 3))
+        a = e if train and r.random() < 0.9 else int(r.integers(0, 3))             # training: exe and acct mostly correlated
+        t = int(r.integers(0, 3))
+        ln = 'type=%s msg=audit(%d.000:%d): pid=%d acct="%s" exe="%s" hostname=%s terminal=%s res=%s' % (
+            types[t], 1642723741 + i, i, r.integers(1, 999), accts[a], exes[e], "h1" if train or r.random() < 0.98 else "h%d" % r.integers(2, 5),
+            terms[t if train else int(r.integers(0, 3))], "success" if train or r.random() < 0.7 else "failed")
+        if r.random() < 0.05:
+            ln = ln.replace(' acct="%s"' % accts[a], "")                           # a member missing: combination skipped
+        out.append(ln.encode())
+    return out
+
+
+def raw_oracle(lines):
+    orc = NewValueComboDetectorOracle(config=RAW_CFG, clock=lambda: 1773848383)
+    from oracle.nvcd import combo_alert_key
+    n = len(orc.monitors)
+    keys = [combo_alert_key(orc.monitors, m) for m in orc.combos]
+    flags, scores, masks, alerts = [], [], [], []
+    for ln in lines:
+        f, s, a = orc.step_line(ln)
+        flags.append(int(f)); scores.append(float(s)); alerts.append(a)
+        masks.append(sum(1 << (n + c) for c, k in enumerate(keys) if k in a))
+    return flags, scores, masks, alerts, orc
+
+
+def test_emu_raw_combo_kernel():
+    import emu_harness
+    lines = raw_lines(2600, seed=8)
+    want_f, want_s, want_m, _, orc = raw_oracle(lines)
+    assert sum(want_f) > 60 and any(s >= 2 for s in want_s)
+    keys = [m.pos.encode() for m in orc.monitors]
+    det = emu_harness.EmuDetector(keys, table_log2=12, variant="lanes")
+    off, flat = [0], []
+    for m in orc.combos:
+        flat += m
+        off.append(len(flat))
+    lib = det.lib
+    lib.emu_set_combos.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
+    lib.emu_set_combos(len(orc.combos), (C.c_uint32 * len(off))(*off), (C.c_uint32 * len(flat))(*flat), (1 << len(keys)) - 1)
+    try:
+        buf = b"\n".join(lines) + b"\n"
+        cut = buf.index(b"\n", len(buf) // 2) + 1
+        f1, s1 = det.process_lines(buf[:cut], 1500)
+        an = det.anomalies()
+        n1 = len(f1)
+        f2, s2 = det.process_lines(buf[cut:], max(0, 1500 - n1))
+        an2 = det.anomalies()
+    finally:
+        lib.emu_set_combos(0, (C.c_uint32 * 1)(0), (C.c_uint32 * 1)(0), 0)
+    assert f1.tolist() + f2.tolist() == want_f and s1.tolist() + s2.tolist() == want_s
+    got_m = {a[0]: a[1] for a in an}
+    got_m.update({a[0] + n1: a[1] for a in an2})
+    assert got_m == {i: m for i, m in enumerate(want_m) if m}
+
+
+def test_component_raw_combo_wording_cpu():
+    """Alert wording of raw records against the oracle, device replaced by per-record masks."""
+    from detectmateservice_b200.component import B200NewValueComboDetector
+    lines = raw_lines(2200, seed=9)
+    _, _, want_m, want_alerts, orc = raw_oracle(lines)
+
+    class FakeRaw:
+        last_n_anomalies = 0
+
+        def __init__(self):
+            self.base = 0
+
+        def process_lines(self, data, n_train_lines=0, copy=True):
+            recs = bytes(data).split(b"\n")[:-1]
+            ms = want_m[self.base:self.base + len(recs)]
+            starts = np.concatenate([[0], np.cumsum([len(r) + 1 for r in recs])[:-1]]) if recs else []
+            self._an = [(i, m, int(starts[i])) for i, m in enumerate(ms) if m]
+            self.last_n_anomalies = len(self._an)
+            self.base += len(recs)
+            f = np.array([1 if m else 0 for m in ms], np.uint8)
+            return f, np.array([bin(m).count("1") for m in ms], np.float32)
+
+        def anomalies(self):
+            return self._an
+
+    comp = B200NewValueComboDetector(config=RAW_CFG)
+    comp._det = FakeRaw()
+    comp.clock = lambda: 1773848383
+    got = []
+    for lo in range(0, len(lines), 550):
+        out = comp.process(b"\n".join(lines[lo:lo + 550]) + b"\n")
+        got += [wire.decode_detector_schema(b) for b in wire.split_delimited(out)] if out else []
+    want = [(i, a) for i, a in enumerate(want_alerts) if a]
+    assert [(int(g["logIDs"][0]), g["alertsObtain"]) for g in got] == want
+    assert all(g["detectorType"] == "new_value_combo_detector" for g in got)
+
+
+@pytest.mark.gpu
+def test_gpu_raw_combo_component_matches_oracle():
+    from detectmateservice_b200.component import B200NewValueComboDetector, decode_compact
+    lines = raw_lines(20000, seed=10)
+    want_f, want_s, _, want_alerts, _ = raw_oracle(lines)
+    comp = B200NewValueComboDetector(config=RAW_CFG)
+    comp.clock = lambda: 1773848383
+    got = []
+    for lo in range(0, len(lines), 4100):
+        out = comp.process(b"\n".join(lines[lo:lo + 4100]) + b"\n")
+        got += [wire.decode_detector_schema(b) for b in wire.split_delimited(out)] if out else []
+    want = [(i, a) for i, a in enumerate(want_alerts) if a]
+    assert [(int(g["logIDs"][0]), g["alertsObtain"]) for g in got] == want
+    assert [g["score"] for g in got] == [want_s[i] for i, _ in want]
+    st = comp.stats()
+    assert st["lines"] == 20000 and st["anomalies"] == sum(want_f)
+    comp.close()
+    comp = B200NewValueComboDetector(config={"detectors": {"NewValueComboDetector": dict(
+        RAW_CFG["detectors"]["NewValueComboDetector"], params={"output_format": "compact"})}})
+    f, s = decode_compact(comp.process(b"\n".join(lines) + b"\n"))
+    assert f.tolist() == want_f and s.tolist() == want_s
+    comp.close()
