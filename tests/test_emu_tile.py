@@ -115,6 +115,7 @@ def test_emu_edge_cases():
 
 
 def test_emu_synthetic_and_split():
+    _default_variant_only()
     from detectmateservice_b200.synth import AuditSynth, MONITORED_KEYS
     g = AuditSynth(seed=5)
     a, _ = g.batch(1500, inject=False)
