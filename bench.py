@@ -344,7 +344,7 @@ def run_gpu(args):
     # dm_submit_lines / dm_collect (two slots): message i+1 crosses PCIe while message i runs;
     # every step's flags and scores are read back into host memory.
     torch.cuda.synchronize()
-    e2e_steps = max(4, min(args.steps, 60))
+    e2e_steps = max(4, min(args.steps, 240))
     pipelined = os.environ.get("DM_KERNEL", "rows") == "rows"
 
     def e2e_loop(n_steps: int) -> int:

@@ -241,7 +241,7 @@ static inline int dm_cta_launch(DmCtaScratch* cs, DmRowsScratch* s, const uint8_
     a.keys = d_keys; a.table = table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
     a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap; a.hdr = d_hdr; a.stats = d_stats;
     a.row_ctr = s->d_row_ctr; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
-    a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = s->ctr_base; a.aux_counts = nullptr; a.line_start = nullptr; a.group = DMR_GROUP;
+    a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = s->ctr_base; a.aux_counts = nullptr; a.line_start = nullptr; a.group = DMR_GROUP; a.static_rows = 0; a.timeline = nullptr;
     int launched = 0;
     dm_k_rowindex<<<a.n_tiles, DMR_A_THREADS, 0, st>>>(a);
     ++launched;

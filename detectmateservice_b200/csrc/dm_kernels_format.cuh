@@ -20,6 +20,7 @@
 //             captures are variables[0..].
 #pragma once
 #include "dm_device.cuh"
+#include "dm_kernels_rows.cuh"       // K_A, dm_pdl_wait
 
 #define DM_FMT_MAX_CHAINS 64          // log_format + 63 templates
 #define DM_FMT_MAX_LITS 512           // literals over all chains
@@ -350,6 +351,7 @@ __global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArg
     __shared__ DmFormat sf;
     __shared__ unsigned int s_unk[DM_MAX_KEYS];
     __shared__ unsigned long long s_anom, s_score, s_bad;
+    dm_pdl_wait();                                    // K_A / the training pass are complete (dm_kernels_rows.cuh)
     {
         // the grid is sized for the worst case (the record count is only known on the device):
         // CTAs without records leave before touching anything
@@ -434,6 +436,7 @@ __global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArg
             }
         }
     }
+    dm_pdl_launch_dependents();                       // the next step's K_A may start streaming its message in
     __syncthreads();
     if (threadIdx.x == 0 && s_bad) atomicAdd(a.stats + 7, s_bad);
     if (!TRAIN) {

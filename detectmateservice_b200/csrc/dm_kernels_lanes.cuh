@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(DM_LANES_THREADS) dm_k_lanes(DmDetectArgs a) {
     __shared__ uint32_t s_q[DM_LANES_Q][DM_LANES_THREADS];
     __shared__ unsigned int s_unk[DM_MAX_KEYS];
     __shared__ unsigned long long s_anom, s_score;
+    dm_pdl_wait();                                                // K_A / the training pass are complete (dm_kernels_rows.cuh)
     {
         // CTAs without records (the grid is sized for the worst case) leave before touching anything
         const uint64_t n_lines0 = a.hdr_in->n_lines;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(DM_LANES_THREADS) dm_k_lanes(DmDetectArgs a) {
             }
         }
     }
+    dm_pdl_launch_dependents();                                   // the next step's K_A may start streaming its message in
     __syncthreads();
     if (!TRAIN) {
         if (threadIdx.x == 0 && s_anom) {
@@ -199,9 +201,9 @@ static inline int dm_lanes_launch(DmRowsScratch* s, uint32_t* d_line_start, cons
     ra.anomalies = d_anoms; ra.anomaly_cap = anomaly_cap; ra.hdr = d_hdr; ra.stats = d_stats;
     ra.row_ctr = s->d_row_ctr; ra.n_train_lines = n_train_lines; ra.max_lines = max_lines;
     ra.line_lo = 0; ra.line_hi = ~0ull; ra.ctr_base = s->ctr_base; ra.aux_counts = nullptr;
-    ra.line_start = d_line_start; ra.group = DMR_GROUP;
+    ra.line_start = d_line_start; ra.group = DMR_GROUP; ra.static_rows = 0; ra.timeline = nullptr;
     int launched = 0;
-    dm_k_rowindex<<<ra.n_tiles, DMR_A_THREADS, 0, st>>>(ra);
+    dm_launch_pdl(dm_k_rowindex, ra.n_tiles, DMR_A_THREADS, st, s->pdl, ra);
     ++launched;
     DmDetectArgs a;
     a.buf = d_buf; a.line_start = d_line_start; a.hdr_in = d_hdr; a.hdr = d_hdr; a.keys = d_keys; a.table = table;
@@ -212,18 +214,21 @@ static inline int dm_lanes_launch(DmRowsScratch* s, uint32_t* d_line_start, cons
     const uint64_t max_recs = std::min<uint64_t>(nbytes / 2 + 1, max_lines);
     const uint64_t want = (max_recs + DM_LANES_THREADS - 1) / DM_LANES_THREADS;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)sm_count * 32));
+    // (the record kernels themselves are launched normally: their records sit in the first CTAs of
+    // a worst-case grid, and an early launch into whatever slots K_A leaves free places those
+    // CTAs unevenly -- measured 2x slower; the next step's K_A still overlaps their tail)
     a.combos = d_combos;
     const size_t smem = d_combos ? (size_t)n_keys * DM_LANES_THREADS * sizeof(unsigned long long) : 0;
     if (n_train_lines > 0) {
         a.line_lo = 0; a.line_hi = n_train_lines;
-        if (d_combos) dm_k_lanes<true, true><<<grid, DM_LANES_THREADS, smem, st>>>(a);
-        else dm_k_lanes<true, false><<<grid, DM_LANES_THREADS, 0, st>>>(a);
+        if (d_combos) dm_launch_pdl_smem(dm_k_lanes<true, true>, (unsigned)grid, DM_LANES_THREADS, smem, st, false, a);
+        else dm_launch_pdl_smem(dm_k_lanes<true, false>, (unsigned)grid, DM_LANES_THREADS, 0, st, false, a);
         ++launched;
     }
     a.line_lo = n_train_lines; a.line_hi = ~0ull;
     if (mark) mark(mark_ctx, st, 0);
-    if (d_combos) dm_k_lanes<false, true><<<grid, DM_LANES_THREADS, smem, st>>>(a);
-    else dm_k_lanes<false, false><<<grid, DM_LANES_THREADS, 0, st>>>(a);
+    if (d_combos) dm_launch_pdl_smem(dm_k_lanes<false, true>, (unsigned)grid, DM_LANES_THREADS, smem, st, false, a);
+    else dm_launch_pdl_smem(dm_k_lanes<false, false>, (unsigned)grid, DM_LANES_THREADS, 0, st, false, a);
     if (mark) mark(mark_ctx, st, 1);
     ++launched;
     if (cudaGetLastError() != cudaSuccess) return DM_ERR_CUDA;

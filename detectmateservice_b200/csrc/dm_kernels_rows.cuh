@@ -24,7 +24,7 @@
 #define DMR_A_THREADS 256
 #define DMR_B_WARPS 8
 #define DMR_B_THREADS (DMR_B_WARPS * 32)
-#define DMR_GROUP 4u          // rows fetched per atomic
+#define DMR_GROUP 2u          // rows fetched per atomic (after the static share)
 #define DMR_Q1CAP 128u
 #define DMR_Q2CAP 64u
 
@@ -52,9 +52,28 @@ struct DmRowsArgs {
     uint64_t max_lines;
     unsigned int* aux_counts;         // staged variant: list counters cleared by K_A (else NULL)
     uint32_t group;                   // rows fetched per atomic by a K_B warp
+    uint32_t static_rows;             // rows every K_B warp takes without asking (warp w: rows [w*S, (w+1)*S))
+    unsigned long long* timeline;     // diagnostics (DM_ROWS_TIMELINE): per K_B warp {smid, t_first, t_work_end, t_exit} in ns, else NULL
     uint32_t* line_start;             // lanes variant: K_A also writes the record index (else NULL):
                                       // line_start[g] = first byte of record g, line_start[n] = end sentinel
 };
+
+// Programmatic dependent launch (PDL).  The two kernels of a step and the first kernel of the
+// next step are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may
+// be scheduled while its predecessor in the stream is still running, does whatever does not
+// depend on it (K_B: key tables to shared memory; K_A: stream the rows in and count), and calls
+// dm_pdl_wait() before it touches anything the predecessor reads or writes.  Launched without the
+// attribute both calls are no-ops.
+__device__ __forceinline__ void dm_pdl_wait() {
+#ifndef DM_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void dm_pdl_launch_dependents() {
+#ifndef DM_EMU
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
 
 // 16-bit '\n' mask of this lane's chunk of a row, slack bytes behind the message dropped
 __device__ __forceinline__ uint32_t dm_row_nl_mask(const uint4& v, uint64_t off, uint64_t nbytes) {
@@ -79,13 +98,7 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x;
 
-    // tile 0 also clears the per-batch counters (ordered before its look-back word is published,
-    // which every later tile -- and K_B -- depends on)
-    if (tile == 0 && threadIdx.x == 0) {
-        a.hdr->n_anomalies = 0; a.hdr->anomaly_list_count = 0; a.hdr->error = 0; a.hdr->n_lines = 0; a.hdr->n_newlines = 0;
-        if (a.aux_counts) { a.aux_counts[0] = 0; a.aux_counts[1] = 0; a.aux_counts[2] = 0; }
-        __threadfence();
-    }
+    dm_pdl_launch_dependents();                       // the detect kernel of this step may be scheduled now
     // newline count of each row of the tile: 8 warps x 8 rows, all 8 loads of a warp in flight
     uint32_t nlm[8];                                  // this lane's '\n' masks (kept for the record index)
     {
@@ -105,6 +118,16 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
             const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
             if (lane == 0) s_rowcnt[rr + i] = c;
         }
+    }
+    // everything above only read the message; from here on the kernel writes scratch and outputs
+    // the previous step's detect kernel may still be using
+    dm_pdl_wait();
+    // tile 0 clears the per-batch counters (ordered before its look-back word is published,
+    // which every later tile -- and K_B -- depends on)
+    if (tile == 0 && threadIdx.x == 0) {
+        a.hdr->n_anomalies = 0; a.hdr->anomaly_list_count = 0; a.hdr->error = 0; a.hdr->n_lines = 0; a.hdr->n_newlines = 0;
+        if (a.aux_counts) { a.aux_counts[0] = 0; a.aux_counts[1] = 0; a.aux_counts[2] = 0; }
+        __threadfence();
     }
     __syncthreads();
 
@@ -241,6 +264,7 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
         for (uint32_t i = threadIdx.x; i < sizeof(DmKeys) / 4; i += DMR_B_THREADS) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    dm_pdl_wait();                                    // K_A (and, for the detect pass, the training pass) are complete
     const uint8_t* __restrict__ buf = a.buf;
     const uint64_t nbytes = a.nbytes;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -326,13 +350,25 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
         __syncwarp();
     };
 
+    // Row distribution.  A 64k-record message is only ~4.6 rows per warp of the grid, so every
+    // warp first takes a STATIC share (a.static_rows contiguous rows, no atomics, no start-up
+    // convoy on the counter); the rest is handed out dynamically in groups of a.group rows, and
+    // the fetch for the following group is issued BEFORE the current one is processed, which
+    // takes the same-address atomic's latency off the critical path.  Every warp does exactly
+    // (groups it received) + 1 atomics, so the host can account for the counter.
+    const uint32_t wid = blockIdx.x * DMR_B_WARPS + warp;
+#ifndef DM_EMU
+    unsigned long long t_first = 0;
+    if (a.timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+#endif
+    const unsigned long long dyn_base = (unsigned long long)gridDim.x * DMR_B_WARPS * a.static_rows;
+    unsigned long long first_row = (unsigned long long)wid * a.static_rows;
+    uint32_t take = a.static_rows;
     for (;;) {
-        unsigned long long first_row = 0;
-        if (lane == 0) first_row = (atomicAdd(a.row_ctr, (unsigned long long)a.group) - a.ctr_base);
-        first_row = __shfl_sync(0xffffffffu, first_row, 0);
-        if (first_row >= a.n_rows) break;
-        const uint32_t r_end = (uint32_t)(first_row + a.group < a.n_rows ? first_row + a.group : a.n_rows);
-        for (uint32_t row = (uint32_t)first_row; row < r_end; ++row) {
+        unsigned long long next = 0;
+        if (lane == 0) next = dyn_base + (atomicAdd(a.row_ctr, (unsigned long long)a.group) - a.ctr_base);
+        const uint32_t r_end = (uint32_t)(first_row + take < a.n_rows ? first_row + take : a.n_rows);
+        for (uint32_t row = (uint32_t)(first_row < a.n_rows ? first_row : a.n_rows); row < r_end; ++row) {
             const uint64_t off = (uint64_t)row * DMR_ROW + (uint64_t)lane * 16;
             uint32_t nl16 = 0, eq16 = 0;
             if (off < nbytes) {
@@ -418,9 +454,28 @@ __global__ void __launch_bounds__(DMR_B_THREADS) dm_k_rows(DmRowsArgs a) {
                 }
             }
         }
+        next = __shfl_sync(0xffffffffu, next, 0);
+        if (next >= a.n_rows) break;
+        first_row = next;
+        take = a.group;
     }
+    dm_pdl_launch_dependents();                       // next step's K_A may start streaming its message in
+#ifndef DM_EMU
+    unsigned long long t_work = 0;
+    if (a.timeline) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_work));
+#endif
     while (q1n) drain1(q1n < 32u ? q1n : 32u);
     while (q2n) drain2(q2n < 32u ? q2n : 32u);
+#ifndef DM_EMU
+    if (a.timeline && lane == 0) {
+        unsigned long long t_exit;
+        uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* o = a.timeline + 4ull * wid;
+        o[0] = smid; o[1] = t_first; o[2] = t_work; o[3] = t_exit;
+    }
+#endif
 }
 
 #ifndef DM_EMU
@@ -436,6 +491,10 @@ struct DmRowsScratch {
     uint32_t epoch = 0;
     int grid_b = 0;
     uint32_t group = DMR_GROUP;       // DM_ROWS_GROUP
+    uint32_t static_pct = 65;         // DM_ROWS_STATIC: share of the rows distributed statically
+    bool pdl = true;                  // DM_PDL=0 switches programmatic dependent launch off
+    unsigned long long* d_timeline = nullptr;   // DM_ROWS_TIMELINE=1: 4 words per K_B warp of the last launch
+    int last_grid = 0;
 };
 
 static inline int dm_rows_scratch_create(DmRowsScratch* s, uint64_t max_batch_bytes, int sm_count) {
@@ -449,6 +508,14 @@ static inline int dm_rows_scratch_create(DmRowsScratch* s, uint64_t max_batch_by
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_rows<false, false>, DMR_B_THREADS, 0) != cudaSuccess) return DM_ERR_CUDA;
     if (per_sm < 1) per_sm = 1;
+    const char* pd = getenv("DM_PDL");
+    if (pd && atoi(pd) == 0) s->pdl = false;
+    const char* tl = getenv("DM_ROWS_TIMELINE");           // diagnostics: per-warp start / end times of K_B
+    if (tl && atoi(tl) == 1) {
+        if (cudaMalloc(&s->d_timeline, (size_t)sm_count * 16 * DMR_B_WARPS * 4 * sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
+    }
+    const char* sp = getenv("DM_ROWS_STATIC");             // tuning knob: % of the rows distributed statically
+    if (sp && atoi(sp) >= 0 && atoi(sp) <= 100) s->static_pct = (uint32_t)atoi(sp);
     const char* grp = getenv("DM_ROWS_GROUP");             // tuning knob: rows per atomic fetch
     if (grp && atoi(grp) >= 1 && atoi(grp) <= 64) s->group = (uint32_t)atoi(grp);
     const char* cap = getenv("DM_ROWS_CTAS_PER_SM");       // tuning knob: fewer, longer-lived warps
@@ -465,6 +532,24 @@ static inline void dm_rows_scratch_destroy(DmRowsScratch* s) {
 }
 
 // Enqueue K_A and K_B for one message.  Returns the number of kernels launched or < 0.
+// <<<>>> with the programmatic-stream-serialization attribute (see dm_pdl_wait)
+template <typename... Args>
+static inline void dm_launch_pdl_smem(void (*kernel)(Args...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                                      bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(block, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+template <typename Arg>
+static inline void dm_launch_pdl(void (*kernel)(Arg), unsigned grid, unsigned block, cudaStream_t st, bool pdl, Arg arg) {
+    dm_launch_pdl_smem(kernel, grid, block, 0, st, pdl, arg);
+}
+
 static inline int dm_rows_launch(DmRowsScratch* s, const uint8_t* d_buf, uint64_t nbytes, uint64_t n_train_lines,
                                  const DmKeys* d_keys, DmTable table, uint8_t* d_flags, float* d_scores,
                                  uint64_t out_cap, dm_anomaly_t* d_anoms, uint32_t anomaly_cap, DmBatchHeader* d_hdr,
@@ -484,26 +569,33 @@ static inline int dm_rows_launch(DmRowsScratch* s, const uint8_t* d_buf, uint64_
     a.row_ctr = s->d_row_ctr; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
     a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = s->ctr_base; a.aux_counts = nullptr; a.line_start = nullptr;
     int launched = 0;
-    dm_k_rowindex<<<a.n_tiles, DMR_A_THREADS, 0, st>>>(a);
+    dm_launch_pdl(dm_k_rowindex, a.n_tiles, DMR_A_THREADS, st, s->pdl, a);
     ++launched;
     const uint32_t G = s->group;
     a.group = G;
-    const uint32_t groups = (n_rows + G - 1) / G;
-    const int warps_needed = (int)((groups + 0) < 1 ? 1 : groups);
-    int grid = (warps_needed + DMR_B_WARPS - 1) / DMR_B_WARPS;
+    a.timeline = s->d_timeline;
+    int grid = (int)((n_rows + DMR_B_WARPS - 1) / DMR_B_WARPS);
     if (grid > s->grid_b) grid = s->grid_b;
-    // every warp of the grid ends with one failing fetch of DMR_GROUP rows
-    const unsigned long long per_launch = (unsigned long long)groups * G + (unsigned long long)grid * DMR_B_WARPS * G;
+    if (grid < 1) grid = 1;
+    s->last_grid = grid;
+    const unsigned long long W = (unsigned long long)grid * DMR_B_WARPS;
+    // static share: s->static_pct % of the rows, rounded down to whole rows per warp
+    const uint32_t S = (uint32_t)(((unsigned long long)n_rows * s->static_pct / 100ull) / W);
+    a.static_rows = S;
+    const unsigned long long dyn_rows = n_rows > W * S ? n_rows - W * S : 0;
+    const unsigned long long dyn_groups = (dyn_rows + G - 1) / G;
+    // every warp's last fetch fails; all fetches advance the counter by G
+    const unsigned long long per_launch = (dyn_groups + W) * G;
     if (n_train_lines > 0) {
         a.line_lo = 0; a.line_hi = n_train_lines; a.ctr_base = s->ctr_base;
-        dm_k_rows<true, true><<<grid, DMR_B_THREADS, 0, st>>>(a);
+        dm_launch_pdl(dm_k_rows<true, true>, (unsigned)grid, DMR_B_THREADS, st, s->pdl, a);
         s->ctr_base += per_launch;
         ++launched;
     }
     a.line_lo = n_train_lines; a.line_hi = ~0ull; a.ctr_base = s->ctr_base;
     if (mark) mark(mark_ctx, st, 0);
-    if (n_train_lines > 0) dm_k_rows<false, true><<<grid, DMR_B_THREADS, 0, st>>>(a);
-    else dm_k_rows<false, false><<<grid, DMR_B_THREADS, 0, st>>>(a);
+    if (n_train_lines > 0) dm_launch_pdl(dm_k_rows<false, true>, (unsigned)grid, DMR_B_THREADS, st, s->pdl, a);
+    else dm_launch_pdl(dm_k_rows<false, false>, (unsigned)grid, DMR_B_THREADS, st, s->pdl, a);
     if (mark) mark(mark_ctx, st, 1);
     s->ctr_base += per_launch;
     ++launched;

@@ -317,7 +317,7 @@ static inline int dm_staged_launch(DmStagedScratch* s, DmRowsScratch* rs, const 
     a.r.line_lo = 0; a.r.line_hi = ~0ull;
     a.cand = s->d_cand; a.fields = s->d_fields; a.counts = s->d_counts; a.cand_cap = s->cand_cap; a.field_cap = s->field_cap;
     int launched = 0;
-    a.r.line_start = nullptr; a.r.group = DMR_GROUP;
+    a.r.line_start = nullptr; a.r.group = DMR_GROUP; a.r.static_rows = 0; a.r.timeline = nullptr;
     a.r.aux_counts = s->d_counts;                      // cleared by tile 0 of K_A
     dm_k_rowindex<<<a.r.n_tiles, DMR_A_THREADS, 0, st>>>(a.r);
     const uint32_t tiles1 = (n_rows + DMS_ROWS_PER_CTA - 1) / DMS_ROWS_PER_CTA;

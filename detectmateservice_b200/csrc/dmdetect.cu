@@ -367,8 +367,8 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
             ra.anomalies = h->d_anoms; ra.anomaly_cap = h->anomaly_cap; ra.hdr = h->d_hdr; ra.stats = h->d_stats;
             ra.row_ctr = h->rows.d_row_ctr; ra.n_train_lines = n_train_lines; ra.max_lines = h->max_lines;
             ra.line_lo = 0; ra.line_hi = ~0ull; ra.ctr_base = h->rows.ctr_base; ra.aux_counts = nullptr;
-            ra.line_start = h->d_line_start; ra.group = DMR_GROUP;
-            dm_k_rowindex<<<ra.n_tiles, DMR_A_THREADS, 0, st>>>(ra);
+            ra.line_start = h->d_line_start; ra.group = DMR_GROUP; ra.static_rows = 0; ra.timeline = nullptr;
+            dm_launch_pdl(dm_k_rowindex, ra.n_tiles, DMR_A_THREADS, st, h->rows.pdl, ra);
             DmDetectArgs a;
             a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
             a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
@@ -379,11 +379,11 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
             const size_t smem = (size_t)2 * h->fmt_slots * DM_FMTL_THREADS * sizeof(uint2);
             if (n_train_lines > 0) {
                 a.line_lo = 0; a.line_hi = n_train_lines;
-                dm_k_format_lanes<true><<<grid, DM_FMTL_THREADS, smem, st>>>(a, h->d_fmt);
+                dm_launch_pdl_smem(dm_k_format_lanes<true>, (unsigned)grid, DM_FMTL_THREADS, smem, st, false, a, (const DmFormat*)h->d_fmt);
             }
             a.line_lo = n_train_lines; a.line_hi = ~0ull;
             dm_prof_mark(h, st, 0);
-            dm_k_format_lanes<false><<<grid, DM_FMTL_THREADS, smem, st>>>(a, h->d_fmt);
+            dm_launch_pdl_smem(dm_k_format_lanes<false>, (unsigned)grid, DM_FMTL_THREADS, smem, st, false, a, (const DmFormat*)h->d_fmt);
             dm_prof_mark(h, st, 1);
             h->launches += 2 + (n_train_lines > 0 ? 1 : 0);
         }
@@ -651,6 +651,20 @@ extern "C" int dm_set_format(dm_handle* h, const char* log_format, const char* c
     }
     delete f;
     return rc;
+}
+
+// diagnostics: start / end times of the K_B warps of the last rows launch (DM_ROWS_TIMELINE=1)
+extern "C" int dm_debug_rows_timeline(dm_handle* h, unsigned long long* out, uint64_t cap_words, uint32_t* n_warps_out) {
+    if (!h || !n_warps_out) return dm_fail(DM_ERR_ARG, "NULL argument");
+    if (!h->rows.d_timeline) return dm_fail(DM_ERR_STATE, "create the handle with DM_ROWS_TIMELINE=1");
+    const uint32_t n = (uint32_t)h->rows.last_grid * DMR_B_WARPS;
+    *n_warps_out = n;
+    if (!out) return DM_OK;
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->last_stream));
+    const uint64_t words = std::min<uint64_t>(cap_words, 4ull * n);
+    DM_CUDA(cudaMemcpy(out, h->rows.d_timeline, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return DM_OK;
 }
 
 extern "C" int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nbytes, uint32_t n_train_records,

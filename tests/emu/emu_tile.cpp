@@ -139,6 +139,9 @@ extern "C" int emu_process(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, ui
 static bool g_emu_cta = false;
 
 // Mirrors dm_rows_launch (dm_kernels_rows.cuh): K_A, optional K_B<train>, K_B<detect>.
+static uint32_t g_emu_rows_static_pct = 60;
+extern "C" void emu_rows_static(uint32_t pct) { g_emu_rows_static_pct = pct; }
+
 static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
                                  float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err, bool staged);
 
@@ -178,7 +181,7 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
         a.keys = &h->keys; a.table = h->table; a.flags = flags; a.scores = scores; a.out_cap = cap;
         a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size(); a.hdr = &h->hdr; a.stats = h->stats;
         a.row_ctr = &h->row_ctr; a.n_train_lines = n_train; a.max_lines = h->max_lines;
-        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base; a.aux_counts = nullptr; a.line_start = nullptr; a.group = DMR_GROUP;
+        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base; a.aux_counts = nullptr; a.line_start = nullptr; a.group = DMR_GROUP; a.static_rows = 0; a.timeline = nullptr;
         if (staged) {
             static std::vector<DmCand> cand;
             static std::vector<DmField> fields;
@@ -221,8 +224,11 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
             *n_lines = h->hdr.n_lines; *n_anoms = h->hdr.n_anomalies; *err = h->hdr.error;
             return 0;
         }
-        const uint32_t groups = (n_rows + DMR_GROUP - 1) / DMR_GROUP;
-        const unsigned long long per_launch = (unsigned long long)groups * DMR_GROUP + (unsigned long long)DMR_B_WARPS * DMR_GROUP;
+        // as dm_rows_launch: a static share of the rows per warp (here 60 %, grid = 1), the rest dynamic
+        const unsigned long long W = DMR_B_WARPS;
+        a.static_rows = (uint32_t)(((unsigned long long)n_rows * g_emu_rows_static_pct / 100ull) / W);
+        const unsigned long long dyn_rows = n_rows > W * a.static_rows ? n_rows - W * a.static_rows : 0;
+        const unsigned long long per_launch = ((dyn_rows + DMR_GROUP - 1) / DMR_GROUP + W) * DMR_GROUP;
         if (n_train > 0) {
             a.line_lo = 0; a.line_hi = n_train; a.ctr_base = h->row_ctr_base;
             emu_launch(DMR_B_THREADS, [&] { dm_k_rows<true, true>(a); });
@@ -368,7 +374,7 @@ extern "C" int emu_process_lanes(EmuHandle* h, const uint8_t* msg_in, uint64_t n
     ra.row_ctr = &h->row_ctr; ra.n_train_lines = n_train; ra.max_lines = h->max_lines;
     ra.line_lo = 0; ra.line_hi = ~0ull; ra.ctr_base = h->row_ctr_base; ra.aux_counts = nullptr;
     std::vector<uint32_t> ls(h->max_lines + 2, 0xDEADBEEFu);
-    ra.line_start = ls.data(); ra.group = DMR_GROUP;
+    ra.line_start = ls.data(); ra.group = DMR_GROUP; ra.static_rows = 0; ra.timeline = nullptr;
     emu_launch_grid(ra.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(ra); });
     const uint64_t n = h->hdr.n_lines;
     if (h->hdr.error == 0 && n <= cap) {
