@@ -338,7 +338,10 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms / max(k_n, 1),
                 "algorithmic_bytes_per_launch": alg_bytes / max(k_n, 1),
-                "kernel": os.environ.get("DM_KERNEL", "default")}
+                "kernel": os.environ.get("DM_KERNEL", "default"),
+                # the whole step (K_A + K_B, overlapped by programmatic dependent launch) on this rank
+                "step_achieved": (alg_bytes / max(n_prof, 1)) / (ms / max(args.steps, 1) * 1e-3) / 1e9,
+                "step_frac": (alg_bytes / max(n_prof, 1)) / (ms / max(args.steps, 1) * 1e-3) / 1e9 / peak}
 
     # ---- e2e: C-ABI calls with pinned HOST buffers, H2D + D2H inside the timed region --------
     # dm_submit_lines / dm_collect (two slots): message i+1 crosses PCIe while message i runs;

@@ -119,16 +119,10 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
             if (lane == 0) s_rowcnt[rr + i] = c;
         }
     }
-    // everything above only read the message; from here on the kernel writes scratch and outputs
-    // the previous step's detect kernel may still be using
-    dm_pdl_wait();
-    // tile 0 clears the per-batch counters (ordered before its look-back word is published,
-    // which every later tile -- and K_B -- depends on)
-    if (tile == 0 && threadIdx.x == 0) {
-        a.hdr->n_anomalies = 0; a.hdr->anomaly_list_count = 0; a.hdr->error = 0; a.hdr->n_lines = 0; a.hdr->n_newlines = 0;
-        if (a.aux_counts) { a.aux_counts[0] = 0; a.aux_counts[1] = 0; a.aux_counts[2] = 0; }
-        __threadfence();
-    }
+    // Everything up to and including the look-back below only reads the message and touches
+    // tile_state, which no other kernel uses (epoch-tagged): under PDL it runs while the previous
+    // step's detect kernel is still busy.  dm_pdl_wait() comes right before the first write to
+    // anything that kernel reads or writes (row_prefix, header, outputs).
     __syncthreads();
 
     if (warp == 0) {
@@ -180,6 +174,7 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
             }
         }
         if (lane == 0) atomicExch(a.tile_state + tile, tag | (DMT_ST_PREFIX << 32) | (unsigned long long)((uint32_t)excl + agg));
+        dm_pdl_wait();
         uint32_t run = (uint32_t)excl + (incl - lane_sum);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -193,9 +188,12 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
             const unsigned long long nl = excl + agg;
             const bool tail = nbytes > 0 && buf[nbytes - 1] != 0x0Au;
             unsigned long long n_lines = nl + (tail ? 1ull : 0ull);
+            // the last tile (the only one that knows the totals) initialises the whole batch header
+            a.hdr->n_anomalies = 0; a.hdr->anomaly_list_count = 0;
+            a.hdr->error = (n_lines > a.max_lines || n_lines > a.out_cap) ? DM_DEVERR_TOO_MANY_LINES : 0u;
             a.hdr->n_newlines = nl;
-            if (n_lines > a.max_lines || n_lines > a.out_cap) atomicOr(&a.hdr->error, DM_DEVERR_TOO_MANY_LINES);
             a.hdr->n_lines = n_lines;
+            if (a.aux_counts) { a.aux_counts[0] = 0; a.aux_counts[1] = 0; a.aux_counts[2] = 0; }
             const unsigned long long tr = a.n_train_lines < n_lines ? a.n_train_lines : n_lines;
             a.stats[0] += n_lines;
             a.stats[1] += tr;
@@ -205,6 +203,7 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
         }
     }
     __syncthreads();
+    dm_pdl_wait();                                    // (warp 0 has waited already; the other warps write below)
     const unsigned long long base = s_base;
     if (a.line_start) {
         // lanes variant: the record index.  The '\n' at byte x with k '\n' in front of it ends
