@@ -257,6 +257,10 @@ def run_gpu(args):
     cap = LINES_PER_MSG + 16
     from detectmateservice_b200.window import DeviceWindow
     dwin = DeviceWindow(det, rank, world, dev)
+    if world > 1 and os.environ.get("DM_WINDOW", "native") == "native":
+        # the library's own NCCL communicator: one C call per window (export, ncclAllReduce, import);
+        # DM_WINDOW=torch keeps the torch.distributed.all_reduce route
+        dwin.init_native()
 
     # the per-window exchange runs on a side stream: in steady state it carries statistics
     # only and gates nothing, so it overlaps the next message's kernels

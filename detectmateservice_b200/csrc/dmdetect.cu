@@ -24,6 +24,8 @@
 #include "dm_kernels_lanes.cuh"
 #include "dm_format_host.h"
 
+static void (*g_nccl_destroy_hook)(void*) = nullptr;   // set once NCCL is loaded (dm_nccl_load)
+
 // ---------------------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------------------
@@ -95,6 +97,9 @@ struct dm_handle {
     bool mons_set = false;
     DmMonitors h_mons;             // host copy (dm_set_monitors + dm_set_combos)
     DmFormat* d_fmt = nullptr;     // log_format + templates (dm_set_format)
+    void* nccl_comm = nullptr;     // own NCCL communicator (dm_nccl_init), one per handle
+    uint32_t nccl_rank = 0, nccl_world = 1;
+    unsigned long long* d_win = nullptr;   // window exchange buffer of dm_window_allreduce
     bool fmt_set = false;
     uint32_t fmt_slots = 1;        // DmFormat.max_slots (dynamic shared memory of the thread-per-record kernel)
     bool fmt_warp_kernel = false;  // DM_FORMAT_KERNEL=warp: one warp per record (the first implementation)
@@ -288,7 +293,8 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
     cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
-    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons); cudaFree(h->d_fmt);
+    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons); cudaFree(h->d_fmt); cudaFree(h->d_win);
+    if (h->nccl_comm && g_nccl_destroy_hook) g_nccl_destroy_hook(h->nccl_comm);
     for (auto& sl : h->slots) {
         cudaFree(sl.d_in); cudaFree(sl.d_flags); cudaFree(sl.d_scores); cudaFree(sl.d_hdr); cudaFree(sl.d_anoms);
         cudaFreeHost(sl.h_hdr); cudaFreeHost(sl.h_flags); cudaFreeHost(sl.h_scores);
@@ -1069,4 +1075,92 @@ extern "C" int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t 
         h->novel_exported = std::min<uint64_t>(cnt[1], h->table.novel_cap);
     }
     return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// The window exchange done natively: export -> ncclAllReduce(sum, uint64) -> import, all
+// enqueued by ONE call (the torch.distributed route costs ~30 us of host time per window,
+// which is what bounds the multi-GPU step).  NCCL is resolved at run time (dlopen of the
+// libnccl.so.2 the process already has -- PyTorch's -- so there is no link-time dependency).
+// ---------------------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace {
+struct DmNcclUniqueId { char internal[128]; };
+typedef int (*fn_ncclGetUniqueId)(DmNcclUniqueId*);
+typedef int (*fn_ncclCommInitRank)(void**, int, DmNcclUniqueId, int);
+typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(void*);
+typedef const char* (*fn_ncclGetErrorString)(int);
+struct DmNccl {
+    void* lib = nullptr;
+    fn_ncclGetUniqueId get_id = nullptr;
+    fn_ncclCommInitRank init_rank = nullptr;
+    fn_ncclAllReduce all_reduce = nullptr;
+    fn_ncclCommDestroy destroy = nullptr;
+    fn_ncclGetErrorString err = nullptr;
+};
+DmNccl g_nccl;
+const int DM_NCCL_UINT64 = 5, DM_NCCL_SUM = 0;      // ncclUint64, ncclSum (stable across NCCL 2.x)
+
+int dm_nccl_load() {
+    if (g_nccl.lib) return DM_OK;
+    const char* names[] = {getenv("DM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        if (!n) continue;
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return dm_fail(DM_ERR_STATE, "libnccl.so.2 not found (set DM_NCCL_LIB): %s", dlerror());
+    g_nccl.get_id = (fn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+    g_nccl.init_rank = (fn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
+    g_nccl.all_reduce = (fn_ncclAllReduce)dlsym(lib, "ncclAllReduce");
+    g_nccl.destroy = (fn_ncclCommDestroy)dlsym(lib, "ncclCommDestroy");
+    g_nccl.err = (fn_ncclGetErrorString)dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.get_id || !g_nccl.init_rank || !g_nccl.all_reduce || !g_nccl.destroy || !g_nccl.err)
+        return dm_fail(DM_ERR_STATE, "libnccl lacks an expected symbol");
+    g_nccl.lib = lib;
+    g_nccl_destroy_hook = [](void* c) { g_nccl.destroy(c); };
+    return DM_OK;
+}
+}  // namespace
+
+extern "C" int dm_nccl_unique_id(uint8_t* out128) {
+    if (!out128) return dm_fail(DM_ERR_ARG, "NULL argument");
+    int rc = dm_nccl_load();
+    if (rc != DM_OK) return rc;
+    DmNcclUniqueId id;
+    const int r = g_nccl.get_id(&id);
+    if (r != 0) return dm_fail(DM_ERR_CUDA, "ncclGetUniqueId: %s", g_nccl.err(r));
+    memcpy(out128, &id, sizeof(id));
+    return DM_OK;
+}
+
+extern "C" int dm_nccl_init(dm_handle* h, const uint8_t* id128, uint32_t rank, uint32_t world) {
+    if (!h || !id128 || world == 0 || rank >= world) return dm_fail(DM_ERR_ARG, "bad arguments");
+    if (h->nccl_comm) return dm_fail(DM_ERR_STATE, "the handle already has a communicator");
+    int rc = dm_nccl_load();
+    if (rc != DM_OK) return rc;
+    DM_CUDA(cudaSetDevice(h->device));
+    DmNcclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    void* comm = nullptr;
+    const int r = g_nccl.init_rank(&comm, (int)world, id, (int)rank);
+    if (r != 0) return dm_fail(DM_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.err(r));
+    DM_CUDA(cudaMalloc(&h->d_win, dm_window_words(h, world, 1) * sizeof(unsigned long long)));
+    h->nccl_comm = comm; h->nccl_rank = rank; h->nccl_world = world;
+    return DM_OK;
+}
+
+extern "C" int dm_window_allreduce(dm_handle* h, int with_keys, void* stream_) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    if (!h->nccl_comm) return dm_fail(DM_ERR_STATE, "dm_nccl_init has not been called");
+    int rc = dm_window_export(h, (uint64_t*)h->d_win, h->nccl_rank, h->nccl_world, with_keys, stream_);
+    if (rc != DM_OK) return rc;
+    cudaStream_t st;
+    dm_pick_stream(h, stream_, &st);
+    const int r = g_nccl.all_reduce(h->d_win, h->d_win, (size_t)dm_window_words(h, h->nccl_world, with_keys),
+                                    DM_NCCL_UINT64, DM_NCCL_SUM, h->nccl_comm, st);
+    if (r != 0) return dm_fail(DM_ERR_CUDA, "ncclAllReduce: %s", g_nccl.err(r));
+    return dm_window_import(h, (const uint64_t*)h->d_win, h->nccl_rank, h->nccl_world, with_keys, stream_);
 }

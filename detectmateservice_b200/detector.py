@@ -308,5 +308,22 @@ class DeviceDetector:
     def window_export(self, dev_ptr: int, rank: int, world: int, with_keys: bool, stream: int = 0) -> None:
         _lib.check(self._lib.dm_window_export(self._h, dev_ptr, rank, world, int(with_keys), stream or None))
 
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        """128-byte NCCL id (call on rank 0, hand the bytes to every rank's nccl_init)."""
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().dm_nccl_unique_id(buf))
+        return buf.raw
+
+    def nccl_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        """Give the handle its own NCCL communicator for window_allreduce()."""
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        _lib.check(self._lib.dm_nccl_init(self._h, unique_id, int(rank), int(world)))
+
+    def window_allreduce(self, with_keys: bool, stream: int = 0) -> None:
+        """export + ncclAllReduce + import of one window, enqueued on `stream` by one call."""
+        _lib.check(self._lib.dm_window_allreduce(self._h, int(with_keys), stream or None))
+
     def window_import(self, dev_ptr: int, rank: int, world: int, with_keys: bool, stream: int = 0) -> None:
         _lib.check(self._lib.dm_window_import(self._h, dev_ptr, rank, world, int(with_keys), stream or None))

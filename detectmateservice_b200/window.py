@@ -90,7 +90,23 @@ class DeviceWindow:
         self.buf = torch.zeros(det.window_words(world, True), dtype=torch.int64, device=device)
         self.buf_stats = self.buf[:det.window_words(world, False)]
 
+    def init_native(self) -> None:
+        """Switch to the library's own NCCL communicator (one C call per window instead of
+        export + torch.distributed.all_reduce + import; the id travels over torch.distributed)."""
+        import torch
+        import torch.distributed as dist
+        dev = self.buf.device
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if self.rank == 0:
+            t.copy_(torch.frombuffer(bytearray(self.det.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        self.det.nccl_init(bytes(t.cpu().numpy().tobytes()), self.rank, self.world)
+        self.native = True
+
     def exchange(self, with_keys: bool, stream_ptr: int) -> None:
+        if getattr(self, "native", False):
+            self.det.window_allreduce(with_keys, stream_ptr)
+            return
         import torch.distributed as dist
         buf = self.buf if with_keys else self.buf_stats
         self.det.window_export(buf.data_ptr(), self.rank, self.world, with_keys, stream_ptr)

@@ -212,6 +212,16 @@ uint64_t dm_table_key(uint32_t field, const uint8_t* value, uint32_t len);
 uint64_t dm_window_words(dm_handle* h, uint32_t world, int with_keys);
 int dm_window_export(dm_handle* h, uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream);
 int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream);
+
+/* The same exchange done by the library itself: export, ncclAllReduce(sum, uint64) over the
+ * handle's own communicator, import -- enqueued on `stream` by ONE call (no host work per
+ * window besides this call).  NCCL is resolved at run time from the libnccl.so.2 the process
+ * has loaded (PyTorch's); rank 0 creates the id (dm_nccl_unique_id), the caller distributes
+ * the 128 bytes (e.g. torch.distributed.broadcast) and every rank calls dm_nccl_init.  This is
+ * the "one all-reduce per window" of the multi-GPU configuration (BASELINE config 4). */
+int dm_nccl_unique_id(uint8_t* out128);
+int dm_nccl_init(dm_handle* h, const uint8_t* id128, uint32_t rank, uint32_t world);
+int dm_window_allreduce(dm_handle* h, int with_keys, void* stream);
 /* Statistics summed over all ranks as of the last dm_window_import. */
 int dm_get_global_stats(dm_handle* h, dm_stats_t* out);
 
