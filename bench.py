@@ -265,16 +265,20 @@ def run_gpu(args):
     # the per-window exchange runs on a side stream: in steady state it carries statistics
     # only and gates nothing, so it overlaps the next message's kernels
     side = torch.cuda.Stream(device=dev)
+    sides = [side, torch.cuda.Stream(device=dev)]
+    win_n = [0]
     win_ev = torch.cuda.Event()
 
     def window(with_keys: bool):
         if with_keys:
             dwin.exchange(True, sp)                 # training window: detection must wait for it
             return
+        sd = sides[win_n[0] & 1]                     # two side streams: two windows' all-reduces in flight
+        win_n[0] += 1
         win_ev.record(stream)
-        side.wait_event(win_ev)
-        with torch.cuda.stream(side):
-            dwin.exchange(False, side.cuda_stream)
+        sd.wait_event(win_ev)
+        with torch.cuda.stream(sd):                  # (the torch.distributed route reduces on the current stream)
+            dwin.exchange(False, sd.cuda_stream)
 
     # training window (untimed): every rank learns its message 0, then one exchange with keys
     det.enqueue_device(d_msgs[0].data_ptr(), nbytes[0], n_lines_msg[0], d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
@@ -306,7 +310,8 @@ def run_gpu(args):
     e0.record(stream)
     for i in range(args.steps):
         lines_timed += n_lines_msg[step(i)]
-    stream.wait_stream(side)                         # the last windows' all-reduces are part of the job
+    stream.wait_stream(sides[0])                     # the last windows' all-reduces are part of the job
+    stream.wait_stream(sides[1])
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)

@@ -116,7 +116,7 @@ SYMBOLS = {
     "dm_window_export": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, _P]),
     "dm_window_import": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, _P]),
     "dm_nccl_unique_id": (C.c_int, [C.c_char_p]),
-    "dm_nccl_init": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.c_uint32]),
+    "dm_nccl_init": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "dm_window_allreduce": (C.c_int, [_P, C.c_int, _P]),
     "dm_get_global_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "dm_profile_enable": (C.c_int, [_P, C.c_int]),

@@ -97,9 +97,11 @@ struct dm_handle {
     bool mons_set = false;
     DmMonitors h_mons;             // host copy (dm_set_monitors + dm_set_combos)
     DmFormat* d_fmt = nullptr;     // log_format + templates (dm_set_format)
-    void* nccl_comm = nullptr;     // own NCCL communicator (dm_nccl_init), one per handle
-    uint32_t nccl_rank = 0, nccl_world = 1;
-    unsigned long long* d_win = nullptr;   // window exchange buffer of dm_window_allreduce
+    void* nccl_comm[2] = {nullptr, nullptr};   // own NCCL communicators (dm_nccl_init): windows alternate between them
+    uint32_t nccl_n = 0, nccl_rank = 0, nccl_world = 1;
+    unsigned long long* d_win[2] = {nullptr, nullptr};   // window exchange buffers of dm_window_allreduce
+    cudaEvent_t ev_win_done[2] = {nullptr, nullptr};
+    uint64_t win_seq = 0;
     bool fmt_set = false;
     uint32_t fmt_slots = 1;        // DmFormat.max_slots (dynamic shared memory of the thread-per-record kernel)
     bool fmt_warp_kernel = false;  // DM_FORMAT_KERNEL=warp: one warp per record (the first implementation)
@@ -293,8 +295,12 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
     cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
-    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons); cudaFree(h->d_fmt); cudaFree(h->d_win);
-    if (h->nccl_comm && g_nccl_destroy_hook) g_nccl_destroy_hook(h->nccl_comm);
+    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons); cudaFree(h->d_fmt);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(h->d_win[k]);
+        if (h->ev_win_done[k]) cudaEventDestroy(h->ev_win_done[k]);
+        if (h->nccl_comm[k] && g_nccl_destroy_hook) g_nccl_destroy_hook(h->nccl_comm[k]);
+    }
     for (auto& sl : h->slots) {
         cudaFree(sl.d_in); cudaFree(sl.d_flags); cudaFree(sl.d_scores); cudaFree(sl.d_hdr); cudaFree(sl.d_anoms);
         cudaFreeHost(sl.h_hdr); cudaFreeHost(sl.h_flags); cudaFreeHost(sl.h_scores);
@@ -1003,8 +1009,7 @@ __global__ void dm_k_window_export(unsigned long long* __restrict__ out, uint64_
         unsigned long long v = 0;
         if (i < DM_STATS_WORDS) {
             unsigned long long cur = (i == 6) ? 0ull : stats[i];
-            v = cur - exported[i];
-            exported[i] = cur;
+            v = cur - atomicExch(exported + i, cur);      // telescopes mod 2^64 whatever the order of in-flight windows
         } else if (with_keys && i >= seg_off && i < seg_off + 1 + DM_WINDOW_KEYS) {
             const uint64_t j = i - seg_off;
             if (j == 0) v = novel_to - novel_from;
@@ -1020,7 +1025,7 @@ __global__ void dm_k_window_import(const unsigned long long* __restrict__ in, ui
                                    int with_keys) {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nth = (uint64_t)gridDim.x * blockDim.x;
-    if (tid < DM_STATS_WORDS) global_stats[tid] += in[tid];
+    if (tid < DM_STATS_WORDS) atomicAdd(global_stats + tid, in[tid]);     // (two windows may be in flight)
     if (!with_keys) return;
     for (uint32_t r = 0; r < world; ++r) {
         if (r == self_rank) continue;            // own keys are already in the local table
@@ -1136,31 +1141,44 @@ extern "C" int dm_nccl_unique_id(uint8_t* out128) {
     return DM_OK;
 }
 
-extern "C" int dm_nccl_init(dm_handle* h, const uint8_t* id128, uint32_t rank, uint32_t world) {
-    if (!h || !id128 || world == 0 || rank >= world) return dm_fail(DM_ERR_ARG, "bad arguments");
-    if (h->nccl_comm) return dm_fail(DM_ERR_STATE, "the handle already has a communicator");
+extern "C" int dm_nccl_init(dm_handle* h, const uint8_t* ids, uint32_t n_comms, uint32_t rank, uint32_t world) {
+    if (!h || !ids || world == 0 || rank >= world || n_comms < 1 || n_comms > 2) return dm_fail(DM_ERR_ARG, "bad arguments");
+    if (h->nccl_n) return dm_fail(DM_ERR_STATE, "the handle already has its communicators");
     int rc = dm_nccl_load();
     if (rc != DM_OK) return rc;
     DM_CUDA(cudaSetDevice(h->device));
-    DmNcclUniqueId id;
-    memcpy(&id, id128, sizeof(id));
-    void* comm = nullptr;
-    const int r = g_nccl.init_rank(&comm, (int)world, id, (int)rank);
-    if (r != 0) return dm_fail(DM_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.err(r));
-    DM_CUDA(cudaMalloc(&h->d_win, dm_window_words(h, world, 1) * sizeof(unsigned long long)));
-    h->nccl_comm = comm; h->nccl_rank = rank; h->nccl_world = world;
+    for (uint32_t k = 0; k < n_comms; ++k) {
+        DmNcclUniqueId id;
+        memcpy(&id, ids + 128 * k, sizeof(id));
+        void* comm = nullptr;
+        const int r = g_nccl.init_rank(&comm, (int)world, id, (int)rank);
+        if (r != 0) return dm_fail(DM_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.err(r));
+        h->nccl_comm[k] = comm;
+        DM_CUDA(cudaMalloc(&h->d_win[k], dm_window_words(h, world, 1) * sizeof(unsigned long long)));
+        DM_CUDA(cudaEventCreateWithFlags(&h->ev_win_done[k], cudaEventDisableTiming));
+    }
+    h->nccl_n = n_comms; h->nccl_rank = rank; h->nccl_world = world;
     return DM_OK;
 }
 
 extern "C" int dm_window_allreduce(dm_handle* h, int with_keys, void* stream_) {
     if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
-    if (!h->nccl_comm) return dm_fail(DM_ERR_STATE, "dm_nccl_init has not been called");
-    int rc = dm_window_export(h, (uint64_t*)h->d_win, h->nccl_rank, h->nccl_world, with_keys, stream_);
-    if (rc != DM_OK) return rc;
+    if (!h->nccl_n) return dm_fail(DM_ERR_STATE, "dm_nccl_init has not been called");
+    // consecutive windows alternate between the communicators (and their buffers): called on
+    // alternating streams, two all-reduces are in flight, which matters at 8 ranks where one
+    // export + all-reduce + import chain is longer than a step
+    const uint32_t k = (uint32_t)(h->win_seq++ % h->nccl_n);
     cudaStream_t st;
     dm_pick_stream(h, stream_, &st);
-    const int r = g_nccl.all_reduce(h->d_win, h->d_win, (size_t)dm_window_words(h, h->nccl_world, with_keys),
-                                    DM_NCCL_UINT64, DM_NCCL_SUM, h->nccl_comm, st);
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamWaitEvent(st, h->ev_win_done[k], 0));           // the buffer's previous window is through
+    int rc = dm_window_export(h, (uint64_t*)h->d_win[k], h->nccl_rank, h->nccl_world, with_keys, stream_);
+    if (rc != DM_OK) return rc;
+    const int r = g_nccl.all_reduce(h->d_win[k], h->d_win[k], (size_t)dm_window_words(h, h->nccl_world, with_keys),
+                                    DM_NCCL_UINT64, DM_NCCL_SUM, h->nccl_comm[k], st);
     if (r != 0) return dm_fail(DM_ERR_CUDA, "ncclAllReduce: %s", g_nccl.err(r));
-    return dm_window_import(h, (const uint64_t*)h->d_win, h->nccl_rank, h->nccl_world, with_keys, stream_);
+    rc = dm_window_import(h, (const uint64_t*)h->d_win[k], h->nccl_rank, h->nccl_world, with_keys, stream_);
+    if (rc != DM_OK) return rc;
+    DM_CUDA(cudaEventRecord(h->ev_win_done[k], st));
+    return DM_OK;
 }

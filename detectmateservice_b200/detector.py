@@ -315,11 +315,12 @@ class DeviceDetector:
         _lib.check(_lib.load().dm_nccl_unique_id(buf))
         return buf.raw
 
-    def nccl_init(self, unique_id: bytes, rank: int, world: int) -> None:
-        """Give the handle its own NCCL communicator for window_allreduce()."""
-        if len(unique_id) != 128:
-            raise ValueError("the NCCL unique id is 128 bytes")
-        _lib.check(self._lib.dm_nccl_init(self._h, unique_id, int(rank), int(world)))
+    def nccl_init(self, unique_ids: bytes, rank: int, world: int) -> None:
+        """Give the handle its own NCCL communicator(s) for window_allreduce(): one or two
+        128-byte ids (two: consecutive windows alternate between them)."""
+        if len(unique_ids) not in (128, 256):
+            raise ValueError("one or two 128-byte NCCL unique ids")
+        _lib.check(self._lib.dm_nccl_init(self._h, unique_ids, len(unique_ids) // 128, int(rank), int(world)))
 
     def window_allreduce(self, with_keys: bool, stream: int = 0) -> None:
         """export + ncclAllReduce + import of one window, enqueued on `stream` by one call."""

@@ -96,9 +96,9 @@ class DeviceWindow:
         import torch
         import torch.distributed as dist
         dev = self.buf.device
-        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        t = torch.zeros(256, dtype=torch.uint8, device=dev)
         if self.rank == 0:
-            t.copy_(torch.frombuffer(bytearray(self.det.nccl_unique_id()), dtype=torch.uint8))
+            t.copy_(torch.frombuffer(bytearray(self.det.nccl_unique_id() + self.det.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(t, src=0)
         self.det.nccl_init(bytes(t.cpu().numpy().tobytes()), self.rank, self.world)
         self.native = True

@@ -216,11 +216,13 @@ int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t rank, uint3
 /* The same exchange done by the library itself: export, ncclAllReduce(sum, uint64) over the
  * handle's own communicator, import -- enqueued on `stream` by ONE call (no host work per
  * window besides this call).  NCCL is resolved at run time from the libnccl.so.2 the process
- * has loaded (PyTorch's); rank 0 creates the id (dm_nccl_unique_id), the caller distributes
- * the 128 bytes (e.g. torch.distributed.broadcast) and every rank calls dm_nccl_init.  This is
- * the "one all-reduce per window" of the multi-GPU configuration (BASELINE config 4). */
+ * has loaded (PyTorch's); rank 0 creates n_comms (1 or 2) ids (dm_nccl_unique_id), the caller
+ * distributes the n_comms x 128 bytes (e.g. torch.distributed.broadcast) and every rank calls
+ * dm_nccl_init.  With two communicators consecutive windows alternate between them, so that --
+ * called on alternating streams -- two all-reduces are in flight.  This is the "one all-reduce
+ * per window" of the multi-GPU configuration (BASELINE config 4). */
 int dm_nccl_unique_id(uint8_t* out128);
-int dm_nccl_init(dm_handle* h, const uint8_t* id128, uint32_t rank, uint32_t world);
+int dm_nccl_init(dm_handle* h, const uint8_t* ids, uint32_t n_comms, uint32_t rank, uint32_t world);
 int dm_window_allreduce(dm_handle* h, int with_keys, void* stream);
 /* Statistics summed over all ranks as of the last dm_window_import. */
 int dm_get_global_stats(dm_handle* h, dm_stats_t* out);
