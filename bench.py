@@ -260,25 +260,29 @@ def run_gpu(args):
     if world > 1 and os.environ.get("DM_WINDOW", "native") == "native":
         # the library's own NCCL communicator: one C call per window (export, ncclAllReduce, import);
         # DM_WINDOW=torch keeps the torch.distributed.all_reduce route
-        dwin.init_native()
+        dwin.init_native(n_comms=2 if os.environ.get("DM_WINDOW_COMMS", "1") == "2" else 1)
 
     # the per-window exchange runs on a side stream: in steady state it carries statistics
     # only and gates nothing, so it overlaps the next message's kernels
     side = torch.cuda.Stream(device=dev)
     sides = [side, torch.cuda.Stream(device=dev)]
     win_n = [0]
+    n_sides = 2 if os.environ.get("DM_WINDOW_COMMS", "1") == "2" else 1
     win_ev = torch.cuda.Event()
 
     def window(with_keys: bool):
         if with_keys:
             dwin.exchange(True, sp)                 # training window: detection must wait for it
             return
-        sd = sides[win_n[0] & 1]                     # two side streams: two windows' all-reduces in flight
+        sd = sides[win_n[0] % n_sides]               # DM_WINDOW_COMMS=2: two windows' all-reduces in flight
         win_n[0] += 1
         win_ev.record(stream)
         sd.wait_event(win_ev)
-        with torch.cuda.stream(sd):                  # (the torch.distributed route reduces on the current stream)
+        if getattr(dwin, "native", False):
             dwin.exchange(False, sd.cuda_stream)
+        else:
+            with torch.cuda.stream(sd):              # the torch.distributed route reduces on the current stream
+                dwin.exchange(False, sd.cuda_stream)
 
     # training window (untimed): every rank learns its message 0, then one exchange with keys
     det.enqueue_device(d_msgs[0].data_ptr(), nbytes[0], n_lines_msg[0], d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)

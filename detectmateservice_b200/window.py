@@ -90,15 +90,16 @@ class DeviceWindow:
         self.buf = torch.zeros(det.window_words(world, True), dtype=torch.int64, device=device)
         self.buf_stats = self.buf[:det.window_words(world, False)]
 
-    def init_native(self) -> None:
+    def init_native(self, n_comms: int = 1) -> None:
         """Switch to the library's own NCCL communicator (one C call per window instead of
         export + torch.distributed.all_reduce + import; the id travels over torch.distributed)."""
         import torch
         import torch.distributed as dist
         dev = self.buf.device
-        t = torch.zeros(256, dtype=torch.uint8, device=dev)
+        t = torch.zeros(128 * n_comms, dtype=torch.uint8, device=dev)
         if self.rank == 0:
-            t.copy_(torch.frombuffer(bytearray(self.det.nccl_unique_id() + self.det.nccl_unique_id()), dtype=torch.uint8))
+            ids = b"".join(self.det.nccl_unique_id() for _ in range(n_comms))
+            t.copy_(torch.frombuffer(bytearray(ids), dtype=torch.uint8))
         dist.broadcast(t, src=0)
         self.det.nccl_init(bytes(t.cpu().numpy().tobytes()), self.rank, self.world)
         self.native = True
