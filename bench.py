@@ -260,14 +260,14 @@ def run_gpu(args):
     if world > 1 and os.environ.get("DM_WINDOW", "native") == "native":
         # the library's own NCCL communicator: one C call per window (export, ncclAllReduce, import);
         # DM_WINDOW=torch keeps the torch.distributed.all_reduce route
-        dwin.init_native(n_comms=2 if os.environ.get("DM_WINDOW_COMMS", "1") == "2" else 1)
+        dwin.init_native(n_comms=2 if os.environ.get("DM_WINDOW_COMMS", "2") == "2" else 1)
 
     # the per-window exchange runs on a side stream: in steady state it carries statistics
     # only and gates nothing, so it overlaps the next message's kernels
     side = torch.cuda.Stream(device=dev)
     sides = [side, torch.cuda.Stream(device=dev)]
     win_n = [0]
-    n_sides = 2 if os.environ.get("DM_WINDOW_COMMS", "1") == "2" else 1
+    n_sides = 2 if os.environ.get("DM_WINDOW_COMMS", "2") == "2" else 1
     win_ev = torch.cuda.Event()
 
     def window(with_keys: bool):
