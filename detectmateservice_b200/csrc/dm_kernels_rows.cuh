@@ -10,12 +10,14 @@
 //        in its tile and writes the batch header.  The record index of ANY byte is then
 //        row_prefix[row] + (number of '\n' in front of it inside its row): no ownership of
 //        records by warps, no extension rows.
-//   K_B  dm_k_rows       every warp fetches groups of rows from an atomic counter (the message
-//        is still in L2: 16 MiB << 126 MB) and treats each row on its own: classify '\n' / '=',
-//        compact the '=' into queue 1, identify keys (stage 1), hash + probe values (stage 2),
-//        re-check the rare unknown values exactly, apply alerts with atomics.  No block-level
-//        synchronisation after the key tables are loaded, so all warps of the grid finish
-//        within one row group of each other.
+//   K_B  dm_k_rows       every warp takes a static share of the rows and then fetches groups of
+//        rows from an atomic counter (the message is still in L2: 16 MiB << 126 MB) and treats
+//        each row on its own: classify '\n' / '=', compact the '=' into queue 1, identify keys
+//        (stage 1), hash + probe values (stage 2), re-check the rare unknown values exactly,
+//        apply alerts with atomics.  No block-level synchronisation after the key tables are
+//        loaded.
+//   The kernels of consecutive steps overlap through programmatic dependent launch (dm_pdl_wait):
+//   K_B is scheduled while K_A runs, the next step's K_A streams its message in while K_B drains.
 #pragma once
 #include "dm_kernels_tile.cuh"
 
