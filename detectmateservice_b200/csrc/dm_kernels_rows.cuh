@@ -217,7 +217,6 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
             if (n_lines <= a.max_lines) a.line_start[n_lines] = (uint32_t)(nbytes + 1);
         }
         const uint32_t rr = warp * 8;
-        const uint32_t lt = dm_lanemask_lt();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             uint32_t m = nlm[i];
@@ -228,7 +227,6 @@ __global__ void __launch_bounds__(DMR_A_THREADS) dm_k_rowindex(DmRowsArgs a) {
                 const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
                 if ((int)lane >= d) incl += y;
             }
-            (void)lt;
             unsigned long long k = base + s_rowpre[rr + i] + (incl - (uint32_t)__popc(m));
             const uint64_t off = ((uint64_t)tile * DMR_TILE_ROWS + rr + i) * DMR_ROW + (uint64_t)lane * 16;
             while (m) {
