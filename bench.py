@@ -243,15 +243,19 @@ def run_gpu(args):
     assert sp != 0
 
     # device-resident copies (value) and pinned-host copies (e2e)
+    # (pinned buffers are allocated with the thread bound to the GPU's NUMA node: a buffer on the
+    # other socket halves the host->device rate, detectmateservice_b200/numa.py)
+    from detectmateservice_b200.numa import bound_to_gpu_node
     d_msgs, h_msgs = [], []
-    for m in msgs:
-        t = torch.zeros(len(m) + 64, dtype=torch.uint8, device=dev)
-        src = torch.frombuffer(bytearray(m), dtype=torch.uint8)
-        t[:len(m)].copy_(src)
-        d_msgs.append(t)
-        hp = torch.empty(len(m), dtype=torch.uint8, pin_memory=True)
-        hp.copy_(src)
-        h_msgs.append(hp)
+    with bound_to_gpu_node(local_rank) as numa_cpus:
+        for m in msgs:
+            t = torch.zeros(len(m) + 64, dtype=torch.uint8, device=dev)
+            src = torch.frombuffer(bytearray(m), dtype=torch.uint8)
+            t[:len(m)].copy_(src)
+            d_msgs.append(t)
+            hp = torch.empty(len(m), dtype=torch.uint8, pin_memory=True)
+            hp.copy_(src)
+            h_msgs.append(hp)
     d_flags = torch.zeros(LINES_PER_MSG + 16, dtype=torch.uint8, device=dev)
     d_scores = torch.zeros(LINES_PER_MSG + 16, dtype=torch.float32, device=dev)
     cap = LINES_PER_MSG + 16
@@ -381,7 +385,8 @@ def run_gpu(args):
                 lines += f.size
         return lines
 
-    e2e_loop(4)
+    with bound_to_gpu_node(local_rank):              # the library's pinned result buffers are created here
+        e2e_loop(4)
     barrier()
     t0 = time.perf_counter()
     e2e_lines = e2e_loop(e2e_steps)
@@ -406,7 +411,8 @@ def run_gpu(args):
            "d2h_bytes_per_step": 5 * n_lines_msg[1] + 32, "steps": e2e_steps,
            "api": ("dm_submit_lines/dm_collect (2 slots, pinned host buffers)" if pipelined else
                    "dm_process_lines(host pinned buffer)") + " via DeviceDetector",
-           "ms_per_step": 1e3 * float(t.item()) / e2e_steps, "h2d_gbs_pinned": h2d_gbs}
+           "ms_per_step": 1e3 * float(t.item()) / e2e_steps, "h2d_gbs_pinned": h2d_gbs,
+           "pinned_numa_local_cpus": len(numa_cpus) if numa_cpus else None}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None

@@ -194,9 +194,12 @@ class B200NewValueDetector(CoreComponent):
                     self._frames = []
                 else:
                     self._frames = []
-                    for _ in range(self.FRAME_SLOTS):
-                        t = torch.empty(self.max_batch_bytes + 64, dtype=torch.uint8, pin_memory=True)
-                        self._frames.append([t, memoryview(t.numpy()), False])
+                    from .numa import bound_to_gpu_node
+                    with bound_to_gpu_node(self.device):       # pinned memory on the GPU's NUMA node
+                        for _ in range(self.FRAME_SLOTS):
+                            t = torch.empty(self.max_batch_bytes + 64, dtype=torch.uint8, pin_memory=True)
+                            t.zero_()                           # first touch while bound
+                            self._frames.append([t, memoryview(t.numpy()), False])
             deadline = time.monotonic() + 0.2
             while self._frames:
                 for slot in self._frames:

@@ -528,3 +528,12 @@ def test_engine_lends_receive_frames(tmp_path, golden_dir):
     assert p.kinds[7] == "bytes"                                  # small frames are plain bytes
     assert p.kinds[8] == "bytearray"                              # too large for a slot -> transport allocates
     assert p.lent == 7 and p.released == 7 and p.busy == [False, False]
+
+
+def test_numa_helpers(tmp_path):
+    from detectmateservice_b200 import numa
+    assert numa.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa.parse_cpulist("") == set()
+    with numa.bound_to_gpu_node(0) as cpus:                # no GPU here: topology unknown, affinity untouched
+        assert cpus is None or isinstance(cpus, set)
+    assert os.sched_getaffinity(0) == os.sched_getaffinity(0)
