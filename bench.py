@@ -256,6 +256,11 @@ def run_gpu(args):
             hp = torch.empty(len(m), dtype=torch.uint8, pin_memory=True)
             hp.copy_(src)
             h_msgs.append(hp)
+    # the set-up just wrote these buffers: evict them from the CPU caches, else the H2D copies
+    # of whichever buffers are still cached run at a fraction of the link rate (dmdetect.cu)
+    from detectmateservice_b200 import _lib as _dmlib
+    for hp in h_msgs:
+        _dmlib.check(_dmlib.load().dm_host_cache_flush(hp.data_ptr(), hp.numel()))
     d_flags = torch.zeros(LINES_PER_MSG + 16, dtype=torch.uint8, device=dev)
     d_scores = torch.zeros(LINES_PER_MSG + 16, dtype=torch.float32, device=dev)
     cap = LINES_PER_MSG + 16

@@ -98,6 +98,7 @@ SYMBOLS = {
                                     _P, _P, _P, C.POINTER(C.c_uint64)]),
     "dm_set_monitors": (C.c_int, [_P, C.c_uint32, C.POINTER(Monitor)]),
     "dm_set_combos": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]),
+    "dm_host_cache_flush": (C.c_int, [_P, C.c_uint64]),
     "dm_debug_rows_timeline": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint32)]),
     "dm_set_format": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p)]),
     "dm_process_records": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64,

@@ -163,6 +163,10 @@ int dm_set_combos(dm_handle* h, uint32_t n_combos, const uint32_t* member_off, c
  * log_format = NULL switches back.  At most 63 templates, 32 captures per chain. */
 int dm_set_format(dm_handle* h, const char* log_format, const char* content_name, uint32_t n_templates,
                   const char* const* templates);
+/* Host utility: write a host buffer back to memory and evict it from the CPU caches (x86:
+ * clflush), so that device DMA streams it from DRAM instead of snooping dirty cache lines. */
+int dm_host_cache_flush(const void* p, uint64_t nbytes);
+
 /* Diagnostics: {smid, t_first, t_work_end, t_exit} (globaltimer ns) of every warp of the last
  * rows-variant detect kernel; only for handles created with DM_ROWS_TIMELINE=1 in the environment. */
 int dm_debug_rows_timeline(dm_handle* h, unsigned long long* out, uint64_t cap_words, uint32_t* n_warps_out);
