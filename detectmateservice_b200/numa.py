@@ -60,7 +60,7 @@ def gpu_numa_node(device: int = 0, sysfs: str = "/sys") -> Optional[int]:
 
 
 _SYS_SET_MEMPOLICY = 238          # x86_64
-_MPOL_DEFAULT, _MPOL_BIND = 0, 2
+_MPOL_DEFAULT, _MPOL_PREFERRED = 0, 1
 
 
 def _set_mempolicy(mode: int, node: Optional[int]) -> bool:
@@ -86,7 +86,7 @@ def _set_mempolicy(mode: int, node: Optional[int]) -> bool:
 @contextlib.contextmanager
 def bound_to_gpu_node(device: int = 0):
     """Run the body with the calling thread bound to the GPU's NUMA node: memory policy
-    MPOL_BIND to that node (what decides where pinned pages come from) and CPU affinity to its
+    MPOL_PREFERRED for that node (what decides where pinned pages come from) and CPU affinity to its
     cores (first touch).  Everything is restored afterwards; a no-op when the topology cannot
     be read.  Yields the CPU set used, or None."""
     cpus = gpu_numa_cpus(device)
@@ -100,7 +100,7 @@ def bound_to_gpu_node(device: int = 0):
         except OSError:
             old, cpus = None, None
     if node is not None:
-        policy = _set_mempolicy(_MPOL_BIND, node)
+        policy = _set_mempolicy(_MPOL_PREFERRED, node)   # preferred, not strict: falls back if the node is full
     try:
         yield cpus
     finally:
