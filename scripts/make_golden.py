@@ -13,6 +13,9 @@
   docs_golden.json            the documented NewValueDetector example
                               (docs/getting_started.md:423-435,510).
   audit_stats.json            probe statistics of the full audit.log (SURVEY 8c iv).
+  audit_templates.txt         the nine `<*>` templates of the reference's parser test data
+                              (tests/library_integration/audit_templates.txt; test DATA, copied
+                              verbatim as a fixture like audit_sample.log).
 """
 import collections
 import json
@@ -34,6 +37,8 @@ N_TRAIN = 200
 
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(REF, "tests/library_integration/audit_templates.txt"), "rb") as f:
+        open(os.path.join(OUT, "audit_templates.txt"), "wb").write(f.read())
     raw = open(os.path.join(REF, "tests/library_integration/audit.log"), "rb").read()
     lines = rtok.split_records(raw)
     counts = collections.Counter(l.split(b" ")[0][5:].decode() for l in lines)
