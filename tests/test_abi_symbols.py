@@ -65,3 +65,14 @@ def test_bad_arguments_rejected_before_touching_device():
     assert lib.dm_create(0, 1, b"type", lens, 1 << 20, 0, 5, C.byref(h)) == _lib.DM_ERR_ARG
     assert lib.dm_create(0, 40, b"type", lens, 1 << 20, 0, 16, C.byref(h)) == _lib.DM_ERR_ARG
     assert lib.dm_process_lines(None, None, 0, 0, 0, None, None, 0, 0, None, None, None) == _lib.DM_ERR_ARG
+
+
+def test_host_cache_flush_is_harmless():
+    """dm_host_cache_flush is a host-only utility (clflush): contents are unchanged."""
+    import numpy as np
+    from detectmateservice_b200 import _lib
+    a = np.arange(1 << 16, dtype=np.uint8).copy()
+    before = a.copy()
+    assert _lib.load().dm_host_cache_flush(a.ctypes.data + 3, a.size - 7) == 0      # unaligned start / length
+    assert (a == before).all()
+    assert _lib.load().dm_host_cache_flush(None, 0) == 0
