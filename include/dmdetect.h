@@ -96,6 +96,10 @@ int dm_destroy(dm_handle* h);
  *                      output was requested the call only ENQUEUES work on `stream` and
  *                      returns without synchronising (device-resident pipelines);
  *                      otherwise it returns after the results are complete.
+ * Consecutive calls on one stream overlap through programmatic dependent launch: a call may
+ * start READING its own `buf` while the previous call's kernels are still running; it writes
+ * outputs and scratch only after they have finished, so stream order still protects every
+ * buffer the caller produces or consumes with stream-ordered work (DM_PDL=0 disables it).
  * Replaces: per-record CoreComponent.process calls made by core.py:201-203. */
 int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbytes, int buf_on_device,
                      uint64_t n_train_lines,
