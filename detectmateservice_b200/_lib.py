@@ -121,6 +121,7 @@ SYMBOLS = {
     "dm_window_allreduce": (C.c_int, [_P, C.c_int, _P]),
     "dm_get_global_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "dm_profile_enable": (C.c_int, [_P, C.c_int]),
+    "dm_set_overlap": (C.c_int, [_P, C.c_int]),
     "dm_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
@@ -140,8 +141,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.dm_abi_version() != 2:
-        raise RuntimeError(f"libdmdetect ABI version {lib.dm_abi_version()} != 2")
+    if lib.dm_abi_version() != 3:
+        raise RuntimeError(f"libdmdetect ABI version {lib.dm_abi_version()} != 3")
     _lib = lib
     return lib
 

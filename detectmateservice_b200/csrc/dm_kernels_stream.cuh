@@ -1,0 +1,861 @@
+// dm_kernels_stream.cuh -- the "stream" variant of the fused tokenizer + detector (sm_100a), default.
+//
+// Replaces, per record: MatcherParser field extraction + NewValueDetector.train / .detect of the
+// un-vendored detectmatelibrary, which the reference drives one record at a time from
+// Service.process (/root/reference/src/service/core.py:201-203).  Rules: DESIGN.md R-tok L1-L7 and
+// R-spec 1-4.  ONE kernel per message in steady state (261 B per 256-byte record, read once):
+//
+//   * every warp owns a CONTIGUOUS range of 512-byte rows and streams it through a private 4 KiB
+//     shared-memory ring: one elected lane issues TMA bulk copies (cp.async.bulk global -> shared,
+//     mbarrier complete_tx) four rows ahead; no LDG in the row loop, no registers held by loads in
+//     flight, and every later access to the text (key bytes in front of an '=', the value behind
+//     it) is a shared-memory read at any alignment;
+//   * row phase (one 16-byte chunk per lane): count '\n' (for the record index, see epilogue),
+//     flag '=' bytes with SIMD-in-register compares, and for the '=' of every 4-byte word take the
+//     4 bytes in front of it and look them up in a perfect-hash table of the monitored keys'
+//     last four bytes (3-byte keys: delimiter + key).  Only hits -- about as many as there are
+//     monitored fields -- go to the per-warp field queue;
+//   * field phase (one queued field per lane, 32 at a time): finish the key compare (bytes 5..12
+//     in front of the '=' and the field-start delimiter), find the value's end from ONE byte
+//     class ("stop bytes" < 0x23: space, '"', '\n', controls) over a 32-byte window, dm_fp64,
+//     table probe;
+//   * quote parity (R-tok L2-L4) and first-occurrence-wins (L6) are NOT tracked on that path: they
+//     can only change the outcome for a value that is not in the table, so exactly those rare
+//     candidates are re-checked exactly, by their own lane, walking the record backwards
+//     (dmx_verify_thread);
+//   * the record index of a byte is needed for ALERTS only: alerts are staged as (offset of the
+//     record's first byte, field) and the last CTA to finish runs the epilogue -- exclusive scan of
+//     the per-row '\n' counts, batch header, zero-fill of flags / scores, record index of each
+//     alert, atomics on scores / flags / statistics, anomaly list.
+//
+// Consecutive launches overlap (programmatic dependent launch): a launch never waits for its
+// predecessor kernel; what has to be ordered is ordered by sequence numbers in device memory
+// (DmxShared): scratch buffers alternate between two parities and a launch starts only after the
+// epilogue of the launch two before it has finished; epilogues run one after the other.
+#pragma once
+#include "dm_kernels_rows.cuh"     // device helpers (dm_eqflags, dm_chunk_mask, dm_pdl_*, dm_launch_pdl_smem)
+
+#define DMX_ROW 512u
+#define DMX_SLOTS 8u
+#define DMX_RING (DMX_ROW * DMX_SLOTS)      // bytes of ring per warp
+#define DMX_MIRROR 64u                      // the first bytes of the ring again behind it: reads never wrap
+#define DMX_WARPS 8
+#define DMX_THREADS (DMX_WARPS * 32)
+#define DMX_QCAP 64u                        // field queue entries per warp (circular)
+#define DMX_DEPTH 4u                        // rows loaded ahead
+#define DMX_L1 1024u                        // slots of the level-1 key table
+#define DMX_WIN 32u                         // bytes of value looked at by the fast path
+#define DMX_FULL 0x100u                     // level-1 info: the four bytes decide alone (3-byte key + delimiter)
+#define DMX_DYN_SMEM (DMX_WARPS * (DMX_RING + DMX_MIRROR))
+
+#define DM_DEVERR_ANOMALY_OVERFLOW 8u
+
+struct DmxL1 { uint32_t pat; uint32_t info; };      // info: 0 = empty, else (first key of the chain + 1) | DMX_FULL
+
+// Monitored keys as the stream kernel sees them (copied to shared memory per CTA).
+struct DmxKeyTab {
+    uint32_t n;
+    uint32_t mult;                           // level-1 slot of the 4 bytes t in front of an '=': (t * mult) >> shift
+    uint32_t shift;
+    uint32_t l1_slots;
+    uint32_t n_short;                        // keys of 1..2 bytes: tried one by one after a level-1 miss
+    uint32_t short_idx[DM_MAX_KEYS];
+    uint32_t len[DM_MAX_KEYS];
+    uint32_t next[DM_MAX_KEYS];              // next key (index + 1) with the same last four bytes, 0 = none
+    uint64_t salt[DM_MAX_KEYS];
+    alignas(16) uint32_t pat[DM_MAX_KEYS][4];   // {bits, mask} of bytes q-8..q-5 and {bits, mask} of bytes q-12..q-9
+    uint8_t bytes[DM_MAX_KEYS][DM_MAX_KEYLEN];
+    DmxL1 l1[DMX_L1];
+};
+
+// Ordering state of one handle (device memory, zeroed at creation).
+struct DmxShared {
+    unsigned int done_ctr[4];                // CTAs of launch (seq & 3) that have finished their rows
+    unsigned long long epi_done_seq;         // sequence number of the last launch whose epilogue is complete
+};
+
+struct DmxArgs {
+    const uint8_t* buf;
+    uint64_t nbytes;
+    uint32_t n_rows;
+    uint32_t rows_per_warp;
+    const DmxKeyTab* keys;
+    DmTable table;
+    unsigned short* row_cnt;                 // '\n' per row (this launch's parity)
+    dm_anomaly_t* alerts;                    // staged alerts of this launch: {line = offset of the '=', mask = field, offset = record start}
+    unsigned int* alert_count;
+    uint32_t alert_cap;
+    uint8_t* flags;
+    float* scores;
+    uint64_t out_cap;
+    dm_anomaly_t* anomalies;
+    uint32_t anomaly_cap;
+    DmBatchHeader* hdr;
+    unsigned long long* stats;
+    uint64_t n_train_lines;
+    uint64_t max_lines;
+    DmxShared* sh;
+    unsigned long long seq;                  // 1, 2, 3 ... per handle
+    const unsigned long long* bound_ptr;     // message with training AND detection records: byte offset of the
+                                             // first detection record (dm_k_bound), else NULL
+    uint32_t keep_error;                     // the epilogue ORs into hdr->error instead of assigning it
+};
+
+// ---------------------------------------------------------------------------------------
+// host: key tables
+// ---------------------------------------------------------------------------------------
+// Returns false if no perfect hash was found (cannot happen for <= 96 patterns in 1024 slots in practice).
+static inline bool dmx_keytab_build(const DmKeys& k, DmxKeyTab* t) {
+    memset(t, 0, sizeof(*t));
+    t->n = k.n;
+    uint32_t pats[3 * DM_MAX_KEYS], info[3 * DM_MAX_KEYS], np = 0;
+    static const uint8_t delims[3] = {0x20, 0x27, 0x0A};
+    for (uint32_t i = 0; i < k.n; ++i) {
+        const uint32_t L = k.len[i];
+        t->len[i] = L;
+        t->salt[i] = k.salt[i];
+        memcpy(t->bytes[i], k.bytes[i], DM_MAX_KEYLEN);
+        uint32_t mb = 0, mm = 0, ab = 0, am = 0;
+        for (uint32_t d = 5; d <= L && d <= 12; ++d) {              // d = distance from the '='
+            const uint32_t byte = k.bytes[i][L - d];
+            if (d <= 8) { mb |= byte << (8 * (8 - d)); mm |= 0xFFu << (8 * (8 - d)); }
+            else { ab |= byte << (8 * (12 - d)); am |= 0xFFu << (8 * (12 - d)); }
+        }
+        t->pat[i][0] = mb; t->pat[i][1] = mm; t->pat[i][2] = ab; t->pat[i][3] = am;
+        if (L <= 2) { t->short_idx[t->n_short++] = i; continue; }
+        if (L == 3) {
+            for (int d = 0; d < 3; ++d) {
+                pats[np] = (uint32_t)delims[d] | ((uint32_t)k.bytes[i][0] << 8) | ((uint32_t)k.bytes[i][1] << 16) | ((uint32_t)k.bytes[i][2] << 24);
+                info[np++] = (i + 1) | DMX_FULL;
+            }
+            continue;
+        }
+        const uint32_t p = (uint32_t)k.bytes[i][L - 4] | ((uint32_t)k.bytes[i][L - 3] << 8) | ((uint32_t)k.bytes[i][L - 2] << 16) |
+                           ((uint32_t)k.bytes[i][L - 1] << 24);
+        uint32_t j = 0;
+        for (; j < np; ++j)
+            if (pats[j] == p) break;
+        if (j < np) {                                               // same last four bytes as an earlier key: chain
+            uint32_t c = (info[j] & 0xFFu) - 1;
+            while (t->next[c]) c = t->next[c] - 1;
+            t->next[c] = i + 1;
+        } else {
+            pats[np] = p; info[np++] = i + 1;
+        }
+    }
+    for (uint32_t lg = 6; lg <= 10; ++lg) {
+        const uint32_t slots = 1u << lg;
+        if (np > slots / 2 && lg < 10) continue;
+        uint64_t x = 0x9E3779B97F4A7C15ull;
+        for (int trial = 0; trial < 200000; ++trial) {
+            x = dm_splitmix64(x);
+            const uint32_t mult = (uint32_t)x | 1u;
+            bool used[DMX_L1];
+            memset(used, 0, sizeof(used));
+            bool ok = true;
+            for (uint32_t j = 0; j < np && ok; ++j) {
+                const uint32_t s = (pats[j] * mult) >> (32 - lg);
+                if (used[s]) ok = false;
+                used[s] = true;
+            }
+            if (!ok) continue;
+            t->mult = mult; t->shift = 32 - lg; t->l1_slots = slots;
+            for (uint32_t s = 0; s < slots; ++s) {                  // an empty slot holds a pattern that hashes elsewhere
+                uint32_t p = 0;
+                while (((p * mult) >> (32 - lg)) == s) ++p;
+                t->l1[s].pat = p; t->l1[s].info = 0;
+            }
+            for (uint32_t j = 0; j < np; ++j) {
+                const uint32_t s = (pats[j] * mult) >> (32 - lg);
+                t->l1[s].pat = pats[j]; t->l1[s].info = info[j];
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// device: shared-memory ring fed by TMA bulk copies
+// ---------------------------------------------------------------------------------------
+#ifndef DM_EMU
+__device__ __forceinline__ uint32_t dmx_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dmx_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dmx_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dmx_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void dmx_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ unsigned long long dmx_ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dmx_st_release(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t dmx_ldcg32(const uint32_t* p) { return __ldcg(p); }
+#else
+static inline unsigned long long dmx_ld_acquire(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline uint32_t dmx_ldcg32(const uint32_t* p) { return *p; }
+static inline void dmx_st_release(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#endif
+
+// One warp's ring: issue() is called by lane 0 only, wait() by the whole warp.
+struct DmxRing {
+    uint8_t* ring;                  // DMX_RING + DMX_MIRROR bytes
+    const uint8_t* buf;
+    uint64_t nb16;                  // readable extent of the message (nbytes rounded up to 16)
+    uint32_t r0, r1;                // rows [r0, r1) of this warp; row r1 (if it exists) is loaded as a 64-byte look-ahead
+#ifndef DM_EMU
+    uint32_t ring_s, bar_s;
+#endif
+
+    __device__ __forceinline__ void issue(uint32_t i) const {
+        const uint32_t row = r0 + i;
+        const uint64_t off = (uint64_t)row * DMX_ROW;
+        uint32_t bytes = (uint32_t)(nb16 - off < DMX_ROW ? nb16 - off : DMX_ROW);
+        if (row == r1 && bytes > DMX_MIRROR) bytes = DMX_MIRROR;
+        const uint32_t slot = row & (DMX_SLOTS - 1);
+        const uint32_t mbytes = slot == 0 ? (bytes < DMX_MIRROR ? bytes : DMX_MIRROR) : 0u;
+        const bool pre = i == 0 && off > 0;            // the 16 bytes in front of the range (key bytes of its first '=')
+#ifndef DM_EMU
+        const uint32_t bar = bar_s + 8u * slot;
+        dmx_mbar_expect_tx(bar, bytes + mbytes + (pre ? 16u : 0u));
+        dmx_bulk_g2s(ring_s + slot * DMX_ROW, buf + off, bytes, bar);
+        if (mbytes) dmx_bulk_g2s(ring_s + DMX_RING, buf + off, mbytes, bar);
+        if (pre) dmx_bulk_g2s(ring_s + (uint32_t)((off - 16) & (DMX_RING - 1)), buf + off - 16, 16u, bar);
+#else
+        memcpy(ring + slot * DMX_ROW, buf + off, bytes);
+        if (mbytes) memcpy(ring + DMX_RING, buf + off, mbytes);
+        if (pre) memcpy(ring + ((off - 16) & (DMX_RING - 1)), buf + off - 16, 16);
+#endif
+    }
+    __device__ __forceinline__ void wait(uint32_t i) const {
+#ifndef DM_EMU
+        dmx_mbar_wait(bar_s + 8u * ((r0 + i) & (DMX_SLOTS - 1)), (i >> 3) & 1u);
+#else
+        (void)i;
+        __syncwarp();
+#endif
+    }
+    __device__ __forceinline__ uint32_t ld32(uint32_t ring_off) const { return *reinterpret_cast<const uint32_t*>(ring + ring_off); }
+};
+
+__device__ __forceinline__ bool dmx_is_delim(uint32_t d) { return d == 0x20u || d == 0x27u || d == 0x0Au; }
+
+// 0x80 in every byte of w that is below 0x23 (space, '!', '"', '\n', controls)
+__device__ __forceinline__ uint32_t dmx_stopflags(uint32_t w) {
+    const uint32_t t = (w | 0x80808080u) - 0x23232323u;
+    return ~(t | w) & 0x80808080u;
+}
+
+// Which monitored key (if any) ends right before the '=' at q, given the level-1 hit `info`?  Reads
+// bytes q-12 .. q-5 from the ring (the 16 bytes in front of the message are '\n').
+__device__ __forceinline__ int dmx_resolve_key(const DmxRing& rg, const uint8_t* __restrict__ buf, uint32_t q, uint32_t info,
+                                               const DmxKeyTab& sk) {
+    if (info & DMX_FULL) return (int)(info & 0xFFu) - 1;
+    const uint32_t base = ((q - 12u) & ~3u) & (DMX_RING - 1);
+    const uint32_t sh = (q & 3u) * 8u;
+    const uint32_t x0 = rg.ld32(base), x1 = rg.ld32(base + 4), x2 = rg.ld32(base + 8);
+    const uint32_t w_a = __funnelshift_r(x0, x1, sh);     // bytes q-12 .. q-9
+    const uint32_t w_b = __funnelshift_r(x1, x2, sh);     // bytes q-8 .. q-5
+    for (uint32_t k1 = info & 0xFFu; k1; k1 = sk.next[k1 - 1]) {
+        const uint32_t k = k1 - 1;
+        const uint4 p = *reinterpret_cast<const uint4*>(sk.pat[k]);
+        if ((((w_b ^ p.x) & p.y) | ((w_a ^ p.z) & p.w)) != 0) continue;
+        const uint32_t L = sk.len[k];
+        if (L <= 11u) {                                   // the field-start delimiter (R-tok L4) is inside the window
+            const uint32_t d = L <= 7u ? (w_b >> (8u * (7u - L))) & 0xFFu : (w_a >> (8u * (11u - L))) & 0xFFu;
+            if (dmx_is_delim(d)) return (int)k;
+            continue;
+        }
+        // keys of 12 bytes and more: the rest byte by byte from global memory
+        if (q < L) continue;
+        const uint32_t st = q - L;
+        bool ok = st == 0 || dmx_is_delim(dm_ld8(buf, st - 1));
+        for (uint32_t i = 0; ok && i + 12u < L; ++i) ok = dm_ld8(buf, st + i) == sk.bytes[k][i];
+        if (ok) return (int)k;
+    }
+    return -1;
+}
+
+// Keys of one or two bytes (none in the usual configurations): t = the 4 bytes in front of the '='.
+__device__ __forceinline__ uint32_t dmx_short_key(uint32_t t, const DmxKeyTab& sk) {
+    for (uint32_t s = 0; s < sk.n_short; ++s) {
+        const uint32_t k = sk.short_idx[s];
+        if (sk.len[k] == 2u) {
+            if ((t >> 16) == ((uint32_t)sk.bytes[k][0] | ((uint32_t)sk.bytes[k][1] << 8)) && dmx_is_delim((t >> 8) & 0xFFu))
+                return (k + 1) | DMX_FULL;
+        } else if ((t >> 24) == (uint32_t)sk.bytes[k][0] && dmx_is_delim((t >> 16) & 0xFFu)) {
+            return (k + 1) | DMX_FULL;
+        }
+    }
+    return 0;
+}
+
+// Value length by the letter of R-tok L3/L5 (slow path: values longer than the window).
+__device__ __forceinline__ uint32_t dmx_value_len_slow(const uint8_t* __restrict__ buf, uint64_t nbytes, uint64_t vpos) {
+    uint32_t par = 0;
+    uint64_t p = vpos;
+    for (; p < nbytes; ++p) {
+        const uint32_t c = dm_ld8(buf, p);
+        if (c == 0x0Au || (c == 0x20u && !par)) break;
+        if (c == 0x22u) par ^= 1u;
+    }
+    return (uint32_t)(p - vpos);
+}
+
+// dm_fp64 of the value that starts at vpos (R-tok L5: it ends at the first space outside double
+// quotes counted from the value start, at '\n', or at the end of the message).
+__device__ __forceinline__ uint64_t dmx_value_fp(const DmxRing& rg, const uint8_t* __restrict__ buf, uint64_t nbytes, uint32_t vpos) {
+    const uint32_t vr = vpos & (DMX_RING - 1);
+    const uint32_t base = vr & ~3u;
+    const uint32_t sh = (vpos & 3u) * 8u;
+    uint32_t w[8];
+    {
+        uint32_t lo = rg.ld32(base);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t hi = rg.ld32(base + 4u * (i + 1));
+            w[i] = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+        }
+    }
+    const uint64_t avail = nbytes > vpos ? nbytes - vpos : 0;
+    const uint32_t lim = avail < DMX_WIN ? (uint32_t)avail : DMX_WIN;
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
+    if (lim < DMX_WIN) m &= (1u << lim) - 1u;
+    uint32_t n = 0xFFFFFFFFu, par = 0;
+    while (m) {
+        const uint32_t j = (uint32_t)__ffs(m) - 1u;
+        m &= m - 1u;
+        const uint32_t c = rg.ring[vr + j];
+        if (c == 0x0Au || (c == 0x20u && !par)) { n = j; break; }
+        if (c == 0x22u) par ^= 1u;
+    }
+    if (n == 0xFFFFFFFFu) {
+        if (lim < DMX_WIN) n = lim;                       // the message ends inside the window: that ends the value
+        else {
+            // longer than the window: by the letter, from global memory
+            n = dmx_value_len_slow(buf, nbytes, vpos);
+            return dm_fp64_bytes(buf + vpos, n);
+        }
+    }
+    DmHashState st;
+    dm_hash_init(st);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (n > 4u * i) {
+            const uint32_t nb = n - 4u * i;
+            dm_hash_word(st, nb >= 4u ? w[i] : (w[i] & ((1u << (8u * nb)) - 1u)));
+        }
+    }
+    return dm_hash_final(st, n);
+}
+
+// Exact re-check of one candidate by ONE thread: is the '=' at q the first true field (R-tok L2-L6)
+// with key k of its record?  Walks the record backwards in 16-byte chunks: finds its first byte,
+// the quote parity of the candidate's field start, and whether an earlier field start with the same
+// key and the same parity exists (keys hold no quotes, so the parity at an earlier key's start is
+// the parity at its '=').  The candidate's own key bytes and delimiter are known to match.
+__device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ buf, uint32_t q, uint32_t k, const DmxKeyTab& sk,
+                                                  uint32_t* line_start) {
+    const uint32_t L = sk.len[k];
+    const uint32_t p0 = q - L;
+    uint32_t par = 0, s = 0;
+    bool dup = false;
+    if (p0 > 0) {
+        for (long long c = (long long)((p0 - 1) >> 4); c >= 0; --c) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(buf + c * 16));
+            const uint32_t cb = (uint32_t)c * 16u;
+            uint32_t keep = 0xFFFFu;
+            if (p0 - cb < 16u) keep = (1u << (p0 - cb)) - 1u;               // bytes in front of p0 only
+            const uint32_t nl = dm_chunk_mask(v, 0x0A0A0A0Au) & keep;
+            bool found = false;
+            if (nl) {
+                const uint32_t top = 31u - (uint32_t)__clz((int)nl);
+                s = cb + top + 1u;
+                keep &= ~((2u << top) - 1u);                                // bytes of this record only
+                found = true;
+            }
+            const uint32_t dq = dm_chunk_mask(v, 0x22222222u) & keep;
+            uint32_t eq = dm_chunk_mask(v, 0x3D3D3D3Du) & keep;
+            while (eq) {
+                const uint32_t j = (uint32_t)__ffs(eq) - 1u;
+                eq &= eq - 1u;
+                const uint32_t e = cb + j;
+                if (e < L) continue;
+                const uint32_t pe = par ^ ((uint32_t)__popc(dq >> (j + 1u)) & 1u);       // quotes in (e, p0)
+                if (pe) continue;
+                const uint32_t ks = e - L;
+                bool ok = ks == 0 || dmx_is_delim(dm_ld8(buf, ks - 1));
+                for (uint32_t i = 0; ok && i < L; ++i) ok = dm_ld8(buf, ks + i) == sk.bytes[k][i];
+                if (ok) dup = true;
+            }
+            par ^= (uint32_t)__popc(dq) & 1u;
+            if (found) break;
+        }
+    }
+    *line_start = s;
+    return par == 0 && !dup;
+}
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+template <bool TRAIN>
+__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_pre);
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(DMX_THREADS, 3) dm_k_stream(DmxArgs a) {
+#ifdef DM_EMU
+    uint8_t* s_dyn = g_emu_dyn_smem.data();
+#else
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+#endif
+    __shared__ DmxKeyTab sk;
+    __shared__ uint2 s_q[DMX_WARPS][DMX_QCAP];
+    __shared__ unsigned long long s_bar[DMX_WARPS][DMX_SLOTS];
+    __shared__ int s_last;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = dm_lanemask_lt();
+    dm_pdl_launch_dependents();                       // the next launch may be scheduled as soon as there is room
+    {
+        const uint32_t words = (uint32_t)((sizeof(DmxKeyTab) - sizeof(DmxL1) * DMX_L1) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.keys);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sk);
+        const uint32_t total = words + 2u * __ldg(&a.keys->l1_slots);
+        for (uint32_t i = threadIdx.x; i < total; i += DMX_THREADS) dst[i] = __ldg(src + i);
+    }
+#ifndef DM_EMU
+    if (lane == 0) {
+        for (uint32_t s = 0; s < DMX_SLOTS; ++s) dmx_mbar_init(dmx_smem_u32(&s_bar[warp][s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+#endif
+    // this launch's scratch (row counts, staged alerts) was last used by launch seq-2: its epilogue must be through
+    if (threadIdx.x == 0)
+        while (dmx_ld_acquire(&a.sh->epi_done_seq) + 2ull < a.seq) __nanosleep(64);
+    __syncthreads();
+
+    const uint8_t* __restrict__ buf = a.buf;
+    const uint64_t nbytes = a.nbytes;
+    const uint32_t bound = a.bound_ptr ? (uint32_t)(*a.bound_ptr > 0xFFFFFFFFull ? 0xFFFFFFFFull : *a.bound_ptr) : (TRAIN ? 0xFFFFFFFFu : 0u);
+    const uint32_t l1_mult = sk.mult, l1_shift = sk.shift, n_short = sk.n_short;
+    const uint32_t gw = blockIdx.x * DMX_WARPS + warp;
+    const uint64_t r0l = (uint64_t)gw * a.rows_per_warp;
+    if (r0l < a.n_rows) {
+        DmxRing rg;
+        rg.ring = s_dyn + warp * (DMX_RING + DMX_MIRROR);
+        rg.buf = buf;
+        rg.nb16 = (nbytes + 15ull) & ~15ull;
+        rg.r0 = (uint32_t)r0l;
+        rg.r1 = (uint32_t)(r0l + a.rows_per_warp < a.n_rows ? r0l + a.rows_per_warp : a.n_rows);
+#ifndef DM_EMU
+        rg.ring_s = dmx_smem_u32(rg.ring);
+        rg.bar_s = dmx_smem_u32(&s_bar[warp][0]);
+#endif
+        const uint32_t n_own = rg.r1 - rg.r0;
+        const uint32_t n_loads = n_own + (rg.r1 < a.n_rows ? 1u : 0u);
+        uint2* q = s_q[warp];
+        uint32_t qh = 0, qn = 0;
+        if (rg.r0 == 0) {
+            // the message starts a record: the 16 bytes "in front of it" read as '\n'
+            if (lane < 4) reinterpret_cast<uint32_t*>(rg.ring + DMX_RING - 16)[lane] = 0x0A0A0A0Au;
+            __syncwarp();
+        }
+        if (lane == 0)
+            for (uint32_t i = 0; i < DMX_DEPTH && i < n_loads; ++i) rg.issue(i);
+
+        // field phase: one queued field per lane
+        auto drain = [&](uint32_t n) {
+            bool cand = false;
+            uint64_t ckey = 0;
+            uint32_t cq = 0, ck = 0;
+            if (lane < n) {
+                const uint2 e = q[(qh + lane) & (DMX_QCAP - 1)];
+                if (TRAIN ? (e.x < bound) : (e.x >= bound)) {
+                    const int k = dmx_resolve_key(rg, buf, e.x, e.y, sk);
+                    if (k >= 0) {
+                        const uint64_t fp = dmx_value_fp(rg, buf, nbytes, e.x + 1u);
+                        ckey = dm_make_key(fp, sk.salt[k]);
+                        cand = !(TRAIN ? dm_table_contains_volatile(a.table, ckey) : dm_table_contains(a.table, ckey));
+                        cq = e.x; ck = (uint32_t)k;
+                    }
+                }
+            }
+            qh += n;
+            qn -= n;
+            if (__any_sync(0xffffffffu, cand)) {
+                if (cand) {
+                    uint32_t ls = 0;
+                    if (dmx_verify_thread(buf, cq, ck, sk, &ls)) {
+                        if (TRAIN) {
+                            dm_table_insert(a.table, ckey, &a.hdr->error);
+                        } else {
+                            const unsigned int idx = atomicAdd(a.alert_count, 1u);
+                            if (idx < a.alert_cap) {
+                                dm_anomaly_t r;
+                                r.line = cq; r.mask = ck; r.offset = ls;
+                                a.alerts[idx] = r;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        };
+
+        for (uint32_t i = 0; i < n_own; ++i) {
+            const uint32_t row = rg.r0 + i;
+            rg.wait(i);
+            if (i + 1 < n_loads) rg.wait(i + 1);
+            const uint32_t sb = (row & (DMX_SLOTS - 1)) * DMX_ROW + lane * 16u;
+            uint4 v = *reinterpret_cast<const uint4*>(rg.ring + sb);
+            const uint32_t prev = rg.ld32((sb - 4u) & (DMX_RING - 1));
+            const uint64_t off = (uint64_t)row * DMX_ROW + lane * 16u;
+            if ((uint64_t)(row + 1) * DMX_ROW > nbytes) {
+                // last row: bytes behind the message are nobody's
+                const uint32_t vb = nbytes > off ? (uint32_t)(nbytes - off < 16 ? nbytes - off : 16) : 0u;
+                uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t nb = vb > 4u * j ? vb - 4u * j : 0u;
+                    if (nb < 4u) vw[j] = nb ? (vw[j] & ((1u << (8u * nb)) - 1u)) : 0u;
+                }
+            }
+            {
+                // '\n' of the row (the epilogue turns the counts into record indices)
+                const uint32_t n0 = dm_eqflags(v.x, 0x0A0A0A0Au), n1 = dm_eqflags(v.y, 0x0A0A0A0Au);
+                const uint32_t n2 = dm_eqflags(v.z, 0x0A0A0A0Au), n3 = dm_eqflags(v.w, 0x0A0A0A0Au);
+                const uint32_t c = (uint32_t)__popc(n0 | (n1 >> 1) | (n2 >> 2) | (n3 >> 3));
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0) a.row_cnt[row] = (unsigned short)tot;
+            }
+            // the '=' of each 4-byte word: level-1 lookup of the 4 bytes in front of it
+            auto word = [&](uint32_t lo, uint32_t cur, uint32_t woff) {
+                uint32_t f = dm_eqflags(cur, 0x3D3D3D3Du);
+                for (;;) {
+                    bool hit = false;
+                    uint2 e = make_uint2(0u, 0u);
+                    if (f) {
+                        const uint32_t sh = (uint32_t)__ffs(f) - 8u;           // 8 * (byte index of the '=')
+                        const uint32_t t = __funnelshift_r(lo, cur, sh);
+                        const DmxL1 l = sk.l1[(t * l1_mult) >> l1_shift];
+                        uint32_t info = l.pat == t ? l.info : 0u;
+                        if (!info && n_short) info = dmx_short_key(t, sk);
+                        hit = info != 0;
+                        e = make_uint2((uint32_t)off + woff + (sh >> 3), info);
+                    }
+                    const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                    if (hb) {
+                        if (hit) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
+                        qn += (uint32_t)__popc(hb);
+                        __syncwarp();
+                        if (qn >= 32u) drain(32u);
+                    }
+                    f &= f - 1u;
+                    if (!__any_sync(0xffffffffu, f != 0)) break;
+                }
+            };
+            word(prev, v.x, 0u);
+            word(v.x, v.y, 4u);
+            word(v.y, v.z, 8u);
+            word(v.z, v.w, 12u);
+
+            if (i + DMX_DEPTH < n_loads) {
+                // row i+DEPTH overwrites the slot of row (row + DEPTH - 8): fields of rows up to (row - 3)
+                // (their key bytes may lie in the row before) must have left the queue
+                if (qn) {
+                    const uint32_t head = q[qh & (DMX_QCAP - 1)].x;
+                    if ((head >> 9) + (DMX_SLOTS - DMX_DEPTH - 1u) <= row) drain(qn);
+                }
+                __syncwarp();
+                if (lane == 0) rg.issue(i + DMX_DEPTH);
+            }
+        }
+        while (qn) drain(qn < 32u ? qn : 32u);
+    }
+
+    // ---- the last CTA to get here runs the epilogue ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int old = atomicAdd(&a.sh->done_ctr[a.seq & 3ull], 1u);
+        s_last = old == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    dmx_epilogue<TRAIN>(a, reinterpret_cast<unsigned long long*>(&s_q[0][0]));
+}
+
+// Epilogue (one CTA): header, zero-fill, record index of every staged alert, outputs.
+template <bool TRAIN>
+__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_pre /* DMX_THREADS + 2 words */) {
+    const uint32_t tid = threadIdx.x;
+    // epilogues run in launch order (they write the caller's outputs, the header and the statistics)
+    if (tid == 0)
+        while (dmx_ld_acquire(&a.sh->epi_done_seq) + 1ull < a.seq) __nanosleep(64);
+    __syncthreads();
+    if (!TRAIN) {
+        const uint32_t per = (a.n_rows + DMX_THREADS - 1) / DMX_THREADS;
+        {
+            const uint32_t lo = tid * per < a.n_rows ? tid * per : a.n_rows;
+            const uint32_t hi = lo + per < a.n_rows ? lo + per : a.n_rows;
+            unsigned long long s = 0;
+            for (uint32_t r = lo; r < hi; ++r) s += *((volatile unsigned short*)(a.row_cnt + r));
+            s_pre[tid] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long run = 0;
+            for (uint32_t t = 0; t < DMX_THREADS; ++t) { const unsigned long long c = s_pre[t]; s_pre[t] = run; run += c; }
+            const unsigned long long nl = run;
+            const bool tail = a.nbytes > 0 && a.buf[a.nbytes - 1] != 0x0Au;
+            const unsigned long long n_lines = nl + (tail ? 1ull : 0ull);
+            s_pre[DMX_THREADS] = n_lines;
+            const unsigned int staged = *((volatile unsigned int*)a.alert_count);
+            unsigned int err = (n_lines > a.max_lines || n_lines > a.out_cap) ? DM_DEVERR_TOO_MANY_LINES : 0u;
+            if (staged > a.alert_cap) err |= DM_DEVERR_ANOMALY_OVERFLOW;
+            a.hdr->n_anomalies = 0; a.hdr->anomaly_list_count = 0;
+            a.hdr->error = a.keep_error ? (a.hdr->error | err) : err;
+            a.hdr->n_newlines = nl;
+            a.hdr->n_lines = n_lines;
+            const unsigned long long tr = a.n_train_lines < n_lines ? a.n_train_lines : n_lines;
+            a.stats[0] += n_lines;
+            a.stats[1] += tr;
+            a.stats[2] += n_lines - tr;
+            a.stats[5] += a.nbytes;
+        }
+        __syncthreads();
+        const unsigned long long n_lines = s_pre[DMX_THREADS];
+        const unsigned long long n_out = n_lines < a.out_cap ? n_lines : a.out_cap;
+        {
+            // 16-byte stores where the caller's buffers allow it
+            const unsigned long long nv = ((((uintptr_t)a.flags) | ((uintptr_t)a.scores)) & 15) == 0 ? (n_out & ~15ull) : 0ull;
+            for (unsigned long long i = (unsigned long long)tid * 16; i < nv; i += DMX_THREADS * 16ull) {
+                *reinterpret_cast<uint4*>(a.flags + i) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(a.scores + i + 4 * j) = make_uint4(0, 0, 0, 0);
+            }
+            for (unsigned long long i = nv + tid; i < n_out; i += DMX_THREADS) { a.flags[i] = 0; a.scores[i] = 0.0f; }
+        }
+        __syncthreads();
+        const unsigned int staged = *((volatile unsigned int*)a.alert_count);
+        const unsigned int n_al = staged < a.alert_cap ? staged : a.alert_cap;
+        for (unsigned int i = tid; i < n_al; i += DMX_THREADS) {
+            dm_anomaly_t al;
+            al.line = dmx_ldcg32(&a.alerts[i].line); al.mask = dmx_ldcg32(&a.alerts[i].mask);
+            al.offset = dmx_ldcg32(reinterpret_cast<const uint32_t*>(&a.alerts[i].offset));
+            const uint32_t s = (uint32_t)al.offset, k = al.mask;
+            // record index = '\n' in front of the record's first byte
+            const uint32_t row = s >> 9;
+            const uint32_t t = row / per;
+            unsigned long long g = s_pre[t];
+            for (uint32_t r = t * per; r < row; ++r) g += *((volatile unsigned short*)(a.row_cnt + r));
+            for (uint32_t c = row * (DMX_ROW / 16); c < (s >> 4); ++c)
+                g += (uint32_t)__popc(dm_chunk_mask(__ldg(reinterpret_cast<const uint4*>(a.buf) + c), 0x0A0A0A0Au));
+            if (s & 15u)
+                g += (uint32_t)__popc(dm_chunk_mask(__ldg(reinterpret_cast<const uint4*>(a.buf) + (s >> 4)), 0x0A0A0A0Au) & ((1u << (s & 15u)) - 1u));
+            bool first = false;
+            if (g < a.out_cap) {
+                const float old = atomicAdd(a.scores + g, 1.0f);
+                a.flags[g] = 1;
+                first = old == 0.0f;
+            }
+            atomicAdd(a.stats + 8 + k, 1ull);
+            atomicAdd(a.stats + 4, 1ull);
+            if (first) { atomicAdd(&a.hdr->n_anomalies, 1ull); atomicAdd(a.stats + 3, 1ull); }
+            const unsigned int idx = atomicAdd(&a.hdr->anomaly_list_count, 1u);
+            if (idx < a.anomaly_cap) {
+                dm_anomaly_t r;
+                r.line = (uint32_t)g; r.mask = 1u << k; r.offset = s;
+                a.anomalies[idx] = r;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *a.alert_count = 0;
+        a.sh->done_ctr[a.seq & 3ull] = 0;
+        __threadfence();
+        dmx_st_release(&a.sh->epi_done_seq, a.seq);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// messages that hold training AND detection records: where does detection start?
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dm_k_rowcount(const uint8_t* __restrict__ buf, uint64_t nbytes, uint32_t n_rows,
+                                                     unsigned short* __restrict__ row_cnt) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t row = w; row < n_rows; row += nw) {
+        const uint64_t off = (uint64_t)row * DMX_ROW + lane * 16u;
+        uint32_t m = 0;
+        if (off < nbytes) m = dm_row_nl_mask(__ldg(reinterpret_cast<const uint4*>(buf + off)), off, nbytes);
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
+        if (lane == 0) row_cnt[row] = (unsigned short)tot;
+    }
+}
+
+// One CTA: byte offset of record n_train (= behind the n_train-th '\n'), nbytes if the message has fewer.
+__global__ void __launch_bounds__(256) dm_k_bound(const uint8_t* __restrict__ buf, uint64_t nbytes, uint32_t n_rows,
+                                                  const unsigned short* __restrict__ row_cnt, uint64_t n_train,
+                                                  unsigned long long* bound_out, DmBatchHeader* hdr) {
+    __shared__ unsigned long long s_sum[256];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (n_rows + 255) / 256;
+    const uint32_t lo = tid * per < n_rows ? tid * per : n_rows;
+    const uint32_t hi = lo + per < n_rows ? lo + per : n_rows;
+    unsigned long long s = 0;
+    for (uint32_t r = lo; r < hi; ++r) s += row_cnt[r];
+    s_sum[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        hdr->error = 0;
+        unsigned long long bound = nbytes;
+        unsigned long long run = 0;
+        uint32_t t = 0;
+        while (t < 256 && run + s_sum[t] < n_train) { run += s_sum[t]; ++t; }
+        if (n_train == 0) bound = 0;
+        else if (t < 256) {
+            uint32_t r = t * per;
+            while (run + row_cnt[r] < n_train) { run += row_cnt[r]; ++r; }
+            uint64_t p = (uint64_t)r * DMX_ROW;
+            for (;; ++p)
+                if (buf[p] == 0x0Au && ++run == n_train) break;
+            bound = p + 1;
+        }
+        *bound_out = bound;
+    }
+}
+
+#ifndef DM_EMU
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct DmxScratch {
+    DmxKeyTab* d_keys = nullptr;
+    unsigned short* d_row_cnt[2] = {nullptr, nullptr};
+    unsigned short* d_bound_cnt = nullptr;
+    dm_anomaly_t* d_alerts[2] = {nullptr, nullptr};
+    unsigned int* d_alert_count = nullptr;      // 2 words
+    unsigned long long* d_bound = nullptr;
+    DmxShared* d_shared = nullptr;
+    uint32_t alert_cap = 0;
+    uint64_t max_rows = 0;
+    unsigned long long seq = 0;
+    int ctas_per_sm = 0;
+    int max_grid = 0;
+    bool overlap = false;                       // programmatic dependent launch between consecutive detect launches
+    cudaStream_t chain_stream = nullptr;        // stream of the last launch, if it was a plain detect launch (else NULL)
+};
+
+static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t max_batch_bytes, uint32_t alert_cap, int sm_count) {
+    DmxKeyTab* t = new (std::nothrow) DmxKeyTab;
+    if (!t) return DM_ERR_CUDA;
+    const bool ok = dmx_keytab_build(keys, t);
+    cudaError_t e = ok ? cudaMalloc(&s->d_keys, sizeof(DmxKeyTab)) : cudaErrorUnknown;
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_keys, t, sizeof(DmxKeyTab), cudaMemcpyHostToDevice);
+    delete t;
+    if (e != cudaSuccess) return DM_ERR_CUDA;
+    s->max_rows = (max_batch_bytes + DMX_ROW - 1) / DMX_ROW + 1;
+    s->alert_cap = alert_cap;
+    for (int b = 0; b < 2; ++b) {
+        if (cudaMalloc(&s->d_row_cnt[b], s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
+        if (cudaMalloc(&s->d_alerts[b], (size_t)alert_cap * sizeof(dm_anomaly_t)) != cudaSuccess) return DM_ERR_CUDA;
+    }
+    if (cudaMalloc(&s->d_bound_cnt, s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_alert_count, 2 * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMemset(s->d_alert_count, 0, 2 * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_bound, sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_shared, sizeof(DmxShared)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMemset(s->d_shared, 0, sizeof(DmxShared)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaFuncSetAttribute(dm_k_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DMX_DYN_SMEM) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaFuncSetAttribute(dm_k_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DMX_DYN_SMEM) != cudaSuccess) return DM_ERR_CUDA;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_stream<false>, DMX_THREADS, DMX_DYN_SMEM) != cudaSuccess) return DM_ERR_CUDA;
+    if (per_sm < 1) per_sm = 1;
+    const char* cap = getenv("DM_STREAM_CTAS_PER_SM");     // tuning knob
+    if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
+    s->ctas_per_sm = per_sm;
+    s->max_grid = sm_count * per_sm;
+    return DM_OK;
+}
+
+static inline void dmx_scratch_destroy(DmxScratch* s) {
+    cudaFree(s->d_keys);
+    for (int b = 0; b < 2; ++b) { cudaFree(s->d_row_cnt[b]); cudaFree(s->d_alerts[b]); }
+    cudaFree(s->d_bound_cnt); cudaFree(s->d_alert_count); cudaFree(s->d_bound); cudaFree(s->d_shared);
+    *s = DmxScratch();
+}
+
+// Enqueue the kernels for one message.  Returns the number of kernels launched or < 0.
+static inline int dmx_launch(DmxScratch* s, const uint8_t* d_buf, uint64_t nbytes, uint64_t n_train_lines, DmTable table,
+                             uint8_t* d_flags, float* d_scores, uint64_t out_cap, dm_anomaly_t* d_anoms, uint32_t anomaly_cap,
+                             DmBatchHeader* d_hdr, unsigned long long* d_stats, uint64_t max_lines, cudaStream_t st,
+                             bool allow_overlap, void (*mark)(void*, cudaStream_t, int), void* mark_ctx) {
+    const uint32_t n_rows = (uint32_t)((nbytes + DMX_ROW - 1) / DMX_ROW);
+    if (n_rows == 0) return 0;
+    if (n_rows > s->max_rows) return DM_ERR_CAPACITY;
+    DmxArgs a;
+    a.buf = d_buf; a.nbytes = nbytes; a.n_rows = n_rows;
+    a.keys = s->d_keys; a.table = table;
+    a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap; a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap;
+    a.hdr = d_hdr; a.stats = d_stats; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
+    a.sh = s->d_shared; a.alert_cap = s->alert_cap; a.bound_ptr = nullptr; a.keep_error = 0;
+    // geometry: every warp gets the same number of contiguous rows
+    const unsigned long long warps_max = (unsigned long long)s->max_grid * DMX_WARPS;
+    const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
+    const unsigned long long warps = (n_rows + rpw - 1) / rpw;
+    const unsigned grid = (unsigned)((warps + DMX_WARPS - 1) / DMX_WARPS);
+    a.rows_per_warp = rpw;
+    int launched = 0;
+    auto bind = [&]() {
+        a.seq = ++s->seq;
+        const int p = (int)(a.seq & 1ull);
+        a.row_cnt = s->d_row_cnt[p]; a.alerts = s->d_alerts[p]; a.alert_count = s->d_alert_count + p;
+    };
+    if (n_train_lines > 0) {
+        // where detection starts is only known on the device
+        dm_k_rowcount<<<(unsigned)std::min<uint64_t>((n_rows + 7) / 8, 2048), 256, 0, st>>>(d_buf, nbytes, n_rows, s->d_bound_cnt);
+        dm_k_bound<<<1, 256, 0, st>>>(d_buf, nbytes, n_rows, s->d_bound_cnt, n_train_lines, s->d_bound, d_hdr);
+        a.bound_ptr = s->d_bound; a.keep_error = 1;
+        bind();
+        dm_launch_pdl_smem(dm_k_stream<true>, grid, DMX_THREADS, (size_t)DMX_DYN_SMEM, st, false, a);
+        launched += 3;
+    }
+    bind();
+    const bool pdl = allow_overlap && n_train_lines == 0 && s->chain_stream == st;
+    if (mark) mark(mark_ctx, st, 0);
+    dm_launch_pdl_smem(dm_k_stream<false>, grid, DMX_THREADS, (size_t)DMX_DYN_SMEM, st, pdl, a);
+    if (mark) mark(mark_ctx, st, 1);
+    s->chain_stream = st;
+    ++launched;
+    if (cudaGetLastError() != cudaSuccess) return DM_ERR_CUDA;
+    return launched;
+}
+#endif  // DM_EMU

@@ -16,6 +16,7 @@
 #include "dm_kernels_v1.cuh"
 #include "dm_kernels_tile.cuh"
 #include "dm_kernels_rows.cuh"
+#include "dm_kernels_stream.cuh"
 #include "dm_kernels_staged.cuh"
 #include "dm_kernels_cta.cuh"
 #include "dm_kernels_values.cuh"
@@ -65,7 +66,7 @@ struct dm_handle {
     uint64_t max_batch_bytes = 0, max_lines = 0;
     uint32_t table_log2 = 0;
     uint32_t n_keys = 0;
-    int kernel_variant = 2;              // 0 = v1 (line index + warp per record), 1 = fused tile kernel, 2 = rows (row index + independent rows)
+    int kernel_variant = 6;              // 6 = stream (default), 2 = rows, 5 = lanes; 0 v1, 1 tile, 3 staged, 4 cta
 
     DmKeys h_keys;
     DmKeys* d_keys = nullptr;
@@ -87,6 +88,7 @@ struct dm_handle {
     uint64_t novel_exported = 0;         // novel keys already shipped in a window
     DmTileScratch tile;                  // fused-kernel scratch
     DmRowsScratch rows;                  // rows-variant scratch
+    DmxScratch dmx;                      // stream-variant scratch (default kernel)
     DmStagedScratch staged;              // staged-variant scratch (candidate / field lists)
     DmCtaScratch cta;                    // cta-variant launch geometry
     uint64_t last_nbytes = 0;
@@ -141,6 +143,12 @@ static int dm_pick_stream(dm_handle* h, void* stream, cudaStream_t* out) {
     *out = stream ? (cudaStream_t)stream : h->stream;
     h->last_stream = *out;
     return DM_OK;
+}
+
+// Anything this library enqueues that is not a stream-variant detect launch ends the chain of
+// overlapping launches on that stream: the next detect launch is then ordered behind it in full.
+static void dm_break_chain(dm_handle* h, cudaStream_t st) {
+    if (h->dmx.chain_stream == st) h->dmx.chain_stream = nullptr;
 }
 
 extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, const uint32_t* key_lens,
@@ -233,6 +241,9 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
     if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "tile scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     rc = dm_rows_scratch_create(&h->rows, max_batch_bytes, h->sm_count);
     if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "rows scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    rc = dmx_scratch_create(&h->dmx, h->h_keys, max_batch_bytes, h->anomaly_cap, h->sm_count);
+    if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "stream scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    { const char* ov = getenv("DM_OVERLAP"); if (ov) h->dmx.overlap = atoi(ov) != 0; }
     const char* env = getenv("DM_KERNEL");
     if (env && strcmp(env, "v1") == 0) h->kernel_variant = 0;
     if (env && strcmp(env, "tile") == 0) h->kernel_variant = 1;
@@ -240,6 +251,7 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
     if (env && strcmp(env, "staged") == 0) h->kernel_variant = 3;
     if (env && strcmp(env, "cta") == 0) h->kernel_variant = 4;
     if (env && strcmp(env, "lanes") == 0) h->kernel_variant = 5;
+    if (env && strcmp(env, "stream") == 0) h->kernel_variant = 6;
     if (h->kernel_variant == 4) {
         rc = dm_cta_scratch_create(&h->cta, h->sm_count);
         if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "cta occupancy query failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -250,6 +262,13 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
     }
     DM_CUDA(cudaDeviceSynchronize());
     *out = h;
+    return DM_OK;
+}
+
+extern "C" int dm_set_overlap(dm_handle* h, int on) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    h->dmx.overlap = on != 0;
+    h->dmx.chain_stream = nullptr;
     return DM_OK;
 }
 
@@ -290,6 +309,7 @@ extern "C" int dm_destroy(dm_handle* h) {
     for (auto& e : h->ev) cudaEventDestroy(e);
     dm_tile_scratch_destroy(&h->tile);
     dm_rows_scratch_destroy(&h->rows);
+    dmx_scratch_destroy(&h->dmx);
     dm_staged_scratch_destroy(&h->staged);
     cudaFree(h->d_keys); cudaFree(h->d_in); cudaFree(h->d_tile_counts); cudaFree(h->d_tile_base);
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
@@ -321,6 +341,8 @@ static int dm_check_device_errors(dm_handle* h) {
         return dm_fail(DM_ERR_TABLE_FULL, "known-set table over its load limit (2^%u slots); recreate with a larger table_log2_slots", h->table_log2);
     if (err & DM_DEVERR_NOVEL_OVERFLOW)
         return dm_fail(DM_ERR_TABLE_FULL, "more than %u distinct values learnt; novel-key list full", h->table.novel_cap);
+    if (err & DM_DEVERR_ANOMALY_OVERFLOW)
+        return dm_fail(DM_ERR_CAPACITY, "more than %u unknown values in one batch; the anomaly list is full", h->anomaly_cap);
     if (err & DM_DEVERR_TOO_MANY_LINES)
         return dm_fail(DM_ERR_CAPACITY, "batch holds more than max_lines=%llu records", (unsigned long long)h->max_lines);
     return DM_OK;
@@ -358,7 +380,8 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
     const uint64_t out_cap = std::min(cap_flags, cap_scores);
     (void)dev_cap;
 
-    // (the rows variant clears the per-batch header in its first kernel)
+    bool stream_kernel = false;
+    // (the rows and stream variants write the per-batch header themselves)
     if (h->kernel_variant < 2 || nbytes == 0 || h->fmt_set) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
     h->last_nbytes = nbytes;
 
@@ -464,6 +487,12 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
                                         st, dm_prof_mark_cb, h);
         if (rc < 0) return dm_fail(DM_ERR_CUDA, "staged kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         h->launches += (uint64_t)rc;
+    } else if (h->kernel_variant == 6) {
+        stream_kernel = true;
+        const int rc = dmx_launch(&h->dmx, d_buf, nbytes, n_train_lines, h->table, d_flags, d_scores, out_cap, h->d_anoms,
+                                  h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st, h->dmx.overlap, dm_prof_mark_cb, h);
+        if (rc < 0) return dm_fail(DM_ERR_CUDA, "stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->launches += (uint64_t)rc;
     } else if (h->kernel_variant == 2) {
         const int rc = dm_rows_launch(&h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,
                                       out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st,
@@ -479,6 +508,7 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
         h->launches += (uint64_t)rc;
     }
     DM_CUDA(cudaGetLastError());
+    if (!stream_kernel) h->dmx.chain_stream = nullptr;     // (a launch that is not the stream kernel's ends the overlap chain)
 
     const bool want_sync = host_out || n_lines_out || n_anomalies_out;
     if (!want_sync) return DM_OK;
@@ -520,6 +550,7 @@ extern "C" int dm_process_values(dm_handle* h, const uint8_t* blob, uint64_t blo
     DM_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     h->last_stream = st;
+    dm_break_chain(h, st);
     if (n_values > h->vals_cap) {
         if (h->d_vals) DM_CUDA(cudaFree(h->d_vals));
         h->vals_cap = std::max<uint64_t>(2ull * n_values, 4096);
@@ -711,6 +742,7 @@ extern "C" int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nby
     DM_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     h->last_stream = st;
+    dm_break_chain(h, st);
     if (2ull * n_records > 3ull * h->vals_cap) {
         if (h->d_vals) DM_CUDA(cudaFree(h->d_vals));
         h->vals_cap = std::max<uint64_t>(2ull * n_records, 4096);
@@ -787,7 +819,7 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     if (nbytes > h->max_batch_bytes)
         return dm_fail(DM_ERR_CAPACITY, "message of %llu bytes exceeds max_batch_bytes=%llu", (unsigned long long)nbytes, (unsigned long long)h->max_batch_bytes);
     if (nbytes && !host_buf) return dm_fail(DM_ERR_ARG, "host_buf is NULL");
-    if (h->kernel_variant < 2 || h->kernel_variant == 5) return dm_fail(DM_ERR_STATE, "the pipelined path needs the rows or staged kernels");
+    if (h->kernel_variant < 2 || h->kernel_variant == 5) return dm_fail(DM_ERR_STATE, "the pipelined path needs the stream or rows kernels");
     if (h->fmt_set) return dm_fail(DM_ERR_STATE, "the pipelined path tokenises key=value records; with a log_format use dm_process_lines");
     if (h->mons_set && h->h_mons.n_combos > 0) return dm_fail(DM_ERR_STATE, "combination monitors run in dm_process_lines / dm_process_records, not in the pipelined path");
     DM_CUDA(cudaSetDevice(h->device));
@@ -802,7 +834,10 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     h->last_stream = st;
     DM_CUDA(cudaStreamWaitEvent(st, sl.ev_in, 0));
     if (nbytes == 0) DM_CUDA(cudaMemsetAsync(sl.d_hdr, 0, sizeof(DmBatchHeader), st));
-    const int launched = h->kernel_variant == 4
+    const int launched = h->kernel_variant == 6
+        ? dmx_launch(&h->dmx, sl.d_in, nbytes, n_train_lines, h->table, sl.d_flags, sl.d_scores, h->max_lines, sl.d_anoms,
+                     h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, true, dm_prof_mark_cb, h)
+        : h->kernel_variant == 4
         ? dm_cta_launch(&h->cta, &h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
                         h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, dm_prof_mark_cb, h)
         : h->kernel_variant == 3
@@ -968,6 +1003,7 @@ extern "C" int dm_import_known(dm_handle* h, const uint64_t* keys, uint64_t n) {
     DM_CUDA(cudaMalloc(&d_tmp, n * sizeof(unsigned long long)));
     DM_CUDA(cudaMemcpy(d_tmp, keys, n * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), h->last_stream));
+    dm_break_chain(h, h->last_stream);
     dm_k_insert_keys<<<std::max(1, (int)std::min<uint64_t>((n + 255) / 256, 1024)), 256, 0, h->last_stream>>>(h->table, d_tmp, n, &h->d_hdr->error);
     DM_CUDA(cudaGetLastError());
     int rc = dm_sync(h, nullptr, nullptr);
@@ -1041,8 +1077,8 @@ __global__ void dm_k_window_import(const unsigned long long* __restrict__ in, ui
 extern "C" int dm_window_export(dm_handle* h, uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream_) {
     if (!h || !dev_buf || rank >= world) return dm_fail(DM_ERR_ARG, "bad window arguments");
     DM_CUDA(cudaSetDevice(h->device));
-    cudaStream_t st;
-    dm_pick_stream(h, stream_, &st);
+    cudaStream_t st = stream_ ? (cudaStream_t)stream_ : h->stream;     // (not recorded as the compute stream)
+    dm_break_chain(h, st);
     uint64_t novel_to = h->novel_exported;
     if (with_keys) {
         // the number of keys learnt so far is needed on the host to bound the segment
@@ -1067,8 +1103,8 @@ extern "C" int dm_window_export(dm_handle* h, uint64_t* dev_buf, uint32_t rank, 
 extern "C" int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream_) {
     if (!h || !dev_buf || rank >= world) return dm_fail(DM_ERR_ARG, "bad window arguments");
     DM_CUDA(cudaSetDevice(h->device));
-    cudaStream_t st;
-    dm_pick_stream(h, stream_, &st);
+    cudaStream_t st = stream_ ? (cudaStream_t)stream_ : h->stream;     // (not recorded as the compute stream)
+    dm_break_chain(h, st);
     dm_k_window_import<<<with_keys ? 256 : 1, 256, 0, st>>>((const unsigned long long*)dev_buf, world, rank,
                                                           h->d_stats_global, h->table, &h->d_hdr->error, with_keys);
     DM_CUDA(cudaGetLastError());
@@ -1168,8 +1204,7 @@ extern "C" int dm_window_allreduce(dm_handle* h, int with_keys, void* stream_) {
     // alternating streams, two all-reduces are in flight, which matters at 8 ranks where one
     // export + all-reduce + import chain is longer than a step
     const uint32_t k = (uint32_t)(h->win_seq++ % h->nccl_n);
-    cudaStream_t st;
-    dm_pick_stream(h, stream_, &st);
+    cudaStream_t st = stream_ ? (cudaStream_t)stream_ : h->stream;     // (not recorded as the compute stream)
     DM_CUDA(cudaSetDevice(h->device));
     DM_CUDA(cudaStreamWaitEvent(st, h->ev_win_done[k], 0));           // the buffer's previous window is through
     int rc = dm_window_export(h, (uint64_t*)h->d_win[k], h->nccl_rank, h->nccl_world, with_keys, stream_);

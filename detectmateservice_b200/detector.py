@@ -290,6 +290,11 @@ class DeviceDetector:
         return int(self._lib.dm_table_key(int(field), value, len(value)))
 
     # ------------------------------------------------------------------ measurement
+    def set_overlap(self, on: bool = True) -> None:
+        """Let consecutive device-resident detection calls on one stream overlap (dm_set_overlap:
+        the caller promises not to rewrite a call's input with a kernel enqueued between calls)."""
+        _lib.check(self._lib.dm_set_overlap(self._h, int(on)))
+
     def profile_enable(self, on: bool = True) -> None:
         _lib.check(self._lib.dm_profile_enable(self._h, int(on)))
 

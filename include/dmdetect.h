@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 2
+#define DM_ABI_VERSION 3
 #define DM_MAX_KEYS 32      /* monitored fields per detector                         */
 #define DM_MAX_KEYLEN 32    /* bytes per monitored key                                */
 
@@ -96,15 +96,23 @@ int dm_destroy(dm_handle* h);
  *                      output was requested the call only ENQUEUES work on `stream` and
  *                      returns without synchronising (device-resident pipelines);
  *                      otherwise it returns after the results are complete.
- * Consecutive calls on one stream overlap through programmatic dependent launch: a call may
- * start READING its own `buf` while the previous call's kernels are still running; it writes
- * outputs and scratch only after they have finished, so stream order still protects every
- * buffer the caller produces or consumes with stream-ordered work (DM_PDL=0 disables it).
+ * By default a call is ordered behind everything enqueued on `stream` before it.  After
+ * dm_set_overlap(h, 1) consecutive device-resident detection calls on one stream overlap
+ * (programmatic dependent launch): a call may then start READING its `buf` and the known-set
+ * table while the previous call's kernel is still running (outputs, header and statistics are
+ * still written in call order).  That is only safe when the caller does not enqueue, between
+ * two calls on that stream, a KERNEL that writes the next call's `buf` -- copies (cudaMemcpyAsync)
+ * and event waits are fine, they are ordered in full.  dm_submit_lines always overlaps (its
+ * inputs arrive by copy).
  * Replaces: per-record CoreComponent.process calls made by core.py:201-203. */
 int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbytes, int buf_on_device,
                      uint64_t n_train_lines,
                      uint8_t* flags_out, float* scores_out, uint64_t out_cap_lines, int out_on_device,
                      uint64_t* n_lines_out, uint64_t* n_anomalies_out, void* stream);
+
+/* Switch the overlap of consecutive dm_process_lines calls (see above) on or off; off at creation
+ * (DM_OVERLAP=1 in the environment turns it on for every handle). */
+int dm_set_overlap(dm_handle* h, int on);
 
 /* Record mode: the detector fed with already-extracted values, as when the upstream parser
  * sends one ParserSchema per message (engine.py:163-187; the host decodes the protobuf

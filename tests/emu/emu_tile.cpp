@@ -9,6 +9,7 @@
 
 #include "dm_kernels_tile.cuh"
 #include "dm_kernels_rows.cuh"
+#include "dm_kernels_stream.cuh"
 #include "dm_kernels_staged.cuh"
 #include "dm_kernels_records.cuh"
 #include "dm_kernels_cta.cuh"
@@ -64,6 +65,7 @@ struct EmuHandle {
     std::vector<unsigned long long> rows_tile_state;
     unsigned long long row_ctr = 0, row_ctr_base = 0;
     uint32_t rows_epoch = 0;
+    struct EmuStream* xs = nullptr;      // stream variant (created on first use)
 };
 
 extern "C" EmuHandle* emu_create(uint32_t n_keys, const uint8_t* blob, const uint32_t* lens, uint32_t table_log2,
@@ -96,7 +98,8 @@ extern "C" EmuHandle* emu_create(uint32_t n_keys, const uint8_t* blob, const uin
     return h;
 }
 
-extern "C" void emu_destroy(EmuHandle* h) { delete h; }
+void emu_stream_free(struct EmuStream*);
+extern "C" void emu_destroy(EmuHandle* h) { emu_stream_free(h->xs); delete h; }
 
 // Mirrors dm_tile_launch (dm_kernels_tile.cuh): optional TRAIN launch, then the DETECT launch.
 extern "C" int emu_process(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
@@ -239,6 +242,72 @@ static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbyt
         else emu_launch(DMR_B_THREADS, [&] { dm_k_rows<false, false>(a); });
         h->row_ctr_base += per_launch;
     }
+    free(buf);
+    *n_lines = h->hdr.n_lines;
+    *n_anoms = h->hdr.n_anomalies;
+    *err = h->hdr.error;
+    return 0;
+}
+
+// Mirrors dmx_launch (dm_kernels_stream.cuh): [row counts, boundary, TRAIN launch,] DETECT launch.  The grid is
+// `g_emu_stream_ctas` CTAs run one after the other (the last one runs the epilogue).
+static uint32_t g_emu_stream_ctas = 3;
+extern "C" void emu_stream_ctas(uint32_t n) { g_emu_stream_ctas = n ? n : 1; }
+struct EmuStream {
+    DmxKeyTab tab;
+    DmxShared sh;
+    std::vector<unsigned short> row_cnt[2], bound_cnt;
+    std::vector<dm_anomaly_t> alerts[2];
+    unsigned int alert_count[2] = {0, 0};
+    unsigned long long bound = 0, seq = 0;
+    bool ready = false;
+};
+void emu_stream_free(EmuStream* x) { delete x; }
+extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                  float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    if (!h->xs) {
+        h->xs = new EmuStream();
+        if (!dmx_keytab_build(h->keys, &h->xs->tab)) return -7;
+        memset(&h->xs->sh, 0, sizeof(h->xs->sh));
+    }
+    EmuStream& g_xs = *h->xs;
+    uint8_t* buf = (uint8_t*)aligned_alloc(64, ((nbytes + 64 + 63) / 64) * 64 + 64);
+    memcpy(buf, msg, nbytes);
+    for (int i = 0; i < 64; ++i) buf[nbytes + i] = (i & 1) ? '\n' : '=';      // hostile slack
+    memset(&h->hdr, 0, sizeof(h->hdr));
+    *n_lines = 0; *n_anoms = 0; *err = 0;
+    const uint32_t n_rows = (uint32_t)((nbytes + DMX_ROW - 1) / DMX_ROW);
+    if (n_rows == 0) { free(buf); return 0; }
+    for (int b = 0; b < 2; ++b) {
+        if (g_xs.row_cnt[b].size() < n_rows + 1) g_xs.row_cnt[b].assign(n_rows + 1, 0xBEEF);
+        if (g_xs.alerts[b].size() < h->anoms.size()) g_xs.alerts[b].resize(h->anoms.size());
+    }
+    g_xs.bound_cnt.assign(n_rows + 1, 0xBEEF);
+    g_emu_dyn_smem.assign(DMX_DYN_SMEM, 0xEE);
+    DmxArgs a;
+    a.buf = buf; a.nbytes = nbytes; a.n_rows = n_rows; a.keys = &g_xs.tab; a.table = h->table;
+    a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
+    a.hdr = &h->hdr; a.stats = h->stats; a.n_train_lines = n_train; a.max_lines = h->max_lines;
+    a.sh = &g_xs.sh; a.alert_cap = (uint32_t)h->anoms.size(); a.bound_ptr = nullptr; a.keep_error = 0;
+    const unsigned long long warps_max = (unsigned long long)g_emu_stream_ctas * DMX_WARPS;
+    const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
+    const unsigned long long warps = (n_rows + rpw - 1) / rpw;
+    const unsigned grid = (unsigned)((warps + DMX_WARPS - 1) / DMX_WARPS);
+    a.rows_per_warp = rpw;
+    auto bind = [&]() {
+        a.seq = ++g_xs.seq;
+        const int p = (int)(a.seq & 1ull);
+        a.row_cnt = g_xs.row_cnt[p].data(); a.alerts = g_xs.alerts[p].data(); a.alert_count = &g_xs.alert_count[p];
+    };
+    if (n_train > 0) {
+        emu_launch_grid(2, 256, [&] { dm_k_rowcount(buf, nbytes, n_rows, g_xs.bound_cnt.data()); });
+        emu_launch(256, [&] { dm_k_bound(buf, nbytes, n_rows, g_xs.bound_cnt.data(), n_train, &g_xs.bound, &h->hdr); });
+        a.bound_ptr = &g_xs.bound; a.keep_error = 1;
+        bind();
+        emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<true>(a); });
+    }
+    bind();
+    emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<false>(a); });
     free(buf);
     *n_lines = h->hdr.n_lines;
     *n_anoms = h->hdr.n_anomalies;

@@ -47,6 +47,8 @@ class EmuDetector:
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_process_lanes.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.emu_process_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.c_uint32, C.c_char_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint64, C.c_uint64]
         L.emu_destroy.argtypes = [C.c_void_p]
@@ -74,7 +76,7 @@ class EmuDetector:
         scores = np.full(cap, -1, dtype=np.float32)
         n_lines, n_anom, err = C.c_uint64(), C.c_uint64(), C.c_uint32()
         fn = {"rows": self.lib.emu_process_rows, "staged": self.lib.emu_process_staged, "cta": self.lib.emu_process_cta,
-              "lanes": self.lib.emu_process_lanes}.get(self.variant, self.lib.emu_process)
+              "lanes": self.lib.emu_process_lanes, "stream": self.lib.emu_process_stream}.get(self.variant, self.lib.emu_process)
         rc = fn(self.h, msg, len(msg), n_train, flags.ctypes.data, scores.ctypes.data, cap,
                                   C.byref(n_lines), C.byref(n_anom), C.byref(err))
         assert rc == 0 and err.value == 0, (rc, err.value)

@@ -15,7 +15,7 @@ from oracle.native import NativeOracle
 from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines
 
 
-@pytest.fixture(params=["cta", "staged", "rows", "tile", "lanes"], autouse=True)
+@pytest.fixture(params=["stream", "cta", "staged", "rows", "tile", "lanes"], autouse=True)
 def emu_variant(request):
     """Every test runs against both device decompositions (DM_KERNEL=rows / tile)."""
     global VARIANT
@@ -34,7 +34,7 @@ def _default_variant_only():
     """The full matrix (fuzz, variable length, all-unknown) runs for the default kernels here
     and for EVERY variant on the B200 (test_gpu_parity.py); the other variants get the golden,
     edge-case and train/detect-split tests in the CPU tier, which keeps it to a few minutes."""
-    if VARIANT not in ("rows", "lanes"):
+    if VARIANT not in ("stream", "rows", "lanes"):
         pytest.skip("full emulator matrix only for the default variant; all variants run on the GPU")
 
 

@@ -16,7 +16,7 @@ from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["v1", "tile", "rows", "staged", "cta", "lanes"]
+VARIANTS = ["stream", "v1", "tile", "rows", "staged", "cta", "lanes"]
 SCORE_TOL = 1e-5
 
 
@@ -305,12 +305,13 @@ def test_window_exchange_two_ranks_on_one_gpu(variant):
         assert gs["score_sum"] == int(ws.sum()) and gs == d1.global_stats()
 
 
-def test_pipelined_submit_collect(monkeypatch):
+@pytest.mark.parametrize("kernel", ["stream", "rows"])
+def test_pipelined_submit_collect(monkeypatch, kernel):
     """dm_submit_lines / dm_collect (two slots in flight) give the same flags, scores and
     anomaly lists as the synchronous call, in submission order, training included."""
     import torch
     from detectmateservice_b200.synth import AuditSynth, MONITORED_KEYS
-    monkeypatch.setenv("DM_KERNEL", "rows")
+    monkeypatch.setenv("DM_KERNEL", kernel)
     g = AuditSynth(seed=31)
     msgs = [g.batch(5000, inject=False)[0]] + [g.batch(5000, inject=True)[0] for _ in range(6)] + [b"", b"type=A\n"]
     n_train = [3000] + [0] * (len(msgs) - 1)
