@@ -41,16 +41,16 @@
 #define DMX_MIRROR 64u                      // the first bytes of the ring again behind it: reads never wrap
 #define DMX_WARPS 8
 #define DMX_THREADS (DMX_WARPS * 32)
-#define DMX_QCAP 64u                        // field queue entries per warp (circular)
-#define DMX_DEPTH 4u                        // rows loaded ahead
-#define DMX_L1 1024u                        // slots of the level-1 key table
+#define DMX_QCAP 256u                       // field queue entries per warp (circular; a row adds at most 128 at once)
+#define DMX_DEPTH 2u                        // rows loaded ahead (queued fields may then be up to 5 rows old)
+#define DMX_L1 512u                         // slots of the level-1 key table
 #define DMX_WIN 32u                         // bytes of value looked at by the fast path
-#define DMX_FULL 0x100u                     // level-1 info: the four bytes decide alone (3-byte key + delimiter)
+#define DMX_FULL 0x40u                      // level-1 info: the four bytes decide alone (3-byte key + delimiter)
 #define DMX_DYN_SMEM (DMX_WARPS * (DMX_RING + DMX_MIRROR))
 
 #define DM_DEVERR_ANOMALY_OVERFLOW 8u
 
-struct DmxL1 { uint32_t pat; uint32_t info; };      // info: 0 = empty, else (first key of the chain + 1) | DMX_FULL
+struct DmxL1 { uint32_t pat; uint32_t info; };      // info (7 bits): 0 = empty, else (first key of the chain + 1) | DMX_FULL
 
 // Monitored keys as the stream kernel sees them (copied to shared memory per CTA).
 struct DmxKeyTab {
@@ -72,6 +72,8 @@ struct DmxKeyTab {
 struct DmxShared {
     unsigned int done_ctr[4];                // CTAs of launch (seq & 3) that have finished their rows
     unsigned long long epi_done_seq;         // sequence number of the last launch whose epilogue is complete
+    unsigned long long zero_bound;           // records of the previous detect message: that many output entries are
+                                             // zero-filled by all CTAs together, the epilogue does the rest (if any)
 };
 
 struct DmxArgs {
@@ -81,8 +83,11 @@ struct DmxArgs {
     uint32_t rows_per_warp;
     const DmxKeyTab* keys;
     DmTable table;
+    uint32_t rows_per_cta;
     unsigned short* row_cnt;                 // '\n' per row (this launch's parity)
-    dm_anomaly_t* alerts;                    // staged alerts of this launch: {line = offset of the '=', mask = field, offset = record start}
+    unsigned int* cta_cnt;                   // '\n' per CTA (this launch's parity)
+    dm_anomaly_t* alerts;                    // staged alerts of this launch: {line = '\n' between the start of the 512-byte
+                                             // row and the record start, mask = field, offset = record start}
     unsigned int* alert_count;
     uint32_t alert_cap;
     uint8_t* flags;
@@ -99,12 +104,24 @@ struct DmxArgs {
     const unsigned long long* bound_ptr;     // message with training AND detection records: byte offset of the
                                              // first detection record (dm_k_bound), else NULL
     uint32_t keep_error;                     // the epilogue ORs into hdr->error instead of assigning it
+    unsigned long long* timeline;            // diagnostics (DM_STREAM_TIMELINE=1): per CTA {smid, t_start, t_rows_done, t_exit},
+                                             // then 8 epilogue stamps (globaltimer ns); else NULL
 };
+
+__device__ __forceinline__ unsigned long long dmx_now() {
+#ifndef DM_EMU
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#else
+    return 0;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------
 // host: key tables
 // ---------------------------------------------------------------------------------------
-// Returns false if no perfect hash was found (cannot happen for <= 96 patterns in 1024 slots in practice).
+// Returns false if no perfect hash was found (<= 96 patterns in 512 slots: a few thousand multipliers at worst).
 static inline bool dmx_keytab_build(const DmKeys& k, DmxKeyTab* t) {
     memset(t, 0, sizeof(*t));
     t->n = k.n;
@@ -136,18 +153,18 @@ static inline bool dmx_keytab_build(const DmKeys& k, DmxKeyTab* t) {
         for (; j < np; ++j)
             if (pats[j] == p) break;
         if (j < np) {                                               // same last four bytes as an earlier key: chain
-            uint32_t c = (info[j] & 0xFFu) - 1;
+            uint32_t c = (info[j] & 0x3Fu) - 1;
             while (t->next[c]) c = t->next[c] - 1;
             t->next[c] = i + 1;
         } else {
             pats[np] = p; info[np++] = i + 1;
         }
     }
-    for (uint32_t lg = 6; lg <= 10; ++lg) {
+    for (uint32_t lg = 6; lg <= 9; ++lg) {
         const uint32_t slots = 1u << lg;
-        if (np > slots / 2 && lg < 10) continue;
+        if (np > slots / 4 && lg < 9) continue;
         uint64_t x = 0x9E3779B97F4A7C15ull;
-        for (int trial = 0; trial < 200000; ++trial) {
+        for (int trial = 0; trial < 2000000; ++trial) {
             x = dm_splitmix64(x);
             const uint32_t mult = (uint32_t)x | 1u;
             bool used[DMX_L1];
@@ -222,30 +239,29 @@ static inline void dmx_st_release(unsigned long long* p, unsigned long long v) {
 struct DmxRing {
     uint8_t* ring;                  // DMX_RING + DMX_MIRROR bytes
     const uint8_t* buf;
-    uint64_t nb16;                  // readable extent of the message (nbytes rounded up to 16)
     uint32_t r0, r1;                // rows [r0, r1) of this warp; row r1 (if it exists) is loaded as a 64-byte look-ahead
+    uint32_t last_row, last_bytes;  // the message's last row holds last_bytes readable bytes (a multiple of 16)
 #ifndef DM_EMU
     uint32_t ring_s, bar_s;
 #endif
 
+    // bytes of row `row` that are loaded into its slot
+    __device__ __forceinline__ uint32_t row_bytes(uint32_t row) const {
+        uint32_t bytes = row == last_row ? last_bytes : DMX_ROW;
+        if (row == r1 && bytes > DMX_MIRROR) bytes = DMX_MIRROR;
+        return bytes;
+    }
     __device__ __forceinline__ void issue(uint32_t i) const {
         const uint32_t row = r0 + i;
-        const uint64_t off = (uint64_t)row * DMX_ROW;
-        uint32_t bytes = (uint32_t)(nb16 - off < DMX_ROW ? nb16 - off : DMX_ROW);
-        if (row == r1 && bytes > DMX_MIRROR) bytes = DMX_MIRROR;
+        const uint8_t* src = buf + (uint64_t)row * DMX_ROW;
+        const uint32_t bytes = row_bytes(row);
         const uint32_t slot = row & (DMX_SLOTS - 1);
-        const uint32_t mbytes = slot == 0 ? (bytes < DMX_MIRROR ? bytes : DMX_MIRROR) : 0u;
-        const bool pre = i == 0 && off > 0;            // the 16 bytes in front of the range (key bytes of its first '=')
 #ifndef DM_EMU
         const uint32_t bar = bar_s + 8u * slot;
-        dmx_mbar_expect_tx(bar, bytes + mbytes + (pre ? 16u : 0u));
-        dmx_bulk_g2s(ring_s + slot * DMX_ROW, buf + off, bytes, bar);
-        if (mbytes) dmx_bulk_g2s(ring_s + DMX_RING, buf + off, mbytes, bar);
-        if (pre) dmx_bulk_g2s(ring_s + (uint32_t)((off - 16) & (DMX_RING - 1)), buf + off - 16, 16u, bar);
+        dmx_mbar_expect_tx(bar, bytes);
+        dmx_bulk_g2s(ring_s + slot * DMX_ROW, src, bytes, bar);
 #else
-        memcpy(ring + slot * DMX_ROW, buf + off, bytes);
-        if (mbytes) memcpy(ring + DMX_RING, buf + off, mbytes);
-        if (pre) memcpy(ring + ((off - 16) & (DMX_RING - 1)), buf + off - 16, 16);
+        memcpy(ring + slot * DMX_ROW, src, bytes);
 #endif
     }
     __device__ __forceinline__ void wait(uint32_t i) const {
@@ -256,8 +272,9 @@ struct DmxRing {
         __syncwarp();
 #endif
     }
-    __device__ __forceinline__ uint32_t ld32(uint32_t ring_off) const { return *reinterpret_cast<const uint32_t*>(ring + ring_off); }
 };
+
+__device__ __forceinline__ uint32_t dmx_ld32(const uint8_t* ring, uint32_t ring_off) { return *reinterpret_cast<const uint32_t*>(ring + ring_off); }
 
 __device__ __forceinline__ bool dmx_is_delim(uint32_t d) { return d == 0x20u || d == 0x27u || d == 0x0Au; }
 
@@ -269,15 +286,15 @@ __device__ __forceinline__ uint32_t dmx_stopflags(uint32_t w) {
 
 // Which monitored key (if any) ends right before the '=' at q, given the level-1 hit `info`?  Reads
 // bytes q-12 .. q-5 from the ring (the 16 bytes in front of the message are '\n').
-__device__ __forceinline__ int dmx_resolve_key(const DmxRing& rg, const uint8_t* __restrict__ buf, uint32_t q, uint32_t info,
+__device__ __forceinline__ int dmx_resolve_key(const uint8_t* ring, const uint8_t* __restrict__ buf, uint32_t q, uint32_t info,
                                                const DmxKeyTab& sk) {
-    if (info & DMX_FULL) return (int)(info & 0xFFu) - 1;
+    if (info & DMX_FULL) return (int)(info & 0x3Fu) - 1;
     const uint32_t base = ((q - 12u) & ~3u) & (DMX_RING - 1);
     const uint32_t sh = (q & 3u) * 8u;
-    const uint32_t x0 = rg.ld32(base), x1 = rg.ld32(base + 4), x2 = rg.ld32(base + 8);
+    const uint32_t x0 = dmx_ld32(ring, base), x1 = dmx_ld32(ring, base + 4), x2 = dmx_ld32(ring, base + 8);
     const uint32_t w_a = __funnelshift_r(x0, x1, sh);     // bytes q-12 .. q-9
     const uint32_t w_b = __funnelshift_r(x1, x2, sh);     // bytes q-8 .. q-5
-    for (uint32_t k1 = info & 0xFFu; k1; k1 = sk.next[k1 - 1]) {
+    for (uint32_t k1 = info & 0x3Fu; k1; k1 = sk.next[k1 - 1]) {
         const uint32_t k = k1 - 1;
         const uint4 p = *reinterpret_cast<const uint4*>(sk.pat[k]);
         if ((((w_b ^ p.x) & p.y) | ((w_a ^ p.z) & p.w)) != 0) continue;
@@ -321,56 +338,6 @@ __device__ __forceinline__ uint32_t dmx_value_len_slow(const uint8_t* __restrict
         if (c == 0x22u) par ^= 1u;
     }
     return (uint32_t)(p - vpos);
-}
-
-// dm_fp64 of the value that starts at vpos (R-tok L5: it ends at the first space outside double
-// quotes counted from the value start, at '\n', or at the end of the message).
-__device__ __forceinline__ uint64_t dmx_value_fp(const DmxRing& rg, const uint8_t* __restrict__ buf, uint64_t nbytes, uint32_t vpos) {
-    const uint32_t vr = vpos & (DMX_RING - 1);
-    const uint32_t base = vr & ~3u;
-    const uint32_t sh = (vpos & 3u) * 8u;
-    uint32_t w[8];
-    {
-        uint32_t lo = rg.ld32(base);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t hi = rg.ld32(base + 4u * (i + 1));
-            w[i] = __funnelshift_r(lo, hi, sh);
-            lo = hi;
-        }
-    }
-    const uint64_t avail = nbytes > vpos ? nbytes - vpos : 0;
-    const uint32_t lim = avail < DMX_WIN ? (uint32_t)avail : DMX_WIN;
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
-    if (lim < DMX_WIN) m &= (1u << lim) - 1u;
-    uint32_t n = 0xFFFFFFFFu, par = 0;
-    while (m) {
-        const uint32_t j = (uint32_t)__ffs(m) - 1u;
-        m &= m - 1u;
-        const uint32_t c = rg.ring[vr + j];
-        if (c == 0x0Au || (c == 0x20u && !par)) { n = j; break; }
-        if (c == 0x22u) par ^= 1u;
-    }
-    if (n == 0xFFFFFFFFu) {
-        if (lim < DMX_WIN) n = lim;                       // the message ends inside the window: that ends the value
-        else {
-            // longer than the window: by the letter, from global memory
-            n = dmx_value_len_slow(buf, nbytes, vpos);
-            return dm_fp64_bytes(buf + vpos, n);
-        }
-    }
-    DmHashState st;
-    dm_hash_init(st);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (n > 4u * i) {
-            const uint32_t nb = n - 4u * i;
-            dm_hash_word(st, nb >= 4u ? w[i] : (w[i] & ((1u << (8u * nb)) - 1u)));
-        }
-    }
-    return dm_hash_final(st, n);
 }
 
 // Exact re-check of one candidate by ONE thread: is the '=' at q the first true field (R-tok L2-L6)
@@ -423,23 +390,195 @@ __device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ bu
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
-template <bool TRAIN>
-__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_pre);
+// Level-1 lookup for the FIRST '=' of one 4-byte word (f = its '=' flags, 0x80 per byte): the 4 bytes in front of
+// it, taken from the word and its predecessor.  Branch-free; with f == 0 the lookup reads some slot and the
+// result is discarded.  entry = queue entry of the field: ((offset of the '=' in this warp's range) << 7) | info.
+__device__ __forceinline__ bool dmx_probe(uint32_t lo, uint32_t cur, uint32_t f, const DmxL1* __restrict__ l1, uint32_t mult,
+                                          uint32_t shift, uint32_t qrel, uint32_t* entry, uint32_t* t_out) {
+    const uint32_t sh = ((uint32_t)__ffs(f) - 8u) & 31u;              // 8 * (byte index of the '=')
+    const uint32_t t = __funnelshift_r(lo, cur, sh);
+    const DmxL1 l = l1[(t * mult) >> shift];
+    *entry = ((qrel + (sh >> 3)) << 7) | l.info;
+    *t_out = t;
+    return f != 0u && l.pat == t;
+}
+
+// zero-fill of output entries [lo, hi): 16-byte stores where the caller's buffers allow it
+__device__ __forceinline__ void dmx_zero_outputs(uint8_t* flags, float* scores, unsigned long long lo, unsigned long long hi,
+                                                 uint32_t tid, uint32_t nthreads) {
+    if (hi <= lo) return;
+    unsigned long long v0 = lo, v1 = lo;
+    if ((((uintptr_t)flags) | ((uintptr_t)scores)) % 16 == 0) {
+        v0 = (lo + 15ull) & ~15ull;
+        v1 = hi & ~15ull;
+        if (v1 < v0) v0 = v1 = lo;
+    }
+    for (unsigned long long i = v0 + (unsigned long long)tid * 16; i < v1; i += nthreads * 16ull) {
+        *reinterpret_cast<uint4*>(flags + i) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(scores + i + 4 * j) = make_uint4(0, 0, 0, 0);
+    }
+    for (unsigned long long i = lo + tid; i < v0; i += nthreads) { flags[i] = 0; scores[i] = 0.0f; }
+    for (unsigned long long i = v1 + tid; i < hi; i += nthreads) { flags[i] = 0; scores[i] = 0.0f; }
+}
 
 template <bool TRAIN>
-__global__ void __launch_bounds__(DMX_THREADS, 3) dm_k_stream(DmxArgs a) {
+__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_excl);
+
+// Field phase: n (<= 32) queued fields, one per lane.  ONE copy of this code per kernel (not inlined), and the
+// lanes are brought back together (__syncwarp) after every data-dependent stretch: without that they drift apart
+// for the rest of the function and every later instruction is issued several times for a few lanes each.
+// (what it needs of the kernel arguments sits in shared memory: a reference to the parameter block itself would
+// force a copy of it into local memory)
+struct DmxDrainCtx {
+    const uint8_t* buf;
+    uint64_t nbytes;
+    DmTable table;
+    dm_anomaly_t* alerts;
+    unsigned int* alert_count;
+    unsigned int* err;
+    uint32_t alert_cap;
+};
+#ifdef DM_EMU
+#define __noinline__
+#endif
+template <bool TRAIN>
+__device__ __noinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab& sk, const uint8_t* ring, const uint32_t* q, uint32_t qh,
+                                       uint32_t n, uint32_t seg_base, uint32_t bound) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint8_t* __restrict__ buf = a.buf;
+    const uint64_t nbytes = a.nbytes;
+    uint32_t qpos = 0;
+    int k = -1;
+    if (lane < n) {
+        const uint32_t e = q[(qh + lane) & (DMX_QCAP - 1)];
+        qpos = seg_base + (e >> 7);
+        if (TRAIN ? (qpos < bound) : (qpos >= bound)) k = dmx_resolve_key(ring, buf, qpos, e & 0x7Fu, sk);
+    }
+    __syncwarp();
+    const bool act = k >= 0;
+    // ---- the value (R-tok L5): it ends at the first space outside double quotes counted from its start, at '\n',
+    // or at the end of the message.  One byte class ("stop bytes" < 0x23) over a 32-byte window. ----
+    const uint32_t vpos = qpos + 1u;
+    const uint32_t vr = vpos & (DMX_RING - 1);
+    uint32_t w[8];
+    uint32_t m = 0, lim = 0;
+    if (act) {
+        const uint32_t base = vr & ~3u;
+        const uint32_t sh = (vpos & 3u) * 8u;
+        uint32_t lo = dmx_ld32(ring, base);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t hi = dmx_ld32(ring, base + 4u * (i + 1));
+            w[i] = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+        }
+        const uint64_t avail = nbytes > vpos ? nbytes - vpos : 0;
+        lim = avail < DMX_WIN ? (uint32_t)avail : DMX_WIN;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
+        if (lim < DMX_WIN) m &= (1u << lim) - 1u;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = 0;
+    }
+    uint32_t nv = 0xFFFFFFFFu;
+    {
+        uint32_t par = 0;
+        while (m) {
+            const uint32_t j = (uint32_t)__ffs(m) - 1u;
+            m &= m - 1u;
+            const uint32_t c = ring[vr + j];
+            if (c == 0x0Au || (c == 0x20u && !par)) { nv = j; break; }
+            if (c == 0x22u) par ^= 1u;
+        }
+    }
+    __syncwarp();
+    bool slow = false;
+    if (act && nv == 0xFFFFFFFFu) {
+        if (lim < DMX_WIN) nv = lim;                      // the message ends inside the window: that ends the value
+        else slow = true;                                 // longer than the window
+    }
+    if (!act || slow) nv = 0;
+    DmHashState st;
+    dm_hash_init(st);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (nv > 4u * i) {
+            const uint32_t nb = nv - 4u * i;
+            dm_hash_word(st, nb >= 4u ? w[i] : (w[i] & ((1u << (8u * nb)) - 1u)));
+        }
+    }
+    uint64_t fp = dm_hash_final(st, nv);
+    if (__any_sync(0xffffffffu, slow)) {
+        if (slow) {                                       // by the letter, from global memory
+            const uint32_t len = dmx_value_len_slow(buf, nbytes, vpos);
+            fp = dm_fp64_bytes(buf + vpos, len);
+        }
+        __syncwarp();
+    }
+    bool cand = false;
+    uint64_t ckey = 0;
+    if (act) {
+        ckey = dm_make_key(fp, sk.salt[k]);
+        cand = !(TRAIN ? dm_table_contains_volatile(a.table, ckey) : dm_table_contains(a.table, ckey));
+    }
+    if (__any_sync(0xffffffffu, cand)) {
+        if (cand) {
+            uint32_t ls = 0;
+            if (dmx_verify_thread(buf, qpos, (uint32_t)k, sk, &ls)) {
+                if (TRAIN) {
+                    dm_table_insert(a.table, ckey, a.err);
+                } else {
+                    // an alert: unknown value in monitored field k of the record that starts at ls
+                    uint32_t inrow = 0;
+                    const uint4* b16 = reinterpret_cast<const uint4*>(buf);
+                    for (uint32_t c = (ls & ~(DMX_ROW - 1)) >> 4; c < (ls >> 4); ++c)
+                        inrow += (uint32_t)__popc(dm_chunk_mask(__ldg(b16 + c), 0x0A0A0A0Au));
+                    if (ls & 15u)
+                        inrow += (uint32_t)__popc(dm_chunk_mask(__ldg(b16 + (ls >> 4)), 0x0A0A0A0Au) & ((1u << (ls & 15u)) - 1u));
+                    const unsigned int idx = atomicAdd(a.alert_count, 1u);
+                    if (idx < a.alert_cap) {
+                        dm_anomaly_t r;
+                        r.line = inrow; r.mask = (uint32_t)k; r.offset = ls;
+                        a.alerts[idx] = r;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(DMX_THREADS, 4) dm_k_stream(DmxArgs a) {
 #ifdef DM_EMU
     uint8_t* s_dyn = g_emu_dyn_smem.data();
 #else
     extern __shared__ __align__(128) uint8_t s_dyn[];
 #endif
     __shared__ DmxKeyTab sk;
-    __shared__ uint2 s_q[DMX_WARPS][DMX_QCAP];
+    __shared__ uint32_t s_q[DMX_WARPS][DMX_QCAP];
     __shared__ unsigned long long s_bar[DMX_WARPS][DMX_SLOTS];
+    __shared__ uint32_t s_cnt[DMX_WARPS];
+    __shared__ unsigned long long s_bound;
     __shared__ int s_last;
+    __shared__ DmxDrainCtx s_ctx;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = dm_lanemask_lt();
     dm_pdl_launch_dependents();                       // the next launch may be scheduled as soon as there is room
+    if (threadIdx.x == 0) {
+        s_ctx.buf = a.buf; s_ctx.nbytes = a.nbytes; s_ctx.table = a.table; s_ctx.alerts = a.alerts;
+        s_ctx.alert_count = a.alert_count; s_ctx.err = &a.hdr->error; s_ctx.alert_cap = a.alert_cap;
+    }
+    if (a.timeline && threadIdx.x == 0) {
+        uint32_t smid = 0;
+#ifndef DM_EMU
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+#endif
+        a.timeline[4ull * blockIdx.x] = smid;
+        a.timeline[4ull * blockIdx.x + 1] = dmx_now();
+    }
     {
         const uint32_t words = (uint32_t)((sizeof(DmxKeyTab) - sizeof(DmxL1) * DMX_L1) / 4);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.keys);
@@ -447,19 +586,19 @@ __global__ void __launch_bounds__(DMX_THREADS, 3) dm_k_stream(DmxArgs a) {
         const uint32_t total = words + 2u * __ldg(&a.keys->l1_slots);
         for (uint32_t i = threadIdx.x; i < total; i += DMX_THREADS) dst[i] = __ldg(src + i);
     }
-#ifndef DM_EMU
     if (lane == 0) {
+        s_cnt[warp] = 0;
+#ifndef DM_EMU
         for (uint32_t s = 0; s < DMX_SLOTS; ++s) dmx_mbar_init(dmx_smem_u32(&s_bar[warp][s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
 #endif
+    }
     // this launch's scratch (row counts, staged alerts) was last used by launch seq-2: its epilogue must be through
     if (threadIdx.x == 0)
         while (dmx_ld_acquire(&a.sh->epi_done_seq) + 2ull < a.seq) __nanosleep(64);
     __syncthreads();
 
-    const uint8_t* __restrict__ buf = a.buf;
     const uint64_t nbytes = a.nbytes;
     const uint32_t bound = a.bound_ptr ? (uint32_t)(*a.bound_ptr > 0xFFFFFFFFull ? 0xFFFFFFFFull : *a.bound_ptr) : (TRAIN ? 0xFFFFFFFFu : 0u);
     const uint32_t l1_mult = sk.mult, l1_shift = sk.shift, n_short = sk.n_short;
@@ -468,76 +607,59 @@ __global__ void __launch_bounds__(DMX_THREADS, 3) dm_k_stream(DmxArgs a) {
     if (r0l < a.n_rows) {
         DmxRing rg;
         rg.ring = s_dyn + warp * (DMX_RING + DMX_MIRROR);
-        rg.buf = buf;
-        rg.nb16 = (nbytes + 15ull) & ~15ull;
+        rg.buf = a.buf;
         rg.r0 = (uint32_t)r0l;
         rg.r1 = (uint32_t)(r0l + a.rows_per_warp < a.n_rows ? r0l + a.rows_per_warp : a.n_rows);
+        rg.last_row = a.n_rows - 1;
+        rg.last_bytes = (uint32_t)(((nbytes + 15ull) & ~15ull) - (uint64_t)rg.last_row * DMX_ROW);
 #ifndef DM_EMU
         rg.ring_s = dmx_smem_u32(rg.ring);
         rg.bar_s = dmx_smem_u32(&s_bar[warp][0]);
 #endif
+        const uint8_t* ring = rg.ring;
         const uint32_t n_own = rg.r1 - rg.r0;
         const uint32_t n_loads = n_own + (rg.r1 < a.n_rows ? 1u : 0u);
-        uint2* q = s_q[warp];
-        uint32_t qh = 0, qn = 0;
-        if (rg.r0 == 0) {
-            // the message starts a record: the 16 bytes "in front of it" read as '\n'
-            if (lane < 4) reinterpret_cast<uint32_t*>(rg.ring + DMX_RING - 16)[lane] = 0x0A0A0A0Au;
-            __syncwarp();
+        const uint32_t seg_base = rg.r0 * DMX_ROW;            // (messages are shorter than 4 GiB)
+        const uint32_t tail_bytes = (uint32_t)(nbytes & (DMX_ROW - 1));   // valid bytes of a partial last row (0 = full)
+        uint32_t* q = s_q[warp];
+        uint32_t qh = 0, qn = 0, nl_w = 0;
+        // the 16 bytes in front of the range (key bytes of its first '='); a message starts a record: '\n' there
+        if (lane < 4) {
+            uint32_t x = 0x0A0A0A0Au;
+            if (rg.r0 > 0) x = __ldg(reinterpret_cast<const uint32_t*>(a.buf + (uint64_t)rg.r0 * DMX_ROW - 16) + lane);
+            reinterpret_cast<uint32_t*>(rg.ring + ((rg.r0 * DMX_ROW - 16u) & (DMX_RING - 1)))[lane] = x;
         }
+        __syncwarp();
         if (lane == 0)
             for (uint32_t i = 0; i < DMX_DEPTH && i < n_loads; ++i) rg.issue(i);
 
-        // field phase: one queued field per lane
-        auto drain = [&](uint32_t n) {
-            bool cand = false;
-            uint64_t ckey = 0;
-            uint32_t cq = 0, ck = 0;
-            if (lane < n) {
-                const uint2 e = q[(qh + lane) & (DMX_QCAP - 1)];
-                if (TRAIN ? (e.x < bound) : (e.x >= bound)) {
-                    const int k = dmx_resolve_key(rg, buf, e.x, e.y, sk);
-                    if (k >= 0) {
-                        const uint64_t fp = dmx_value_fp(rg, buf, nbytes, e.x + 1u);
-                        ckey = dm_make_key(fp, sk.salt[k]);
-                        cand = !(TRAIN ? dm_table_contains_volatile(a.table, ckey) : dm_table_contains(a.table, ckey));
-                        cq = e.x; ck = (uint32_t)k;
-                    }
-                }
+        // one hit per lane at most (rows dense in '=', keys of 1..2 bytes)
+        auto push1 = [&](bool hit, uint32_t e) {
+            const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+            if (hb) {
+                if (hit) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
+                qn += (uint32_t)__popc(hb);
+                __syncwarp();
             }
-            qh += n;
-            qn -= n;
-            if (__any_sync(0xffffffffu, cand)) {
-                if (cand) {
-                    uint32_t ls = 0;
-                    if (dmx_verify_thread(buf, cq, ck, sk, &ls)) {
-                        if (TRAIN) {
-                            dm_table_insert(a.table, ckey, &a.hdr->error);
-                        } else {
-                            const unsigned int idx = atomicAdd(a.alert_count, 1u);
-                            if (idx < a.alert_cap) {
-                                dm_anomaly_t r;
-                                r.line = cq; r.mask = ck; r.offset = ls;
-                                a.alerts[idx] = r;
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
         };
 
         for (uint32_t i = 0; i < n_own; ++i) {
             const uint32_t row = rg.r0 + i;
             rg.wait(i);
             if (i + 1 < n_loads) rg.wait(i + 1);
+            if ((i == 0 && (row & (DMX_SLOTS - 1)) == 0) || (i + 1 < n_loads && ((row + 1) & (DMX_SLOTS - 1)) == 0)) {
+                // a row has arrived at the start of the ring: its first bytes again behind the ring's end, so that reads
+                // that start in the row before it (or in the 16 bytes in front of the range) never wrap
+                if (lane < DMX_MIRROR / 4) reinterpret_cast<uint32_t*>(rg.ring + DMX_RING)[lane] = reinterpret_cast<const uint32_t*>(rg.ring)[lane];
+                __syncwarp();
+            }
             const uint32_t sb = (row & (DMX_SLOTS - 1)) * DMX_ROW + lane * 16u;
-            uint4 v = *reinterpret_cast<const uint4*>(rg.ring + sb);
-            const uint32_t prev = rg.ld32((sb - 4u) & (DMX_RING - 1));
-            const uint64_t off = (uint64_t)row * DMX_ROW + lane * 16u;
-            if ((uint64_t)(row + 1) * DMX_ROW > nbytes) {
-                // last row: bytes behind the message are nobody's
-                const uint32_t vb = nbytes > off ? (uint32_t)(nbytes - off < 16 ? nbytes - off : 16) : 0u;
+            uint4 v = *reinterpret_cast<const uint4*>(ring + sb);
+            const uint32_t prev = dmx_ld32(ring, (sb - 4u) & (DMX_RING - 1));
+            if (row == rg.last_row && tail_bytes) {
+                // partial last row: bytes behind the message are nobody's
+                const uint32_t lo = lane * 16u;
+                const uint32_t vb = tail_bytes > lo ? (tail_bytes - lo < 16u ? tail_bytes - lo : 16u) : 0u;
                 uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -552,90 +674,171 @@ __global__ void __launch_bounds__(DMX_THREADS, 3) dm_k_stream(DmxArgs a) {
                 const uint32_t c = (uint32_t)__popc(n0 | (n1 >> 1) | (n2 >> 2) | (n3 >> 3));
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
                 if (lane == 0) a.row_cnt[row] = (unsigned short)tot;
+                nl_w += tot;
             }
-            // the '=' of each 4-byte word: level-1 lookup of the 4 bytes in front of it
-            auto word = [&](uint32_t lo, uint32_t cur, uint32_t woff) {
-                uint32_t f = dm_eqflags(cur, 0x3D3D3D3Du);
-                for (;;) {
-                    bool hit = false;
-                    uint2 e = make_uint2(0u, 0u);
-                    if (f) {
-                        const uint32_t sh = (uint32_t)__ffs(f) - 8u;           // 8 * (byte index of the '=')
-                        const uint32_t t = __funnelshift_r(lo, cur, sh);
-                        const DmxL1 l = sk.l1[(t * l1_mult) >> l1_shift];
-                        uint32_t info = l.pat == t ? l.info : 0u;
-                        if (!info && n_short) info = dmx_short_key(t, sk);
-                        hit = info != 0;
-                        e = make_uint2((uint32_t)off + woff + (sh >> 3), info);
-                    }
-                    const uint32_t hb = __ballot_sync(0xffffffffu, hit);
-                    if (hb) {
-                        if (hit) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
-                        qn += (uint32_t)__popc(hb);
-                        __syncwarp();
-                        if (qn >= 32u) drain(32u);
-                    }
-                    f &= f - 1u;
-                    if (!__any_sync(0xffffffffu, f != 0)) break;
+            const uint32_t f0 = dm_eqflags(v.x, 0x3D3D3D3Du), f1 = dm_eqflags(v.y, 0x3D3D3D3Du);
+            const uint32_t f2 = dm_eqflags(v.z, 0x3D3D3D3Du), f3 = dm_eqflags(v.w, 0x3D3D3D3Du);
+            const uint32_t qrel = i * DMX_ROW + lane * 16u;
+            uint32_t g0 = f0, g1 = f1, g2 = f2, g3 = f3;
+            if (!n_short) {
+                // the first '=' of each word, all four words at once; one compaction per row
+                uint32_t e0, e1, e2, e3, t;
+                const bool h0 = dmx_probe(prev, v.x, f0, sk.l1, l1_mult, l1_shift, qrel, &e0, &t);
+                const bool h1 = dmx_probe(v.x, v.y, f1, sk.l1, l1_mult, l1_shift, qrel + 4u, &e1, &t);
+                const bool h2 = dmx_probe(v.y, v.z, f2, sk.l1, l1_mult, l1_shift, qrel + 8u, &e2, &t);
+                const bool h3 = dmx_probe(v.z, v.w, f3, sk.l1, l1_mult, l1_shift, qrel + 12u, &e3, &t);
+                const uint32_t c = (uint32_t)h0 + (uint32_t)h1 + (uint32_t)h2 + (uint32_t)h3;
+                const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1u), b1 = __ballot_sync(0xffffffffu, c & 2u);
+                const uint32_t b2 = __ballot_sync(0xffffffffu, c & 4u);
+                if (b0 | b1 | b2) {
+                    uint32_t slot = qh + qn + (uint32_t)__popc(b0 & lt) + 2u * (uint32_t)__popc(b1 & lt) + 4u * (uint32_t)__popc(b2 & lt);
+                    if (h0) q[slot++ & (DMX_QCAP - 1)] = e0;
+                    if (h1) q[slot++ & (DMX_QCAP - 1)] = e1;
+                    if (h2) q[slot++ & (DMX_QCAP - 1)] = e2;
+                    if (h3) q[slot++ & (DMX_QCAP - 1)] = e3;
+                    qn += (uint32_t)__popc(b0) + 2u * (uint32_t)__popc(b1) + 4u * (uint32_t)__popc(b2);
+                    __syncwarp();
                 }
-            };
-            word(prev, v.x, 0u);
-            word(v.x, v.y, 4u);
-            word(v.y, v.z, 8u);
-            word(v.z, v.w, 12u);
-
-            if (i + DMX_DEPTH < n_loads) {
-                // row i+DEPTH overwrites the slot of row (row + DEPTH - 8): fields of rows up to (row - 3)
-                // (their key bytes may lie in the row before) must have left the queue
-                if (qn) {
-                    const uint32_t head = q[qh & (DMX_QCAP - 1)].x;
-                    if ((head >> 9) + (DMX_SLOTS - DMX_DEPTH - 1u) <= row) drain(qn);
+                g0 &= g0 - 1u; g1 &= g1 - 1u; g2 &= g2 - 1u; g3 &= g3 - 1u;
+            }
+            if (__any_sync(0xffffffffu, (g0 | g1 | g2 | g3) != 0u)) {
+                // every further '=' of a word, one per round (rows dense in '='; all '=' when there are keys of 1..2 bytes)
+#pragma unroll 1
+                for (int wi = 0; wi < 4; ++wi) {
+                    const uint32_t lo = wi == 0 ? prev : (wi == 1 ? v.x : (wi == 2 ? v.y : v.z));
+                    const uint32_t cur = wi == 0 ? v.x : (wi == 1 ? v.y : (wi == 2 ? v.z : v.w));
+                    uint32_t g = wi == 0 ? g0 : (wi == 1 ? g1 : (wi == 2 ? g2 : g3));
+                    while (__any_sync(0xffffffffu, g != 0u)) {
+                        uint32_t e = 0, t = 0;
+                        bool hit = dmx_probe(lo, cur, g, sk.l1, l1_mult, l1_shift, qrel + 4u * wi, &e, &t);
+                        if (g != 0u && !hit && n_short) {
+                            const uint32_t info = dmx_short_key(t, sk);
+                            if (info) { hit = true; e = (e & ~0x7Fu) | info; }
+                        }
+                        push1(hit, e);
+                        while (qn > DMX_QCAP - 64u) { dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, 32u, seg_base, bound); qh += 32u; qn -= 32u; }
+                        g &= g - 1u;
+                    }
                 }
+            }
+            // drain: full passes; and, before row i+DEPTH overwrites the slot of row (i + DEPTH - 8), whatever is left of
+            // rows up to (i + DEPTH - 7) (a field's key bytes may lie in the row before it)
+            const bool more = i + DMX_DEPTH < n_loads;
+            for (;;) {
+                uint32_t n = 0;
+                if (qn >= 32u) n = 32u;
+                else if (qn && (i + 1 == n_own || (more && (q[qh & (DMX_QCAP - 1)] >> 16) + (DMX_SLOTS - DMX_DEPTH - 1u) <= i))) n = qn;
+                if (!n) break;
+                dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound);
+                qh += n;
+                qn -= n;
+            }
+            if (more) {
                 __syncwarp();
                 if (lane == 0) rg.issue(i + DMX_DEPTH);
             }
         }
-        while (qn) drain(qn < 32u ? qn : 32u);
+        if (lane == 0) s_cnt[warp] = nl_w;
     }
 
-    // ---- the last CTA to get here runs the epilogue ----
+    // ---- end of the CTA's rows ----
     __syncthreads();
+    if (!TRAIN) {
+        if (threadIdx.x == 0) {
+            if (a.timeline) a.timeline[4ull * blockIdx.x + 2] = dmx_now();
+            uint32_t c = 0;
+            for (uint32_t w = 0; w < DMX_WARPS; ++w) c += s_cnt[w];
+            a.cta_cnt[blockIdx.x] = c;
+            // the previous call's outputs are complete once its epilogue is through; then every CTA zero-fills its
+            // share of as many entries as the previous message had records
+            while (dmx_ld_acquire(&a.sh->epi_done_seq) + 1ull < a.seq) __nanosleep(64);
+            const unsigned long long zb = *((volatile unsigned long long*)&a.sh->zero_bound);
+            s_bound = zb < a.out_cap ? zb : a.out_cap;
+        }
+        __syncthreads();
+        const unsigned long long zb = s_bound;
+        const unsigned long long per = (((zb + gridDim.x - 1) / gridDim.x) + 15ull) & ~15ull;
+        const unsigned long long lo = per * blockIdx.x < zb ? per * blockIdx.x : zb;
+        dmx_zero_outputs(a.flags, a.scores, lo, lo + per < zb ? lo + per : zb, threadIdx.x, DMX_THREADS);
+        __syncthreads();
+    } else if (a.timeline && threadIdx.x == 0) {
+        a.timeline[4ull * blockIdx.x + 2] = dmx_now();
+    }
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int old = atomicAdd(&a.sh->done_ctr[a.seq & 3ull], 1u);
         s_last = old == gridDim.x - 1 ? 1 : 0;
+        if (a.timeline && !s_last) a.timeline[4ull * blockIdx.x + 3] = dmx_now();
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    dmx_epilogue<TRAIN>(a, reinterpret_cast<unsigned long long*>(&s_q[0][0]));
+    dmx_epilogue<TRAIN>(a, reinterpret_cast<unsigned long long*>(s_dyn));
 }
 
-// Epilogue (one CTA): header, zero-fill, record index of every staged alert, outputs.
+// Sum of the 8 counters of one 16-byte vector of row counts
+__device__ __forceinline__ uint32_t dmx_sum8(const uint4& v) {
+    return (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16) + (v.z & 0xFFFFu) + (v.z >> 16) + (v.w & 0xFFFFu) + (v.w >> 16);
+}
+// '\n' counts of rows [lo, hi), lo a multiple of 8 (16-byte aligned): vector loads that bypass L1 (other CTAs wrote them)
+__device__ __forceinline__ unsigned long long dmx_count_rows(const unsigned short* cnt, uint32_t lo, uint32_t hi) {
+    unsigned long long s = 0;
+    uint32_t r = lo;
+#ifndef DM_EMU
+    for (; r + 32 <= hi; r += 32) {
+        const uint4 v0 = __ldcg(reinterpret_cast<const uint4*>(cnt + r)), v1 = __ldcg(reinterpret_cast<const uint4*>(cnt + r + 8));
+        const uint4 v2 = __ldcg(reinterpret_cast<const uint4*>(cnt + r + 16)), v3 = __ldcg(reinterpret_cast<const uint4*>(cnt + r + 24));
+        s += dmx_sum8(v0) + dmx_sum8(v1) + dmx_sum8(v2) + dmx_sum8(v3);
+    }
+    for (; r + 8 <= hi; r += 8) s += dmx_sum8(__ldcg(reinterpret_cast<const uint4*>(cnt + r)));
+#endif
+    for (; r < hi; ++r) s += *((volatile const unsigned short*)(cnt + r));
+    return s;
+}
+
+// Epilogue (the last CTA of a launch): batch header, rest of the zero-fill, record index of every staged alert,
+// scores / flags / statistics / anomaly list.  s_excl: gridDim.x + 12 words of shared memory.
 template <bool TRAIN>
-__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_pre /* DMX_THREADS + 2 words */) {
+__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_excl) {
     const uint32_t tid = threadIdx.x;
+    unsigned long long* tl = a.timeline ? a.timeline + 4ull * gridDim.x : nullptr;
+    if (tl && tid == 0) tl[0] = dmx_now();
     // epilogues run in launch order (they write the caller's outputs, the header and the statistics)
     if (tid == 0)
         while (dmx_ld_acquire(&a.sh->epi_done_seq) + 1ull < a.seq) __nanosleep(64);
     __syncthreads();
+    if (tl && tid == 0) tl[1] = dmx_now();
     if (!TRAIN) {
-        const uint32_t per = (a.n_rows + DMX_THREADS - 1) / DMX_THREADS;
+        const uint32_t G = gridDim.x;
+        // exclusive prefix of the per-CTA '\n' counts: every thread takes a few consecutive CTAs, the warps scan by shuffles
+        const uint32_t cpt = (G + DMX_THREADS - 1) / DMX_THREADS;
         {
-            const uint32_t lo = tid * per < a.n_rows ? tid * per : a.n_rows;
-            const uint32_t hi = lo + per < a.n_rows ? lo + per : a.n_rows;
-            unsigned long long s = 0;
-            for (uint32_t r = lo; r < hi; ++r) s += *((volatile unsigned short*)(a.row_cnt + r));
-            s_pre[tid] = s;
+            const uint32_t lo = tid * cpt < G ? tid * cpt : G, hi = lo + cpt < G ? lo + cpt : G;
+            unsigned long long c = 0;
+            for (uint32_t i = lo; i < hi; ++i) c += dmx_ldcg32(a.cta_cnt + i);
+            unsigned long long incl = c;
+            const uint32_t ln = tid & 31;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)ln >= d) incl += y;
+            }
+            if (ln == 31) s_excl[G + 4 + (tid >> 5)] = incl;
+            __syncthreads();
+            unsigned long long run = incl - c;
+            for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_excl[G + 4 + w];
+            for (uint32_t i = lo; i < hi; ++i) { s_excl[i] = run; run += dmx_ldcg32(a.cta_cnt + i); }
+            if (tid == DMX_THREADS - 1) s_excl[G + 2] = run;               // all '\n' of the message
         }
         __syncthreads();
         if (tid == 0) {
-            unsigned long long run = 0;
-            for (uint32_t t = 0; t < DMX_THREADS; ++t) { const unsigned long long c = s_pre[t]; s_pre[t] = run; run += c; }
+            const unsigned long long run = s_excl[G + 2];
             const unsigned long long nl = run;
             const bool tail = a.nbytes > 0 && a.buf[a.nbytes - 1] != 0x0Au;
             const unsigned long long n_lines = nl + (tail ? 1ull : 0ull);
-            s_pre[DMX_THREADS] = n_lines;
+            s_excl[G] = n_lines;
+            s_excl[G + 1] = a.sh->zero_bound;
+            a.sh->zero_bound = n_lines;
             const unsigned int staged = *((volatile unsigned int*)a.alert_count);
             unsigned int err = (n_lines > a.max_lines || n_lines > a.out_cap) ? DM_DEVERR_TOO_MANY_LINES : 0u;
             if (staged > a.alert_cap) err |= DM_DEVERR_ANOMALY_OVERFLOW;
@@ -650,35 +853,22 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             a.stats[5] += a.nbytes;
         }
         __syncthreads();
-        const unsigned long long n_lines = s_pre[DMX_THREADS];
+        if (tl && tid == 0) tl[2] = dmx_now();
+        const unsigned long long n_lines = s_excl[G];
         const unsigned long long n_out = n_lines < a.out_cap ? n_lines : a.out_cap;
-        {
-            // 16-byte stores where the caller's buffers allow it
-            const unsigned long long nv = ((((uintptr_t)a.flags) | ((uintptr_t)a.scores)) & 15) == 0 ? (n_out & ~15ull) : 0ull;
-            for (unsigned long long i = (unsigned long long)tid * 16; i < nv; i += DMX_THREADS * 16ull) {
-                *reinterpret_cast<uint4*>(a.flags + i) = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(a.scores + i + 4 * j) = make_uint4(0, 0, 0, 0);
-            }
-            for (unsigned long long i = nv + tid; i < n_out; i += DMX_THREADS) { a.flags[i] = 0; a.scores[i] = 0.0f; }
-        }
+        // (the CTAs zero-filled [0, zero_bound); more records than that only when the messages grow)
+        dmx_zero_outputs(a.flags, a.scores, s_excl[G + 1] < n_out ? s_excl[G + 1] : n_out, n_out, tid, DMX_THREADS);
         __syncthreads();
+        if (tl && tid == 0) tl[3] = dmx_now();
         const unsigned int staged = *((volatile unsigned int*)a.alert_count);
         const unsigned int n_al = staged < a.alert_cap ? staged : a.alert_cap;
         for (unsigned int i = tid; i < n_al; i += DMX_THREADS) {
-            dm_anomaly_t al;
-            al.line = dmx_ldcg32(&a.alerts[i].line); al.mask = dmx_ldcg32(&a.alerts[i].mask);
-            al.offset = dmx_ldcg32(reinterpret_cast<const uint32_t*>(&a.alerts[i].offset));
-            const uint32_t s = (uint32_t)al.offset, k = al.mask;
+            const uint32_t inrow = dmx_ldcg32(&a.alerts[i].line), k = dmx_ldcg32(&a.alerts[i].mask);
+            const uint32_t s = dmx_ldcg32(reinterpret_cast<const uint32_t*>(&a.alerts[i].offset));
             // record index = '\n' in front of the record's first byte
             const uint32_t row = s >> 9;
-            const uint32_t t = row / per;
-            unsigned long long g = s_pre[t];
-            for (uint32_t r = t * per; r < row; ++r) g += *((volatile unsigned short*)(a.row_cnt + r));
-            for (uint32_t c = row * (DMX_ROW / 16); c < (s >> 4); ++c)
-                g += (uint32_t)__popc(dm_chunk_mask(__ldg(reinterpret_cast<const uint4*>(a.buf) + c), 0x0A0A0A0Au));
-            if (s & 15u)
-                g += (uint32_t)__popc(dm_chunk_mask(__ldg(reinterpret_cast<const uint4*>(a.buf) + (s >> 4)), 0x0A0A0A0Au) & ((1u << (s & 15u)) - 1u));
+            const uint32_t cta = row / a.rows_per_cta;
+            const unsigned long long g = s_excl[cta] + dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row) + inrow;
             bool first = false;
             if (g < a.out_cap) {
                 const float old = atomicAdd(a.scores + g, 1.0f);
@@ -696,12 +886,15 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             }
         }
         __syncthreads();
+        if (tl && tid == 0) tl[4] = dmx_now();
     }
     if (tid == 0) {
         *a.alert_count = 0;
         a.sh->done_ctr[a.seq & 3ull] = 0;
         __threadfence();
         dmx_st_release(&a.sh->epi_done_seq, a.seq);
+        if (tl) tl[5] = dmx_now();
+        if (a.timeline) a.timeline[4ull * blockIdx.x + 3] = dmx_now();
     }
 }
 
@@ -760,6 +953,7 @@ __global__ void __launch_bounds__(256) dm_k_bound(const uint8_t* __restrict__ bu
 struct DmxScratch {
     DmxKeyTab* d_keys = nullptr;
     unsigned short* d_row_cnt[2] = {nullptr, nullptr};
+    unsigned int* d_cta_cnt[2] = {nullptr, nullptr};
     unsigned short* d_bound_cnt = nullptr;
     dm_anomaly_t* d_alerts[2] = {nullptr, nullptr};
     unsigned int* d_alert_count = nullptr;      // 2 words
@@ -772,6 +966,8 @@ struct DmxScratch {
     int max_grid = 0;
     bool overlap = false;                       // programmatic dependent launch between consecutive detect launches
     cudaStream_t chain_stream = nullptr;        // stream of the last launch, if it was a plain detect launch (else NULL)
+    unsigned long long* d_timeline = nullptr;   // DM_STREAM_TIMELINE=1
+    unsigned last_grid = 0;
 };
 
 static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t max_batch_bytes, uint32_t alert_cap, int sm_count) {
@@ -782,18 +978,8 @@ static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t
     if (e == cudaSuccess) e = cudaMemcpy(s->d_keys, t, sizeof(DmxKeyTab), cudaMemcpyHostToDevice);
     delete t;
     if (e != cudaSuccess) return DM_ERR_CUDA;
-    s->max_rows = (max_batch_bytes + DMX_ROW - 1) / DMX_ROW + 1;
+    s->max_rows = (max_batch_bytes + DMX_ROW - 1) / DMX_ROW + 64;
     s->alert_cap = alert_cap;
-    for (int b = 0; b < 2; ++b) {
-        if (cudaMalloc(&s->d_row_cnt[b], s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
-        if (cudaMalloc(&s->d_alerts[b], (size_t)alert_cap * sizeof(dm_anomaly_t)) != cudaSuccess) return DM_ERR_CUDA;
-    }
-    if (cudaMalloc(&s->d_bound_cnt, s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaMalloc(&s->d_alert_count, 2 * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaMemset(s->d_alert_count, 0, 2 * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaMalloc(&s->d_bound, sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaMalloc(&s->d_shared, sizeof(DmxShared)) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaMemset(s->d_shared, 0, sizeof(DmxShared)) != cudaSuccess) return DM_ERR_CUDA;
     if (cudaFuncSetAttribute(dm_k_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DMX_DYN_SMEM) != cudaSuccess) return DM_ERR_CUDA;
     if (cudaFuncSetAttribute(dm_k_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DMX_DYN_SMEM) != cudaSuccess) return DM_ERR_CUDA;
     int per_sm = 0;
@@ -803,13 +989,30 @@ static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t
     if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
     s->ctas_per_sm = per_sm;
     s->max_grid = sm_count * per_sm;
+    if ((size_t)s->max_grid * 8 + 128 > DMX_DYN_SMEM) s->max_grid = (int)((DMX_DYN_SMEM - 128) / 8);   // (epilogue prefix lives in the rings)
+    for (int b = 0; b < 2; ++b) {
+        if (cudaMalloc(&s->d_row_cnt[b], s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
+        if (cudaMalloc(&s->d_cta_cnt[b], (size_t)s->max_grid * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
+        if (cudaMalloc(&s->d_alerts[b], (size_t)alert_cap * sizeof(dm_anomaly_t)) != cudaSuccess) return DM_ERR_CUDA;
+    }
+    if (cudaMalloc(&s->d_bound_cnt, s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_alert_count, 2 * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMemset(s->d_alert_count, 0, 2 * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_bound, sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_shared, sizeof(DmxShared)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMemset(s->d_shared, 0, sizeof(DmxShared)) != cudaSuccess) return DM_ERR_CUDA;
+    const char* tl = getenv("DM_STREAM_TIMELINE");
+    if (tl && atoi(tl) == 1) {
+        if (cudaMalloc(&s->d_timeline, ((size_t)s->max_grid * 4 + 8) * sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
+        cudaMemset(s->d_timeline, 0, ((size_t)s->max_grid * 4 + 8) * sizeof(unsigned long long));
+    }
     return DM_OK;
 }
 
 static inline void dmx_scratch_destroy(DmxScratch* s) {
     cudaFree(s->d_keys);
-    for (int b = 0; b < 2; ++b) { cudaFree(s->d_row_cnt[b]); cudaFree(s->d_alerts[b]); }
-    cudaFree(s->d_bound_cnt); cudaFree(s->d_alert_count); cudaFree(s->d_bound); cudaFree(s->d_shared);
+    for (int b = 0; b < 2; ++b) { cudaFree(s->d_row_cnt[b]); cudaFree(s->d_cta_cnt[b]); cudaFree(s->d_alerts[b]); }
+    cudaFree(s->d_bound_cnt); cudaFree(s->d_alert_count); cudaFree(s->d_bound); cudaFree(s->d_shared); cudaFree(s->d_timeline);
     *s = DmxScratch();
 }
 
@@ -826,18 +1029,20 @@ static inline int dmx_launch(DmxScratch* s, const uint8_t* d_buf, uint64_t nbyte
     a.keys = s->d_keys; a.table = table;
     a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap; a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap;
     a.hdr = d_hdr; a.stats = d_stats; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
-    a.sh = s->d_shared; a.alert_cap = s->alert_cap; a.bound_ptr = nullptr; a.keep_error = 0;
+    a.sh = s->d_shared; a.alert_cap = s->alert_cap; a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = s->d_timeline;
     // geometry: every warp gets the same number of contiguous rows
     const unsigned long long warps_max = (unsigned long long)s->max_grid * DMX_WARPS;
     const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
     const unsigned long long warps = (n_rows + rpw - 1) / rpw;
     const unsigned grid = (unsigned)((warps + DMX_WARPS - 1) / DMX_WARPS);
     a.rows_per_warp = rpw;
+    a.rows_per_cta = rpw * DMX_WARPS;
+    s->last_grid = grid;
     int launched = 0;
     auto bind = [&]() {
         a.seq = ++s->seq;
         const int p = (int)(a.seq & 1ull);
-        a.row_cnt = s->d_row_cnt[p]; a.alerts = s->d_alerts[p]; a.alert_count = s->d_alert_count + p;
+        a.row_cnt = s->d_row_cnt[p]; a.cta_cnt = s->d_cta_cnt[p]; a.alerts = s->d_alerts[p]; a.alert_count = s->d_alert_count + p;
     };
     if (n_train_lines > 0) {
         // where detection starts is only known on the device

@@ -699,6 +699,16 @@ extern "C" int dm_set_format(dm_handle* h, const char* log_format, const char* c
 // diagnostics: start / end times of the K_B warps of the last rows launch (DM_ROWS_TIMELINE=1)
 extern "C" int dm_debug_rows_timeline(dm_handle* h, unsigned long long* out, uint64_t cap_words, uint32_t* n_warps_out) {
     if (!h || !n_warps_out) return dm_fail(DM_ERR_ARG, "NULL argument");
+    if (h->dmx.d_timeline) {
+        // stream variant: per CTA {smid, t_start, t_rows_done, t_exit}, then 8 epilogue stamps
+        *n_warps_out = h->dmx.last_grid;
+        if (!out) return DM_OK;
+        DM_CUDA(cudaSetDevice(h->device));
+        DM_CUDA(cudaStreamSynchronize(h->last_stream));
+        const uint64_t words = std::min<uint64_t>(cap_words, 4ull * h->dmx.last_grid + 8);
+        DM_CUDA(cudaMemcpy(out, h->dmx.d_timeline, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        return DM_OK;
+    }
     if (!h->rows.d_timeline) return dm_fail(DM_ERR_STATE, "create the handle with DM_ROWS_TIMELINE=1");
     const uint32_t n = (uint32_t)h->rows.last_grid * DMR_B_WARPS;
     *n_warps_out = n;

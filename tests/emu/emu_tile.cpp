@@ -257,6 +257,7 @@ struct EmuStream {
     DmxKeyTab tab;
     DmxShared sh;
     std::vector<unsigned short> row_cnt[2], bound_cnt;
+    std::vector<unsigned int> cta_cnt[2];
     std::vector<dm_anomaly_t> alerts[2];
     unsigned int alert_count[2] = {0, 0};
     unsigned long long bound = 0, seq = 0;
@@ -281,6 +282,7 @@ extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nby
     for (int b = 0; b < 2; ++b) {
         if (g_xs.row_cnt[b].size() < n_rows + 1) g_xs.row_cnt[b].assign(n_rows + 1, 0xBEEF);
         if (g_xs.alerts[b].size() < h->anoms.size()) g_xs.alerts[b].resize(h->anoms.size());
+        g_xs.cta_cnt[b].assign(g_emu_stream_ctas + 1, 0xDEADBEEFu);
     }
     g_xs.bound_cnt.assign(n_rows + 1, 0xBEEF);
     g_emu_dyn_smem.assign(DMX_DYN_SMEM, 0xEE);
@@ -288,16 +290,17 @@ extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nby
     a.buf = buf; a.nbytes = nbytes; a.n_rows = n_rows; a.keys = &g_xs.tab; a.table = h->table;
     a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
     a.hdr = &h->hdr; a.stats = h->stats; a.n_train_lines = n_train; a.max_lines = h->max_lines;
-    a.sh = &g_xs.sh; a.alert_cap = (uint32_t)h->anoms.size(); a.bound_ptr = nullptr; a.keep_error = 0;
+    a.sh = &g_xs.sh; a.alert_cap = (uint32_t)h->anoms.size(); a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = nullptr;
     const unsigned long long warps_max = (unsigned long long)g_emu_stream_ctas * DMX_WARPS;
     const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
     const unsigned long long warps = (n_rows + rpw - 1) / rpw;
     const unsigned grid = (unsigned)((warps + DMX_WARPS - 1) / DMX_WARPS);
     a.rows_per_warp = rpw;
+    a.rows_per_cta = rpw * DMX_WARPS;
     auto bind = [&]() {
         a.seq = ++g_xs.seq;
         const int p = (int)(a.seq & 1ull);
-        a.row_cnt = g_xs.row_cnt[p].data(); a.alerts = g_xs.alerts[p].data(); a.alert_count = &g_xs.alert_count[p];
+        a.row_cnt = g_xs.row_cnt[p].data(); a.cta_cnt = g_xs.cta_cnt[p].data(); a.alerts = g_xs.alerts[p].data(); a.alert_count = &g_xs.alert_count[p];
     };
     if (n_train > 0) {
         emu_launch_grid(2, 256, [&] { dm_k_rowcount(buf, nbytes, n_rows, g_xs.bound_cnt.data()); });
