@@ -53,7 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libdmdetect.so (no CPU fallback exists)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    extra = os.environ.get("DM_NVCC_EXTRA", "").split()          # development knob (e.g. -DDMX_MIN_CTAS=3)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
         "-o", SO_PATH, os.path.join(CSRC, "dmdetect.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -47,6 +47,9 @@
 #define DMX_WIN 32u                         // bytes of value looked at by the fast path
 #define DMX_FULL 0x40u                      // level-1 info: the four bytes decide alone (3-byte key + delimiter)
 #define DMX_DYN_SMEM (DMX_WARPS * (DMX_RING + DMX_MIRROR))
+#ifndef DMX_MIN_CTAS
+#define DMX_MIN_CTAS 4                      // CTAs per SM the register allocation aims at
+#endif
 
 #define DM_DEVERR_ANOMALY_OVERFLOW 8u
 
@@ -395,10 +398,10 @@ __device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ bu
 // result is discarded.  entry = queue entry of the field: ((offset of the '=' in this warp's range) << 7) | info.
 __device__ __forceinline__ bool dmx_probe(uint32_t lo, uint32_t cur, uint32_t f, const DmxL1* __restrict__ l1, uint32_t mult,
                                           uint32_t shift, uint32_t qrel, uint32_t* entry, uint32_t* t_out) {
-    const uint32_t sh = ((uint32_t)__ffs(f) - 8u) & 31u;              // 8 * (byte index of the '=')
-    const uint32_t t = __funnelshift_r(lo, cur, sh);
+    const uint32_t fs = (uint32_t)__ffs(f);                            // 8 * (byte index of the '=') + 8 (0: no '=')
+    const uint32_t t = __funnelshift_r(lo, cur, fs - 8u);              // (the shift wraps modulo 32)
     const DmxL1 l = l1[(t * mult) >> shift];
-    *entry = ((qrel + (sh >> 3)) << 7) | l.info;
+    *entry = ((qrel + (fs >> 3) - 1u) << 7) | l.info;
     *t_out = t;
     return f != 0u && l.pat == t;
 }
@@ -425,9 +428,9 @@ __device__ __forceinline__ void dmx_zero_outputs(uint8_t* flags, float* scores, 
 template <bool TRAIN>
 __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_excl);
 
-// Field phase: n (<= 32) queued fields, one per lane.  ONE copy of this code per kernel (not inlined), and the
-// lanes are brought back together (__syncwarp) after every data-dependent stretch: without that they drift apart
-// for the rest of the function and every later instruction is issued several times for a few lanes each.
+// Field phase: n (<= 32) queued fields, one per lane.  Called from ONE place in the kernel (one copy of the code);
+// the lanes are brought back together (__syncwarp) after every data-dependent stretch: without that they drift
+// apart for the rest of the function and every later instruction is issued several times for a few lanes each.
 // (what it needs of the kernel arguments sits in shared memory: a reference to the parameter block itself would
 // force a copy of it into local memory)
 struct DmxDrainCtx {
@@ -443,7 +446,7 @@ struct DmxDrainCtx {
 #define __noinline__
 #endif
 template <bool TRAIN>
-__device__ __noinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab& sk, const uint8_t* ring, const uint32_t* q, uint32_t qh,
+__device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab& sk, const uint8_t* ring, const uint32_t* q, uint32_t qh,
                                        uint32_t n, uint32_t seg_base, uint32_t bound) {
     const uint32_t lane = threadIdx.x & 31;
     const uint8_t* __restrict__ buf = a.buf;
@@ -551,7 +554,7 @@ __device__ __noinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab& sk
 }
 
 template <bool TRAIN>
-__global__ void __launch_bounds__(DMX_THREADS, 4) dm_k_stream(DmxArgs a) {
+__global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs a) {
 #ifdef DM_EMU
     uint8_t* s_dyn = g_emu_dyn_smem.data();
 #else
@@ -633,21 +636,14 @@ __global__ void __launch_bounds__(DMX_THREADS, 4) dm_k_stream(DmxArgs a) {
         if (lane == 0)
             for (uint32_t i = 0; i < DMX_DEPTH && i < n_loads; ++i) rg.issue(i);
 
-        // one hit per lane at most (rows dense in '=', keys of 1..2 bytes)
-        auto push1 = [&](bool hit, uint32_t e) {
-            const uint32_t hb = __ballot_sync(0xffffffffu, hit);
-            if (hb) {
-                if (hit) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
-                qn += (uint32_t)__popc(hb);
-                __syncwarp();
-            }
-        };
-
+        // rows arrive in order: row 0 now, then always the row AFTER the one being worked on (look-ahead of its fields)
+        rg.wait(0);
+        const uint32_t tail_row = tail_bytes ? rg.last_row : 0xFFFFFFFFu;
         for (uint32_t i = 0; i < n_own; ++i) {
             const uint32_t row = rg.r0 + i;
-            rg.wait(i);
-            if (i + 1 < n_loads) rg.wait(i + 1);
-            if ((i == 0 && (row & (DMX_SLOTS - 1)) == 0) || (i + 1 < n_loads && ((row + 1) & (DMX_SLOTS - 1)) == 0)) {
+            const bool has_next = i + 1 < n_loads;
+            if (has_next) rg.wait(i + 1);
+            if ((i == 0 && (row & (DMX_SLOTS - 1)) == 0) || (has_next && ((row + 1) & (DMX_SLOTS - 1)) == 0)) {
                 // a row has arrived at the start of the ring: its first bytes again behind the ring's end, so that reads
                 // that start in the row before it (or in the 16 bytes in front of the range) never wrap
                 if (lane < DMX_MIRROR / 4) reinterpret_cast<uint32_t*>(rg.ring + DMX_RING)[lane] = reinterpret_cast<const uint32_t*>(rg.ring)[lane];
@@ -656,7 +652,7 @@ __global__ void __launch_bounds__(DMX_THREADS, 4) dm_k_stream(DmxArgs a) {
             const uint32_t sb = (row & (DMX_SLOTS - 1)) * DMX_ROW + lane * 16u;
             uint4 v = *reinterpret_cast<const uint4*>(ring + sb);
             const uint32_t prev = dmx_ld32(ring, (sb - 4u) & (DMX_RING - 1));
-            if (row == rg.last_row && tail_bytes) {
+            if (row == tail_row) {
                 // partial last row: bytes behind the message are nobody's
                 const uint32_t lo = lane * 16u;
                 const uint32_t vb = tail_bytes > lo ? (tail_bytes - lo < 16u ? tail_bytes - lo : 16u) : 0u;
@@ -679,60 +675,70 @@ __global__ void __launch_bounds__(DMX_THREADS, 4) dm_k_stream(DmxArgs a) {
             const uint32_t f0 = dm_eqflags(v.x, 0x3D3D3D3Du), f1 = dm_eqflags(v.y, 0x3D3D3D3Du);
             const uint32_t f2 = dm_eqflags(v.z, 0x3D3D3D3Du), f3 = dm_eqflags(v.w, 0x3D3D3D3Du);
             const uint32_t qrel = i * DMX_ROW + lane * 16u;
-            uint32_t g0 = f0, g1 = f1, g2 = f2, g3 = f3;
+            const bool more = i + DMX_DEPTH < n_loads;
+            bool row_done = false;
+            int wi = 0;
+            uint32_t gs = f0;
+            do {
             if (!n_short) {
-                // the first '=' of each word, all four words at once; one compaction per row
+                // The FIRST '=' of each 4-byte word, all four words at once.  (With keys of three bytes and more a later
+                // '=' of the same word cannot follow a key: the key would have to hold the earlier '='.)
                 uint32_t e0, e1, e2, e3, t;
-                const bool h0 = dmx_probe(prev, v.x, f0, sk.l1, l1_mult, l1_shift, qrel, &e0, &t);
-                const bool h1 = dmx_probe(v.x, v.y, f1, sk.l1, l1_mult, l1_shift, qrel + 4u, &e1, &t);
-                const bool h2 = dmx_probe(v.y, v.z, f2, sk.l1, l1_mult, l1_shift, qrel + 8u, &e2, &t);
-                const bool h3 = dmx_probe(v.z, v.w, f3, sk.l1, l1_mult, l1_shift, qrel + 12u, &e3, &t);
-                const uint32_t c = (uint32_t)h0 + (uint32_t)h1 + (uint32_t)h2 + (uint32_t)h3;
-                const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1u), b1 = __ballot_sync(0xffffffffu, c & 2u);
-                const uint32_t b2 = __ballot_sync(0xffffffffu, c & 4u);
-                if (b0 | b1 | b2) {
-                    uint32_t slot = qh + qn + (uint32_t)__popc(b0 & lt) + 2u * (uint32_t)__popc(b1 & lt) + 4u * (uint32_t)__popc(b2 & lt);
-                    if (h0) q[slot++ & (DMX_QCAP - 1)] = e0;
-                    if (h1) q[slot++ & (DMX_QCAP - 1)] = e1;
-                    if (h2) q[slot++ & (DMX_QCAP - 1)] = e2;
-                    if (h3) q[slot++ & (DMX_QCAP - 1)] = e3;
-                    qn += (uint32_t)__popc(b0) + 2u * (uint32_t)__popc(b1) + 4u * (uint32_t)__popc(b2);
-                    __syncwarp();
+                bool h0 = dmx_probe(prev, v.x, f0, sk.l1, l1_mult, l1_shift, qrel, &e0, &t);
+                bool h1 = dmx_probe(v.x, v.y, f1, sk.l1, l1_mult, l1_shift, qrel + 4u, &e1, &t);
+                bool h2 = dmx_probe(v.y, v.z, f2, sk.l1, l1_mult, l1_shift, qrel + 8u, &e2, &t);
+                bool h3 = dmx_probe(v.z, v.w, f3, sk.l1, l1_mult, l1_shift, qrel + 12u, &e3, &t);
+                // one field per lane and round (a 16-byte chunk seldom holds two monitored fields)
+                uint32_t hb = __ballot_sync(0xffffffffu, h0 || h1 || h2 || h3);
+                while (hb) {
+                    const uint32_t e = h0 ? e0 : (h1 ? e1 : (h2 ? e2 : e3));
+                    if (h0 || h1 || h2 || h3) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
+                    qn += (uint32_t)__popc(hb);
+                    if (h0) h0 = false; else if (h1) h1 = false; else if (h2) h2 = false; else h3 = false;
+                    hb = __ballot_sync(0xffffffffu, h0 || h1 || h2 || h3);
                 }
-                g0 &= g0 - 1u; g1 &= g1 - 1u; g2 &= g2 - 1u; g3 &= g3 - 1u;
-            }
-            if (__any_sync(0xffffffffu, (g0 | g1 | g2 | g3) != 0u)) {
-                // every further '=' of a word, one per round (rows dense in '='; all '=' when there are keys of 1..2 bytes)
-#pragma unroll 1
-                for (int wi = 0; wi < 4; ++wi) {
+                __syncwarp();
+                row_done = true;
+            } else {
+                // keys of 1..2 bytes: every '=' of every word, one per lane and round; when the queue fills up the loop
+                // is left for the drain below and resumed afterwards
+                while (wi < 4) {
                     const uint32_t lo = wi == 0 ? prev : (wi == 1 ? v.x : (wi == 2 ? v.y : v.z));
                     const uint32_t cur = wi == 0 ? v.x : (wi == 1 ? v.y : (wi == 2 ? v.z : v.w));
-                    uint32_t g = wi == 0 ? g0 : (wi == 1 ? g1 : (wi == 2 ? g2 : g3));
-                    while (__any_sync(0xffffffffu, g != 0u)) {
-                        uint32_t e = 0, t = 0;
-                        bool hit = dmx_probe(lo, cur, g, sk.l1, l1_mult, l1_shift, qrel + 4u * wi, &e, &t);
-                        if (g != 0u && !hit && n_short) {
-                            const uint32_t info = dmx_short_key(t, sk);
-                            if (info) { hit = true; e = (e & ~0x7Fu) | info; }
-                        }
-                        push1(hit, e);
-                        while (qn > DMX_QCAP - 64u) { dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, 32u, seg_base, bound); qh += 32u; qn -= 32u; }
-                        g &= g - 1u;
+                    if (!__any_sync(0xffffffffu, gs != 0u)) {
+                        ++wi;
+                        gs = wi == 1 ? f1 : (wi == 2 ? f2 : f3);
+                        continue;
                     }
+                    uint32_t e = 0, t = 0;
+                    bool hit = dmx_probe(lo, cur, gs, sk.l1, l1_mult, l1_shift, qrel + 4u * wi, &e, &t);
+                    if (gs != 0u && !hit) {
+                        const uint32_t info = dmx_short_key(t, sk);
+                        if (info) { hit = true; e = (e & ~0x7Fu) | info; }
+                    }
+                    const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                    if (hb) {
+                        if (hit) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
+                        qn += (uint32_t)__popc(hb);
+                        __syncwarp();
+                    }
+                    gs &= gs - 1u;
+                    if (qn > DMX_QCAP - 64u) break;
                 }
+                row_done = wi >= 4;
             }
-            // drain: full passes; and, before row i+DEPTH overwrites the slot of row (i + DEPTH - 8), whatever is left of
-            // rows up to (i + DEPTH - 7) (a field's key bytes may lie in the row before it)
-            const bool more = i + DMX_DEPTH < n_loads;
+            // drain: full passes; and, at the end of the row, before row i+DEPTH overwrites the slot of row (i + DEPTH - 8),
+            // whatever is left of rows up to (i + DEPTH - 7) (a field's key bytes may lie in the row before it)
             for (;;) {
                 uint32_t n = 0;
                 if (qn >= 32u) n = 32u;
-                else if (qn && (i + 1 == n_own || (more && (q[qh & (DMX_QCAP - 1)] >> 16) + (DMX_SLOTS - DMX_DEPTH - 1u) <= i))) n = qn;
+                else if (qn && row_done && (i + 1 == n_own || (more && (q[qh & (DMX_QCAP - 1)] >> 16) + (DMX_SLOTS - DMX_DEPTH - 1u) <= i))) n = qn;
                 if (!n) break;
                 dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound);
                 qh += n;
                 qn -= n;
             }
+            } while (!row_done);
             if (more) {
                 __syncwarp();
                 if (lane == 0) rg.issue(i + DMX_DEPTH);
