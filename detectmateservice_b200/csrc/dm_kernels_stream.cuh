@@ -5,16 +5,16 @@
 // Service.process (/root/reference/src/service/core.py:201-203).  Rules: DESIGN.md R-tok L1-L7 and
 // R-spec 1-4.  ONE kernel per message in steady state (261 B per 256-byte record, read once):
 //
-//   * every warp owns a CONTIGUOUS range of 512-byte rows and streams it through a private 4 KiB
-//     shared-memory ring: one elected lane issues TMA bulk copies (cp.async.bulk global -> shared,
-//     mbarrier complete_tx) four rows ahead; no LDG in the row loop, no registers held by loads in
+//   * every warp owns a CONTIGUOUS range of 1 KiB rows and streams it through a private shared-memory
+//     ring of four slots: one elected lane issues TMA bulk copies (cp.async.bulk global -> shared,
+//     mbarrier complete_tx) one row ahead; no LDG in the row loop, no registers held by loads in
 //     flight, and every later access to the text (key bytes in front of an '=', the value behind
 //     it) is a shared-memory read at any alignment;
-//   * row phase (one 16-byte chunk per lane): count '\n' (for the record index, see epilogue),
-//     flag '=' bytes with SIMD-in-register compares, and for the '=' of every 4-byte word take the
-//     4 bytes in front of it and look them up in a perfect-hash table of the monitored keys'
-//     last four bytes (3-byte keys: delimiter + key).  Only hits -- about as many as there are
-//     monitored fields -- go to the per-warp field queue;
+//   * row phase (32 bytes per lane): count '\n' (for the record index, see epilogue), flag the '='
+//     bytes with SIMD-in-register compares into one 32-bit mask per lane, then one '=' per lane and
+//     round: the 4 bytes in front of it are looked up in a perfect-hash table of the monitored
+//     keys' last four bytes (3-byte keys: delimiter + key).  Only hits -- about as many as there
+//     are monitored fields -- go to the per-warp field queue;
 //   * field phase (one queued field per lane, 32 at a time): finish the key compare (bytes 5..12
 //     in front of the '=' and the field-start delimiter), find the value's end from ONE byte
 //     class ("stop bytes" < 0x23: space, '"', '\n', controls) over a 32-byte window, dm_fp64,
@@ -24,38 +24,45 @@
 //     candidates are re-checked exactly, by their own lane, walking the record backwards
 //     (dmx_verify_thread);
 //   * the record index of a byte is needed for ALERTS only: alerts are staged as (offset of the
-//     record's first byte, field) and the last CTA to finish runs the epilogue -- exclusive scan of
-//     the per-row '\n' counts, batch header, zero-fill of flags / scores, record index of each
-//     alert, atomics on scores / flags / statistics, anomaly list.
+//     record's first byte, field) and the last CTA to finish runs the epilogue -- prefix of the
+//     per-CTA '\n' counts, batch header, record index of each alert, atomics on scores / flags /
+//     statistics, anomaly list.  The zero-fill of flags / scores is spread over all CTAs.
 //
-// Consecutive launches overlap (programmatic dependent launch): a launch never waits for its
+// CTAs are small (2 warps): a CTA's slot is free again as soon as its two warps are through, and
+// consecutive launches overlap (programmatic dependent launch): a launch never waits for its
 // predecessor kernel; what has to be ordered is ordered by sequence numbers in device memory
 // (DmxShared): scratch buffers alternate between two parities and a launch starts only after the
 // epilogue of the launch two before it has finished; epilogues run one after the other.
 #pragma once
 #include "dm_kernels_rows.cuh"     // device helpers (dm_eqflags, dm_chunk_mask, dm_pdl_*, dm_launch_pdl_smem)
 
-#define DMX_ROW 512u
-#define DMX_SLOTS 8u
-#define DMX_RING (DMX_ROW * DMX_SLOTS)      // bytes of ring per warp
-#define DMX_MIRROR 64u                      // the first bytes of the ring again behind it: reads never wrap
-#define DMX_WARPS 8
+#define DMX_ROW 1024u
+#define DMX_ROW_LOG2 10
+#define DMX_SLOTS 4u
+#define DMX_PRE 16u                         // every slot also holds the 16 bytes in front of its row (key bytes of its first
+#define DMX_POST 64u                        // '=') and the 64 bytes behind it (value of its last field): a field only ever
+#define DMX_SLOT (DMX_PRE + DMX_ROW + DMX_POST)   // touches its own slot
+#define DMX_RING (DMX_SLOT * DMX_SLOTS)     // bytes of ring per warp
+#ifndef DMX_WARPS
+#define DMX_WARPS 2
+#endif
 #define DMX_THREADS (DMX_WARPS * 32)
-#define DMX_QCAP 256u                       // field queue entries per warp (circular; a row adds at most 128 at once)
-#define DMX_DEPTH 2u                        // rows loaded ahead (queued fields may then be up to 5 rows old)
-#define DMX_L1 512u                         // slots of the level-1 key table
+#define DMX_QCAP 256u                       // field queue entries per warp (circular)
+#define DMX_DEPTH 1u                        // rows loaded ahead (queued fields may then be up to 3 rows old)
+#define DMX_L1 512u                         // most slots of the level-1 key table
 #define DMX_WIN 32u                         // bytes of value looked at by the fast path
 #define DMX_FULL 0x40u                      // level-1 info: the four bytes decide alone (3-byte key + delimiter)
-#define DMX_DYN_SMEM (DMX_WARPS * (DMX_RING + DMX_MIRROR))
+#define DMX_RING_SMEM (DMX_WARPS * DMX_RING)
 #ifndef DMX_MIN_CTAS
-#define DMX_MIN_CTAS 4                      // CTAs per SM the register allocation aims at
+#define DMX_MIN_CTAS 16                     // CTAs per SM the register allocation aims at
 #endif
+#define DMB_ROW 512u                        // row of the boundary kernels (dm_k_rowcount / dm_k_bound)
 
 #define DM_DEVERR_ANOMALY_OVERFLOW 8u
 
 struct DmxL1 { uint32_t pat; uint32_t info; };      // info (7 bits): 0 = empty, else (first key of the chain + 1) | DMX_FULL
 
-// Monitored keys as the stream kernel sees them (copied to shared memory per CTA).
+// Monitored keys as the stream kernel sees them.
 struct DmxKeyTab {
     uint32_t n;
     uint32_t mult;                           // level-1 slot of the 4 bytes t in front of an '=': (t * mult) >> shift
@@ -67,9 +74,10 @@ struct DmxKeyTab {
     uint32_t next[DM_MAX_KEYS];              // next key (index + 1) with the same last four bytes, 0 = none
     uint64_t salt[DM_MAX_KEYS];
     alignas(16) uint32_t pat[DM_MAX_KEYS][4];   // {bits, mask} of bytes q-8..q-5 and {bits, mask} of bytes q-12..q-9
-    uint8_t bytes[DM_MAX_KEYS][DM_MAX_KEYLEN];
-    DmxL1 l1[DMX_L1];
+    DmxL1 l1[DMX_L1];                        // (the first l1_slots are used; everything up to there is copied to shared memory)
+    uint8_t bytes[DM_MAX_KEYS][DM_MAX_KEYLEN];  // read from global memory (slow paths only)
 };
+#define DMX_KEYTAB_HOT(slots) (offsetof(DmxKeyTab, l1) + (size_t)(slots) * sizeof(DmxL1))
 
 // Ordering state of one handle (device memory, zeroed at creation).
 struct DmxShared {
@@ -87,6 +95,7 @@ struct DmxArgs {
     const DmxKeyTab* keys;
     DmTable table;
     uint32_t rows_per_cta;
+    uint32_t ring_smem;                      // bytes of dynamic shared memory in front of the key table
     unsigned short* row_cnt;                 // '\n' per row (this launch's parity)
     unsigned int* cta_cnt;                   // '\n' per CTA (this launch's parity)
     dm_anomaly_t* alerts;                    // staged alerts of this launch: {line = '\n' between the start of the 512-byte
@@ -238,38 +247,35 @@ static inline uint32_t dmx_ldcg32(const uint32_t* p) { return *p; }
 static inline void dmx_st_release(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #endif
 
-// One warp's ring: issue() is called by lane 0 only, wait() by the whole warp.
+// One warp's ring: issue() is called by lane 0 only, wait() by the whole warp.  Row r lives in slot r % SLOTS as
+// [16 bytes in front of it | the row | 64 bytes behind it].
 struct DmxRing {
-    uint8_t* ring;                  // DMX_RING + DMX_MIRROR bytes
+    uint8_t* ring;                  // DMX_RING bytes
     const uint8_t* buf;
-    uint32_t r0, r1;                // rows [r0, r1) of this warp; row r1 (if it exists) is loaded as a 64-byte look-ahead
-    uint32_t last_row, last_bytes;  // the message's last row holds last_bytes readable bytes (a multiple of 16)
+    uint64_t nb16;                  // readable extent of the message (nbytes rounded up to 16)
+    uint32_t r0;                    // first row of this warp
 #ifndef DM_EMU
     uint32_t ring_s, bar_s;
 #endif
 
-    // bytes of row `row` that are loaded into its slot
-    __device__ __forceinline__ uint32_t row_bytes(uint32_t row) const {
-        uint32_t bytes = row == last_row ? last_bytes : DMX_ROW;
-        if (row == r1 && bytes > DMX_MIRROR) bytes = DMX_MIRROR;
-        return bytes;
-    }
     __device__ __forceinline__ void issue(uint32_t i) const {
         const uint32_t row = r0 + i;
-        const uint8_t* src = buf + (uint64_t)row * DMX_ROW;
-        const uint32_t bytes = row_bytes(row);
         const uint32_t slot = row & (DMX_SLOTS - 1);
+        const uint32_t pre = row ? DMX_PRE : 0u;           // (the 16 bytes in front of the message are filled in by hand)
+        const uint64_t off = (uint64_t)row * DMX_ROW - pre;
+        const uint64_t left = nb16 - off;
+        const uint32_t bytes = left < DMX_SLOT - DMX_PRE + pre ? (uint32_t)left : DMX_SLOT - DMX_PRE + pre;
 #ifndef DM_EMU
         const uint32_t bar = bar_s + 8u * slot;
         dmx_mbar_expect_tx(bar, bytes);
-        dmx_bulk_g2s(ring_s + slot * DMX_ROW, src, bytes, bar);
+        dmx_bulk_g2s(ring_s + slot * DMX_SLOT + DMX_PRE - pre, buf + off, bytes, bar);
 #else
-        memcpy(ring + slot * DMX_ROW, src, bytes);
+        memcpy(ring + slot * DMX_SLOT + DMX_PRE - pre, buf + off, bytes);
 #endif
     }
     __device__ __forceinline__ void wait(uint32_t i) const {
 #ifndef DM_EMU
-        dmx_mbar_wait(bar_s + 8u * ((r0 + i) & (DMX_SLOTS - 1)), (i >> 3) & 1u);
+        dmx_mbar_wait(bar_s + 8u * ((r0 + i) & (DMX_SLOTS - 1)), (i / DMX_SLOTS) & 1u);
 #else
         (void)i;
         __syncwarp();
@@ -288,12 +294,12 @@ __device__ __forceinline__ uint32_t dmx_stopflags(uint32_t w) {
 }
 
 // Which monitored key (if any) ends right before the '=' at q, given the level-1 hit `info`?  Reads
-// bytes q-12 .. q-5 from the ring (the 16 bytes in front of the message are '\n').
-__device__ __forceinline__ int dmx_resolve_key(const uint8_t* ring, const uint8_t* __restrict__ buf, uint32_t q, uint32_t info,
-                                               const DmxKeyTab& sk) {
+// bytes q-12 .. q-5 from the field's ring slot (the 16 bytes in front of the message are '\n').
+__device__ __forceinline__ int dmx_resolve_key(const uint8_t* ring, uint32_t ra, const uint8_t* __restrict__ buf, uint32_t q, uint32_t info,
+                                               const DmxKeyTab& sk, const DmxKeyTab* gk) {
     if (info & DMX_FULL) return (int)(info & 0x3Fu) - 1;
-    const uint32_t base = ((q - 12u) & ~3u) & (DMX_RING - 1);
-    const uint32_t sh = (q & 3u) * 8u;
+    const uint32_t base = (ra - 12u) & ~3u;              // ra = place of the '=' in the ring (q = its offset in the message)
+    const uint32_t sh = (ra & 3u) * 8u;
     const uint32_t x0 = dmx_ld32(ring, base), x1 = dmx_ld32(ring, base + 4), x2 = dmx_ld32(ring, base + 8);
     const uint32_t w_a = __funnelshift_r(x0, x1, sh);     // bytes q-12 .. q-9
     const uint32_t w_b = __funnelshift_r(x1, x2, sh);     // bytes q-8 .. q-5
@@ -311,20 +317,20 @@ __device__ __forceinline__ int dmx_resolve_key(const uint8_t* ring, const uint8_
         if (q < L) continue;
         const uint32_t st = q - L;
         bool ok = st == 0 || dmx_is_delim(dm_ld8(buf, st - 1));
-        for (uint32_t i = 0; ok && i + 12u < L; ++i) ok = dm_ld8(buf, st + i) == sk.bytes[k][i];
+        for (uint32_t i = 0; ok && i + 12u < L; ++i) ok = dm_ld8(buf, st + i) == gk->bytes[k][i];
         if (ok) return (int)k;
     }
     return -1;
 }
 
 // Keys of one or two bytes (none in the usual configurations): t = the 4 bytes in front of the '='.
-__device__ __forceinline__ uint32_t dmx_short_key(uint32_t t, const DmxKeyTab& sk) {
+__device__ __forceinline__ uint32_t dmx_short_key(uint32_t t, const DmxKeyTab& sk, const DmxKeyTab* gk) {
     for (uint32_t s = 0; s < sk.n_short; ++s) {
         const uint32_t k = sk.short_idx[s];
         if (sk.len[k] == 2u) {
-            if ((t >> 16) == ((uint32_t)sk.bytes[k][0] | ((uint32_t)sk.bytes[k][1] << 8)) && dmx_is_delim((t >> 8) & 0xFFu))
+            if ((t >> 16) == ((uint32_t)gk->bytes[k][0] | ((uint32_t)gk->bytes[k][1] << 8)) && dmx_is_delim((t >> 8) & 0xFFu))
                 return (k + 1) | DMX_FULL;
-        } else if ((t >> 24) == (uint32_t)sk.bytes[k][0] && dmx_is_delim((t >> 16) & 0xFFu)) {
+        } else if ((t >> 24) == (uint32_t)gk->bytes[k][0] && dmx_is_delim((t >> 16) & 0xFFu)) {
             return (k + 1) | DMX_FULL;
         }
     }
@@ -348,9 +354,9 @@ __device__ __forceinline__ uint32_t dmx_value_len_slow(const uint8_t* __restrict
 // the quote parity of the candidate's field start, and whether an earlier field start with the same
 // key and the same parity exists (keys hold no quotes, so the parity at an earlier key's start is
 // the parity at its '=').  The candidate's own key bytes and delimiter are known to match.
-__device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ buf, uint32_t q, uint32_t k, const DmxKeyTab& sk,
+__device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ buf, uint32_t q, uint32_t k, const DmxKeyTab* gk,
                                                   uint32_t* line_start) {
-    const uint32_t L = sk.len[k];
+    const uint32_t L = gk->len[k];
     const uint32_t p0 = q - L;
     uint32_t par = 0, s = 0;
     bool dup = false;
@@ -379,7 +385,7 @@ __device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ bu
                 if (pe) continue;
                 const uint32_t ks = e - L;
                 bool ok = ks == 0 || dmx_is_delim(dm_ld8(buf, ks - 1));
-                for (uint32_t i = 0; ok && i < L; ++i) ok = dm_ld8(buf, ks + i) == sk.bytes[k][i];
+                for (uint32_t i = 0; ok && i < L; ++i) ok = dm_ld8(buf, ks + i) == gk->bytes[k][i];
                 if (ok) dup = true;
             }
             par ^= (uint32_t)__popc(dq) & 1u;
@@ -393,19 +399,6 @@ __device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ bu
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
-// Level-1 lookup for the FIRST '=' of one 4-byte word (f = its '=' flags, 0x80 per byte): the 4 bytes in front of
-// it, taken from the word and its predecessor.  Branch-free; with f == 0 the lookup reads some slot and the
-// result is discarded.  entry = queue entry of the field: ((offset of the '=' in this warp's range) << 7) | info.
-__device__ __forceinline__ bool dmx_probe(uint32_t lo, uint32_t cur, uint32_t f, const DmxL1* __restrict__ l1, uint32_t mult,
-                                          uint32_t shift, uint32_t qrel, uint32_t* entry, uint32_t* t_out) {
-    const uint32_t fs = (uint32_t)__ffs(f);                            // 8 * (byte index of the '=') + 8 (0: no '=')
-    const uint32_t t = __funnelshift_r(lo, cur, fs - 8u);              // (the shift wraps modulo 32)
-    const DmxL1 l = l1[(t * mult) >> shift];
-    *entry = ((qrel + (fs >> 3) - 1u) << 7) | l.info;
-    *t_out = t;
-    return f != 0u && l.pat == t;
-}
-
 // zero-fill of output entries [lo, hi): 16-byte stores where the caller's buffers allow it
 __device__ __forceinline__ void dmx_zero_outputs(uint8_t* flags, float* scores, unsigned long long lo, unsigned long long hi,
                                                  uint32_t tid, uint32_t nthreads) {
@@ -425,50 +418,58 @@ __device__ __forceinline__ void dmx_zero_outputs(uint8_t* flags, float* scores, 
     for (unsigned long long i = v1 + tid; i < hi; i += nthreads) { flags[i] = 0; scores[i] = 0.0f; }
 }
 
-template <bool TRAIN>
-__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_excl);
+// The bytes of a 16-byte chunk equal to `pat` as bits 8b+i of the result (byte b of word i), i.e. UNORDERED: cheaper
+// than a mask in position order, and all that is done with it is to count or to enumerate.
+__device__ __forceinline__ uint32_t dmx_chunk_bits(const uint4& v, uint32_t pat) {
+    const uint32_t f0 = dm_eqflags(v.x, pat), f1 = dm_eqflags(v.y, pat), f2 = dm_eqflags(v.z, pat), f3 = dm_eqflags(v.w, pat);
+    return (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
+}
 
-// Field phase: n (<= 32) queued fields, one per lane.  Called from ONE place in the kernel (one copy of the code);
-// the lanes are brought back together (__syncwarp) after every data-dependent stretch: without that they drift
-// apart for the rest of the function and every later instruction is issued several times for a few lanes each.
-// (what it needs of the kernel arguments sits in shared memory: a reference to the parameter block itself would
-// force a copy of it into local memory)
+template <bool TRAIN>
+__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_pre);
+
+// (what the field phase needs of the kernel arguments sits in shared memory: a reference to the parameter block
+// itself would force a copy of it into local memory)
 struct DmxDrainCtx {
     const uint8_t* buf;
     uint64_t nbytes;
     DmTable table;
+    const DmxKeyTab* gk;
     dm_anomaly_t* alerts;
     unsigned int* alert_count;
     unsigned int* err;
     uint32_t alert_cap;
 };
-#ifdef DM_EMU
-#define __noinline__
-#endif
+
+// Field phase: n (<= 32) queued fields, one per lane.  Called from ONE place in the kernel (one copy of the code);
+// the lanes are brought back together (__syncwarp) after every data-dependent stretch: without that they drift
+// apart for the rest of the function and every later instruction is issued several times for a few lanes each.
 template <bool TRAIN>
 __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab& sk, const uint8_t* ring, const uint32_t* q, uint32_t qh,
-                                       uint32_t n, uint32_t seg_base, uint32_t bound) {
+                                          uint32_t n, uint32_t seg_base, uint32_t bound) {
     const uint32_t lane = threadIdx.x & 31;
     const uint8_t* __restrict__ buf = a.buf;
     const uint64_t nbytes = a.nbytes;
-    uint32_t qpos = 0;
+    uint32_t qpos = 0, ra = 0;
     int k = -1;
     if (lane < n) {
         const uint32_t e = q[(qh + lane) & (DMX_QCAP - 1)];
-        qpos = seg_base + (e >> 7);
-        if (TRAIN ? (qpos < bound) : (qpos >= bound)) k = dmx_resolve_key(ring, buf, qpos, e & 0x7Fu, sk);
+        const uint32_t qrel = e >> 7;                                              // offset of the '=' in this warp's range
+        qpos = seg_base + qrel;
+        ra = (((seg_base >> DMX_ROW_LOG2) + (qrel >> DMX_ROW_LOG2)) & (DMX_SLOTS - 1)) * DMX_SLOT + DMX_PRE + (qrel & (DMX_ROW - 1));
+        if (TRAIN ? (qpos < bound) : (qpos >= bound)) k = dmx_resolve_key(ring, ra, buf, qpos, e & 0x7Fu, sk, a.gk);
     }
     __syncwarp();
     const bool act = k >= 0;
     // ---- the value (R-tok L5): it ends at the first space outside double quotes counted from its start, at '\n',
     // or at the end of the message.  One byte class ("stop bytes" < 0x23) over a 32-byte window. ----
     const uint32_t vpos = qpos + 1u;
-    const uint32_t vr = vpos & (DMX_RING - 1);
+    const uint32_t vr = ra + 1u;                              // the value's place in the ring
     uint32_t w[8];
     uint32_t m = 0, lim = 0;
     if (act) {
         const uint32_t base = vr & ~3u;
-        const uint32_t sh = (vpos & 3u) * 8u;
+        const uint32_t sh = (vr & 3u) * 8u;
         uint32_t lo = dmx_ld32(ring, base);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -529,7 +530,7 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
     if (__any_sync(0xffffffffu, cand)) {
         if (cand) {
             uint32_t ls = 0;
-            if (dmx_verify_thread(buf, qpos, (uint32_t)k, sk, &ls)) {
+            if (dmx_verify_thread(buf, qpos, (uint32_t)k, a.gk, &ls)) {
                 if (TRAIN) {
                     dm_table_insert(a.table, ckey, a.err);
                 } else {
@@ -560,7 +561,8 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
 #else
     extern __shared__ __align__(128) uint8_t s_dyn[];
 #endif
-    __shared__ DmxKeyTab sk;
+    // dynamic shared memory: DMX_WARPS rings, then the key table up to its last level-1 slot
+    const DmxKeyTab& sk = *reinterpret_cast<const DmxKeyTab*>(s_dyn + a.ring_smem);
     __shared__ uint32_t s_q[DMX_WARPS][DMX_QCAP];
     __shared__ unsigned long long s_bar[DMX_WARPS][DMX_SLOTS];
     __shared__ uint32_t s_cnt[DMX_WARPS];
@@ -571,22 +573,21 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
     const uint32_t lt = dm_lanemask_lt();
     dm_pdl_launch_dependents();                       // the next launch may be scheduled as soon as there is room
     if (threadIdx.x == 0) {
-        s_ctx.buf = a.buf; s_ctx.nbytes = a.nbytes; s_ctx.table = a.table; s_ctx.alerts = a.alerts;
+        s_ctx.buf = a.buf; s_ctx.nbytes = a.nbytes; s_ctx.table = a.table; s_ctx.gk = a.keys; s_ctx.alerts = a.alerts;
         s_ctx.alert_count = a.alert_count; s_ctx.err = &a.hdr->error; s_ctx.alert_cap = a.alert_cap;
-    }
-    if (a.timeline && threadIdx.x == 0) {
-        uint32_t smid = 0;
+        if (a.timeline) {
+            uint32_t smid = 0;
 #ifndef DM_EMU
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
 #endif
-        a.timeline[4ull * blockIdx.x] = smid;
-        a.timeline[4ull * blockIdx.x + 1] = dmx_now();
+            a.timeline[4ull * blockIdx.x] = smid;
+            a.timeline[4ull * blockIdx.x + 1] = dmx_now();
+        }
     }
     {
-        const uint32_t words = (uint32_t)((sizeof(DmxKeyTab) - sizeof(DmxL1) * DMX_L1) / 4);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.keys);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sk);
-        const uint32_t total = words + 2u * __ldg(&a.keys->l1_slots);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_dyn + a.ring_smem);
+        const uint32_t total = (uint32_t)(offsetof(DmxKeyTab, l1) / 4) + 2u * __ldg(&a.keys->l1_slots);
         for (uint32_t i = threadIdx.x; i < total; i += DMX_THREADS) dst[i] = __ldg(src + i);
     }
     if (lane == 0) {
@@ -609,140 +610,104 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
     const uint64_t r0l = (uint64_t)gw * a.rows_per_warp;
     if (r0l < a.n_rows) {
         DmxRing rg;
-        rg.ring = s_dyn + warp * (DMX_RING + DMX_MIRROR);
+        rg.ring = s_dyn + warp * DMX_RING;
         rg.buf = a.buf;
+        rg.nb16 = (nbytes + 15ull) & ~15ull;
         rg.r0 = (uint32_t)r0l;
-        rg.r1 = (uint32_t)(r0l + a.rows_per_warp < a.n_rows ? r0l + a.rows_per_warp : a.n_rows);
-        rg.last_row = a.n_rows - 1;
-        rg.last_bytes = (uint32_t)(((nbytes + 15ull) & ~15ull) - (uint64_t)rg.last_row * DMX_ROW);
 #ifndef DM_EMU
         rg.ring_s = dmx_smem_u32(rg.ring);
         rg.bar_s = dmx_smem_u32(&s_bar[warp][0]);
 #endif
         const uint8_t* ring = rg.ring;
-        const uint32_t n_own = rg.r1 - rg.r0;
-        const uint32_t n_loads = n_own + (rg.r1 < a.n_rows ? 1u : 0u);
+        const uint32_t n_own = (uint32_t)(r0l + a.rows_per_warp < a.n_rows ? a.rows_per_warp : a.n_rows - r0l);
         const uint32_t seg_base = rg.r0 * DMX_ROW;            // (messages are shorter than 4 GiB)
         const uint32_t tail_bytes = (uint32_t)(nbytes & (DMX_ROW - 1));   // valid bytes of a partial last row (0 = full)
+        const uint32_t tail_row = tail_bytes ? a.n_rows - 1 : 0xFFFFFFFFu;
         uint32_t* q = s_q[warp];
         uint32_t qh = 0, qn = 0, nl_w = 0;
-        // the 16 bytes in front of the range (key bytes of its first '='); a message starts a record: '\n' there
-        if (lane < 4) {
-            uint32_t x = 0x0A0A0A0Au;
-            if (rg.r0 > 0) x = __ldg(reinterpret_cast<const uint32_t*>(a.buf + (uint64_t)rg.r0 * DMX_ROW - 16) + lane);
-            reinterpret_cast<uint32_t*>(rg.ring + ((rg.r0 * DMX_ROW - 16u) & (DMX_RING - 1)))[lane] = x;
+        if (rg.r0 == 0) {
+            // a message starts a record: the 16 bytes "in front of it" read as '\n'
+            if (lane < 4) reinterpret_cast<uint32_t*>(rg.ring)[lane] = 0x0A0A0A0Au;
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0)
-            for (uint32_t i = 0; i < DMX_DEPTH && i < n_loads; ++i) rg.issue(i);
+        if (lane == 0) rg.issue(0);
+        // lane l owns bytes [32 l, 32 l + 32) of a row; it reads its two 16-byte chunks in an order that keeps the
+        // eight lanes of a shared-memory phase on different banks
+        const uint32_t c_first = (lane >> 2) & 1u;
 
-        // rows arrive in order: row 0 now, then always the row AFTER the one being worked on (look-ahead of its fields)
-        rg.wait(0);
-        const uint32_t tail_row = tail_bytes ? rg.last_row : 0xFFFFFFFFu;
         for (uint32_t i = 0; i < n_own; ++i) {
             const uint32_t row = rg.r0 + i;
-            const bool has_next = i + 1 < n_loads;
-            if (has_next) rg.wait(i + 1);
-            if ((i == 0 && (row & (DMX_SLOTS - 1)) == 0) || (has_next && ((row + 1) & (DMX_SLOTS - 1)) == 0)) {
-                // a row has arrived at the start of the ring: its first bytes again behind the ring's end, so that reads
-                // that start in the row before it (or in the 16 bytes in front of the range) never wrap
-                if (lane < DMX_MIRROR / 4) reinterpret_cast<uint32_t*>(rg.ring + DMX_RING)[lane] = reinterpret_cast<const uint32_t*>(rg.ring)[lane];
+            if (i + 1 < n_own) {
+                // row i+1 goes into the slot of row i-3, whose fields have left the queue (see the end of the loop body)
                 __syncwarp();
+                if (lane == 0) rg.issue(i + 1);
             }
-            const uint32_t sb = (row & (DMX_SLOTS - 1)) * DMX_ROW + lane * 16u;
-            uint4 v = *reinterpret_cast<const uint4*>(ring + sb);
-            const uint32_t prev = dmx_ld32(ring, (sb - 4u) & (DMX_RING - 1));
+            rg.wait(i);
+            const uint32_t lb = (row & (DMX_SLOTS - 1)) * DMX_SLOT + DMX_PRE + lane * 32u;      // this lane's bytes in the ring
+            uint4 va = *reinterpret_cast<const uint4*>(ring + lb + 16u * c_first);
+            uint4 vb = *reinterpret_cast<const uint4*>(ring + lb + 16u * (1u - c_first));
             if (row == tail_row) {
                 // partial last row: bytes behind the message are nobody's
-                const uint32_t lo = lane * 16u;
-                const uint32_t vb = tail_bytes > lo ? (tail_bytes - lo < 16u ? tail_bytes - lo : 16u) : 0u;
-                uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+                uint32_t* wa = reinterpret_cast<uint32_t*>(&va);
+                uint32_t* wb = reinterpret_cast<uint32_t*>(&vb);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t nb = vb > 4u * j ? vb - 4u * j : 0u;
-                    if (nb < 4u) vw[j] = nb ? (vw[j] & ((1u << (8u * nb)) - 1u)) : 0u;
+                    const uint32_t oa = lane * 32u + 16u * c_first + 4u * j, ob = lane * 32u + 16u * (1u - c_first) + 4u * j;
+                    const uint32_t na = tail_bytes > oa ? tail_bytes - oa : 0u, nb = tail_bytes > ob ? tail_bytes - ob : 0u;
+                    if (na < 4u) wa[j] = na ? (wa[j] & ((1u << (8u * na)) - 1u)) : 0u;
+                    if (nb < 4u) wb[j] = nb ? (wb[j] & ((1u << (8u * nb)) - 1u)) : 0u;
                 }
             }
             {
                 // '\n' of the row (the epilogue turns the counts into record indices)
-                const uint32_t n0 = dm_eqflags(v.x, 0x0A0A0A0Au), n1 = dm_eqflags(v.y, 0x0A0A0A0Au);
-                const uint32_t n2 = dm_eqflags(v.z, 0x0A0A0A0Au), n3 = dm_eqflags(v.w, 0x0A0A0A0Au);
-                const uint32_t c = (uint32_t)__popc(n0 | (n1 >> 1) | (n2 >> 2) | (n3 >> 3));
+                const uint32_t c = (uint32_t)__popc(dmx_chunk_bits(va, 0x0A0A0A0Au)) + (uint32_t)__popc(dmx_chunk_bits(vb, 0x0A0A0A0Au));
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
                 if (lane == 0) a.row_cnt[row] = (unsigned short)tot;
                 nl_w += tot;
             }
-            const uint32_t f0 = dm_eqflags(v.x, 0x3D3D3D3Du), f1 = dm_eqflags(v.y, 0x3D3D3D3Du);
-            const uint32_t f2 = dm_eqflags(v.z, 0x3D3D3D3Du), f3 = dm_eqflags(v.w, 0x3D3D3D3Du);
-            const uint32_t qrel = i * DMX_ROW + lane * 16u;
-            const bool more = i + DMX_DEPTH < n_loads;
+            // the '=' of this lane's 32 bytes: bit 8b + 4c + w = byte b of word w of chunk c
+            uint32_t g = (dmx_chunk_bits(va, 0x3D3D3D3Du) << (4u * c_first)) | (dmx_chunk_bits(vb, 0x3D3D3D3Du) << (4u * (1u - c_first)));
+            const uint32_t qrel = i * DMX_ROW + lane * 32u;
+            // one '=' per lane and round: the 4 bytes in front of it (shared memory, any alignment) -> level-1 table.
+            // When the queue fills up the loop is left for the drain below and resumed afterwards.
             bool row_done = false;
-            int wi = 0;
-            uint32_t gs = f0;
             do {
-            if (!n_short) {
-                // The FIRST '=' of each 4-byte word, all four words at once.  (With keys of three bytes and more a later
-                // '=' of the same word cannot follow a key: the key would have to hold the earlier '='.)
-                uint32_t e0, e1, e2, e3, t;
-                bool h0 = dmx_probe(prev, v.x, f0, sk.l1, l1_mult, l1_shift, qrel, &e0, &t);
-                bool h1 = dmx_probe(v.x, v.y, f1, sk.l1, l1_mult, l1_shift, qrel + 4u, &e1, &t);
-                bool h2 = dmx_probe(v.y, v.z, f2, sk.l1, l1_mult, l1_shift, qrel + 8u, &e2, &t);
-                bool h3 = dmx_probe(v.z, v.w, f3, sk.l1, l1_mult, l1_shift, qrel + 12u, &e3, &t);
-                // one field per lane and round (a 16-byte chunk seldom holds two monitored fields)
-                uint32_t hb = __ballot_sync(0xffffffffu, h0 || h1 || h2 || h3);
-                while (hb) {
-                    const uint32_t e = h0 ? e0 : (h1 ? e1 : (h2 ? e2 : e3));
-                    if (h0 || h1 || h2 || h3) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
-                    qn += (uint32_t)__popc(hb);
-                    if (h0) h0 = false; else if (h1) h1 = false; else if (h2) h2 = false; else h3 = false;
-                    hb = __ballot_sync(0xffffffffu, h0 || h1 || h2 || h3);
-                }
-                __syncwarp();
-                row_done = true;
-            } else {
-                // keys of 1..2 bytes: every '=' of every word, one per lane and round; when the queue fills up the loop
-                // is left for the drain below and resumed afterwards
-                while (wi < 4) {
-                    const uint32_t lo = wi == 0 ? prev : (wi == 1 ? v.x : (wi == 2 ? v.y : v.z));
-                    const uint32_t cur = wi == 0 ? v.x : (wi == 1 ? v.y : (wi == 2 ? v.z : v.w));
-                    if (!__any_sync(0xffffffffu, gs != 0u)) {
-                        ++wi;
-                        gs = wi == 1 ? f1 : (wi == 2 ? f2 : f3);
-                        continue;
-                    }
-                    uint32_t e = 0, t = 0;
-                    bool hit = dmx_probe(lo, cur, gs, sk.l1, l1_mult, l1_shift, qrel + 4u * wi, &e, &t);
-                    if (gs != 0u && !hit) {
-                        const uint32_t info = dmx_short_key(t, sk);
-                        if (info) { hit = true; e = (e & ~0x7Fu) | info; }
+                while (__any_sync(0xffffffffu, g != 0u)) {
+                    bool hit = false;
+                    uint32_t e = 0;
+                    if (g) {
+                        const uint32_t x = (uint32_t)__ffs(g) - 1u;
+                        g &= g - 1u;
+                        const uint32_t pos = ((x & 7u) << 2) + (x >> 3);               // byte of the '=' inside the 32 bytes
+                        const uint32_t at = lb + pos - 4u;                               // the 4 bytes in front of it
+                        const uint32_t t = __funnelshift_r(dmx_ld32(ring, at & ~3u), dmx_ld32(ring, (at & ~3u) + 4u), (at & 3u) * 8u);
+                        const DmxL1 l = sk.l1[(t * l1_mult) >> l1_shift];
+                        uint32_t info = l.pat == t ? l.info : 0u;
+                        if (!info && n_short) info = dmx_short_key(t, sk, a.keys);
+                        hit = info != 0u;
+                        e = ((qrel + pos) << 7) | info;
                     }
                     const uint32_t hb = __ballot_sync(0xffffffffu, hit);
                     if (hb) {
                         if (hit) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
                         qn += (uint32_t)__popc(hb);
-                        __syncwarp();
+                        if (qn > DMX_QCAP - 32u) break;
                     }
-                    gs &= gs - 1u;
-                    if (qn > DMX_QCAP - 64u) break;
                 }
-                row_done = wi >= 4;
-            }
-            // drain: full passes; and, at the end of the row, before row i+DEPTH overwrites the slot of row (i + DEPTH - 8),
-            // whatever is left of rows up to (i + DEPTH - 7) (a field's key bytes may lie in the row before it)
-            for (;;) {
-                uint32_t n = 0;
-                if (qn >= 32u) n = 32u;
-                else if (qn && row_done && (i + 1 == n_own || (more && (q[qh & (DMX_QCAP - 1)] >> 16) + (DMX_SLOTS - DMX_DEPTH - 1u) <= i))) n = qn;
-                if (!n) break;
-                dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound);
-                qh += n;
-                qn -= n;
-            }
-            } while (!row_done);
-            if (more) {
                 __syncwarp();
-                if (lane == 0) rg.issue(i + DMX_DEPTH);
-            }
+                row_done = !__any_sync(0xffffffffu, g != 0u);
+                // drain: full passes; and, at the end of the row, whatever is left of rows up to (i + 2 - SLOTS): the next
+                // iteration loads row i+2 into that row's slot
+                for (;;) {
+                    uint32_t n = 0;
+                    if (qn >= 32u) n = 32u;
+                    else if (qn && row_done && (i + 1 == n_own || (q[qh & (DMX_QCAP - 1)] >> (7 + DMX_ROW_LOG2)) + (DMX_SLOTS - 2u) <= i)) n = qn;
+                    if (!n) break;
+                    dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound);
+                    qh += n;
+                    qn -= n;
+                }
+            } while (!row_done);
         }
         if (lane == 0) s_cnt[warp] = nl_w;
     }
@@ -786,10 +751,11 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
 __device__ __forceinline__ uint32_t dmx_sum8(const uint4& v) {
     return (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16) + (v.z & 0xFFFFu) + (v.z >> 16) + (v.w & 0xFFFFu) + (v.w >> 16);
 }
-// '\n' counts of rows [lo, hi), lo a multiple of 8 (16-byte aligned): vector loads that bypass L1 (other CTAs wrote them)
+// '\n' counts of rows [lo, hi): vector loads that bypass L1 (other CTAs wrote them)
 __device__ __forceinline__ unsigned long long dmx_count_rows(const unsigned short* cnt, uint32_t lo, uint32_t hi) {
     unsigned long long s = 0;
     uint32_t r = lo;
+    for (; r < hi && (r & 7u); ++r) s += *((volatile const unsigned short*)(cnt + r));
 #ifndef DM_EMU
     for (; r + 32 <= hi; r += 32) {
         const uint4 v0 = __ldcg(reinterpret_cast<const uint4*>(cnt + r)), v1 = __ldcg(reinterpret_cast<const uint4*>(cnt + r + 8));
@@ -803,9 +769,9 @@ __device__ __forceinline__ unsigned long long dmx_count_rows(const unsigned shor
 }
 
 // Epilogue (the last CTA of a launch): batch header, rest of the zero-fill, record index of every staged alert,
-// scores / flags / statistics / anomaly list.  s_excl: gridDim.x + 12 words of shared memory.
+// scores / flags / statistics / anomaly list.  s_pre: DMX_THREADS + 16 words of shared memory.
 template <bool TRAIN>
-__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_excl) {
+__device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_pre) {
     const uint32_t tid = threadIdx.x;
     unsigned long long* tl = a.timeline ? a.timeline + 4ull * gridDim.x : nullptr;
     if (tl && tid == 0) tl[0] = dmx_now();
@@ -816,7 +782,7 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
     if (tl && tid == 0) tl[1] = dmx_now();
     if (!TRAIN) {
         const uint32_t G = gridDim.x;
-        // exclusive prefix of the per-CTA '\n' counts: every thread takes a few consecutive CTAs, the warps scan by shuffles
+        // '\n' in front of every group of cpt consecutive CTAs (thread t: CTAs [t cpt, (t+1) cpt)); the warps scan by shuffles
         const uint32_t cpt = (G + DMX_THREADS - 1) / DMX_THREADS;
         {
             const uint32_t lo = tid * cpt < G ? tid * cpt : G, hi = lo + cpt < G ? lo + cpt : G;
@@ -829,21 +795,20 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
                 const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, d);
                 if ((int)ln >= d) incl += y;
             }
-            if (ln == 31) s_excl[G + 4 + (tid >> 5)] = incl;
+            if (ln == 31) s_pre[DMX_THREADS + 4 + (tid >> 5)] = incl;
             __syncthreads();
             unsigned long long run = incl - c;
-            for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_excl[G + 4 + w];
-            for (uint32_t i = lo; i < hi; ++i) { s_excl[i] = run; run += dmx_ldcg32(a.cta_cnt + i); }
-            if (tid == DMX_THREADS - 1) s_excl[G + 2] = run;               // all '\n' of the message
+            for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_pre[DMX_THREADS + 4 + w];
+            s_pre[tid] = run;
+            if (tid == DMX_THREADS - 1) s_pre[DMX_THREADS + 2] = run + c;          // all '\n' of the message
         }
         __syncthreads();
         if (tid == 0) {
-            const unsigned long long run = s_excl[G + 2];
-            const unsigned long long nl = run;
+            const unsigned long long nl = s_pre[DMX_THREADS + 2];
             const bool tail = a.nbytes > 0 && a.buf[a.nbytes - 1] != 0x0Au;
             const unsigned long long n_lines = nl + (tail ? 1ull : 0ull);
-            s_excl[G] = n_lines;
-            s_excl[G + 1] = a.sh->zero_bound;
+            s_pre[DMX_THREADS] = n_lines;
+            s_pre[DMX_THREADS + 1] = a.sh->zero_bound;
             a.sh->zero_bound = n_lines;
             const unsigned int staged = *((volatile unsigned int*)a.alert_count);
             unsigned int err = (n_lines > a.max_lines || n_lines > a.out_cap) ? DM_DEVERR_TOO_MANY_LINES : 0u;
@@ -860,10 +825,10 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
         }
         __syncthreads();
         if (tl && tid == 0) tl[2] = dmx_now();
-        const unsigned long long n_lines = s_excl[G];
+        const unsigned long long n_lines = s_pre[DMX_THREADS];
         const unsigned long long n_out = n_lines < a.out_cap ? n_lines : a.out_cap;
         // (the CTAs zero-filled [0, zero_bound); more records than that only when the messages grow)
-        dmx_zero_outputs(a.flags, a.scores, s_excl[G + 1] < n_out ? s_excl[G + 1] : n_out, n_out, tid, DMX_THREADS);
+        dmx_zero_outputs(a.flags, a.scores, s_pre[DMX_THREADS + 1] < n_out ? s_pre[DMX_THREADS + 1] : n_out, n_out, tid, DMX_THREADS);
         __syncthreads();
         if (tl && tid == 0) tl[3] = dmx_now();
         const unsigned int staged = *((volatile unsigned int*)a.alert_count);
@@ -871,10 +836,13 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
         for (unsigned int i = tid; i < n_al; i += DMX_THREADS) {
             const uint32_t inrow = dmx_ldcg32(&a.alerts[i].line), k = dmx_ldcg32(&a.alerts[i].mask);
             const uint32_t s = dmx_ldcg32(reinterpret_cast<const uint32_t*>(&a.alerts[i].offset));
-            // record index = '\n' in front of the record's first byte
-            const uint32_t row = s >> 9;
+            // record index = '\n' in front of the record's first byte: CTA groups, CTAs of the group, rows of the CTA, row
+            const uint32_t row = s >> DMX_ROW_LOG2;
             const uint32_t cta = row / a.rows_per_cta;
-            const unsigned long long g = s_excl[cta] + dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row) + inrow;
+            const uint32_t t = cta / cpt;
+            unsigned long long g = s_pre[t] + inrow;
+            for (uint32_t c = t * cpt; c < cta; ++c) g += dmx_ldcg32(a.cta_cnt + c);
+            g += dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row);
             bool first = false;
             if (g < a.out_cap) {
                 const float old = atomicAdd(a.scores + g, 1.0f);
@@ -912,7 +880,7 @@ __global__ void __launch_bounds__(256) dm_k_rowcount(const uint8_t* __restrict__
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t row = w; row < n_rows; row += nw) {
-        const uint64_t off = (uint64_t)row * DMX_ROW + lane * 16u;
+        const uint64_t off = (uint64_t)row * DMB_ROW + lane * 16u;
         uint32_t m = 0;
         if (off < nbytes) m = dm_row_nl_mask(__ldg(reinterpret_cast<const uint4*>(buf + off)), off, nbytes);
         const uint32_t tot = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
@@ -943,7 +911,7 @@ __global__ void __launch_bounds__(256) dm_k_bound(const uint8_t* __restrict__ bu
         else if (t < 256) {
             uint32_t r = t * per;
             while (run + row_cnt[r] < n_train) { run += row_cnt[r]; ++r; }
-            uint64_t p = (uint64_t)r * DMX_ROW;
+            uint64_t p = (uint64_t)r * DMB_ROW;
             for (;; ++p)
                 if (buf[p] == 0x0Au && ++run == n_train) break;
             bound = p + 1;
@@ -966,6 +934,7 @@ struct DmxScratch {
     unsigned long long* d_bound = nullptr;
     DmxShared* d_shared = nullptr;
     uint32_t alert_cap = 0;
+    uint32_t dyn_smem = 0;                      // rings + key table
     uint64_t max_rows = 0;
     unsigned long long seq = 0;
     int ctas_per_sm = 0;
@@ -980,22 +949,22 @@ static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t
     DmxKeyTab* t = new (std::nothrow) DmxKeyTab;
     if (!t) return DM_ERR_CUDA;
     const bool ok = dmx_keytab_build(keys, t);
+    s->dyn_smem = (uint32_t)(DMX_RING_SMEM + ((DMX_KEYTAB_HOT(t->l1_slots) + 15) & ~(size_t)15));
     cudaError_t e = ok ? cudaMalloc(&s->d_keys, sizeof(DmxKeyTab)) : cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaMemcpy(s->d_keys, t, sizeof(DmxKeyTab), cudaMemcpyHostToDevice);
     delete t;
     if (e != cudaSuccess) return DM_ERR_CUDA;
-    s->max_rows = (max_batch_bytes + DMX_ROW - 1) / DMX_ROW + 64;
+    s->max_rows = (max_batch_bytes + DMB_ROW - 1) / DMB_ROW + 64;
     s->alert_cap = alert_cap;
-    if (cudaFuncSetAttribute(dm_k_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DMX_DYN_SMEM) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaFuncSetAttribute(dm_k_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DMX_DYN_SMEM) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaFuncSetAttribute(dm_k_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaFuncSetAttribute(dm_k_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_stream<false>, DMX_THREADS, DMX_DYN_SMEM) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_stream<false>, DMX_THREADS, s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
     if (per_sm < 1) per_sm = 1;
     const char* cap = getenv("DM_STREAM_CTAS_PER_SM");     // tuning knob
     if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
     s->ctas_per_sm = per_sm;
     s->max_grid = sm_count * per_sm;
-    if ((size_t)s->max_grid * 8 + 128 > DMX_DYN_SMEM) s->max_grid = (int)((DMX_DYN_SMEM - 128) / 8);   // (epilogue prefix lives in the rings)
     for (int b = 0; b < 2; ++b) {
         if (cudaMalloc(&s->d_row_cnt[b], s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
         if (cudaMalloc(&s->d_cta_cnt[b], (size_t)s->max_grid * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
@@ -1028,14 +997,15 @@ static inline int dmx_launch(DmxScratch* s, const uint8_t* d_buf, uint64_t nbyte
                              DmBatchHeader* d_hdr, unsigned long long* d_stats, uint64_t max_lines, cudaStream_t st,
                              bool allow_overlap, void (*mark)(void*, cudaStream_t, int), void* mark_ctx) {
     const uint32_t n_rows = (uint32_t)((nbytes + DMX_ROW - 1) / DMX_ROW);
+    const uint32_t b_rows = (uint32_t)((nbytes + DMB_ROW - 1) / DMB_ROW);
     if (n_rows == 0) return 0;
-    if (n_rows > s->max_rows) return DM_ERR_CAPACITY;
+    if (b_rows > s->max_rows) return DM_ERR_CAPACITY;
     DmxArgs a;
     a.buf = d_buf; a.nbytes = nbytes; a.n_rows = n_rows;
     a.keys = s->d_keys; a.table = table;
     a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap; a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap;
     a.hdr = d_hdr; a.stats = d_stats; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
-    a.sh = s->d_shared; a.alert_cap = s->alert_cap; a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = s->d_timeline;
+    a.sh = s->d_shared; a.alert_cap = s->alert_cap; a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = s->d_timeline; a.ring_smem = DMX_RING_SMEM;
     // geometry: every warp gets the same number of contiguous rows
     const unsigned long long warps_max = (unsigned long long)s->max_grid * DMX_WARPS;
     const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
@@ -1052,17 +1022,17 @@ static inline int dmx_launch(DmxScratch* s, const uint8_t* d_buf, uint64_t nbyte
     };
     if (n_train_lines > 0) {
         // where detection starts is only known on the device
-        dm_k_rowcount<<<(unsigned)std::min<uint64_t>((n_rows + 7) / 8, 2048), 256, 0, st>>>(d_buf, nbytes, n_rows, s->d_bound_cnt);
-        dm_k_bound<<<1, 256, 0, st>>>(d_buf, nbytes, n_rows, s->d_bound_cnt, n_train_lines, s->d_bound, d_hdr);
+        dm_k_rowcount<<<(unsigned)std::min<uint64_t>((b_rows + 7) / 8, 2048), 256, 0, st>>>(d_buf, nbytes, b_rows, s->d_bound_cnt);
+        dm_k_bound<<<1, 256, 0, st>>>(d_buf, nbytes, b_rows, s->d_bound_cnt, n_train_lines, s->d_bound, d_hdr);
         a.bound_ptr = s->d_bound; a.keep_error = 1;
         bind();
-        dm_launch_pdl_smem(dm_k_stream<true>, grid, DMX_THREADS, (size_t)DMX_DYN_SMEM, st, false, a);
+        dm_launch_pdl_smem(dm_k_stream<true>, grid, DMX_THREADS, (size_t)s->dyn_smem, st, false, a);
         launched += 3;
     }
     bind();
     const bool pdl = allow_overlap && n_train_lines == 0 && s->chain_stream == st;
     if (mark) mark(mark_ctx, st, 0);
-    dm_launch_pdl_smem(dm_k_stream<false>, grid, DMX_THREADS, (size_t)DMX_DYN_SMEM, st, pdl, a);
+    dm_launch_pdl_smem(dm_k_stream<false>, grid, DMX_THREADS, (size_t)s->dyn_smem, st, pdl, a);
     if (mark) mark(mark_ctx, st, 1);
     s->chain_stream = st;
     ++launched;

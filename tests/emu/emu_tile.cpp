@@ -285,12 +285,12 @@ extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nby
         g_xs.cta_cnt[b].assign(g_emu_stream_ctas + 1, 0xDEADBEEFu);
     }
     g_xs.bound_cnt.assign(n_rows + 1, 0xBEEF);
-    g_emu_dyn_smem.assign(DMX_DYN_SMEM, 0xEE);
+    g_emu_dyn_smem.assign(DMX_RING_SMEM + sizeof(DmxKeyTab), 0xEE);
     DmxArgs a;
     a.buf = buf; a.nbytes = nbytes; a.n_rows = n_rows; a.keys = &g_xs.tab; a.table = h->table;
     a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
     a.hdr = &h->hdr; a.stats = h->stats; a.n_train_lines = n_train; a.max_lines = h->max_lines;
-    a.sh = &g_xs.sh; a.alert_cap = (uint32_t)h->anoms.size(); a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = nullptr;
+    a.sh = &g_xs.sh; a.alert_cap = (uint32_t)h->anoms.size(); a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = nullptr; a.ring_smem = DMX_RING_SMEM;
     const unsigned long long warps_max = (unsigned long long)g_emu_stream_ctas * DMX_WARPS;
     const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
     const unsigned long long warps = (n_rows + rpw - 1) / rpw;
@@ -303,8 +303,10 @@ extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nby
         a.row_cnt = g_xs.row_cnt[p].data(); a.cta_cnt = g_xs.cta_cnt[p].data(); a.alerts = g_xs.alerts[p].data(); a.alert_count = &g_xs.alert_count[p];
     };
     if (n_train > 0) {
-        emu_launch_grid(2, 256, [&] { dm_k_rowcount(buf, nbytes, n_rows, g_xs.bound_cnt.data()); });
-        emu_launch(256, [&] { dm_k_bound(buf, nbytes, n_rows, g_xs.bound_cnt.data(), n_train, &g_xs.bound, &h->hdr); });
+        const uint32_t b_rows = (uint32_t)((nbytes + DMB_ROW - 1) / DMB_ROW);
+        g_xs.bound_cnt.assign(b_rows + 1, 0xBEEF);
+        emu_launch_grid(2, 256, [&] { dm_k_rowcount(buf, nbytes, b_rows, g_xs.bound_cnt.data()); });
+        emu_launch(256, [&] { dm_k_bound(buf, nbytes, b_rows, g_xs.bound_cnt.data(), n_train, &g_xs.bound, &h->hdr); });
         a.bound_ptr = &g_xs.bound; a.keep_error = 1;
         bind();
         emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<true>(a); });
