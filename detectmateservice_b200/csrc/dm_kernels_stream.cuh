@@ -83,8 +83,8 @@ struct DmxKeyTab {
 struct DmxShared {
     unsigned int done_ctr[4];                // CTAs of launch (seq & 3) that have finished their rows
     unsigned long long epi_done_seq;         // sequence number of the last launch whose epilogue is complete
-    unsigned long long zero_bound;           // records of the previous detect message: that many output entries are
-                                             // zero-filled by all CTAs together, the epilogue does the rest (if any)
+    unsigned long long zero_bound[2];        // [seq & 1]: records of detect message seq-2: launch seq's CTAs zero-fill that
+                                             // many output entries between them, its epilogue does the rest (if any)
 };
 
 struct DmxArgs {
@@ -599,8 +599,11 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
 #endif
     }
     // this launch's scratch (row counts, staged alerts) was last used by launch seq-2: its epilogue must be through
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         while (dmx_ld_acquire(&a.sh->epi_done_seq) + 2ull < a.seq) __nanosleep(64);
+        const unsigned long long zb = *((volatile unsigned long long*)&a.sh->zero_bound[a.seq & 1ull]);
+        s_bound = zb < a.out_cap ? zb : a.out_cap;
+    }
     __syncthreads();
 
     const uint64_t nbytes = a.nbytes;
@@ -720,13 +723,9 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
             uint32_t c = 0;
             for (uint32_t w = 0; w < DMX_WARPS; ++w) c += s_cnt[w];
             a.cta_cnt[blockIdx.x] = c;
-            // the previous call's outputs are complete once its epilogue is through; then every CTA zero-fills its
-            // share of as many entries as the previous message had records
-            while (dmx_ld_acquire(&a.sh->epi_done_seq) + 1ull < a.seq) __nanosleep(64);
-            const unsigned long long zb = *((volatile unsigned long long*)&a.sh->zero_bound);
-            s_bound = zb < a.out_cap ? zb : a.out_cap;
         }
-        __syncthreads();
+        // every CTA zero-fills its share of as many output entries as message seq-2 had records.  (The previous call's
+        // epilogue may still be adding ITS alerts to the same buffers: this launch's epilogue takes them out again.)
         const unsigned long long zb = s_bound;
         const unsigned long long per = (((zb + gridDim.x - 1) / gridDim.x) + 15ull) & ~15ull;
         const unsigned long long lo = per * blockIdx.x < zb ? per * blockIdx.x : zb;
@@ -782,12 +781,25 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
     if (tl && tid == 0) tl[1] = dmx_now();
     if (!TRAIN) {
         const uint32_t G = gridDim.x;
-        // '\n' in front of every group of cpt consecutive CTAs (thread t: CTAs [t cpt, (t+1) cpt)); the warps scan by shuffles
+        // the alerts of the previous call may have landed in these output buffers after this launch's CTAs zero-filled
+        // them: take them out again (its anomaly list and header are still in place); a list that overflowed is no use
+        const unsigned int prev_n = *((volatile unsigned int*)&a.hdr->anomaly_list_count);
+        const bool prev_lost = prev_n > a.anomaly_cap;
+        for (unsigned int i = tid; i < prev_n && !prev_lost; i += DMX_THREADS) {
+            const uint32_t g = dmx_ldcg32(&a.anomalies[i].line);
+            if (g < a.out_cap) { a.flags[g] = 0; a.scores[g] = 0.0f; }
+        }
+        // per-CTA '\n' counts -> exclusive prefix, in place (thread t: CTAs [t cpt, (t+1) cpt)); the warps scan by shuffles
         const uint32_t cpt = (G + DMX_THREADS - 1) / DMX_THREADS;
         {
             const uint32_t lo = tid * cpt < G ? tid * cpt : G, hi = lo + cpt < G ? lo + cpt : G;
             unsigned long long c = 0;
-            for (uint32_t i = lo; i < hi; ++i) c += dmx_ldcg32(a.cta_cnt + i);
+            uint32_t i = lo;
+            for (; i + 4 <= hi; i += 4) {
+                const uint32_t c0 = dmx_ldcg32(a.cta_cnt + i), c1 = dmx_ldcg32(a.cta_cnt + i + 1), c2 = dmx_ldcg32(a.cta_cnt + i + 2), c3 = dmx_ldcg32(a.cta_cnt + i + 3);
+                c += (unsigned long long)c0 + c1 + c2 + c3;
+            }
+            for (; i < hi; ++i) c += dmx_ldcg32(a.cta_cnt + i);
             unsigned long long incl = c;
             const uint32_t ln = tid & 31;
 #pragma unroll
@@ -799,8 +811,8 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             __syncthreads();
             unsigned long long run = incl - c;
             for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_pre[DMX_THREADS + 4 + w];
-            s_pre[tid] = run;
             if (tid == DMX_THREADS - 1) s_pre[DMX_THREADS + 2] = run + c;          // all '\n' of the message
+            for (i = lo; i < hi; ++i) { const uint32_t ci = dmx_ldcg32(a.cta_cnt + i); a.cta_cnt[i] = (unsigned int)run; run += ci; }
         }
         __syncthreads();
         if (tid == 0) {
@@ -808,8 +820,8 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             const bool tail = a.nbytes > 0 && a.buf[a.nbytes - 1] != 0x0Au;
             const unsigned long long n_lines = nl + (tail ? 1ull : 0ull);
             s_pre[DMX_THREADS] = n_lines;
-            s_pre[DMX_THREADS + 1] = a.sh->zero_bound;
-            a.sh->zero_bound = n_lines;
+            s_pre[DMX_THREADS + 1] = a.sh->zero_bound[a.seq & 1ull];
+            a.sh->zero_bound[a.seq & 1ull] = n_lines;
             const unsigned int staged = *((volatile unsigned int*)a.alert_count);
             unsigned int err = (n_lines > a.max_lines || n_lines > a.out_cap) ? DM_DEVERR_TOO_MANY_LINES : 0u;
             if (staged > a.alert_cap) err |= DM_DEVERR_ANOMALY_OVERFLOW;
@@ -818,45 +830,67 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             a.hdr->n_newlines = nl;
             a.hdr->n_lines = n_lines;
             const unsigned long long tr = a.n_train_lines < n_lines ? a.n_train_lines : n_lines;
-            a.stats[0] += n_lines;
-            a.stats[1] += tr;
-            a.stats[2] += n_lines - tr;
-            a.stats[5] += a.nbytes;
+            atomicAdd(a.stats + 0, n_lines);
+            atomicAdd(a.stats + 1, tr);
+            atomicAdd(a.stats + 2, n_lines - tr);
+            atomicAdd(a.stats + 5, (unsigned long long)a.nbytes);
         }
         __syncthreads();
         if (tl && tid == 0) tl[2] = dmx_now();
         const unsigned long long n_lines = s_pre[DMX_THREADS];
         const unsigned long long n_out = n_lines < a.out_cap ? n_lines : a.out_cap;
-        // (the CTAs zero-filled [0, zero_bound); more records than that only when the messages grow)
-        dmx_zero_outputs(a.flags, a.scores, s_pre[DMX_THREADS + 1] < n_out ? s_pre[DMX_THREADS + 1] : n_out, n_out, tid, DMX_THREADS);
+        {
+            // the CTAs zero-filled [0, bound); more records than that when the messages grow, and everything again if
+            // the previous call's anomaly list is not complete
+            const unsigned long long zb = s_pre[DMX_THREADS + 1] < a.out_cap ? s_pre[DMX_THREADS + 1] : a.out_cap;
+            dmx_zero_outputs(a.flags, a.scores, prev_lost ? 0ull : (zb < n_out ? zb : n_out), n_out, tid, DMX_THREADS);
+        }
+        __threadfence_block();
         __syncthreads();
         if (tl && tid == 0) tl[3] = dmx_now();
         const unsigned int staged = *((volatile unsigned int*)a.alert_count);
         const unsigned int n_al = staged < a.alert_cap ? staged : a.alert_cap;
-        for (unsigned int i = tid; i < n_al; i += DMX_THREADS) {
-            const uint32_t inrow = dmx_ldcg32(&a.alerts[i].line), k = dmx_ldcg32(&a.alerts[i].mask);
-            const uint32_t s = dmx_ldcg32(reinterpret_cast<const uint32_t*>(&a.alerts[i].offset));
-            // record index = '\n' in front of the record's first byte: CTA groups, CTAs of the group, rows of the CTA, row
-            const uint32_t row = s >> DMX_ROW_LOG2;
-            const uint32_t cta = row / a.rows_per_cta;
-            const uint32_t t = cta / cpt;
-            unsigned long long g = s_pre[t] + inrow;
-            for (uint32_t c = t * cpt; c < cta; ++c) g += dmx_ldcg32(a.cta_cnt + c);
-            g += dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row);
-            bool first = false;
-            if (g < a.out_cap) {
-                const float old = atomicAdd(a.scores + g, 1.0f);
-                a.flags[g] = 1;
-                first = old == 0.0f;
+        for (unsigned int i0 = 0; i0 < n_al; i0 += 2 * DMX_THREADS) {
+            // two alerts per thread and round: their loads overlap
+            uint32_t inrow[2], k[2], s[2];
+            unsigned long long g[2];
+            bool on[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const unsigned int i = i0 + tid + j * DMX_THREADS;
+                on[j] = i < n_al;
+                inrow[j] = 0; k[j] = 0; s[j] = 0;
+                if (on[j]) {
+                    inrow[j] = dmx_ldcg32(&a.alerts[i].line); k[j] = dmx_ldcg32(&a.alerts[i].mask);
+                    s[j] = dmx_ldcg32(reinterpret_cast<const uint32_t*>(&a.alerts[i].offset));
+                }
             }
-            atomicAdd(a.stats + 8 + k, 1ull);
-            atomicAdd(a.stats + 4, 1ull);
-            if (first) { atomicAdd(&a.hdr->n_anomalies, 1ull); atomicAdd(a.stats + 3, 1ull); }
-            const unsigned int idx = atomicAdd(&a.hdr->anomaly_list_count, 1u);
-            if (idx < a.anomaly_cap) {
-                dm_anomaly_t r;
-                r.line = (uint32_t)g; r.mask = 1u << k; r.offset = s;
-                a.anomalies[idx] = r;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                // record index = '\n' in front of the record's first byte: in front of its CTA, in the CTA's rows before its row, in its row
+                const uint32_t row = s[j] >> DMX_ROW_LOG2;
+                const uint32_t cta = row / a.rows_per_cta;
+                g[j] = 0;
+                if (on[j]) g[j] = (unsigned long long)dmx_ldcg32(a.cta_cnt + cta) + dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row) + inrow[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (!on[j]) continue;
+                bool first = false;
+                if (g[j] < a.out_cap) {
+                    const float old = atomicAdd(a.scores + g[j], 1.0f);
+                    a.flags[g[j]] = 1;
+                    first = old == 0.0f;
+                }
+                atomicAdd(a.stats + 8 + k[j], 1ull);
+                atomicAdd(a.stats + 4, 1ull);
+                if (first) { atomicAdd(&a.hdr->n_anomalies, 1ull); atomicAdd(a.stats + 3, 1ull); }
+                const unsigned int idx = atomicAdd(&a.hdr->anomaly_list_count, 1u);
+                if (idx < a.anomaly_cap) {
+                    dm_anomaly_t r;
+                    r.line = (uint32_t)g[j]; r.mask = 1u << k[j]; r.offset = s[j];
+                    a.anomalies[idx] = r;
+                }
             }
         }
         __syncthreads();
