@@ -11,10 +11,11 @@
 //     flight, and every later access to the text (key bytes in front of an '=', the value behind
 //     it) is a shared-memory read at any alignment;
 //   * row phase (32 bytes per lane): count '\n' (for the record index, see epilogue), flag the '='
-//     bytes with SIMD-in-register compares into one 32-bit mask per lane, then one '=' per lane and
-//     round: the 4 bytes in front of it are looked up in a perfect-hash table of the monitored
-//     keys' last four bytes (3-byte keys: delimiter + key).  Only hits -- about as many as there
-//     are monitored fields -- go to the per-warp field queue;
+//     bytes with SIMD-in-register compares into one 32-bit mask per lane, and append their
+//     positions to a per-warp position queue (one prefix over the lanes per row);
+//   * lookup phase (one queued '=' per lane, 32 at a time): the 4 bytes in front of it are looked up
+//     in a perfect-hash table of the monitored keys' last four bytes (3-byte keys: delimiter +
+//     key).  Only hits -- about as many as there are monitored fields -- go to the field queue;
 //   * field phase (one queued field per lane, 32 at a time): finish the key compare (bytes 5..12
 //     in front of the '=' and the field-start delimiter), find the value's end from ONE byte
 //     class ("stop bytes" < 0x23: space, '"', '\n', controls) over a 32-byte window, dm_fp64,
@@ -47,7 +48,8 @@
 #define DMX_WARPS 2
 #endif
 #define DMX_THREADS (DMX_WARPS * 32)
-#define DMX_QCAP 256u                       // field queue entries per warp (circular)
+#define DMX_QCAP 128u                       // field queue entries per warp (circular)
+#define DMX_PCAP 256u                       // position queue entries per warp (circular; a round adds at most 128)
 #define DMX_DEPTH 1u                        // rows loaded ahead (queued fields may then be up to 3 rows old)
 #define DMX_L1 512u                         // most slots of the level-1 key table
 #define DMX_WIN 32u                         // bytes of value looked at by the fast path
@@ -564,6 +566,7 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
     // dynamic shared memory: DMX_WARPS rings, then the key table up to its last level-1 slot
     const DmxKeyTab& sk = *reinterpret_cast<const DmxKeyTab*>(s_dyn + a.ring_smem);
     __shared__ uint32_t s_q[DMX_WARPS][DMX_QCAP];
+    __shared__ uint32_t s_p[DMX_WARPS][DMX_PCAP];
     __shared__ unsigned long long s_bar[DMX_WARPS][DMX_SLOTS];
     __shared__ uint32_t s_cnt[DMX_WARPS];
     __shared__ unsigned long long s_bound;
@@ -626,8 +629,9 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
         const uint32_t seg_base = rg.r0 * DMX_ROW;            // (messages are shorter than 4 GiB)
         const uint32_t tail_bytes = (uint32_t)(nbytes & (DMX_ROW - 1));   // valid bytes of a partial last row (0 = full)
         const uint32_t tail_row = tail_bytes ? a.n_rows - 1 : 0xFFFFFFFFu;
-        uint32_t* q = s_q[warp];
-        uint32_t qh = 0, qn = 0, nl_w = 0;
+        uint32_t* q = s_q[warp];                               // fields waiting for the field phase
+        uint32_t* pq = s_p[warp];                              // '=' waiting for the level-1 lookup
+        uint32_t qh = 0, qn = 0, ph = 0, pn = 0, nl_w = 0;
         if (rg.r0 == 0) {
             // a message starts a record: the 16 bytes "in front of it" read as '\n'
             if (lane < 4) reinterpret_cast<uint32_t*>(rg.ring)[lane] = 0x0A0A0A0Au;
@@ -671,44 +675,71 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
             // the '=' of this lane's 32 bytes: bit 8b + 4c + w = byte b of word w of chunk c
             uint32_t g = (dmx_chunk_bits(va, 0x3D3D3D3Du) << (4u * c_first)) | (dmx_chunk_bits(vb, 0x3D3D3D3Du) << (4u * (1u - c_first)));
             const uint32_t qrel = i * DMX_ROW + lane * 32u;
-            // one '=' per lane and round: the 4 bytes in front of it (shared memory, any alignment) -> level-1 table.
-            // When the queue fills up the loop is left for the drain below and resumed afterwards.
-            bool row_done = false;
+            const bool last = i + 1 == n_own;
+            bool row_done;
             do {
-                while (__any_sync(0xffffffffu, g != 0u)) {
-                    bool hit = false;
-                    uint32_t e = 0;
-                    if (g) {
-                        const uint32_t x = (uint32_t)__ffs(g) - 1u;
-                        g &= g - 1u;
-                        const uint32_t pos = ((x & 7u) << 2) + (x >> 3);               // byte of the '=' inside the 32 bytes
-                        const uint32_t at = lb + pos - 4u;                               // the 4 bytes in front of it
-                        const uint32_t t = __funnelshift_r(dmx_ld32(ring, at & ~3u), dmx_ld32(ring, (at & ~3u) + 4u), (at & 3u) * 8u);
-                        const DmxL1 l = sk.l1[(t * l1_mult) >> l1_shift];
-                        uint32_t info = l.pat == t ? l.info : 0u;
-                        if (!info && n_short) info = dmx_short_key(t, sk, a.keys);
-                        hit = info != 0u;
-                        e = ((qrel + pos) << 7) | info;
+                // ---- every '=' goes to the position queue: up to 4 per lane and round (prefix over the lanes, then
+                // each lane writes its own); the queue is what keeps all 32 lanes busy in the lookups below ----
+                {
+                    const uint32_t have = (uint32_t)__popc(g);
+                    const uint32_t cnt = have < 4u ? have : 4u;
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                        if ((int)lane >= d) incl += y;
                     }
-                    const uint32_t hb = __ballot_sync(0xffffffffu, hit);
-                    if (hb) {
-                        if (hit) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
-                        qn += (uint32_t)__popc(hb);
-                        if (qn > DMX_QCAP - 32u) break;
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t slot = ph + pn + incl - cnt;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if ((uint32_t)j < cnt) {
+                            const uint32_t x = (uint32_t)__ffs(g) - 1u;
+                            g &= g - 1u;
+                            pq[slot & (DMX_PCAP - 1)] = qrel + ((x & 7u) << 2) + (x >> 3);      // offset of the '=' in this warp's range
+                            ++slot;
+                        }
                     }
+                    pn += total;
+                    row_done = !__any_sync(0xffffffffu, g != 0u);
+                    __syncwarp();
                 }
-                __syncwarp();
-                row_done = !__any_sync(0xffffffffu, g != 0u);
-                // drain: full passes; and, at the end of the row, whatever is left of rows up to (i + 2 - SLOTS): the next
-                // iteration loads row i+2 into that row's slot
+                // ---- full passes; at the end of a row also whatever is left of rows up to (i + 2 - SLOTS): the next
+                // iteration loads row i+2 into that row's slot ----
                 for (;;) {
-                    uint32_t n = 0;
-                    if (qn >= 32u) n = 32u;
-                    else if (qn && row_done && (i + 1 == n_own || (q[qh & (DMX_QCAP - 1)] >> (7 + DMX_ROW_LOG2)) + (DMX_SLOTS - 2u) <= i)) n = qn;
-                    if (!n) break;
-                    dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound);
-                    qh += n;
-                    qn -= n;
+                    if (qn >= 32u || (qn && row_done && ((last && !pn) || (q[qh & (DMX_QCAP - 1)] >> (7 + DMX_ROW_LOG2)) + (DMX_SLOTS - 2u) <= i))) {
+                        const uint32_t n = qn < 32u ? qn : 32u;
+                        dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound);
+                        qh += n;
+                        qn -= n;
+                        continue;
+                    }
+                    if (pn >= 32u || (pn && row_done && (last || (pq[ph & (DMX_PCAP - 1)] >> DMX_ROW_LOG2) + (DMX_SLOTS - 2u) <= i))) {
+                        // one '=' per lane: the 4 bytes in front of it (shared memory, any alignment) -> level-1 table
+                        const uint32_t n = pn < 32u ? pn : 32u;
+                        bool hit = false;
+                        uint32_t e = 0;
+                        if (lane < n) {
+                            const uint32_t pr = pq[(ph + lane) & (DMX_PCAP - 1)];
+                            const uint32_t at = (((seg_base >> DMX_ROW_LOG2) + (pr >> DMX_ROW_LOG2)) & (DMX_SLOTS - 1)) * DMX_SLOT + DMX_PRE + (pr & (DMX_ROW - 1)) - 4u;
+                            const uint32_t t = __funnelshift_r(dmx_ld32(ring, at & ~3u), dmx_ld32(ring, (at & ~3u) + 4u), (at & 3u) * 8u);
+                            const DmxL1 l = sk.l1[(t * l1_mult) >> l1_shift];
+                            uint32_t info = l.pat == t ? l.info : 0u;
+                            if (!info && n_short) info = dmx_short_key(t, sk, a.keys);
+                            hit = info != 0u;
+                            e = (pr << 7) | info;
+                        }
+                        ph += n;
+                        pn -= n;
+                        const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                        if (hb) {
+                            if (hit) q[(qh + qn + (uint32_t)__popc(hb & lt)) & (DMX_QCAP - 1)] = e;
+                            qn += (uint32_t)__popc(hb);
+                        }
+                        __syncwarp();
+                        continue;
+                    }
+                    break;
                 }
             } while (!row_done);
         }
