@@ -82,11 +82,13 @@ struct DmxKeyTab {
 #define DMX_KEYTAB_HOT(slots) (offsetof(DmxKeyTab, l1) + (size_t)(slots) * sizeof(DmxL1))
 
 // Ordering state of one handle (device memory, zeroed at creation).
+#define DMX_NPAR 4u                          // launches in flight: scratch buffers rotate over this many sets
 struct DmxShared {
-    unsigned int done_ctr[4];                // CTAs of launch (seq & 3) that have finished their rows
+    unsigned int done_ctr[2 * DMX_NPAR];     // CTAs of launch (seq % 8) that have finished their rows
     unsigned long long epi_done_seq;         // sequence number of the last launch whose epilogue is complete
-    unsigned long long zero_bound[2];        // [seq & 1]: records of detect message seq-2: launch seq's CTAs zero-fill that
-                                             // many output entries between them, its epilogue does the rest (if any)
+    unsigned long long zero_bound[DMX_NPAR]; // [seq % NPAR]: records of detect message seq-NPAR: launch seq's CTAs zero-fill
+                                             // that many output entries between them, its epilogue does the rest (if any)
+    unsigned int grp_cnt[DMX_NPAR][DMX_THREADS];   // '\n' per group of CTAs (thread t of the epilogue owns group t)
 };
 
 struct DmxArgs {
@@ -100,6 +102,7 @@ struct DmxArgs {
     uint32_t ring_smem;                      // bytes of dynamic shared memory in front of the key table
     unsigned short* row_cnt;                 // '\n' per row (this launch's parity)
     unsigned int* cta_cnt;                   // '\n' per CTA (this launch's parity)
+    uint32_t ctas_per_grp;                   // CTAs per group of DmxShared::grp_cnt
     dm_anomaly_t* alerts;                    // staged alerts of this launch: {line = '\n' between the start of the 512-byte
                                              // row and the record start, mask = field, offset = record start}
     unsigned int* alert_count;
@@ -601,10 +604,10 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
     }
-    // this launch's scratch (row counts, staged alerts) was last used by launch seq-2: its epilogue must be through
+    // this launch's scratch (row counts, staged alerts) was last used by launch seq-NPAR: its epilogue must be through
     if (threadIdx.x == 0) {
-        while (dmx_ld_acquire(&a.sh->epi_done_seq) + 2ull < a.seq) __nanosleep(64);
-        const unsigned long long zb = *((volatile unsigned long long*)&a.sh->zero_bound[a.seq & 1ull]);
+        while (dmx_ld_acquire(&a.sh->epi_done_seq) + DMX_NPAR < a.seq) __nanosleep(64);
+        const unsigned long long zb = *((volatile unsigned long long*)&a.sh->zero_bound[a.seq % DMX_NPAR]);
         s_bound = zb < a.out_cap ? zb : a.out_cap;
     }
     __syncthreads();
@@ -754,6 +757,7 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
             uint32_t c = 0;
             for (uint32_t w = 0; w < DMX_WARPS; ++w) c += s_cnt[w];
             a.cta_cnt[blockIdx.x] = c;
+            if (c) atomicAdd(&a.sh->grp_cnt[a.seq % DMX_NPAR][blockIdx.x / a.ctas_per_grp], c);
         }
         // every CTA zero-fills its share of as many output entries as message seq-2 had records.  (The previous call's
         // epilogue may still be adding ITS alerts to the same buffers: this launch's epilogue takes them out again.)
@@ -767,7 +771,7 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
     }
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned int old = atomicAdd(&a.sh->done_ctr[a.seq & 3ull], 1u);
+        const unsigned int old = atomicAdd(&a.sh->done_ctr[a.seq % (2 * DMX_NPAR)], 1u);
         s_last = old == gridDim.x - 1 ? 1 : 0;
         if (a.timeline && !s_last) a.timeline[4ull * blockIdx.x + 3] = dmx_now();
     }
@@ -820,17 +824,10 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             const uint32_t g = dmx_ldcg32(&a.anomalies[i].line);
             if (g < a.out_cap) { a.flags[g] = 0; a.scores[g] = 0.0f; }
         }
-        // per-CTA '\n' counts -> exclusive prefix, in place (thread t: CTAs [t cpt, (t+1) cpt)); the warps scan by shuffles
-        const uint32_t cpt = (G + DMX_THREADS - 1) / DMX_THREADS;
+        // '\n' in front of every group of CTAs (thread t owns group t; the CTAs added their counts up with atomics)
         {
-            const uint32_t lo = tid * cpt < G ? tid * cpt : G, hi = lo + cpt < G ? lo + cpt : G;
-            unsigned long long c = 0;
-            uint32_t i = lo;
-            for (; i + 4 <= hi; i += 4) {
-                const uint32_t c0 = dmx_ldcg32(a.cta_cnt + i), c1 = dmx_ldcg32(a.cta_cnt + i + 1), c2 = dmx_ldcg32(a.cta_cnt + i + 2), c3 = dmx_ldcg32(a.cta_cnt + i + 3);
-                c += (unsigned long long)c0 + c1 + c2 + c3;
-            }
-            for (; i < hi; ++i) c += dmx_ldcg32(a.cta_cnt + i);
+            const unsigned long long c = dmx_ldcg32(&a.sh->grp_cnt[a.seq % DMX_NPAR][tid]);
+            a.sh->grp_cnt[a.seq % DMX_NPAR][tid] = 0;
             unsigned long long incl = c;
             const uint32_t ln = tid & 31;
 #pragma unroll
@@ -842,8 +839,8 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             __syncthreads();
             unsigned long long run = incl - c;
             for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_pre[DMX_THREADS + 4 + w];
+            s_pre[tid] = run;
             if (tid == DMX_THREADS - 1) s_pre[DMX_THREADS + 2] = run + c;          // all '\n' of the message
-            for (i = lo; i < hi; ++i) { const uint32_t ci = dmx_ldcg32(a.cta_cnt + i); a.cta_cnt[i] = (unsigned int)run; run += ci; }
         }
         __syncthreads();
         if (tid == 0) {
@@ -851,8 +848,8 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             const bool tail = a.nbytes > 0 && a.buf[a.nbytes - 1] != 0x0Au;
             const unsigned long long n_lines = nl + (tail ? 1ull : 0ull);
             s_pre[DMX_THREADS] = n_lines;
-            s_pre[DMX_THREADS + 1] = a.sh->zero_bound[a.seq & 1ull];
-            a.sh->zero_bound[a.seq & 1ull] = n_lines;
+            s_pre[DMX_THREADS + 1] = a.sh->zero_bound[a.seq % DMX_NPAR];
+            a.sh->zero_bound[a.seq % DMX_NPAR] = n_lines;
             const unsigned int staged = *((volatile unsigned int*)a.alert_count);
             unsigned int err = (n_lines > a.max_lines || n_lines > a.out_cap) ? DM_DEVERR_TOO_MANY_LINES : 0u;
             if (staged > a.alert_cap) err |= DM_DEVERR_ANOMALY_OVERFLOW;
@@ -898,11 +895,17 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                // record index = '\n' in front of the record's first byte: in front of its CTA, in the CTA's rows before its row, in its row
+                // record index = '\n' in front of the record's first byte: in front of its group of CTAs, in the group's CTAs
+                // before its CTA, in the CTA's rows before its row, in its row
                 const uint32_t row = s[j] >> DMX_ROW_LOG2;
                 const uint32_t cta = row / a.rows_per_cta;
+                const uint32_t grp = cta / a.ctas_per_grp;
                 g[j] = 0;
-                if (on[j]) g[j] = (unsigned long long)dmx_ldcg32(a.cta_cnt + cta) + dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row) + inrow[j];
+                if (on[j]) {
+                    unsigned long long x = s_pre[grp] + inrow[j];
+                    for (uint32_t c = grp * a.ctas_per_grp; c < cta; ++c) x += dmx_ldcg32(a.cta_cnt + c);
+                    g[j] = x + dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -929,7 +932,7 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
     }
     if (tid == 0) {
         *a.alert_count = 0;
-        a.sh->done_ctr[a.seq & 3ull] = 0;
+        a.sh->done_ctr[a.seq % (2 * DMX_NPAR)] = 0;
         __threadfence();
         dmx_st_release(&a.sh->epi_done_seq, a.seq);
         if (tl) tl[5] = dmx_now();
@@ -991,11 +994,11 @@ __global__ void __launch_bounds__(256) dm_k_bound(const uint8_t* __restrict__ bu
 // ---------------------------------------------------------------------------------------
 struct DmxScratch {
     DmxKeyTab* d_keys = nullptr;
-    unsigned short* d_row_cnt[2] = {nullptr, nullptr};
-    unsigned int* d_cta_cnt[2] = {nullptr, nullptr};
+    unsigned short* d_row_cnt[DMX_NPAR] = {};
+    unsigned int* d_cta_cnt[DMX_NPAR] = {};
     unsigned short* d_bound_cnt = nullptr;
-    dm_anomaly_t* d_alerts[2] = {nullptr, nullptr};
-    unsigned int* d_alert_count = nullptr;      // 2 words
+    dm_anomaly_t* d_alerts[DMX_NPAR] = {};
+    unsigned int* d_alert_count = nullptr;      // NPAR words
     unsigned long long* d_bound = nullptr;
     DmxShared* d_shared = nullptr;
     uint32_t alert_cap = 0;
@@ -1030,14 +1033,14 @@ static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t
     if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
     s->ctas_per_sm = per_sm;
     s->max_grid = sm_count * per_sm;
-    for (int b = 0; b < 2; ++b) {
+    for (unsigned b = 0; b < DMX_NPAR; ++b) {
         if (cudaMalloc(&s->d_row_cnt[b], s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
         if (cudaMalloc(&s->d_cta_cnt[b], (size_t)s->max_grid * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
         if (cudaMalloc(&s->d_alerts[b], (size_t)alert_cap * sizeof(dm_anomaly_t)) != cudaSuccess) return DM_ERR_CUDA;
     }
     if (cudaMalloc(&s->d_bound_cnt, s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaMalloc(&s->d_alert_count, 2 * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaMemset(s->d_alert_count, 0, 2 * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMalloc(&s->d_alert_count, DMX_NPAR * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaMemset(s->d_alert_count, 0, DMX_NPAR * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
     if (cudaMalloc(&s->d_bound, sizeof(unsigned long long)) != cudaSuccess) return DM_ERR_CUDA;
     if (cudaMalloc(&s->d_shared, sizeof(DmxShared)) != cudaSuccess) return DM_ERR_CUDA;
     if (cudaMemset(s->d_shared, 0, sizeof(DmxShared)) != cudaSuccess) return DM_ERR_CUDA;
@@ -1051,7 +1054,7 @@ static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t
 
 static inline void dmx_scratch_destroy(DmxScratch* s) {
     cudaFree(s->d_keys);
-    for (int b = 0; b < 2; ++b) { cudaFree(s->d_row_cnt[b]); cudaFree(s->d_cta_cnt[b]); cudaFree(s->d_alerts[b]); }
+    for (unsigned b = 0; b < DMX_NPAR; ++b) { cudaFree(s->d_row_cnt[b]); cudaFree(s->d_cta_cnt[b]); cudaFree(s->d_alerts[b]); }
     cudaFree(s->d_bound_cnt); cudaFree(s->d_alert_count); cudaFree(s->d_bound); cudaFree(s->d_shared); cudaFree(s->d_timeline);
     *s = DmxScratch();
 }
@@ -1078,11 +1081,12 @@ static inline int dmx_launch(DmxScratch* s, const uint8_t* d_buf, uint64_t nbyte
     const unsigned grid = (unsigned)((warps + DMX_WARPS - 1) / DMX_WARPS);
     a.rows_per_warp = rpw;
     a.rows_per_cta = rpw * DMX_WARPS;
+    a.ctas_per_grp = (grid + DMX_THREADS - 1) / DMX_THREADS;
     s->last_grid = grid;
     int launched = 0;
     auto bind = [&]() {
         a.seq = ++s->seq;
-        const int p = (int)(a.seq & 1ull);
+        const int p = (int)(a.seq % DMX_NPAR);
         a.row_cnt = s->d_row_cnt[p]; a.cta_cnt = s->d_cta_cnt[p]; a.alerts = s->d_alerts[p]; a.alert_count = s->d_alert_count + p;
     };
     if (n_train_lines > 0) {

@@ -256,10 +256,10 @@ extern "C" void emu_stream_ctas(uint32_t n) { g_emu_stream_ctas = n ? n : 1; }
 struct EmuStream {
     DmxKeyTab tab;
     DmxShared sh;
-    std::vector<unsigned short> row_cnt[2], bound_cnt;
-    std::vector<unsigned int> cta_cnt[2];
-    std::vector<dm_anomaly_t> alerts[2];
-    unsigned int alert_count[2] = {0, 0};
+    std::vector<unsigned short> row_cnt[DMX_NPAR], bound_cnt;
+    std::vector<unsigned int> cta_cnt[DMX_NPAR];
+    std::vector<dm_anomaly_t> alerts[DMX_NPAR];
+    unsigned int alert_count[DMX_NPAR] = {};
     unsigned long long bound = 0, seq = 0;
     bool ready = false;
 };
@@ -279,7 +279,7 @@ extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nby
     *n_lines = 0; *n_anoms = 0; *err = 0;
     const uint32_t n_rows = (uint32_t)((nbytes + DMX_ROW - 1) / DMX_ROW);
     if (n_rows == 0) { free(buf); return 0; }
-    for (int b = 0; b < 2; ++b) {
+    for (unsigned b = 0; b < DMX_NPAR; ++b) {
         if (g_xs.row_cnt[b].size() < n_rows + 1) g_xs.row_cnt[b].assign(n_rows + 1, 0xBEEF);
         if (g_xs.alerts[b].size() < h->anoms.size()) g_xs.alerts[b].resize(h->anoms.size());
         g_xs.cta_cnt[b].assign(g_emu_stream_ctas + 1, 0xDEADBEEFu);
@@ -297,9 +297,10 @@ extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nby
     const unsigned grid = (unsigned)((warps + DMX_WARPS - 1) / DMX_WARPS);
     a.rows_per_warp = rpw;
     a.rows_per_cta = rpw * DMX_WARPS;
+    a.ctas_per_grp = (grid + DMX_THREADS - 1) / DMX_THREADS;
     auto bind = [&]() {
         a.seq = ++g_xs.seq;
-        const int p = (int)(a.seq & 1ull);
+        const int p = (int)(a.seq % DMX_NPAR);
         a.row_cnt = g_xs.row_cnt[p].data(); a.cta_cnt = g_xs.cta_cnt[p].data(); a.alerts = g_xs.alerts[p].data(); a.alert_count = &g_xs.alert_count[p];
     };
     if (n_train > 0) {
