@@ -88,7 +88,6 @@ struct DmxShared {
     unsigned long long epi_done_seq;         // sequence number of the last launch whose epilogue is complete
     unsigned long long zero_bound[DMX_NPAR]; // [seq % NPAR]: records of detect message seq-NPAR: launch seq's CTAs zero-fill
                                              // that many output entries between them, its epilogue does the rest (if any)
-    unsigned int grp_cnt[DMX_NPAR][DMX_THREADS];   // '\n' per group of CTAs (thread t of the epilogue owns group t)
 };
 
 struct DmxArgs {
@@ -102,7 +101,7 @@ struct DmxArgs {
     uint32_t ring_smem;                      // bytes of dynamic shared memory in front of the key table
     unsigned short* row_cnt;                 // '\n' per row (this launch's parity)
     unsigned int* cta_cnt;                   // '\n' per CTA (this launch's parity)
-    uint32_t ctas_per_grp;                   // CTAs per group of DmxShared::grp_cnt
+    uint32_t ctas_per_grp;                   // CTAs per thread of the epilogue's prefix
     dm_anomaly_t* alerts;                    // staged alerts of this launch: {line = '\n' between the start of the 512-byte
                                              // row and the record start, mask = field, offset = record start}
     unsigned int* alert_count;
@@ -757,7 +756,6 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
             uint32_t c = 0;
             for (uint32_t w = 0; w < DMX_WARPS; ++w) c += s_cnt[w];
             a.cta_cnt[blockIdx.x] = c;
-            if (c) atomicAdd(&a.sh->grp_cnt[a.seq % DMX_NPAR][blockIdx.x / a.ctas_per_grp], c);
         }
         // every CTA zero-fills its share of as many output entries as message seq-2 had records.  (The previous call's
         // epilogue may still be adding ITS alerts to the same buffers: this launch's epilogue takes them out again.)
@@ -824,10 +822,25 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             const uint32_t g = dmx_ldcg32(&a.anomalies[i].line);
             if (g < a.out_cap) { a.flags[g] = 0; a.scores[g] = 0.0f; }
         }
-        // '\n' in front of every group of CTAs (thread t owns group t; the CTAs added their counts up with atomics)
+        // per-CTA '\n' counts -> shared memory (asynchronous copies, all in flight at once) -> exclusive prefix in place
+        // (thread t: CTAs [t cpt, (t+1) cpt)); the warps scan their threads' sums by shuffles
+        uint32_t* s_cta = reinterpret_cast<uint32_t*>(s_pre) + 256;           // G words, behind the DMX_THREADS + 16 u64 of s_pre
+        const uint32_t cpt = a.ctas_per_grp;
+        for (uint32_t i = tid; i < G; i += DMX_THREADS) {
+#ifndef DM_EMU
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dmx_smem_u32(s_cta + i)), "l"(a.cta_cnt + i) : "memory");
+#else
+            s_cta[i] = a.cta_cnt[i];
+#endif
+        }
+#ifndef DM_EMU
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+        __syncthreads();
         {
-            const unsigned long long c = dmx_ldcg32(&a.sh->grp_cnt[a.seq % DMX_NPAR][tid]);
-            a.sh->grp_cnt[a.seq % DMX_NPAR][tid] = 0;
+            const uint32_t lo = tid * cpt < G ? tid * cpt : G, hi = lo + cpt < G ? lo + cpt : G;
+            unsigned long long c = 0;
+            for (uint32_t i = lo; i < hi; ++i) c += s_cta[i];
             unsigned long long incl = c;
             const uint32_t ln = tid & 31;
 #pragma unroll
@@ -839,8 +852,8 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             __syncthreads();
             unsigned long long run = incl - c;
             for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_pre[DMX_THREADS + 4 + w];
-            s_pre[tid] = run;
             if (tid == DMX_THREADS - 1) s_pre[DMX_THREADS + 2] = run + c;          // all '\n' of the message
+            for (uint32_t i = lo; i < hi; ++i) { const uint32_t ci = s_cta[i]; s_cta[i] = (uint32_t)run; run += ci; }
         }
         __syncthreads();
         if (tid == 0) {
@@ -895,17 +908,11 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                // record index = '\n' in front of the record's first byte: in front of its group of CTAs, in the group's CTAs
-                // before its CTA, in the CTA's rows before its row, in its row
+                // record index = '\n' in front of the record's first byte: in front of its CTA, in the CTA's rows before its row, in its row
                 const uint32_t row = s[j] >> DMX_ROW_LOG2;
                 const uint32_t cta = row / a.rows_per_cta;
-                const uint32_t grp = cta / a.ctas_per_grp;
                 g[j] = 0;
-                if (on[j]) {
-                    unsigned long long x = s_pre[grp] + inrow[j];
-                    for (uint32_t c = grp * a.ctas_per_grp; c < cta; ++c) x += dmx_ldcg32(a.cta_cnt + c);
-                    g[j] = x + dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row);
-                }
+                if (on[j]) g[j] = (unsigned long long)s_cta[cta] + inrow[j] + dmx_count_rows(a.row_cnt, cta * a.rows_per_cta, row);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -1033,6 +1040,7 @@ static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t
     if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
     s->ctas_per_sm = per_sm;
     s->max_grid = sm_count * per_sm;
+    if (1024u + 4u * (unsigned)s->max_grid > s->dyn_smem) s->max_grid = (int)((s->dyn_smem - 1024u) / 4u);   // (epilogue: per-CTA prefix in shared memory)
     for (unsigned b = 0; b < DMX_NPAR; ++b) {
         if (cudaMalloc(&s->d_row_cnt[b], s->max_rows * sizeof(unsigned short)) != cudaSuccess) return DM_ERR_CUDA;
         if (cudaMalloc(&s->d_cta_cnt[b], (size_t)s->max_grid * sizeof(unsigned int)) != cudaSuccess) return DM_ERR_CUDA;
