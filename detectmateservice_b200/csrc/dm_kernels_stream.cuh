@@ -510,11 +510,15 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
     if (!act || slow) nv = 0;
     DmHashState st;
     dm_hash_init(st);
+    {
+        const uint32_t nmax = __reduce_max_sync(0xffffffffu, nv);     // words no lane needs are skipped by the whole warp
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (nv > 4u * i) {
-            const uint32_t nb = nv - 4u * i;
-            dm_hash_word(st, nb >= 4u ? w[i] : (w[i] & ((1u << (8u * nb)) - 1u)));
+        for (int i = 0; i < 8; ++i) {
+            if (nmax <= 4u * i) break;
+            if (nv > 4u * i) {
+                const uint32_t nb = nv - 4u * i;
+                dm_hash_word(st, nb >= 4u ? w[i] : (w[i] & ((1u << (8u * nb)) - 1u)));
+            }
         }
     }
     uint64_t fp = dm_hash_final(st, nv);

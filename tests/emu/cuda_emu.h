@@ -137,6 +137,15 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
     return r;
 }
 static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return emu_reduce(v, 1); }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    EmuWarp& w = emu_warp();
+    w.slot[emu_lane()] = v;
+    w.bar.sync(32);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r = (unsigned)w.slot[i] > r ? (unsigned)w.slot[i] : r;
+    w.bar.sync(32);
+    return r;
+}
 
 // ---- scalar intrinsics -------------------------------------------------------------------
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
