@@ -197,3 +197,146 @@ struct DmDetectArgs {
     uint64_t nbytes;                  // message size
     const void* combos;               // lanes kernel with combinations: const DmMonitors* (else NULL)
 };
+
+// ---------------------------------------------------------------------------------------
+// byte-level helpers shared by the kernels (R-tok)
+// ---------------------------------------------------------------------------------------
+// look-back states of the row index kernel (dm_kernels_index.cuh)
+#define DMT_ST_AGG 1ull
+#define DMT_ST_PREFIX 2ull
+
+// 0x80 in every byte of w that equals the byte replicated in pat (pat bytes < 0x80).
+__device__ __forceinline__ uint32_t dm_eqflags(uint32_t w, uint32_t pat) {
+    const uint32_t x = w ^ pat;
+    const uint32_t a = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(a | x) & 0x80808080u;
+}
+// 0x80 flags (bits 7,15,23,31) -> 4-bit mask
+__device__ __forceinline__ uint32_t dm_flags_to_nib(uint32_t f) { return (f * 0x00204081u) >> 28; }
+
+__device__ __forceinline__ uint32_t dm_ld8(const uint8_t* __restrict__ buf, uint64_t p) { return __ldg(buf + p); }
+__device__ __forceinline__ uint32_t dm_ld32(const uint8_t* __restrict__ buf, uint64_t p_aligned) {
+    return __ldg(reinterpret_cast<const uint32_t*>(buf + p_aligned));
+}
+
+// Byte-wise check that key k ends right before the '=' at q and starts at a field start
+// (R-tok L4 delimiter; quote parity is re-checked later, see file header).  The last
+// `skip_tail` key bytes are known to match already.
+__device__ __forceinline__ bool dm_key_check(const uint8_t* __restrict__ buf, uint64_t q, uint32_t k, const DmKeys& sk,
+                                             uint32_t skip_tail) {
+    const uint32_t len = sk.len[k];
+    if (q < len) return false;
+    const uint64_t st = q - len;
+    if (st > 0) {
+        const uint32_t c = dm_ld8(buf, st - 1);
+        if (c != 0x20u && c != 0x27u && c != 0x0Au) return false;
+    }
+    const uint32_t n = len - skip_tail;
+    for (uint32_t i = 0; i < n; ++i)
+        if (dm_ld8(buf, st + i) != sk.bytes[k][i]) return false;
+    return true;
+}
+
+// Which monitored key (if any) ends right before the '=' at q?  Word-parallel: the 12 bytes
+// in front of q are compared against every key's precomputed patterns.
+__device__ __forceinline__ int dm_key_identify(const uint8_t* __restrict__ buf, uint64_t q, const DmKeys& sk) {
+    if (q < 12) {
+        for (uint32_t k = 0; k < sk.n; ++k)
+            if (dm_key_check(buf, q, k, sk, 0)) return (int)k;
+        return -1;
+    }
+    const uint64_t a0 = (q - 12) & ~3ull;
+    const uint32_t sh = (uint32_t)((q - 12) & 3) * 8;
+    const uint32_t x0 = dm_ld32(buf, a0), x1 = dm_ld32(buf, a0 + 4), x2 = dm_ld32(buf, a0 + 8), x3 = dm_ld32(buf, a0 + 12);
+    const uint32_t w_a = __funnelshift_r(x0, x1, sh);    // bytes q-12 .. q-9
+    const uint32_t w_b = __funnelshift_r(x1, x2, sh);    // bytes q-8 .. q-5
+    const uint32_t w_c = __funnelshift_r(x2, x3, sh);    // bytes q-4 .. q-1
+    // first (= longest) key whose last min(len,8) bytes stand in front of the '='
+    uint32_t slot = 0xFFFFFFFFu;
+    for (uint32_t s = 0; s < sk.n; ++s) {
+        const uint4 p = *reinterpret_cast<const uint4*>(sk.pat[s]);
+        const uint32_t diff = ((w_c ^ p.x) & p.y) | ((w_b ^ p.z) & p.w);
+        if (diff == 0 && slot == 0xFFFFFFFFu) slot = s;
+    }
+    if (slot == 0xFFFFFFFFu) return -1;
+    const uint32_t k = sk.order[slot];
+    const uint32_t len = sk.len[k];
+    if (len <= 8) {
+        // field-start delimiter (R-tok L4); a shorter key that is a suffix of this one cannot
+        // be a field start here either, its delimiter position holds a byte of this key
+        const uint32_t sel = sk.dsel[k];
+        const uint32_t dw = sel == 0 ? w_c : (sel == 1 ? w_b : w_a);
+        const uint32_t d = (dw >> sk.dshift[k]) & 0xFFu;
+        return (d == 0x20u || d == 0x27u || d == 0x0Au) ? (int)k : -1;
+    }
+    // keys longer than the 8 compared bytes: finish byte by byte, then fall back to the others
+    if (dm_key_check(buf, q, k, sk, 8)) return (int)k;
+    for (uint32_t s = slot + 1; s < sk.n; ++s) {
+        const uint32_t k2 = sk.order[s];
+        if (dm_key_check(buf, q, k2, sk, 0)) return (int)k2;
+    }
+    return -1;
+}
+
+// dm_fp64 of the value that starts at vpos: ends at the first space outside double quotes
+// (parity counted from the value start, R-tok L5), at '\n', or at the end of the message.
+// Works on 16-byte blocks; quote parity is carried with shift/xor prefix tricks, no branches
+// on the data inside a block.
+__device__ __forceinline__ uint64_t dm_hash_value(const uint8_t* __restrict__ buf, uint64_t nbytes, uint64_t vpos) {
+    DmHashState st;
+    dm_hash_init(st);
+    uint32_t n = 0, in_q = 0;                 // in_q: 0 or 0x80808080
+    uint64_t a = vpos & ~3ull;
+    const uint32_t sh = (uint32_t)(vpos & 3) * 8;
+    uint32_t lo = (a < nbytes) ? dm_ld32(buf, a) : 0u;
+    uint64_t pos = vpos;
+    for (;;) {
+        const uint32_t x1 = (a + 4 < nbytes) ? dm_ld32(buf, a + 4) : 0u;
+        const uint32_t x2 = (a + 8 < nbytes) ? dm_ld32(buf, a + 8) : 0u;
+        const uint32_t x3 = (a + 12 < nbytes) ? dm_ld32(buf, a + 12) : 0u;
+        const uint32_t x4 = (a + 16 < nbytes) ? dm_ld32(buf, a + 16) : 0u;
+        uint32_t w[4];
+        w[0] = __funnelshift_r(lo, x1, sh); w[1] = __funnelshift_r(x1, x2, sh);
+        w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
+        lo = x4;
+        a += 16;
+        uint32_t nvtot = 16;
+        uint32_t q_state = in_q;
+        uint32_t term[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t nl = dm_eqflags(w[i], 0x0A0A0A0Au);
+            const uint32_t sp = dm_eqflags(w[i], 0x20202020u);
+            const uint32_t dq = dm_eqflags(w[i], 0x22222222u);
+            uint32_t incl = dq ^ (dq << 8);
+            incl ^= incl << 16;                                     // quote parity up to and including each byte
+            const uint32_t before = (incl << 8) ^ q_state;          // in-quote state in front of each byte
+            term[i] = nl | (sp & ~before);
+            q_state ^= (uint32_t)((int32_t)incl >> 31) & 0x80808080u;   // parity of the whole word
+        }
+#pragma unroll
+        for (int i = 3; i >= 0; --i)
+            if (term[i]) nvtot = 4u * i + ((uint32_t)(__ffs(term[i]) - 1) >> 3);
+        const uint64_t rem = nbytes > pos ? nbytes - pos : 0;
+        if (rem < nvtot) nvtot = (uint32_t)rem;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (nvtot > 4u * i) {
+                const uint32_t nb = nvtot - 4u * i;                 // valid bytes of this word (>= 1)
+                dm_hash_word(st, nb >= 4u ? w[i] : (w[i] & ((1u << (8 * nb)) - 1u)));
+            }
+        }
+        n += nvtot;
+        if (nvtot < 16) break;
+        in_q = q_state;
+        pos += 16;
+    }
+    return dm_hash_final(st, n);
+}
+
+// 16-bit mask of the bytes of a 16-byte chunk equal to the byte replicated in pat
+__device__ __forceinline__ uint32_t dm_chunk_mask(const uint4& v, uint32_t pat) {
+    return dm_flags_to_nib(dm_eqflags(v.x, pat)) | (dm_flags_to_nib(dm_eqflags(v.y, pat)) << 4) |
+           (dm_flags_to_nib(dm_eqflags(v.z, pat)) << 8) | (dm_flags_to_nib(dm_eqflags(v.w, pat)) << 12);
+}
+

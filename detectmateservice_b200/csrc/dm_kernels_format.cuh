@@ -20,7 +20,7 @@
 //             captures are variables[0..].
 #pragma once
 #include "dm_device.cuh"
-#include "dm_kernels_rows.cuh"       // K_A, dm_pdl_wait
+#include "dm_kernels_index.cuh"      // K_A, dm_pdl_wait
 
 #define DM_FMT_MAX_CHAINS 64          // log_format + 63 templates
 #define DM_FMT_MAX_LITS 512           // literals over all chains
@@ -74,167 +74,6 @@ __device__ __forceinline__ uint64_t dm_fmt_fp64(const uint8_t* __restrict__ buf,
         dm_hash_word(st, w);
     }
     return dm_hash_final(st, n);
-}
-
-// all lanes: does text[q, q+len) equal the literal?  (warp-uniform result; lane j checks word j)
-__device__ __forceinline__ bool dm_fmt_match_at(const uint8_t* __restrict__ buf, uint32_t q, const uint32_t* lit,
-                                                uint32_t len, uint32_t lane) {
-    bool ok = true;
-    for (uint32_t j = lane * 4; j < len; j += 128) {
-        const uint32_t m = len - j >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len - j);
-        ok = ok && (((dm_fmt_load4(buf, q + j) ^ lit[j >> 2]) & m) == 0);
-    }
-    return __all_sync(0xffffffffu, ok);
-}
-
-// all lanes: earliest q in [pos, e - len] with text[q, q+len) == literal, or DM_FMT_NOT_FOUND (len >= 1)
-__device__ __forceinline__ uint32_t dm_fmt_find(const uint8_t* __restrict__ buf, uint32_t pos, uint32_t e,
-                                                const uint32_t* lit, uint32_t len, uint32_t lane) {
-    if (e < pos + len) return DM_FMT_NOT_FOUND;
-    const uint32_t last = e - len;                    // last admissible start
-    const uint32_t w0 = lit[0];
-    const uint32_t m0 = len >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len);
-    for (uint32_t base = pos; base <= last; base += 32) {
-        const uint32_t p = base + lane;
-        bool m = false;
-        if (p <= last && ((dm_fmt_load4(buf, p) ^ w0) & m0) == 0) {
-            m = true;
-            for (uint32_t j = 4; j < len; j += 4) {     // the few lanes whose first word matched
-                const uint32_t lm = len - j >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len - j);
-                if (((dm_fmt_load4(buf, p + j) ^ lit[j >> 2]) & lm) != 0) { m = false; break; }
-            }
-        }
-        const uint32_t b = __ballot_sync(0xffffffffu, m);
-        if (b) return base + (uint32_t)(__ffs(b) - 1);
-    }
-    return DM_FMT_NOT_FOUND;
-}
-
-// Match chain `c` against text [s, e) (byte offsets into buf).  Warp-uniform result; on success
-// lane i holds capture i in (cap_s, cap_l) for i < n_caps (other lanes: cap_l = 0).
-__device__ bool dm_fmt_match_chain(const DmFormat& f, uint32_t c, const uint8_t* __restrict__ buf, uint32_t s,
-                                   uint32_t e, uint32_t lane, uint32_t& cap_s, uint32_t& cap_l, uint32_t& n_caps) {
-    const uint32_t first = f.chain_first[c];
-    const uint32_t n = (uint32_t)f.chain_first[c + 1] - first;
-    const bool endcap = f.chain_endcap[c] != 0;
-    uint32_t pos = s;
-    cap_s = e;
-    cap_l = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t len = f.lit_len[first + i];
-        const uint32_t* lit = f.pool + f.lit_off[first + i];
-        uint32_t q;
-        if (i == 0) {                                             // anchored at the start
-            if (e < pos + len || !dm_fmt_match_at(buf, pos, lit, len, lane)) return false;
-            q = pos;
-        } else if (i == n - 1 && !endcap) {                       // anchored at the end
-            if (e < pos + len) return false;
-            q = e - len;
-            if (!dm_fmt_match_at(buf, q, lit, len, lane)) return false;
-        } else {
-            q = dm_fmt_find(buf, pos, e, lit, len, lane);
-            if (q == DM_FMT_NOT_FOUND) return false;
-        }
-        if (i > 0 && lane == i - 1) { cap_s = pos; cap_l = q - pos; }
-        pos = q + len;
-    }
-    if (endcap) {
-        if (n == 0) { if (lane == 0) { cap_s = s; cap_l = e - s; } }   // the chain is one capture
-        else if (lane == n - 1) { cap_s = pos; cap_l = e - pos; }
-        n_caps = n ? n : 1;
-    } else {
-        if (pos != e) return false;                              // (n == 1: the literal is the whole text)
-        n_caps = n ? n - 1 : 0;
-    }
-    return true;
-}
-
-template <bool TRAIN>
-__global__ void __launch_bounds__(256) dm_k_format_lines(DmDetectArgs a, const DmFormat* __restrict__ gfmt) {
-    __shared__ DmFormat sf;
-    __shared__ unsigned int s_unk[DM_MAX_KEYS];
-    __shared__ unsigned long long s_anom, s_score;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(gfmt);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sf);
-        for (uint32_t i = threadIdx.x; i < sizeof(DmFormat) / 4; i += blockDim.x) dst[i] = src[i];
-        if (threadIdx.x < DM_MAX_KEYS) s_unk[threadIdx.x] = 0;
-        if (threadIdx.x == 0) { s_anom = 0; s_score = 0; }
-    }
-    __syncthreads();
-
-    const uint8_t* __restrict__ buf = a.buf;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const uint64_t warp_id = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint64_t n_lines = a.hdr_in->n_lines;
-    const uint64_t hi = a.line_hi < n_lines ? a.line_hi : n_lines;
-
-    for (uint64_t line = a.line_lo + warp_id; line < hi; line += warps_total) {
-        const uint32_t s = a.line_start[line];
-        const uint32_t e = a.line_start[line + 1] - 1;               // the '\n' (or nbytes)
-        uint32_t hs, vs = e;
-        uint32_t hl, vl = 0, n_hcaps = 0, n_vars = 0;
-        const bool hok = dm_fmt_match_chain(sf, 0, buf, s, e, lane, hs, hl, n_hcaps);
-        int32_t eid = -1;
-        if (hok && sf.content_capture != DM_FMT_NONE && sf.n_chains > 1) {
-            const uint32_t cs = __shfl_sync(0xffffffffu, hs, sf.content_capture);
-            const uint32_t ce = cs + __shfl_sync(0xffffffffu, hl, sf.content_capture);
-            for (uint32_t t = 1; t < sf.n_chains; ++t) {
-                if (dm_fmt_match_chain(sf, t, buf, cs, ce, lane, vs, vl, n_vars)) { eid = (int32_t)t - 1; break; }
-            }
-            if (eid < 0) { vl = 0; n_vars = 0; }
-        }
-        // lane k serves monitor k: fetch its value from the lane that holds the capture
-        const uint32_t k = lane;
-        const bool mon = k < sf.n_mons;
-        const uint32_t src = mon ? sf.mon_source[k] : 0u;
-        const uint32_t idx = mon ? sf.mon_index[k] : DM_FMT_NONE;
-        const uint32_t from = idx & 31u;
-        // (every lane executes all four shuffles: the source register differs per lane)
-        const uint32_t xs_h = __shfl_sync(0xffffffffu, hs, from), xs_v = __shfl_sync(0xffffffffu, vs, from);
-        const uint32_t xl_h = __shfl_sync(0xffffffffu, hl, from), xl_v = __shfl_sync(0xffffffffu, vl, from);
-        const uint32_t xs = src ? xs_v : xs_h;
-        const uint32_t xl = src ? xl_v : xl_h;
-        bool present = hok && mon && idx != DM_FMT_NONE && idx < (src ? n_vars : n_hcaps);
-        if (present && sf.mon_has_event[k] && eid != sf.mon_event[k]) present = false;
-        bool unk = false;
-        if (present) {
-            const uint64_t key = dm_make_key(dm_fmt_fp64(buf, xs, xl), dm_field_salt(k));
-            if (TRAIN) dm_table_insert(a.table, key, &a.hdr->error);
-            else unk = !dm_table_contains(a.table, key);
-        }
-        const uint32_t unknown = __ballot_sync(0xffffffffu, unk);
-        if (lane == 0) {
-            const uint32_t cnt = __popc(unknown);
-            if (line < a.out_cap) {
-                if (a.flags) a.flags[line] = cnt ? 1 : 0;
-                if (a.scores) a.scores[line] = (float)cnt;
-            }
-            if (!hok) atomicAdd(a.stats + 7, 1ull);                 // record the log_format does not match: counted, not scored
-            if (cnt) {
-                atomicAdd(&s_anom, 1ull);
-                atomicAdd(&s_score, (unsigned long long)cnt);
-                uint32_t m = unknown;
-                while (m) { int b = __ffs(m) - 1; m &= m - 1; atomicAdd(&s_unk[b], 1u); }
-                unsigned int at = atomicAdd(&a.hdr->anomaly_list_count, 1u);
-                if (at < a.anomaly_cap) {
-                    dm_anomaly_t r; r.line = (uint32_t)line; r.mask = unknown; r.offset = s;
-                    a.anomalies[at] = r;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (!TRAIN) {
-        if (threadIdx.x == 0 && s_anom) {
-            atomicAdd(&a.hdr->n_anomalies, s_anom);
-            atomicAdd(&a.stats[3], s_anom);
-            atomicAdd(&a.stats[4], s_score);
-        }
-        if (threadIdx.x < DM_MAX_KEYS && s_unk[threadIdx.x])
-            atomicAdd(&a.stats[8 + threadIdx.x], (unsigned long long)s_unk[threadIdx.x]);
-    }
 }
 
 // =========================================================================================
@@ -351,7 +190,7 @@ __global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArg
     __shared__ DmFormat sf;
     __shared__ unsigned int s_unk[DM_MAX_KEYS];
     __shared__ unsigned long long s_anom, s_score, s_bad;
-    dm_pdl_wait();                                    // K_A / the training pass are complete (dm_kernels_rows.cuh)
+    dm_pdl_wait();                                    // K_A / the training pass are complete (dm_kernels_index.cuh)
     {
         // the grid is sized for the worst case (the record count is only known on the device):
         // CTAs without records leave before touching anything

@@ -13,11 +13,10 @@
 //
 // What it replaces: per record, MatcherParser (fields) + NewValueDetector.train / .detect from
 // the un-vendored detectmatelibrary, driven by /root/reference/src/service/core.py:201-203.
-// Needs the line index (dm_kernels_v1.cuh K1-K3).  Rules: DESIGN.md R-tok, R-spec 1-4.
+// Needs the line index (dm_kernels_index.cuh K_A).  Rules: DESIGN.md R-tok, R-spec 1-4.
 #pragma once
 #include "dm_device.cuh"
-#include "dm_kernels_tile.cuh"      // dm_eqflags, dm_key_identify, dm_hash_value
-#include "dm_kernels_rows.cuh"      // K_A (dm_k_rowindex) writes the record index
+#include "dm_kernels_index.cuh"     // K_A (dm_k_rowindex) writes the record index
 #include "dm_kernels_records.cuh"   // DmMonitors: combination monitors (dm_set_combos)
 
 #define DM_LANES_THREADS 64         // small CTAs: a 64k-record message is only 2048 warps, spread them evenly
@@ -62,7 +61,7 @@ __global__ void __launch_bounds__(DM_LANES_THREADS) dm_k_lanes(DmDetectArgs a) {
     __shared__ uint32_t s_q[DM_LANES_Q][DM_LANES_THREADS];
     __shared__ unsigned int s_unk[DM_MAX_KEYS];
     __shared__ unsigned long long s_anom, s_score;
-    dm_pdl_wait();                                                // K_A / the training pass are complete (dm_kernels_rows.cuh)
+    dm_pdl_wait();                                                // K_A / the training pass are complete (dm_kernels_index.cuh)
     {
         // CTAs without records (the grid is sized for the worst case) leave before touching anything
         const uint64_t n_lines0 = a.hdr_in->n_lines;

@@ -35,7 +35,7 @@
 // (DmxShared): scratch buffers alternate between two parities and a launch starts only after the
 // epilogue of the launch two before it has finished; epilogues run one after the other.
 #pragma once
-#include "dm_kernels_rows.cuh"     // device helpers (dm_eqflags, dm_chunk_mask, dm_pdl_*, dm_launch_pdl_smem)
+#include "dm_kernels_index.cuh"    // dm_pdl_*, dm_launch_pdl_smem; byte helpers in dm_device.cuh
 
 #define DMX_ROW 1024u
 #define DMX_ROW_LOG2 10

@@ -13,12 +13,8 @@
 #include <vector>
 
 #include "dm_device.cuh"
-#include "dm_kernels_v1.cuh"
-#include "dm_kernels_tile.cuh"
-#include "dm_kernels_rows.cuh"
+#include "dm_kernels_index.cuh"
 #include "dm_kernels_stream.cuh"
-#include "dm_kernels_staged.cuh"
-#include "dm_kernels_cta.cuh"
 #include "dm_kernels_values.cuh"
 #include "dm_kernels_records.cuh"
 #include "dm_kernels_format.cuh"
@@ -66,13 +62,11 @@ struct dm_handle {
     uint64_t max_batch_bytes = 0, max_lines = 0;
     uint32_t table_log2 = 0;
     uint32_t n_keys = 0;
-    int kernel_variant = 6;              // 6 = stream (default), 2 = rows, 5 = lanes; 0 v1, 1 tile, 3 staged, 4 cta
+    int kernel_variant = 6;              // 6 = stream (default), 5 = lanes (one thread per record; DM_KERNEL=lanes)
 
     DmKeys h_keys;
     DmKeys* d_keys = nullptr;
     uint8_t* d_in = nullptr;             // staging for host input
-    uint32_t* d_tile_counts = nullptr;
-    uint32_t* d_tile_base = nullptr;
     uint32_t* d_line_start = nullptr;
     uint8_t* d_flags = nullptr;
     float* d_scores = nullptr;
@@ -86,11 +80,8 @@ struct dm_handle {
     unsigned long long* h_stats = nullptr;         // pinned
     DmTable table;
     uint64_t novel_exported = 0;         // novel keys already shipped in a window
-    DmTileScratch tile;                  // fused-kernel scratch
-    DmRowsScratch rows;                  // rows-variant scratch
+    DmRowsScratch rows;                  // row / record index scratch (K_A: lanes and log_format kernels)
     DmxScratch dmx;                      // stream-variant scratch (default kernel)
-    DmStagedScratch staged;              // staged-variant scratch (candidate / field lists)
-    DmCtaScratch cta;                    // cta-variant launch geometry
     uint64_t last_nbytes = 0;
     uint32_t* d_vals = nullptr;          // record mode: offsets / fields / record_of
     uint64_t vals_cap = 0;
@@ -106,7 +97,6 @@ struct dm_handle {
     uint64_t win_seq = 0;
     bool fmt_set = false;
     uint32_t fmt_slots = 1;        // DmFormat.max_slots (dynamic shared memory of the thread-per-record kernel)
-    bool fmt_warp_kernel = false;  // DM_FORMAT_KERNEL=warp: one warp per record (the first implementation)
     // pipelined host path: two slots
     struct Slot {
         uint8_t* d_in = nullptr; uint8_t* d_flags = nullptr; float* d_scores = nullptr;
@@ -204,13 +194,10 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
 
     DM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->last_stream = h->stream;
-    const uint64_t n_tiles_max = (max_batch_bytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES + 1;
     DM_CUDA(cudaMalloc(&h->d_keys, sizeof(DmKeys)));
     DM_CUDA(cudaMemcpy(h->d_keys, &h->h_keys, sizeof(DmKeys), cudaMemcpyHostToDevice));
     DM_CUDA(cudaMalloc(&h->d_in, max_batch_bytes + 256));
     DM_CUDA(cudaMemset(h->d_in, 0, max_batch_bytes + 256));
-    DM_CUDA(cudaMalloc(&h->d_tile_counts, n_tiles_max * sizeof(uint32_t)));
-    DM_CUDA(cudaMalloc(&h->d_tile_base, n_tiles_max * sizeof(uint32_t)));
     DM_CUDA(cudaMalloc(&h->d_line_start, (h->max_lines + 2) * sizeof(uint32_t)));
     DM_CUDA(cudaMalloc(&h->d_flags, h->max_lines + 16));
     DM_CUDA(cudaMalloc(&h->d_scores, (h->max_lines + 4) * sizeof(float)));
@@ -237,28 +224,16 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
     DM_CUDA(cudaMemset(h->table.count, 0, 2 * sizeof(unsigned long long)));
     h->table.novel_count = h->table.count + 1;
 
-    int rc = dm_tile_scratch_create(&h->tile, max_batch_bytes, h->sm_count);
-    if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "tile scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
-    rc = dm_rows_scratch_create(&h->rows, max_batch_bytes, h->sm_count);
-    if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "rows scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    int rc = dm_rows_scratch_create(&h->rows, max_batch_bytes, h->sm_count);
+    if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "row index scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     rc = dmx_scratch_create(&h->dmx, h->h_keys, max_batch_bytes, h->anomaly_cap, h->sm_count);
     if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "stream scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     { const char* ov = getenv("DM_OVERLAP"); if (ov) h->dmx.overlap = atoi(ov) != 0; }
     const char* env = getenv("DM_KERNEL");
-    if (env && strcmp(env, "v1") == 0) h->kernel_variant = 0;
-    if (env && strcmp(env, "tile") == 0) h->kernel_variant = 1;
-    if (env && strcmp(env, "rows") == 0) h->kernel_variant = 2;
-    if (env && strcmp(env, "staged") == 0) h->kernel_variant = 3;
-    if (env && strcmp(env, "cta") == 0) h->kernel_variant = 4;
-    if (env && strcmp(env, "lanes") == 0) h->kernel_variant = 5;
-    if (env && strcmp(env, "stream") == 0) h->kernel_variant = 6;
-    if (h->kernel_variant == 4) {
-        rc = dm_cta_scratch_create(&h->cta, h->sm_count);
-        if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "cta occupancy query failed: %s", cudaGetErrorString(cudaGetLastError())); }
-    }
-    if (h->kernel_variant == 3) {
-        rc = dm_staged_scratch_create(&h->staged, max_batch_bytes, h->sm_count);
-        if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "staged scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    if (env && env[0]) {
+        if (strcmp(env, "lanes") == 0) h->kernel_variant = 5;
+        else if (strcmp(env, "stream") == 0) h->kernel_variant = 6;
+        else return dm_fail(DM_ERR_ARG, "DM_KERNEL=%s: the key=value kernels are 'stream' (default) and 'lanes'", env);
     }
     DM_CUDA(cudaDeviceSynchronize());
     *out = h;
@@ -307,11 +282,9 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto& e : h->ev) cudaEventDestroy(e);
-    dm_tile_scratch_destroy(&h->tile);
     dm_rows_scratch_destroy(&h->rows);
     dmx_scratch_destroy(&h->dmx);
-    dm_staged_scratch_destroy(&h->staged);
-    cudaFree(h->d_keys); cudaFree(h->d_in); cudaFree(h->d_tile_counts); cudaFree(h->d_tile_base);
+    cudaFree(h->d_keys); cudaFree(h->d_in);
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
     cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
@@ -381,13 +354,13 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
     (void)dev_cap;
 
     bool stream_kernel = false;
-    // (the rows and stream variants write the per-batch header themselves)
-    if (h->kernel_variant < 2 || nbytes == 0 || h->fmt_set) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
+    // (the stream kernel and K_A write the per-batch header themselves)
+    if (nbytes == 0) DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
     h->last_nbytes = nbytes;
 
     if (h->fmt_set && h->mons_set && h->h_mons.n_combos > 0)
         return dm_fail(DM_ERR_STATE, "combination monitors are not evaluated in log_format mode (use key=value records or ParserSchema input)");
-    if (h->fmt_set && !h->fmt_warp_kernel) {
+    if (h->fmt_set) {
         // log_format / template mode: K_A writes the record index, then one THREAD per record
         const uint32_t n_rows = (uint32_t)((nbytes + DMR_ROW - 1) / DMR_ROW);
         if (n_rows > h->rows.max_rows) return dm_fail(DM_ERR_CAPACITY, "message too large for the row index");
@@ -422,29 +395,6 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
             dm_prof_mark(h, st, 1);
             h->launches += 2 + (n_train_lines > 0 ? 1 : 0);
         }
-    } else if (h->fmt_set) {
-        // log_format / template mode, first implementation: line index, then one warp per record
-        const uint32_t n_tiles = (uint32_t)((nbytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES);
-        const int grid_tiles = std::max(1, std::min<int>((int)n_tiles, h->sm_count * 8));
-        dm_k_count_newlines<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts);
-        dm_k_scan_tiles<<<1, 1024, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts, h->d_tile_base,
-                                             h->d_line_start, h->max_lines, n_train_lines, h->d_hdr, h->d_stats);
-        dm_k_line_starts<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_base,
-                                                                  h->d_line_start, h->max_lines);
-        DmDetectArgs a;
-        a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
-        a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
-        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes; a.combos = nullptr;
-        const int grid = h->sm_count * 8;
-        if (n_train_lines > 0) {
-            a.line_lo = 0; a.line_hi = n_train_lines;
-            dm_k_format_lines<true><<<grid, 256, 0, st>>>(a, h->d_fmt);
-        }
-        a.line_lo = n_train_lines; a.line_hi = ~0ull;
-        dm_prof_mark(h, st, 0);
-        dm_k_format_lines<false><<<grid, 256, 0, st>>>(a, h->d_fmt);
-        dm_prof_mark(h, st, 1);
-        h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
     } else if (h->kernel_variant == 5 || (h->mons_set && h->h_mons.n_combos > 0)) {
         // one thread per record; the only raw-line kernel that evaluates combination monitors
         const bool combos = h->mons_set && h->h_mons.n_combos > 0;
@@ -453,58 +403,11 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
                                        h->sm_count, combos ? (const void*)h->d_mons : nullptr, h->n_keys, st, dm_prof_mark_cb, h);
         if (rc < 0) return dm_fail(DM_ERR_CUDA, "lanes kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         h->launches += (uint64_t)rc;
-    } else if (h->kernel_variant == 0) {
-        const uint32_t n_tiles = (uint32_t)((nbytes + DM_TILE_BYTES - 1) / DM_TILE_BYTES);
-        const int grid_tiles = std::max(1, std::min<int>((int)n_tiles, h->sm_count * 8));
-        dm_k_count_newlines<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts);
-        dm_k_scan_tiles<<<1, 1024, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_counts, h->d_tile_base,
-                                             h->d_line_start, h->max_lines, n_train_lines, h->d_hdr, h->d_stats);
-        dm_k_line_starts<<<grid_tiles, DM_TILE_THREADS, 0, st>>>(d_buf, nbytes, n_tiles, h->d_tile_base,
-                                                                  h->d_line_start, h->max_lines);
-        DmDetectArgs a;
-        a.buf = d_buf; a.line_start = h->d_line_start; a.hdr_in = h->d_hdr; a.hdr = h->d_hdr;
-        a.keys = h->d_keys; a.table = h->table; a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap;
-        a.anomalies = h->d_anoms; a.anomaly_cap = h->anomaly_cap; a.stats = h->d_stats; a.nbytes = nbytes; a.combos = nullptr;
-        const int grid = h->sm_count * 8;
-        if (n_train_lines > 0) {
-            a.line_lo = 0; a.line_hi = n_train_lines;
-            dm_k_detect_lines<true><<<grid, 256, 0, st>>>(a);
-        }
-        a.line_lo = n_train_lines; a.line_hi = ~0ull;
-        dm_prof_mark(h, st, 0);
-        dm_k_detect_lines<false><<<grid, 256, 0, st>>>(a);
-        dm_prof_mark(h, st, 1);
-        h->launches += 4 + (n_train_lines > 0 ? 1 : 0);
-    } else if (h->kernel_variant == 4) {
-        const int rc = dm_cta_launch(&h->cta, &h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,
-                                     out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st,
-                                     dm_prof_mark_cb, h);
-        if (rc < 0) return dm_fail(DM_ERR_CUDA, "cta kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        h->launches += (uint64_t)rc;
-    } else if (h->kernel_variant == 3) {
-        const int rc = dm_staged_launch(&h->staged, &h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags,
-                                        d_scores, out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines,
-                                        st, dm_prof_mark_cb, h);
-        if (rc < 0) return dm_fail(DM_ERR_CUDA, "staged kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        h->launches += (uint64_t)rc;
-    } else if (h->kernel_variant == 6) {
+    } else {
         stream_kernel = true;
         const int rc = dmx_launch(&h->dmx, d_buf, nbytes, n_train_lines, h->table, d_flags, d_scores, out_cap, h->d_anoms,
                                   h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st, h->dmx.overlap, dm_prof_mark_cb, h);
         if (rc < 0) return dm_fail(DM_ERR_CUDA, "stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        h->launches += (uint64_t)rc;
-    } else if (h->kernel_variant == 2) {
-        const int rc = dm_rows_launch(&h->rows, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,
-                                      out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st,
-                                      dm_prof_mark_cb, h);
-        if (rc < 0) return dm_fail(DM_ERR_CUDA, "rows kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        h->launches += (uint64_t)rc;
-    } else {
-        dm_prof_mark(h, st, 0);
-        const int rc = dm_tile_launch(&h->tile, d_buf, nbytes, n_train_lines, h->d_keys, h->table, d_flags, d_scores,
-                                out_cap, h->d_anoms, h->anomaly_cap, h->d_hdr, h->d_stats, h->max_lines, st);
-        dm_prof_mark(h, st, 1);
-        if (rc < 0) return dm_fail(DM_ERR_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         h->launches += (uint64_t)rc;
     }
     DM_CUDA(cudaGetLastError());
@@ -688,8 +591,6 @@ extern "C" int dm_set_format(dm_handle* h, const char* log_format, const char* c
         else {
             h->fmt_set = true;
             h->fmt_slots = f->max_slots;
-            const char* fk = getenv("DM_FORMAT_KERNEL");
-            h->fmt_warp_kernel = fk && strcmp(fk, "warp") == 0;
         }
     }
     delete f;
@@ -709,15 +610,7 @@ extern "C" int dm_debug_rows_timeline(dm_handle* h, unsigned long long* out, uin
         DM_CUDA(cudaMemcpy(out, h->dmx.d_timeline, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         return DM_OK;
     }
-    if (!h->rows.d_timeline) return dm_fail(DM_ERR_STATE, "create the handle with DM_ROWS_TIMELINE=1");
-    const uint32_t n = (uint32_t)h->rows.last_grid * DMR_B_WARPS;
-    *n_warps_out = n;
-    if (!out) return DM_OK;
-    DM_CUDA(cudaSetDevice(h->device));
-    DM_CUDA(cudaStreamSynchronize(h->last_stream));
-    const uint64_t words = std::min<uint64_t>(cap_words, 4ull * n);
-    DM_CUDA(cudaMemcpy(out, h->rows.d_timeline, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    return DM_OK;
+    return dm_fail(DM_ERR_STATE, "create the handle with DM_STREAM_TIMELINE=1");
 }
 
 extern "C" int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nbytes, uint32_t n_train_records,
@@ -829,7 +722,7 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     if (nbytes > h->max_batch_bytes)
         return dm_fail(DM_ERR_CAPACITY, "message of %llu bytes exceeds max_batch_bytes=%llu", (unsigned long long)nbytes, (unsigned long long)h->max_batch_bytes);
     if (nbytes && !host_buf) return dm_fail(DM_ERR_ARG, "host_buf is NULL");
-    if (h->kernel_variant < 2 || h->kernel_variant == 5) return dm_fail(DM_ERR_STATE, "the pipelined path needs the stream or rows kernels");
+    if (h->kernel_variant != 6) return dm_fail(DM_ERR_STATE, "the pipelined path runs the stream kernel (DM_KERNEL=lanes is set)");
     if (h->fmt_set) return dm_fail(DM_ERR_STATE, "the pipelined path tokenises key=value records; with a log_format use dm_process_lines");
     if (h->mons_set && h->h_mons.n_combos > 0) return dm_fail(DM_ERR_STATE, "combination monitors run in dm_process_lines / dm_process_records, not in the pipelined path");
     DM_CUDA(cudaSetDevice(h->device));
@@ -844,18 +737,9 @@ extern "C" int dm_submit_lines(dm_handle* h, const uint8_t* host_buf, uint64_t n
     h->last_stream = st;
     DM_CUDA(cudaStreamWaitEvent(st, sl.ev_in, 0));
     if (nbytes == 0) DM_CUDA(cudaMemsetAsync(sl.d_hdr, 0, sizeof(DmBatchHeader), st));
-    const int launched = h->kernel_variant == 6
-        ? dmx_launch(&h->dmx, sl.d_in, nbytes, n_train_lines, h->table, sl.d_flags, sl.d_scores, h->max_lines, sl.d_anoms,
-                     h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, true, dm_prof_mark_cb, h)
-        : h->kernel_variant == 4
-        ? dm_cta_launch(&h->cta, &h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
-                        h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, dm_prof_mark_cb, h)
-        : h->kernel_variant == 3
-        ? dm_staged_launch(&h->staged, &h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
-                           h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, dm_prof_mark_cb, h)
-        : dm_rows_launch(&h->rows, sl.d_in, nbytes, n_train_lines, h->d_keys, h->table, sl.d_flags, sl.d_scores,
-                         h->max_lines, sl.d_anoms, h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, dm_prof_mark_cb, h);
-    if (launched < 0) return dm_fail(DM_ERR_CUDA, "rows kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const int launched = dmx_launch(&h->dmx, sl.d_in, nbytes, n_train_lines, h->table, sl.d_flags, sl.d_scores, h->max_lines, sl.d_anoms,
+                                    h->anomaly_cap, sl.d_hdr, h->d_stats, h->max_lines, st, true, dm_prof_mark_cb, h);
+    if (launched < 0) return dm_fail(DM_ERR_CUDA, "stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += (uint64_t)launched;
     DM_CUDA(cudaEventRecord(sl.ev_comp, st));
     DM_CUDA(cudaStreamWaitEvent(sl.st_out, sl.ev_comp, 0));

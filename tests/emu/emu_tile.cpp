@@ -1,4 +1,4 @@
-// emu_tile.cpp -- runs the product's fused kernel source (dm_kernels_tile.cuh) on the CPU
+// emu_tile.cpp -- runs the product's kernel sources (dm_kernels_*.cuh) on the CPU
 // emulator.  TEST INFRASTRUCTURE ONLY: built by tests/emu/build.py into tests/emu/_build/,
 // loaded by tests/test_emu_tile.py; never part of libdmdetect.so.
 #include "cuda_emu.h"
@@ -7,12 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "dm_kernels_tile.cuh"
-#include "dm_kernels_rows.cuh"
+#include "dm_kernels_index.cuh"
 #include "dm_kernels_stream.cuh"
-#include "dm_kernels_staged.cuh"
 #include "dm_kernels_records.cuh"
-#include "dm_kernels_cta.cuh"
 #include "dm_kernels_format.cuh"
 #include "dm_kernels_lanes.cuh"
 #include "dm_format_host.h"
@@ -53,9 +50,6 @@ struct EmuHandle {
     DmTable table;
     std::vector<unsigned long long> slots, novel;
     unsigned long long counts[2] = {0, 0};
-    std::vector<unsigned long long> tile_state;
-    unsigned long long tile_ctr = 0, ctr_base = 0;
-    uint32_t epoch = 0;
     unsigned long long stats[DM_STATS_WORDS] = {0};
     DmBatchHeader hdr;
     std::vector<dm_anomaly_t> anoms;
@@ -91,7 +85,7 @@ extern "C" EmuHandle* emu_create(uint32_t n_keys, const uint8_t* blob, const uin
     h->table.novel = h->novel.data();
     h->table.novel_count = &h->counts[1];
     h->table.novel_cap = (uint32_t)(cap / 2);
-    h->tile_state.assign(max_tiles + 1, 0);
+    (void)max_tiles;
     h->anoms.resize(1 << 16);
     h->max_lines = max_lines;
     memset(&h->hdr, 0, sizeof(h->hdr));
@@ -100,154 +94,6 @@ extern "C" EmuHandle* emu_create(uint32_t n_keys, const uint8_t* blob, const uin
 
 void emu_stream_free(struct EmuStream*);
 extern "C" void emu_destroy(EmuHandle* h) { emu_stream_free(h->xs); delete h; }
-
-// Mirrors dm_tile_launch (dm_kernels_tile.cuh): optional TRAIN launch, then the DETECT launch.
-extern "C" int emu_process(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
-                           float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
-    // 16-byte aligned copy with hostile slack bytes ('=' and '\n') after the message
-    uint8_t* buf = (uint8_t*)aligned_alloc(64, ((nbytes + 64 + 63) / 64) * 64 + 64);
-    memcpy(buf, msg, nbytes);
-    for (int i = 0; i < 64; ++i) buf[nbytes + i] = (i & 1) ? '\n' : '=';
-    memset(&h->hdr, 0, sizeof(h->hdr));
-    const uint32_t n_tiles = (uint32_t)((nbytes + DMT_TILE - 1) / DMT_TILE);
-    if (n_tiles >= h->tile_state.size()) { free(buf); return -4; }
-    if (n_tiles > 0) {
-        DmFusedArgs a;
-        a.buf = buf; a.nbytes = nbytes; a.n_tiles = n_tiles; a.keys = &h->keys; a.table = h->table;
-        a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data();
-        a.anomaly_cap = (uint32_t)h->anoms.size(); a.hdr = &h->hdr; a.stats = h->stats;
-        a.tile_state = h->tile_state.data(); a.tile_ctr = &h->tile_ctr; a.n_train_lines = n_train;
-        a.max_lines = h->max_lines;
-        if (n_train > 0) {
-            h->epoch = (h->epoch % 0x3FFFFFFEu) + 1u;
-            a.epoch = h->epoch; a.ctr_base = h->ctr_base;
-            a.line_lo = 0; a.line_hi = n_train; a.range_check = 1; a.zero_fill = 1; a.finalize = 0;
-            emu_launch(DMT_THREADS, [&] { dm_k_tile<true>(a); });
-            h->ctr_base += (unsigned long long)n_tiles;
-        }
-        h->epoch = (h->epoch % 0x3FFFFFFEu) + 1u;
-        a.epoch = h->epoch; a.ctr_base = h->ctr_base;
-        a.line_lo = n_train; a.line_hi = ~0ull; a.range_check = n_train > 0 ? 1 : 0;
-        a.zero_fill = n_train > 0 ? 0 : 1; a.finalize = 1;
-        emu_launch(DMT_THREADS, [&] { dm_k_tile<false>(a); });
-        h->ctr_base += (unsigned long long)n_tiles;
-    }
-    free(buf);
-    *n_lines = h->hdr.n_lines;
-    *n_anoms = h->hdr.n_anomalies;
-    *err = h->hdr.error;
-    return 0;
-}
-
-static bool g_emu_cta = false;
-
-// Mirrors dm_rows_launch (dm_kernels_rows.cuh): K_A, optional K_B<train>, K_B<detect>.
-static uint32_t g_emu_rows_static_pct = 60;
-extern "C" void emu_rows_static(uint32_t pct) { g_emu_rows_static_pct = pct; }
-
-static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
-                                 float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err, bool staged);
-
-extern "C" int emu_process_rows(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
-                                float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
-    return emu_process_rows_impl(h, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err, false);
-}
-
-extern "C" int emu_process_cta(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
-                               float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
-    g_emu_cta = true;
-    const int rc = emu_process_rows_impl(h, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err, false);
-    g_emu_cta = false;
-    return rc;
-}
-
-extern "C" int emu_process_staged(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
-                                  float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
-    return emu_process_rows_impl(h, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err, true);
-}
-
-static int emu_process_rows_impl(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
-                                 float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err, bool staged) {
-    uint8_t* buf = (uint8_t*)aligned_alloc(64, ((nbytes + 64 + 63) / 64) * 64 + 64);
-    memcpy(buf, msg, nbytes);
-    for (int i = 0; i < 64; ++i) buf[nbytes + i] = (i & 1) ? '\n' : '=';
-    memset(&h->hdr, 0, sizeof(h->hdr));
-    const uint32_t n_rows = (uint32_t)((nbytes + DMR_ROW - 1) / DMR_ROW);
-    if (n_rows > 0) {
-        DmRowsArgs a;
-        a.buf = buf; a.nbytes = nbytes; a.n_rows = n_rows; a.n_tiles = (n_rows + DMR_TILE_ROWS - 1) / DMR_TILE_ROWS;
-        h->row_prefix.assign(n_rows + 1, 0xDEADBEEFu);
-        if (h->rows_tile_state.size() < a.n_tiles + 1) h->rows_tile_state.resize(a.n_tiles + 1, 0);
-        a.row_prefix = h->row_prefix.data(); a.tile_state = h->rows_tile_state.data();
-        h->rows_epoch = (h->rows_epoch % 0x3FFFFFFEu) + 1u;
-        a.epoch = h->rows_epoch;
-        a.keys = &h->keys; a.table = h->table; a.flags = flags; a.scores = scores; a.out_cap = cap;
-        a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size(); a.hdr = &h->hdr; a.stats = h->stats;
-        a.row_ctr = &h->row_ctr; a.n_train_lines = n_train; a.max_lines = h->max_lines;
-        a.line_lo = 0; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base; a.aux_counts = nullptr; a.line_start = nullptr; a.group = DMR_GROUP; a.static_rows = 0; a.timeline = nullptr;
-        if (staged) {
-            static std::vector<DmCand> cand;
-            static std::vector<DmField> fields;
-            static unsigned int counts[4];
-            cand.assign(nbytes + 1024, DmCand{0, 0});
-            fields.assign(nbytes / 2 + 1024, DmField{0, 0, 0});
-            counts[0] = 77; counts[1] = 88; counts[2] = 99;          // K_A must clear them
-            DmStagedArgs sa;
-            sa.r = a; sa.r.aux_counts = counts;
-            sa.cand = cand.data(); sa.fields = fields.data(); sa.counts = counts;
-            sa.cand_cap = (uint32_t)cand.size(); sa.field_cap = (uint32_t)fields.size();
-            emu_launch_grid(a.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(sa.r); });
-            const uint32_t tiles1 = (n_rows + DMS_ROWS_PER_CTA - 1) / DMS_ROWS_PER_CTA;
-            emu_launch_grid(tiles1 < 3 ? tiles1 : 3, DMS_THREADS, [&] { dm_k_stage1(sa); });
-            emu_launch(DMS_THREADS, [&] { dm_k_stage2(sa); });
-            if (n_train > 0) {
-                sa.r.line_lo = 0; sa.r.line_hi = n_train;
-                emu_launch(DMS_THREADS, [&] { dm_k_stage3<true>(sa); });
-            }
-            sa.r.line_lo = n_train; sa.r.line_hi = ~0ull;
-            emu_launch(DMS_THREADS, [&] { dm_k_stage3<false>(sa); });
-            free(buf);
-            *n_lines = h->hdr.n_lines; *n_anoms = h->hdr.n_anomalies; *err = h->hdr.error;
-            return 0;
-        }
-        emu_launch_grid(a.n_tiles, DMR_A_THREADS, [&] { dm_k_rowindex(a); });
-        if (g_emu_cta) {
-            const uint32_t rounds = (n_rows + DMC_WARPS - 1) / DMC_WARPS;
-            const unsigned long long per = (unsigned long long)rounds * DMC_WARPS + DMC_WARPS;     // grid = 1
-            if (n_train > 0) {
-                a.line_lo = 0; a.line_hi = n_train; a.ctr_base = h->row_ctr_base;
-                emu_launch(DMC_THREADS, [&] { dm_k_cta<true, true>(a); });
-                h->row_ctr_base += per;
-            }
-            a.line_lo = n_train; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base;
-            if (n_train > 0) emu_launch(DMC_THREADS, [&] { dm_k_cta<false, true>(a); });
-            else emu_launch(DMC_THREADS, [&] { dm_k_cta<false, false>(a); });
-            h->row_ctr_base += per;
-            free(buf);
-            *n_lines = h->hdr.n_lines; *n_anoms = h->hdr.n_anomalies; *err = h->hdr.error;
-            return 0;
-        }
-        // as dm_rows_launch: a static share of the rows per warp (here 60 %, grid = 1), the rest dynamic
-        const unsigned long long W = DMR_B_WARPS;
-        a.static_rows = (uint32_t)(((unsigned long long)n_rows * g_emu_rows_static_pct / 100ull) / W);
-        const unsigned long long dyn_rows = n_rows > W * a.static_rows ? n_rows - W * a.static_rows : 0;
-        const unsigned long long per_launch = ((dyn_rows + DMR_GROUP - 1) / DMR_GROUP + W) * DMR_GROUP;
-        if (n_train > 0) {
-            a.line_lo = 0; a.line_hi = n_train; a.ctr_base = h->row_ctr_base;
-            emu_launch(DMR_B_THREADS, [&] { dm_k_rows<true, true>(a); });
-            h->row_ctr_base += per_launch;
-        }
-        a.line_lo = n_train; a.line_hi = ~0ull; a.ctr_base = h->row_ctr_base;
-        if (n_train > 0) emu_launch(DMR_B_THREADS, [&] { dm_k_rows<false, true>(a); });
-        else emu_launch(DMR_B_THREADS, [&] { dm_k_rows<false, false>(a); });
-        h->row_ctr_base += per_launch;
-    }
-    free(buf);
-    *n_lines = h->hdr.n_lines;
-    *n_anoms = h->hdr.n_anomalies;
-    *err = h->hdr.error;
-    return 0;
-}
 
 // Mirrors dmx_launch (dm_kernels_stream.cuh): [row counts, boundary, TRAIN launch,] DETECT launch.  The grid is
 // `g_emu_stream_ctas` CTAs run one after the other (the last one runs the epilogue).
@@ -378,8 +224,6 @@ extern "C" int emu_process_records(EmuHandle* h, const DmMonitor* mons, uint32_t
 // starts are computed here on the host; the device's index kernels are the v1 ones, GPU-tested).
 static DmFormat g_fmt;
 static bool g_fmt_set = false;
-static bool g_fmt_lanes = true;                       // which of the two format kernels emu_process_format runs
-extern "C" void emu_format_kernel(int lanes) { g_fmt_lanes = lanes != 0; }
 static char g_fmt_err[256];
 extern "C" const char* emu_set_format(const DmMonitor* mons, uint32_t n_mons, const char* log_format, const char* content_name,
                                       uint32_t n_templates, const char* const* templates) {
@@ -414,14 +258,9 @@ extern "C" int emu_process_format(EmuHandle* h, const uint8_t* msg, uint64_t nby
     a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
     a.stats = h->stats; a.combos = nullptr; a.nbytes = nbytes;
     const uint64_t nt = std::min<uint64_t>(n_train, n);
-    if (g_fmt_lanes) {
-        g_emu_dyn_smem.assign((size_t)2 * g_fmt.max_slots * DM_FMTL_THREADS * sizeof(uint2), 0);
-        if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<true>(a, &g_fmt); }); }
-        if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<false>(a, &g_fmt); }); }
-    } else {
-        if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch(256, [&] { dm_k_format_lines<true>(a, &g_fmt); }); }
-        if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch(256, [&] { dm_k_format_lines<false>(a, &g_fmt); }); }
-    }
+    g_emu_dyn_smem.assign((size_t)2 * g_fmt.max_slots * DM_FMTL_THREADS * sizeof(uint2), 0);
+    if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<true>(a, &g_fmt); }); }
+    if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<false>(a, &g_fmt); }); }
     *n_lines = n;
     *n_anoms = h->hdr.n_anomalies;
     return 0;

@@ -1,7 +1,7 @@
 """Loader for the CPU emulation of the fused kernel (tests/emu).  TEST INFRASTRUCTURE.
 
-The emulator compiles the product's kernel SOURCE (detectmateservice_b200/csrc/
-dm_kernels_tile.cuh) with g++ -DDM_EMU and runs one thread block on OS threads; it lets the
+The emulator compiles the product's kernel SOURCES (detectmateservice_b200/csrc/
+dm_kernels_*.cuh) with g++ -DDM_EMU and runs one thread block on OS threads; it lets the
 CPU test tier check the kernel's tokenizer / detector logic against the oracle.  It is not a
 CPU implementation of the product: nothing outside tests/ can reach it.
 """
@@ -35,16 +35,10 @@ class Anomaly(C.Structure):
 
 
 class EmuDetector:
-    def __init__(self, keys, table_log2=12, max_bytes=4 << 20, max_lines=1 << 20, variant="rows"):
+    def __init__(self, keys, table_log2=12, max_bytes=4 << 20, max_lines=1 << 20, variant="stream"):
         self.lib = C.CDLL(build())
         self.variant = variant
         L = self.lib
-        L.emu_process_cta.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
-                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
-        L.emu_process_staged.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
-                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
-        L.emu_process_rows.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
-                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_process_lanes.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_process_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -52,8 +46,6 @@ class EmuDetector:
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.c_uint32, C.c_char_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint64, C.c_uint64]
         L.emu_destroy.argtypes = [C.c_void_p]
-        L.emu_process.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
-                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_get_anomalies.restype = C.c_uint32
         L.emu_get_anomalies.argtypes = [C.c_void_p, C.POINTER(Anomaly), C.c_uint32]
         L.emu_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -75,8 +67,7 @@ class EmuDetector:
         flags = np.full(cap, 7, dtype=np.uint8)
         scores = np.full(cap, -1, dtype=np.float32)
         n_lines, n_anom, err = C.c_uint64(), C.c_uint64(), C.c_uint32()
-        fn = {"rows": self.lib.emu_process_rows, "staged": self.lib.emu_process_staged, "cta": self.lib.emu_process_cta,
-              "lanes": self.lib.emu_process_lanes, "stream": self.lib.emu_process_stream}.get(self.variant, self.lib.emu_process)
+        fn = {"lanes": self.lib.emu_process_lanes, "stream": self.lib.emu_process_stream}[self.variant]
         rc = fn(self.h, msg, len(msg), n_train, flags.ctypes.data, scores.ctypes.data, cap,
                                   C.byref(n_lines), C.byref(n_anom), C.byref(err))
         assert rc == 0 and err.value == 0, (rc, err.value)

@@ -156,9 +156,9 @@ def _monitor_array(mons):
 EMU_KERNEL = "lanes"
 
 
-@pytest.fixture(params=["lanes", "warp"])
+@pytest.fixture(params=["lanes"])
 def emu_kernel(request):
-    """Both device decompositions of the matcher: one thread per record (default) / one warp per record."""
+    """The matcher kernel: one thread per record."""
     global EMU_KERNEL
     EMU_KERNEL = request.param
     yield request.param
@@ -173,7 +173,6 @@ class EmuFormat:
         self.lib = C.CDLL(emu_harness.build())
         self.det = emu_harness.EmuDetector([m.key for m in self.mons], table_log2=12)
         L = self.lib
-        L.emu_format_kernel(1 if EMU_KERNEL == "lanes" else 0)
         L.emu_set_format.restype = C.c_char_p
         L.emu_set_format.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p)]
         L.emu_process_format.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,

@@ -16,20 +16,12 @@ from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["stream", "v1", "tile", "rows", "staged", "cta", "lanes"]
+VARIANTS = ["stream", "lanes"]
 SCORE_TOL = 1e-5
-
-
-def _tile_available():
-    from detectmateservice_b200 import _lib
-    src = open(os.path.join(_lib.CSRC, "dm_kernels_tile.cuh")).read()
-    return "placeholder until it lands" not in src
 
 
 @pytest.fixture(params=VARIANTS)
 def variant(request, monkeypatch):
-    if request.param == "tile" and not _tile_available():
-        pytest.skip("fused tile kernel not built yet")
     monkeypatch.setenv("DM_KERNEL", request.param)
     return request.param
 
@@ -305,8 +297,7 @@ def test_window_exchange_two_ranks_on_one_gpu(variant):
         assert gs["score_sum"] == int(ws.sum()) and gs == d1.global_stats()
 
 
-@pytest.mark.parametrize("kernel", ["stream", "rows"])
-def test_pipelined_submit_collect(monkeypatch, kernel):
+def test_pipelined_submit_collect(monkeypatch, kernel="stream"):
     """dm_submit_lines / dm_collect (two slots in flight) give the same flags, scores and
     anomaly lists as the synchronous call, in submission order, training included."""
     import torch
