@@ -306,7 +306,10 @@ class B200NewValueDetector(CoreComponent):
         frames = wire.split_delimited(data)
         out = []
         for idx in np.flatnonzero(flags):
-            rec = wire.decode_parser_schema(frames[int(idx)], strict=False)
+            try:
+                rec = wire.decode_parser_schema(frames[int(idx)], strict=False)
+            except wire.WireError:
+                continue                     # (a frame the device could walk but the host cannot: skipped, not fatal)
             alerts = self._record_alerts(rec, int(masks[idx]))
             t = (rec.get("logFormatVariables") or {}).get("Time")
             out.append(self._detector_schema(rec.get("logID", ""), float(scores[idx]), alerts, t))

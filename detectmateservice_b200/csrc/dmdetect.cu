@@ -141,32 +141,10 @@ static void dm_break_chain(dm_handle* h, cudaStream_t st) {
     if (h->dmx.chain_stream == st) h->dmx.chain_stream = nullptr;
 }
 
-extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, const uint32_t* key_lens,
-                         uint64_t max_batch_bytes, uint64_t max_lines, uint32_t table_log2_slots,
-                         dm_handle** out) {
-    if (!out) return dm_fail(DM_ERR_ARG, "out is NULL");
-    *out = nullptr;
-    if (n_keys > DM_MAX_KEYS) return dm_fail(DM_ERR_ARG, "n_keys %u > %d", n_keys, DM_MAX_KEYS);
-    if (n_keys && (!keys_blob || !key_lens)) return dm_fail(DM_ERR_ARG, "keys missing");
-    if (max_batch_bytes == 0 || max_batch_bytes > 0xFFFFFF00ull)
-        return dm_fail(DM_ERR_ARG, "max_batch_bytes must be in 1..2^32-256");
-    if (table_log2_slots < 10 || table_log2_slots > 28)
-        return dm_fail(DM_ERR_ARG, "table_log2_slots must be in 10..28");
-    int n_dev = 0;
-    cudaError_t ce = cudaGetDeviceCount(&n_dev);
-    if (ce != cudaSuccess || n_dev <= 0)
-        return dm_fail(DM_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path",
-                       ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
-    if (device < 0 || device >= n_dev) return dm_fail(DM_ERR_ARG, "device %d out of range (0..%d)", device, n_dev - 1);
-    cudaDeviceProp prop;
-    DM_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return dm_fail(DM_ERR_NO_DEVICE, "device %d is sm_%d%d; libdmdetect is built for sm_100a only", device,
-                       prop.major, prop.minor);
-    DM_CUDA(cudaSetDevice(device));
-
-    dm_handle* h = new (std::nothrow) dm_handle();
-    if (!h) return dm_fail(DM_ERR_ARG, "out of host memory");
+extern "C" int dm_destroy(dm_handle* h);
+// Everything dm_create allocates; on failure dm_create frees whatever was allocated so far (dm_destroy).
+static int dm_create_fill(dm_handle* h, int device, const cudaDeviceProp& prop, uint32_t n_keys, const uint8_t* keys_blob,
+                          const uint32_t* key_lens, uint64_t max_batch_bytes, uint64_t max_lines, uint32_t table_log2_slots) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->max_batch_bytes = max_batch_bytes;
@@ -178,14 +156,14 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
     uint64_t off = 0;
     for (uint32_t k = 0; k < n_keys; ++k) {
         uint32_t len = key_lens[k];
-        if (len == 0 || len > DM_MAX_KEYLEN) { delete h; return dm_fail(DM_ERR_ARG, "key %u: length %u not in 1..%d", k, len, DM_MAX_KEYLEN); }
+        if (len == 0 || len > DM_MAX_KEYLEN) { return dm_fail(DM_ERR_ARG, "key %u: length %u not in 1..%d", k, len, DM_MAX_KEYLEN); }
         for (uint32_t i = 0; i < len; ++i) {
             uint8_t c = keys_blob[off + i];
-            if (c == 0x20 || c == 0x22 || c == 0x27 || c == 0x3D || c == 0x0A) { delete h; return dm_fail(DM_ERR_ARG, "key %u holds a separator byte 0x%02x", k, c); }
+            if (c == 0x20 || c == 0x22 || c == 0x27 || c == 0x3D || c == 0x0A) { return dm_fail(DM_ERR_ARG, "key %u holds a separator byte 0x%02x", k, c); }
             h->h_keys.bytes[k][i] = c;
         }
         for (uint32_t j = 0; j < k; ++j)
-            if (h->h_keys.len[j] == len && memcmp(h->h_keys.bytes[j], h->h_keys.bytes[k], len) == 0) { delete h; return dm_fail(DM_ERR_ARG, "key %u duplicates key %u", k, j); }
+            if (h->h_keys.len[j] == len && memcmp(h->h_keys.bytes[j], h->h_keys.bytes[k], len) == 0) { return dm_fail(DM_ERR_ARG, "key %u duplicates key %u", k, j); }
         h->h_keys.len[k] = len;
         h->h_keys.salt[k] = dm_field_salt(k);
         off += len;
@@ -236,6 +214,44 @@ extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, 
         else return dm_fail(DM_ERR_ARG, "DM_KERNEL=%s: the key=value kernels are 'stream' (default) and 'lanes'", env);
     }
     DM_CUDA(cudaDeviceSynchronize());
+    return DM_OK;
+}
+
+
+extern "C" int dm_create(int device, uint32_t n_keys, const uint8_t* keys_blob, const uint32_t* key_lens,
+                         uint64_t max_batch_bytes, uint64_t max_lines, uint32_t table_log2_slots,
+                         dm_handle** out) {
+    if (!out) return dm_fail(DM_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_keys > DM_MAX_KEYS) return dm_fail(DM_ERR_ARG, "n_keys %u > %d", n_keys, DM_MAX_KEYS);
+    if (n_keys && (!keys_blob || !key_lens)) return dm_fail(DM_ERR_ARG, "keys missing");
+    if (max_batch_bytes == 0 || max_batch_bytes > 0xFFFFFF00ull)
+        return dm_fail(DM_ERR_ARG, "max_batch_bytes must be in 1..2^32-256");
+    if (table_log2_slots < 10 || table_log2_slots > 28)
+        return dm_fail(DM_ERR_ARG, "table_log2_slots must be in 10..28");
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev <= 0)
+        return dm_fail(DM_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path",
+                       ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    if (device < 0 || device >= n_dev) return dm_fail(DM_ERR_ARG, "device %d out of range (0..%d)", device, n_dev - 1);
+    cudaDeviceProp prop;
+    DM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return dm_fail(DM_ERR_NO_DEVICE, "device %d is sm_%d%d; libdmdetect is built for sm_100a only", device,
+                       prop.major, prop.minor);
+    DM_CUDA(cudaSetDevice(device));
+
+    dm_handle* h = new (std::nothrow) dm_handle();
+    if (!h) return dm_fail(DM_ERR_ARG, "out of host memory");
+    const int rc = dm_create_fill(h, device, prop, n_keys, keys_blob, key_lens, max_batch_bytes, max_lines, table_log2_slots);
+    if (rc != DM_OK) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        dm_destroy(h);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
     *out = h;
     return DM_OK;
 }
@@ -310,6 +326,7 @@ extern "C" int dm_destroy(dm_handle* h) {
 
 static int dm_check_device_errors(dm_handle* h) {
     unsigned int err = h->h_hdr->error;
+    if (h->h_hdr->anomaly_list_count > h->anomaly_cap) err |= DM_DEVERR_ANOMALY_OVERFLOW;
     if (err & DM_DEVERR_TABLE_FULL)
         return dm_fail(DM_ERR_TABLE_FULL, "known-set table over its load limit (2^%u slots); recreate with a larger table_log2_slots", h->table_log2);
     if (err & DM_DEVERR_NOVEL_OVERFLOW)
@@ -656,6 +673,10 @@ extern "C" int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nby
     uint32_t* d_len = h->d_vals + n_records;
     DM_CUDA(cudaMemsetAsync(h->d_hdr, 0, sizeof(DmBatchHeader), st));
     if (n_records) {
+        // (the kernel skips malformed records without touching their outputs: they read as "no alert")
+        DM_CUDA(cudaMemsetAsync(h->d_flags, 0, n_records, st));
+        DM_CUDA(cudaMemsetAsync(h->d_scores, 0, (uint64_t)n_records * 4, st));
+        DM_CUDA(cudaMemsetAsync(h->d_masks, 0, (uint64_t)n_records * 4, st));
         DM_CUDA(cudaMemcpyAsync(h->d_in, buf, nbytes, cudaMemcpyHostToDevice, st));
         DM_CUDA(cudaMemcpyAsync(d_off, off.data(), (uint64_t)n_records * 4, cudaMemcpyHostToDevice, st));
         DM_CUDA(cudaMemcpyAsync(d_len, len.data(), (uint64_t)n_records * 4, cudaMemcpyHostToDevice, st));

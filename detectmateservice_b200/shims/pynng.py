@@ -13,12 +13,18 @@ with real NNG peers (fluentd's nng plugins, the reference's own services):
   frames        tcp:  len (be64) | payload        ipc:  0x01 | len (be64) | payload
 
 PAIR0 semantics reproduced: one peer at a time; ``dial(block=False)`` keeps retrying in
-the background and reconnects; ``send(block=False)`` without a connected, writable peer
-raises ``TryAgain``; ``recv`` honours ``recv_timeout`` (ms) with ``Timeout``; using a closed
-socket raises ``Closed`` (an ``NNGException``).
+the background and reconnects; ``send(block=False)`` hands the message to the transport at
+once when the kernel takes it, otherwise to a bounded per-connection send queue drained by a
+writer thread, and raises ``TryAgain`` only without a connected peer or when that queue is
+full; ``recv`` honours ``recv_timeout`` (ms) with ``Timeout``; a frame larger than
+``recv_max_size`` closes the connection (NNG's NNG_OPT_RECVMAXSZ; 0 = unlimited, which is the
+default here because the reference's own tests push 1 MiB + 11 bytes through default sockets,
+/root/reference/tests/test_engine_multi_output.py:429-447); using a closed socket raises
+``Closed`` (an ``NNGException``).
 """
 from __future__ import annotations
 
+import collections
 import errno
 import os
 import queue
@@ -80,6 +86,8 @@ class exceptions:  # namespace mirror: pynng.exceptions.AddressInUse ...
 _PAIR0 = 0x0010
 _HANDSHAKE = b"\x00SP\x00" + struct.pack(">H", _PAIR0) + b"\x00\x00"
 _RECONNECT_S = 0.05
+_SENDQ_MSGS = 256                 # messages a connection may hold for its writer thread ...
+_SENDQ_BYTES = 256 << 20          # ... and their bytes (whichever is reached first)
 
 _inproc_lock = threading.Lock()
 _inproc_listeners: Dict[str, "Socket"] = {}
@@ -135,7 +143,11 @@ class _Pipe:
         self.owner, self.sock, self.ipc = owner, sock, ipc
         self.peer = peer                 # inproc: the other end
         self.alive = True
-        self.wlock = threading.Lock()
+        self.wlock = threading.Condition()          # guards the socket's write side and the send queue
+        self.sendq = collections.deque()            # memoryviews waiting for the writer thread
+        self.sendq_bytes = 0
+        self.writing = False                        # the writer thread is inside sendall()
+        self.writer = None
         if sock is not None:
             threading.Thread(target=self._reader, name="sp-pipe-reader", daemon=True).start()
 
@@ -150,6 +162,9 @@ class _Pipe:
             if h is None:
                 break
             (ln,) = struct.unpack(">Q", h)
+            rmax = int(getattr(self.owner, "recv_max_size", 0) or 0)
+            if rmax and ln > rmax:
+                break                              # NNG: an oversized message closes the pipe
             alloc = getattr(self.owner, "frame_allocator", None)
             frame = alloc(ln) if (alloc is not None and ln >= 65536) else None
             if frame is not None:
@@ -165,37 +180,107 @@ class _Pipe:
             self.owner._deliver(body)
         self.close()
 
-    def writable(self) -> bool:
-        if not self.alive:
-            return False
-        if self.sock is None:
-            return self.peer is not None and self.peer.alive
-        try:
-            _, w, _ = select.select([], [self.sock], [], 0)
-            return bool(w)
-        except (OSError, ValueError):
-            return False
+    def _frame(self, data) -> list:
+        hdr = (b"\x01" if self.ipc else b"") + struct.pack(">Q", len(data))
+        return [memoryview(hdr + bytes(data))] if len(data) < 65536 else [memoryview(hdr), memoryview(data)]
 
-    def send(self, data: bytes) -> None:
+    def _writer(self) -> None:
+        while True:
+            with self.wlock:
+                while self.alive and not self.sendq:
+                    self.writing = False
+                    self.wlock.notify_all()
+                    self.wlock.wait(0.2)
+                if not self.alive:
+                    self.writing = False
+                    self.wlock.notify_all()
+                    return
+                mv = self.sendq.popleft()
+                self.sendq_bytes -= len(mv)
+                self.writing = True
+            try:
+                self.sock.sendall(mv)
+            except OSError:
+                self.close()
+                return
+
+    def send_nowait(self, data) -> bool:
+        """Hand one message to the transport without waiting.  False = nothing can take it now."""
+        if self.sock is None:                      # inproc
+            if self.peer is None or not self.peer.alive:
+                raise Closed("peer gone")
+            self.peer.owner._deliver(bytes(data))
+            return True
+        parts = self._frame(data)
+        with self.wlock:
+            if not self.alive:
+                return False
+            if not self.sendq and not self.writing:
+                # nothing queued: try the kernel directly (it takes what fits into the socket buffer)
+                try:
+                    while parts:
+                        n = self.sock.send(parts[0], socket.MSG_DONTWAIT)
+                        if n < len(parts[0]):
+                            parts[0] = parts[0][n:]
+                            break
+                        parts.pop(0)
+                except (BlockingIOError, InterruptedError):
+                    pass
+                except OSError as e:
+                    self.alive and self.close_locked_error(e)
+                    raise Closed(str(e)) from e
+                if not parts:
+                    return True
+                started = True
+            else:
+                started = False
+                if len(self.sendq) >= _SENDQ_MSGS or self.sendq_bytes + sum(len(p) for p in parts) > _SENDQ_BYTES:
+                    return False
+            # (a frame that has started must be finished: it goes to the queue even when the queue is long)
+            _ = started
+            for p_ in parts:
+                self.sendq.append(p_)
+                self.sendq_bytes += len(p_)
+            if self.writer is None:
+                self.writer = threading.Thread(target=self._writer, name="sp-pipe-writer", daemon=True)
+                self.writer.start()
+            self.wlock.notify_all()
+            return True
+
+    def close_locked_error(self, e) -> None:
+        threading.Thread(target=self.close, daemon=True).start()
+
+    def send(self, data, deadline: Optional[float] = None) -> None:
+        """Blocking send: behind whatever is queued, then straight to the socket."""
         if self.sock is None:                      # inproc
             if self.peer is None or not self.peer.alive:
                 raise Closed("peer gone")
             self.peer.owner._deliver(bytes(data))
             return
-        hdr = (b"\x01" if self.ipc else b"") + struct.pack(">Q", len(data))
+        parts = self._frame(data)
         with self.wlock:
+            while self.alive and (self.sendq or self.writing):
+                if deadline is not None and time.monotonic() >= deadline:
+                    raise Timeout("send timed out")
+                self.wlock.wait(0.05)
+            if not self.alive:
+                raise Closed("connection closed")
             try:
-                self.sock.sendall(hdr + data if len(data) < 65536 else hdr)
-                if len(data) >= 65536:
-                    self.sock.sendall(data)
+                for p_ in parts:
+                    self.sock.sendall(p_)
             except OSError as e:
-                self.close()
+                self.close_locked_error(e)
                 raise Closed(str(e)) from e
 
     def close(self) -> None:
         if not self.alive:
             return
         self.alive = False
+        try:
+            with self.wlock:
+                self.wlock.notify_all()
+        except RuntimeError:
+            pass
         if self.sock is not None:
             try:
                 self.sock.shutdown(socket.SHUT_RDWR)
@@ -217,12 +302,13 @@ class Socket:
 
     def __init__(self, listen: Optional[str] = None, dial: Optional[str] = None, recv_timeout: Optional[int] = None,
                  send_timeout: Optional[int] = None, recv_buffer_size: int = 128, send_buffer_size: int = 128,
-                 block_on_dial: Optional[bool] = None, **_ignored) -> None:
+                 block_on_dial: Optional[bool] = None, recv_max_size: int = 0, **_ignored) -> None:
         self.recv_timeout = recv_timeout           # ms, None / negative = wait forever
         self.send_timeout = send_timeout
         self.dial_timeout = 1000
         self.recv_buffer_size = recv_buffer_size
         self.send_buffer_size = send_buffer_size
+        self.recv_max_size = recv_max_size         # bytes; larger frames close the connection (0 = unlimited)
         self._rx: "queue.Queue[bytes]" = queue.Queue()
         self._pipe: Optional[_Pipe] = None
         self._pipe_cv = threading.Condition()
@@ -293,9 +379,9 @@ class Socket:
             return "tcp", (("0.0.0.0" if host == "*" else host), int(u.port))
         if u.scheme == "inproc":
             return "inproc", addr
-        if u.scheme in ("ws", "tls+tcp"):
-            raise NotSupported(f"transport {u.scheme!r} is not implemented by the B200 pynng shim")
-        raise BadScheme(f"unknown address scheme in {addr!r}")
+        # NNG answers NNG_ENOTSUP for a transport it does not know (pynng.exceptions.NotSupported,
+        # /root/reference/tests/test_engine_socket_factory_error_handling.py:96-101)
+        raise NotSupported(f"transport {u.scheme!r} is not supported ({addr!r})")
 
     # ------------------------------------------------------------------ listen / dial
     def listen(self, addr: str, flags: int = 0) -> None:
@@ -431,13 +517,13 @@ class Socket:
     def send(self, data: bytes, block: bool = True) -> None:
         if self._closed:
             raise Closed("socket is closed")
-        data = bytes(data)
+        if not isinstance(data, (bytes, bytearray, memoryview)):
+            data = bytes(data)
         if not block:
             with self._pipe_cv:
                 p = self._pipe
-            if p is None or not p.alive or not p.writable():
+            if p is None or not p.alive or not p.send_nowait(data):
                 raise TryAgain("no peer ready")
-            p.send(data)
             return
         tmo = self.send_timeout
         deadline = None if tmo is None or tmo < 0 else time.monotonic() + tmo / 1000.0
@@ -450,7 +536,7 @@ class Socket:
             if self._closed:
                 raise Closed("socket is closed")
             p = self._pipe
-        p.send(data)
+        p.send(data, deadline)
 
     # ------------------------------------------------------------------ teardown
     def close(self) -> None:

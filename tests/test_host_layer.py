@@ -139,6 +139,36 @@ def test_pair0_late_binding_and_reconnect(tmp_path):
     out.close()
 
 
+def test_pair0_nonblocking_send_queues_and_oversize_frames(tmp_path):
+    """send(block=False) to a connected peer that is not draining does not drop (the reference's
+    fan-out, engine.py:234-243, relies on it: tests/test_service_multi_output_integration.py:298-318);
+    unknown transports are NotSupported; recv_max_size closes the connection on an oversized frame."""
+    addr = f"ipc://{tmp_path}/q.ipc"
+    with pynng.Pair0(listen=addr, recv_timeout=2000) as rx, pynng.Pair0(recv_timeout=2000) as tx:
+        tx.send_buffer_size = 0
+        tx.dial(addr, block=True)
+        time.sleep(0.05)
+        big = b"y" * (300 << 10)                       # larger than a unix socket buffer: must be queued, not dropped
+        for i in range(300):
+            tx.send(b"msg %d" % i, block=False)
+        tx.send(big, block=False)
+        tx.send(b"after", block=False)
+        for i in range(300):
+            assert rx.recv() == b"msg %d" % i
+        assert rx.recv() == big and rx.recv() == b"after"
+    with pytest.raises(pynng.exceptions.NotSupported):
+        pynng.Pair0(listen="invalid://address")
+    addr2 = f"ipc://{tmp_path}/m.ipc"
+    with pynng.Pair0(listen=addr2, recv_timeout=300) as rx, pynng.Pair0(dial=addr2) as tx:
+        rx.recv_max_size = 1024
+        time.sleep(0.05)
+        tx.send(b"a" * 1024)
+        assert rx.recv() == b"a" * 1024
+        tx.send(b"b" * 1025)                           # over the limit: dropped with the connection
+        with pytest.raises(pynng.Timeout):
+            rx.recv()
+
+
 def test_inproc_transport():
     with pynng.Pair0(listen="inproc://t1", recv_timeout=500) as a, pynng.Pair0(dial="inproc://t1", recv_timeout=500) as b:
         b.send(b"abc")
