@@ -1,28 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- log lines/sec through the B200 detector (BASELINE.json metric).
 
-A step = one pass of the hot path over one message of 65 536 synthetic audit records of
-256 B (16 MiB).  Workload = BASELINE config 2 ("detector Service.process on 1xB200, 1M
-synthetic 256B audit-log lines, batch 64k"): 16 distinct messages per GPU (256 MiB, larger
-than the 126 MB L2, so successive steps never re-read a cached message); message 0 is the
-anomaly-free training window (consumed untimed), the timed steps cycle over the 15
-detection messages.  Multi-GPU: the stream shards by message across ranks (weak scaling,
-every rank owns 16 messages), one NCCL all-reduce of the per-window statistics per step.
+Workload (BASELINE config 2 shape, windows as in config 4): every GPU owns 17 synthetic messages of
+65 536 audit records x 256 B (16 MiB each, 272 MiB > the 126 MB L2).  Message 0 is the anomaly-free
+training window (untimed).  A STEP is one WINDOW of 8 consecutive detection messages (512k records,
+128 MiB) and, with more than one GPU, ONE NCCL sum-all-reduce of the window's statistics
+(SURVEY.md 8d, config 4); the timed steps cycle over the 16 detection messages.  Multi-GPU: the
+stream shards by message across ranks (weak scaling), no data-path collective.
 
-  value     lines/s, messages resident in HBM when the timed region starts, CUDA events.
-  e2e       same metric through the C-ABI call with HOST buffers: pinned-host message in,
-            H2D + kernels + D2H of flags/scores inside the timed region.
-  roofline  dominant kernel (tokenizer+detector): algorithmic bytes (record bytes + 1 B flag
-            + 4 B score per record) / its CUDA-event duration, against MEASURED_PEAKS.json.
-  cpu_baseline  the oracle's C restatement (oracle/c/dm_oracle.c) on the host cores, bounded
-            sample; N=1, rank 0 only.
+  value     lines/s, messages resident in HBM when the timed region starts, CUDA events on the
+            launching stream, max over ranks.
+  e2e       the same metric through the reference-facing plugin call:
+            B200NewValueDetector.process(message in PINNED HOST memory) -> compact result bytes,
+            H2D + kernel + D2H inside the timed region; `abi_pipelined` = the C-ABI two-slot path
+            (dm_submit_lines / dm_collect) beside it.
+  roofline  the tokenizer+detector kernel (one launch per message): algorithmic bytes per launch
+            (record bytes + 1 B flag + 4 B score per record) / average launch duration over the
+            timed region, against MEASURED_PEAKS.json.
+  cpu_baseline  rank 0, N=1: the oracle's C restatement on all host cores (pinned pthreads, median
+            of 5 x 2 s) and, as `reference_engine`, the reference's OWN Engine/Service per record.
+  extra.configs  BASELINE configs 3 (through NNG-framed sockets), 4 (windows; = this run) and 5
+            (variable-length records) measured in the same run.
 
-`--impl reference` times that same CPU restatement with all host threads (the reference is
-pure Python whose detector arithmetic is not vendored; see DESIGN.md "Reference arm").
+`--impl reference` times the CPU restatement with all host threads on the same config (the
+reference is pure Python whose detector arithmetic is not vendored; DESIGN.md "Reference arm").
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -36,9 +42,23 @@ import numpy as np  # noqa: E402
 
 LINES_PER_MSG = 65536
 LINE_BYTES = 256
-N_MSGS = 16
+N_DETECT = 16                 # detection messages per GPU
+WINDOW_MSGS = 8               # messages per window = per step
 METRIC = "log lines/sec through detector"
 UNIT = "lines/s"
+
+
+def workload_config(world: int) -> dict:
+    """The same dict in both arms (`--impl b200` and `--impl reference`)."""
+    return {
+        "workload": "config2 shape in config4 windows: detector on synthetic audit records, 64k records x 256 B per "
+                    "message (16 MiB), K=5 monitored fields, p=1e-3 anomalies; step = one window of 8 messages "
+                    "(512k records) + one statistics all-reduce when n_gpus > 1",
+        "lines_per_message": LINES_PER_MSG, "line_bytes": LINE_BYTES, "messages_per_window": WINDOW_MSGS,
+        "detect_messages_per_gpu": N_DETECT, "training_window_lines": LINES_PER_MSG,
+        "l2_policy": "inputs larger than L2 (16 x 16 MiB cycled per GPU)",
+        "parallelism": f"shard-by-message x{world}, 1 stats all-reduce per window" if world > 1 else "single GPU",
+    }
 
 
 def _peaks():
@@ -51,19 +71,30 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def _make_messages(seed_offset: int, n_msgs: int = N_MSGS, lines: int = LINES_PER_MSG):
+def _csrc_sha() -> str:
+    """Fingerprint of the kernel sources: ties profiles/ numbers to the binary they were taken on."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "detectmateservice_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def _make_messages(seed_offset: int, n_detect: int = N_DETECT, lines: int = LINES_PER_MSG, varlen: bool = False):
     from detectmateservice_b200.synth import SEED, AuditSynth
     g = AuditSynth(SEED + seed_offset)
-    msgs = [g.batch(lines, inject=False, line_bytes=LINE_BYTES)[0]]
-    for _ in range(n_msgs - 1):
-        msgs.append(g.batch(lines, inject=True, line_bytes=LINE_BYTES)[0])
+    gen = g.batch_varlen if varlen else (lambda n, inject: g.batch(n, inject=inject, line_bytes=LINE_BYTES))
+    msgs = [gen(lines, inject=False)[0]]
+    for _ in range(n_detect):
+        msgs.append(gen(lines, inject=True)[0])
     return msgs
 
 
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
 
-    def __init__(self, index: int, period: float = 0.002):
+    def __init__(self, index: int, period: float = 0.001):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -113,92 +144,66 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: the oracle's C restatement, threads over shards of the same workload
+# CPU legs (the oracle and the reference engine are executed HERE and nowhere else in the product)
 # ------------------------------------------------------------------------------------------
-def _cpu_oracles(msgs, threads: int):
-    """One trained C-oracle instance per thread (training window = message 0, untimed)."""
+def _cpu_port_rates(msgs, threads: int, min_seconds: float, samples: int):
+    """C restatement on `threads` pinned worker threads: (threads used, rates per sample)."""
     from detectmateservice_b200.synth import MONITORED_KEYS
-    from oracle.native import NativeOracle
+    from oracle import native
+    native.build()
     keys = [k.encode() for k in MONITORED_KEYS]
-    oracles = []
-    for _ in range(threads):
-        o = NativeOracle(keys)
-        o.process(msgs[0], LINES_PER_MSG)
-        oracles.append(o)
-    return oracles
+    used, rates, _ = native.bench_threads(keys, msgs[0], msgs[1], threads, min_seconds, samples)
+    return used, rates
 
 
-def _cpu_throughput(msgs, sample_lines: int, threads: int, repeats: int = 1, oracles=None):
-    """Detect `sample_lines` records per thread with `threads` threads (each owns a trained
-    oracle instance).  Returns (lines/s, seconds)."""
-    if oracles is None:
-        oracles = _cpu_oracles(msgs, threads)
-    nbytes = sample_lines * LINE_BYTES
-    shards = [np.frombuffer(msgs[1 + (t % (len(msgs) - 1))], dtype=np.uint8)[:nbytes] for t in range(threads)]
-    barrier = threading.Barrier(threads + 1)
-
-    def work(t):
-        barrier.wait()
-        for _ in range(repeats):
-            oracles[t].process(shards[t], 0)
-        barrier.wait()
-
-    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-    for th in ths:
-        th.start()
-    barrier.wait()
-    t0 = time.perf_counter()
-    barrier.wait()
-    dt = time.perf_counter() - t0
-    for th in ths:
-        th.join()
-    return threads * sample_lines * repeats / dt, dt
-
-
-def _python_per_record_rate(msgs, n_lines: int = 4000):
-    """The reference's granularity: one record per process() call in pure Python (oracle/nvd.py)."""
+def _reference_engine_leg(msgs, seconds: float = 4.0):
+    """The reference's own Service.process / Engine loop per record."""
     from detectmateservice_b200.synth import MONITORED_KEYS
-    from oracle.nvd import NewValueDetectorOracle
-    from oracle import rtok
-    cfg = {"data_use_training": 2000, "global": {"g": {"header_variables": [{"pos": k} for k in MONITORED_KEYS]}}}
-    det = NewValueDetectorOracle(config=cfg)
-    lines = rtok.split_records(msgs[0][:LINE_BYTES * 2000]) + rtok.split_records(msgs[1][:LINE_BYTES * n_lines])
-    for l in lines[:2000]:
-        det.step_line(l)
-    t0 = time.perf_counter()
-    for l in lines[2000:]:
-        det.step_line(l)
-    return n_lines / (time.perf_counter() - t0)
+    from oracle import ref_engine, rtok
+    if ref_engine.reference_path() is None:
+        return {"unavailable": "reference service neither in baseline/_ref nor in /root/reference/src"}
+    train = rtok.split_records(msgs[0][:LINE_BYTES * 2000])
+    # (anomaly-free records: an alert would be answered on the feeder's socket)
+    detect = rtok.split_records(msgs[0][LINE_BYTES * 2000:LINE_BYTES * 6000])
+    out = {"granularity": "one record per message (the reference's native granularity, engine.py:159-217)",
+           "source": ref_engine.reference_path().replace(ROOT + os.sep, "")}
+    try:
+        rate1, n1 = ref_engine.inprocess_rate(MONITORED_KEYS, train, detect, seconds)
+        out["service_process_1_thread"] = rate1
+        cores = os.cpu_count() or 1
+        p = max(1, cores // 2)                      # one service + one sender process per pair of cores
+        rate_p, n_p, secs = ref_engine.ipc_rate(MONITORED_KEYS, train, detect, p, seconds)
+        out["engine_ipc_processes"] = p
+        out["engine_ipc_box"] = rate_p
+        out["engine_ipc_per_service"] = rate_p / p
+        out["sample"] = f"{n1} records in-process ({seconds:.0f} s); {n_p} records over {p} ipc services ({secs:.1f} s)"
+    except Exception as e:                          # a measurement leg must not take the bench line down
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import native
-    native.build()
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     threads = os.cpu_count() or 1
-    msgs = _make_messages(0, n_msgs=4)
-    # bounded sample per step: 8192 records per thread (about 2 MiB each)
-    sample = 8192
-    oracles = _cpu_oracles(msgs, threads)
-    for _ in range(max(min(args.warmup, 5), 1)):
-        _cpu_throughput(msgs, sample, threads, oracles=oracles)
-    t_total, lines_total = 0.0, 0
-    for _ in range(args.steps):
-        rate, dt = _cpu_throughput(msgs, sample, threads, oracles=oracles)
-        t_total += dt
-        lines_total += sample * threads
-    value = lines_total / t_total
+    msgs = _make_messages(0, n_detect=1)
+    step_s = 1.0                                     # one step = a 1 s sample of the same workload on all host threads
+    used, _ = _cpu_port_rates(msgs, threads, 0.3, max(1, min(args.warmup, 3)))
+    used, rates = _cpu_port_rates(msgs, threads, step_s, args.steps)
+    value = float(np.median(rates))
+    lines_per_step = WINDOW_MSGS * LINES_PER_MSG
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * lines_per_step / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "config2: 64k x 256 B synthetic audit records per message, K=5 monitored fields",
-                   "lines_per_message": LINES_PER_MSG, "line_bytes": LINE_BYTES},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} records per thread per step, {threads} threads, C restatement "
-                                   f"oracle/c/dm_oracle.c (reference detector source is not vendored)"},
+        "config": workload_config(world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
+                         "sample": f"median of {args.steps} samples of {step_s:.0f} s on {used} pinned threads, C restatement "
+                                   f"oracle/c/dm_oracle.c (the reference's detector source is not vendored); ms_per_step = "
+                                   f"one window of {lines_per_step} records at that rate",
+                         "spread": [float(min(rates)), float(max(rates))]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -209,6 +214,72 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+def _component(device: int, max_batch_bytes: int):
+    from detectmateservice_b200.component import B200NewValueDetector
+    from detectmateservice_b200.synth import MONITORED_KEYS
+    cfg = {"detectors": {"B200NewValueDetector": {
+        "method_type": "new_value_detector", "data_use_training": LINES_PER_MSG, "auto_config": False,
+        "params": {"output_format": "compact", "input_format": "raw_lines", "max_batch_bytes": max_batch_bytes,
+                   "device": device, "table_log2_slots": 16},
+        "global": {"g": {"header_variables": [{"pos": k} for k in MONITORED_KEYS]}}}}}
+    return B200NewValueDetector(config=cfg)
+
+
+def _config3_engine(h_msgs, nbytes, device: int, seconds: float = 2.0):
+    """BASELINE config 3: sender -> NNG PAIR0 (ipc) -> DetectorEngine(B200NewValueDetector) -> sink."""
+    import tempfile
+    import pynng
+    from detectmateservice_b200.service import DetectorEngine
+    comp = _component(device, max(nbytes) + 4096)
+    tmp = tempfile.mkdtemp(prefix="dmcfg3")
+    eng_addr, out_addr = f"ipc://{tmp}/det.ipc", f"ipc://{tmp}/out.ipc"
+    sink = pynng.Pair0(listen=out_addr, recv_timeout=30000)
+    lines = [0]
+    res = {}
+    try:
+        with DetectorEngine(comp, eng_addr, out_addr=[out_addr]) as eng:
+            time.sleep(0.3)
+            with pynng.Pair0(dial=eng_addr, block_on_dial=True) as tx:
+                tx.send(memoryview(h_msgs[0].numpy()))    # training window
+                sink.recv()
+                sent = [0]
+                stop = threading.Event()
+
+                def feeder():
+                    i = 0
+                    while not stop.is_set():
+                        tx.send(memoryview(h_msgs[1 + (i % N_DETECT)].numpy()))
+                        sent[0] += 1
+                        i += 1
+                th = threading.Thread(target=feeder, daemon=True)
+                t0 = time.perf_counter()
+                th.start()
+                got = 0
+                while time.perf_counter() - t0 < seconds:
+                    out = sink.recv()
+                    got += 1
+                    lines[0] += int(np.frombuffer(out[:4], dtype="<u4")[0])
+                dt = time.perf_counter() - t0
+                stop.set()
+                # drain what is in flight so that the sender thread can finish
+                sink.recv_timeout = 500
+                try:
+                    while True:
+                        sink.recv()
+                except pynng.Timeout:
+                    pass
+                th.join(timeout=5)
+            res = {"lines_per_s": lines[0] / dt, "messages": got, "seconds": dt, "errors": eng.counters.get("errors"),
+                   "topology": "sender thread -> ipc PAIR0 -> DetectorEngine(B200NewValueDetector, compact output) -> ipc PAIR0 -> sink",
+                   "transport": "python SP/PAIR0 shim (detectmateservice_b200/shims/pynng.py), frames received into pinned slots"}
+    except Exception as e:
+        res = {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        sink.close()
+        comp.close()
+    return res
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -224,9 +295,8 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO prints a banner there)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("DM_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries the one JSON line: NCCL's own log (NCCL_DEBUG is left as the caller set it) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -235,16 +305,16 @@ def run_gpu(args):
     n_lines_msg = [m.count(b"\n") for m in msgs]
     det = DeviceDetector(MONITORED_KEYS, device=local_rank, max_batch_bytes=max(nbytes) + 4096,
                          max_lines=LINES_PER_MSG + 16, table_log2_slots=16)
-    # a dedicated non-default stream: the C ABI treats a NULL stream as "the handle's own
-    # stream", and torch's default stream IS NULL -- events must sit on the launching stream.
+    # The device-resident messages are written once, below, and never again: consecutive calls may overlap
+    # (dm_set_overlap, include/dmdetect.h)
+    det.set_overlap(True)
+    # a dedicated non-default stream: the C ABI treats a NULL stream as "the handle's own stream", and torch's
+    # default stream IS NULL -- events must sit on the launching stream.
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
     assert sp != 0
 
-    # device-resident copies (value) and pinned-host copies (e2e)
-    # (pinned buffers are allocated with the thread bound to the GPU's NUMA node: a buffer on the
-    # other socket halves the host->device rate, detectmateservice_b200/numa.py)
     from detectmateservice_b200.numa import bound_to_gpu_node
     d_msgs, h_msgs = [], []
     with bound_to_gpu_node(local_rank) as numa_cpus:
@@ -256,41 +326,36 @@ def run_gpu(args):
             hp = torch.empty(len(m), dtype=torch.uint8, pin_memory=True)
             hp.copy_(src)
             h_msgs.append(hp)
-    # the set-up just wrote these buffers: evict them from the CPU caches, else the H2D copies
-    # of whichever buffers are still cached run at a fraction of the link rate (dmdetect.cu)
-    from detectmateservice_b200 import _lib as _dmlib
+    # the set-up just wrote these buffers: evict them from the CPU caches, else the H2D copies of whichever buffers
+    # are still cached run at a fraction of the link rate (dmdetect.cu, dm_host_cache_flush)
     for hp in h_msgs:
-        _dmlib.check(_dmlib.load().dm_host_cache_flush(hp.data_ptr(), hp.numel()))
-    d_flags = torch.zeros(LINES_PER_MSG + 16, dtype=torch.uint8, device=dev)
-    d_scores = torch.zeros(LINES_PER_MSG + 16, dtype=torch.float32, device=dev)
+        _lib.check(_lib.load().dm_host_cache_flush(hp.data_ptr(), hp.numel()))
     cap = LINES_PER_MSG + 16
+    d_flags = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    d_scores = torch.zeros(cap, dtype=torch.float32, device=dev)
     from detectmateservice_b200.window import DeviceWindow
     dwin = DeviceWindow(det, rank, world, dev)
     if world > 1 and os.environ.get("DM_WINDOW", "native") == "native":
-        # the library's own NCCL communicator: one C call per window (export, ncclAllReduce, import);
-        # DM_WINDOW=torch keeps the torch.distributed.all_reduce route
-        dwin.init_native(n_comms=2 if os.environ.get("DM_WINDOW_COMMS", "2") == "2" else 1)
+        dwin.init_native(n_comms=2)
 
-    # the per-window exchange runs on a side stream: in steady state it carries statistics
-    # only and gates nothing, so it overlaps the next message's kernels
-    side = torch.cuda.Stream(device=dev)
-    sides = [side, torch.cuda.Stream(device=dev)]
+    # the per-window exchange runs on a side stream: in steady state it carries statistics only and gates
+    # nothing, so it overlaps the next window's kernels (two communicators: two windows' all-reduces in flight)
+    sides = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
     win_n = [0]
-    n_sides = 2 if os.environ.get("DM_WINDOW_COMMS", "2") == "2" else 1
     win_ev = torch.cuda.Event()
 
     def window(with_keys: bool):
         if with_keys:
             dwin.exchange(True, sp)                 # training window: detection must wait for it
             return
-        sd = sides[win_n[0] % n_sides]               # DM_WINDOW_COMMS=2: two windows' all-reduces in flight
+        sd = sides[win_n[0] % 2]
         win_n[0] += 1
         win_ev.record(stream)
         sd.wait_event(win_ev)
         if getattr(dwin, "native", False):
             dwin.exchange(False, sd.cuda_stream)
         else:
-            with torch.cuda.stream(sd):              # the torch.distributed route reduces on the current stream
+            with torch.cuda.stream(sd):
                 dwin.exchange(False, sd.cuda_stream)
 
     # training window (untimed): every rank learns its message 0, then one exchange with keys
@@ -299,11 +364,15 @@ def run_gpu(args):
     det.sync()
 
     def step(i: int):
-        j = 1 + (i % (N_MSGS - 1))
-        det.enqueue_device(d_msgs[j].data_ptr(), nbytes[j], 0, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
+        """One window: 8 messages, then (multi-GPU) one all-reduce of the window's statistics."""
+        n = 0
+        for m in range(WINDOW_MSGS):
+            j = 1 + ((i * WINDOW_MSGS + m) % N_DETECT)
+            det.enqueue_device(d_msgs[j].data_ptr(), nbytes[j], 0, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
+            n += n_lines_msg[j]
         if world > 1:
             window(False)
-        return j
+        return n
 
     def barrier():
         if world > 1:
@@ -322,7 +391,7 @@ def run_gpu(args):
     barrier()
     e0.record(stream)
     for i in range(args.steps):
-        lines_timed += n_lines_msg[step(i)]
+        lines_timed += step(i)
     stream.wait_stream(sides[0])                     # the last windows' all-reduces are part of the job
     stream.wait_stream(sides[1])
     e1.record(stream)
@@ -339,64 +408,61 @@ def run_gpu(args):
     ms_max, lines_all = float(t.item()), float(tot.item())
     value = lines_all / (ms_max * 1e-3)
 
-    # ---- roofline: dominant kernel, event pair inside the library --------------------------
+    # ---- roofline: the tokenizer+detector kernel, one launch per message --------------------
+    # (a) average launch duration over the timed region above (launches overlap, as in production);
+    # (b) one launch at a time, event pair inside the library, nothing else on the GPU.
+    n_launch = args.steps * WINDOW_MSGS
+    alg_bytes = sum(nbytes[1 + (k % N_DETECT)] + 5 * n_lines_msg[1 + (k % N_DETECT)] for k in range(n_launch)) / n_launch
+    kernel_ms = ms / n_launch
+    det.set_overlap(False)
     det.profile_enable(True)
-    alg_bytes = 0
-    n_prof = min(args.steps, 60)
-    for i in range(n_prof):
-        j = step(i)
-        alg_bytes += nbytes[j] + 5 * n_lines_msg[j]
+    for k in range(16):
+        j = 1 + (k % N_DETECT)
+        det.enqueue_device(d_msgs[j].data_ptr(), nbytes[j], 0, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
     k_ms, k_n, _ = det.profile_read()
     det.profile_enable(False)
+    det.set_overlap(True)
     peak, peak_src = _peaks()
-    achieved = (alg_bytes / max(k_n, 1)) / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_latest.json")
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r02_stream_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            if tj.get("csrc_sha") == _csrc_sha():
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r02_stream_traffic.json (ncu --set full of this build)"
+            else:
+                traffic_src = "profiles/r02_stream_traffic.json is from another build of the kernels: not reported"
         except Exception:
-            traffic = None
+            pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms / max(k_n, 1),
-                "algorithmic_bytes_per_launch": alg_bytes / max(k_n, 1),
-                "kernel": os.environ.get("DM_KERNEL", "default"),
-                # the whole step (K_A + K_B, overlapped by programmatic dependent launch) on this rank
-                "step_achieved": (alg_bytes / max(n_prof, 1)) / (ms / max(args.steps, 1) * 1e-3) / 1e9,
-                "step_frac": (alg_bytes / max(n_prof, 1)) / (ms / max(args.steps, 1) * 1e-3) / 1e9 / peak}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "dm_k_stream<false> (one launch per 64k-record message)",
+                "kernel_ms": kernel_ms, "kernel_ms_definition": "timed region / launches (consecutive launches overlap)",
+                "kernel_ms_isolated": (k_ms / k_n) if k_n else None,
+                "algorithmic_bytes_per_launch": alg_bytes, "csrc_sha": _csrc_sha()}
 
-    # ---- e2e: C-ABI calls with pinned HOST buffers, H2D + D2H inside the timed region --------
-    # dm_submit_lines / dm_collect (two slots): message i+1 crosses PCIe while message i runs;
-    # every step's flags and scores are read back into host memory.
+    # ---- e2e: the plugin call with PINNED HOST buffers, H2D + D2H inside the timed region -----
     torch.cuda.synchronize()
-    e2e_steps = max(4, min(args.steps, 240))
-    pipelined = os.environ.get("DM_KERNEL", "rows") == "rows"
+    comp = _component(local_rank, max(nbytes) + 4096)
+    from detectmateservice_b200.component import decode_compact
+    comp.process(memoryview(h_msgs[0].numpy()))                      # training window
+    e2e_steps = max(2, min(args.steps, 24))
 
-    def e2e_loop(n_steps: int) -> int:
-        lines = 0
-        if pipelined:
-            for i in range(n_steps):
-                slot = i & 1
-                if i >= 2:
-                    f, s = det.collect(slot)
-                    lines += f.size
-                det.submit(h_msgs[1 + (i % (N_MSGS - 1))].numpy(), 0, slot)
-            for i in range(max(0, n_steps - 2), n_steps):
-                f, s = det.collect(i & 1)
-                lines += f.size
-        else:
-            for i in range(n_steps):
-                f, s = det.process_lines(h_msgs[1 + (i % (N_MSGS - 1))].numpy(), 0, copy=False)
-                lines += f.size
-        return lines
-
-    with bound_to_gpu_node(local_rank):              # the library's pinned result buffers are created here
-        e2e_loop(4)
+    def e2e_window(i: int) -> int:
+        n = 0
+        for m in range(WINDOW_MSGS):
+            j = 1 + ((i * WINDOW_MSGS + m) % N_DETECT)
+            out = comp.process(memoryview(h_msgs[j].numpy()))        # bytes: [u32 n][n x u8 flag][n x f32 score]
+            n += int.from_bytes(out[:4], "little")
+        return n
+    for i in range(2):
+        e2e_window(i)
     barrier()
     t0 = time.perf_counter()
-    e2e_lines = e2e_loop(e2e_steps)
-    if world > 1:
-        window(False)
+    e2e_lines = 0
+    for i in range(e2e_steps):
+        e2e_lines += e2e_window(i)
     barrier()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -405,47 +471,123 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     e2e_value = float(tot.item()) / float(t.item())
-    # plain H2D bandwidth of the same pinned buffers, for context
+    # parity spot check of the plugin path against the device-resident path
+    f_chk, s_chk = decode_compact(comp.process(memoryview(h_msgs[1].numpy())))
+    det.enqueue_device(d_msgs[1].data_ptr(), nbytes[1], 0, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
+    det.sync()
+    same = bool((d_flags[:n_lines_msg[1]].cpu().numpy() == f_chk).all())
+    comp.close()
+
+    # the C-ABI two-slot path beside it: message i+1 crosses PCIe while message i runs
+    pipe_steps = e2e_steps * WINDOW_MSGS
+
+    def pipe_loop(n_steps: int) -> int:
+        lines = 0
+        for i in range(n_steps):
+            slot = i & 1
+            if i >= 2:
+                f, s = det.collect(slot)
+                lines += f.size
+            det.submit(h_msgs[1 + (i % N_DETECT)].numpy(), 0, slot)
+        for i in range(max(0, n_steps - 2), n_steps):
+            f, s = det.collect(i & 1)
+            lines += f.size
+        return lines
+    with bound_to_gpu_node(local_rank):              # the library's pinned result buffers are created here
+        pipe_loop(4)
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pipe_lines = pipe_loop(pipe_steps)
+    torch.cuda.synchronize()
+    pipe_dt = time.perf_counter() - t0
+    # plain H2D bandwidth of the same pinned buffers, for context
     t0 = time.perf_counter()
     for i in range(8):
         d_msgs[1 + i][:nbytes[1 + i]].copy_(h_msgs[1 + i], non_blocking=True)
     torch.cuda.synchronize()
     h2d_gbs = sum(nbytes[1:9]) / (time.perf_counter() - t0) / 1e9
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes[1],
-           "d2h_bytes_per_step": 5 * n_lines_msg[1] + 32, "steps": e2e_steps,
-           "api": ("dm_submit_lines/dm_collect (2 slots, pinned host buffers)" if pipelined else
-                   "dm_process_lines(host pinned buffer)") + " via DeviceDetector",
-           "ms_per_step": 1e3 * float(t.item()) / e2e_steps, "h2d_gbs_pinned": h2d_gbs,
-           "pinned_numa_local_cpus": len(numa_cpus) if numa_cpus else None}
+    e2e = {"value": e2e_value, "unit": UNIT,
+           "h2d_bytes_per_step": WINDOW_MSGS * nbytes[1], "d2h_bytes_per_step": WINDOW_MSGS * (5 * n_lines_msg[1] + 4 + 32),
+           "steps": e2e_steps, "ms_per_step": 1e3 * float(t.item()) / e2e_steps,
+           "api": "B200NewValueDetector.process(memoryview of a pinned host message) -> compact bytes, one call per message "
+                  "(detectmateservice_b200/component.py; the reference calls it from Service.process, core.py:201-203)",
+           "matches_device_resident_flags": same,
+           "abi_pipelined": {"value": pipe_lines / pipe_dt, "unit": UNIT, "messages": pipe_steps,
+                             "api": "dm_submit_lines / dm_collect, two slots (include/dmdetect.h)"},
+           "h2d_gbs_pinned": h2d_gbs, "pinned_numa_local_cpus": len(numa_cpus) if numa_cpus else None}
 
-    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
+    # ---- the other BASELINE configs, same run --------------------------------------------------
+    extra = {"configs": {}}
+    extra["configs"]["config4_windows"] = {
+        "note": "this run: windows of 8 x 64k records, one NCCL all-reduce per window when n_gpus > 1",
+        "lines_processed_timed": lines_all, "lines_per_s": value, "n_gpus": world}
+    if not args.no_extra:
+        # config 5: variable-length records (32 B - 4 KB mixture), device-resident, every rank its own messages
+        try:
+            vmsgs = _make_messages(3 + 1000 * rank, n_detect=4, lines=LINES_PER_MSG, varlen=True)
+            vdet = DeviceDetector(MONITORED_KEYS, device=local_rank, max_batch_bytes=max(len(m) for m in vmsgs) + 4096,
+                                  max_lines=LINES_PER_MSG + 16, table_log2_slots=16)
+            vdet.set_overlap(True)
+            vd = []
+            for m in vmsgs:
+                tt = torch.zeros(len(m) + 64, dtype=torch.uint8, device=dev)
+                tt[:len(m)].copy_(torch.frombuffer(bytearray(m), dtype=torch.uint8))
+                vd.append(tt)
+            vdet.enqueue_device(vd[0].data_ptr(), len(vmsgs[0]), LINES_PER_MSG, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
+            vdet.sync()
+            v_steps = 24
+            for k in range(4):
+                vdet.enqueue_device(vd[1 + k % 4].data_ptr(), len(vmsgs[1 + k % 4]), 0, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
+            barrier()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record(stream)
+            vb = 0
+            for k in range(v_steps):
+                j = 1 + k % 4
+                vdet.enqueue_device(vd[j].data_ptr(), len(vmsgs[j]), 0, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
+                vb += len(vmsgs[j]) + 5 * LINES_PER_MSG
+            v1.record(stream)
+            barrier()
+            vms = v0.elapsed_time(v1)
+            tv = torch.tensor([vms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            vms = float(tv.item())
+            extra["configs"]["config5_varlen"] = {
+                "lines_per_s": world * v_steps * LINES_PER_MSG / (vms * 1e-3), "n_gpus": world,
+                "mean_record_bytes": float(np.mean([len(m) for m in vmsgs[1:]])) / LINES_PER_MSG,
+                "roofline": {"bound": "hbm", "achieved": vb / (vms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": vb / (vms * 1e-3) / 1e9 / peak},
+                "workload": "64k records per message, lengths 32 B - 4 KB (70/25/5 % log-uniform mixture), quoted values with "
+                            "monitored-key look-alikes; 4 messages cycled, device-resident"}
+            vdet.close()
+        except Exception as e:
+            extra["configs"]["config5_varlen"] = {"error": f"{type(e).__name__}: {e}"}
+        # config 3: through NNG-framed sockets (rank 0 only: one service per GPU would each look the same)
+        if rank == 0:
+            extra["configs"]["config3_nng_pipeline"] = _config3_engine(h_msgs, nbytes, local_rank)
+        barrier()
+
+    # ---- CPU baselines (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import native
-        native.build()
         cores = os.cpu_count() or 1
-        _cpu_throughput(msgs, 4096, cores)
-        rate, secs = _cpu_throughput(msgs, 32768, cores, repeats=4)
-        one, _ = _cpu_throughput(msgs, 32768, 1, repeats=2)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"4 x 32768 records per thread on {cores} threads ({secs:.2f} s), oracle/c/dm_oracle.c; "
-                         f"reference detector (detectmatelibrary) is not vendored",
-               "single_thread": one,
-               "python_per_record": _python_per_record_rate(msgs)}
+        used, rates = _cpu_port_rates(msgs, cores, 2.0, 5)
+        _, one = _cpu_port_rates(msgs, 1, 1.0, 3)
+        cpu = {"value": float(np.median(rates)), "unit": UNIT, "cores": used, "kind": "port",
+               "sample": f"median of 5 samples of 2 s on {used} pinned threads, each thread its own trained detector over its shard "
+                         f"of one 64k-record message; oracle/c/dm_oracle.c (the reference's detector, detectmatelibrary, is not vendored)",
+               "spread": [float(min(rates)), float(max(rates))],
+               "single_thread": float(np.median(one)),
+               "reference_engine": _reference_engine_leg(msgs)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "config2: detector on 64k x 256 B synthetic audit records per message "
-                                   "(1M records = 16 messages per GPU), K=5 monitored fields, p=1e-3 anomalies",
-                       "lines_per_message": LINES_PER_MSG, "line_bytes": LINE_BYTES, "messages_per_gpu": N_MSGS,
-                       "l2_policy": "inputs larger than L2 (15 x 16 MiB cycled per GPU)",
-                       "parallelism": f"shard-by-message x{world}, 1 stats all-reduce per step" if world > 1 else "single GPU"},
+            "dtype": "u8", "data": "synthetic", "config": workload_config(world),
             "e2e": e2e, "gpu_launches": int(launches1 - launches0), "clocks": clocks, "roofline": roofline,
-            "anomalies_last_message": int(n_anom_last),
+            "extra": extra, "anomalies_last_message": int(n_anom_last),
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -459,10 +601,11 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 3 / config 5 legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -13,9 +13,9 @@ _SO = os.path.join(_HERE, "_build", "libdmoracle.so")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "c", "dm_oracle.c")
-    if force or not os.path.exists(_SO) or (
-            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_SO)):
+    srcs = [os.path.join(_HERE, "c", f) for f in ("dm_oracle.c", "dm_oracle_bench.c")]
+    if force or not os.path.exists(_SO) or any(
+            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_SO) for src in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -43,12 +43,32 @@ def lib() -> C.CDLL:
         L.dmo_export_known.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
         L.dmo_fp64.restype = C.c_uint64
         L.dmo_fp64.argtypes = [C.c_char_p, C.c_uint32]
+        L.dmo_bench_threads.restype = C.c_int
+        L.dmo_bench_threads.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                        C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
 
 def fp64(value: bytes) -> int:
     return int(lib().dmo_fp64(value, len(value)))
+
+
+def bench_threads(keys: Sequence[bytes], train, detect, n_threads: int, min_seconds: float = 2.0, n_samples: int = 5):
+    """Records/s of the C restatement on `n_threads` pinned worker threads (oracle/c/dm_oracle_bench.c):
+    returns (threads used, [rate per sample], alerts seen)."""
+    keys = [bytes(k) for k in keys]
+    blob = b"".join(keys)
+    lens = (C.c_uint32 * len(keys))(*[len(k) for k in keys])
+    tr = np.frombuffer(train, dtype=np.uint8) if not isinstance(train, np.ndarray) else train
+    de = np.frombuffer(detect, dtype=np.uint8) if not isinstance(detect, np.ndarray) else detect
+    rates = (C.c_double * n_samples)()
+    anom = C.c_uint64()
+    used = lib().dmo_bench_threads(len(keys), blob, lens, tr.ctypes.data, int(tr.size), de.ctypes.data, int(de.size),
+                                   int(n_threads), float(min_seconds), int(n_samples), rates, C.byref(anom))
+    if used < 0:
+        raise RuntimeError(f"dmo_bench_threads failed: {used}")
+    return used, [float(r) for r in rates], int(anom.value)
 
 
 class NativeOracle:
