@@ -76,6 +76,8 @@ def _csrc_sha() -> str:
     h = hashlib.sha256()
     d = os.path.join(ROOT, "detectmateservice_b200", "csrc")
     for f in sorted(os.listdir(d)):
+        if not f.endswith((".cu", ".cuh", ".h")):
+            continue
         h.update(f.encode())
         h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]

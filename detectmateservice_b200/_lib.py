@@ -35,7 +35,7 @@ class DmError(RuntimeError):
 
 
 def _sources() -> List[str]:
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [HEADER]
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [HEADER]
 
 
 def needs_build() -> bool:
