@@ -399,8 +399,19 @@ def run_gpu(args):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.finish()
     _, _, launches1 = det.profile_read()
+    # The timed region is a few milliseconds, shorter than one NVML query: the same steps are kept running for
+    # another quarter of a second (untimed) under the sampler, so that clocks / throttle reasons are seen under load
+    t_soak = time.perf_counter()
+    k = 0
+    while time.perf_counter() - t_soak < 0.25:
+        step(k)
+        k += 1
+        if k % 8 == 0:
+            stream.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.finish()
+    clocks["window"] = "timed region + 0.25 s of the same steps"
     n_anom_last = det.sync()[1]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(lines_timed)], dtype=torch.float64, device=dev)

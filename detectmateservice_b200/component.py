@@ -34,6 +34,7 @@ raises without a GPU).
 """
 from __future__ import annotations
 
+import os
 import struct
 import threading
 import time
@@ -342,19 +343,67 @@ class B200NewValueDetector(CoreComponent):
         merged = b"".join(o for o in outs if o)
         return merged or None
 
+    PIPE_MIN_BYTES = 4 << 20       # messages at least this large are cut into pieces that overlap copy and compute
+    PIPE_PIECE_BYTES = 4 << 20
+
+    def _detect_pipelined(self, data):
+        """Detection-only message, key=value records: cut it at record boundaries into ~4 MiB pieces and run them
+        through the library's two-slot path (dm_submit_lines / dm_collect): piece k+1 crosses PCIe while piece k is
+        in the kernel.  Returns (flags, scores, anomalies or None) exactly as one dm_process_lines call would."""
+        arr = np.frombuffer(data, dtype=np.uint8)
+        n = int(arr.size)
+        cuts = [0]
+        while n - cuts[-1] > self.PIPE_PIECE_BYTES + (self.PIPE_PIECE_BYTES >> 1):
+            p = cuts[-1] + self.PIPE_PIECE_BYTES
+            nl = np.flatnonzero(arr[p:p + (1 << 16)] == 10)
+            if nl.size == 0:                                  # a record longer than 64 KiB here: look further
+                nl = np.flatnonzero(arr[p:] == 10)
+                if nl.size == 0:
+                    break
+            cuts.append(p + int(nl[0]) + 1)
+        cuts.append(n)
+        k = len(cuts) - 1
+        det = self.det
+        want_anoms = self.output_format != "compact"
+        parts_f, parts_s, anoms, line_base = [], [], [], [0]
+
+        def collect(i):
+            f, s = det.collect(i & 1)
+            if want_anoms and det.last_n_anomalies:
+                anoms.extend((ln + line_base[0], mask, off + cuts[i]) for ln, mask, off in det.collect_anomalies(i & 1))
+            parts_f.append(f.copy())
+            parts_s.append(s.copy())
+            line_base[0] += int(f.size)
+        for i in range(k):
+            if i >= 2:
+                collect(i - 2)
+            det.submit(arr[cuts[i]:cuts[i + 1]], 0, i & 1)
+        for i in range(max(0, k - 2), k):
+            collect(i)
+        return np.concatenate(parts_f), np.concatenate(parts_s), (anoms if want_anoms else None)
+
     def _process_lines_one(self, data: bytes, force_delimited: bool = False) -> Optional[bytes]:
         remaining = max(0, self.data_use_training - self.n_seen)
-        flags, scores = self.det.process_lines(data, n_train_lines=remaining, copy=False)
+        anomalies = None
+        if (remaining == 0 and len(data) >= self.PIPE_MIN_BYTES and self.logformat is None and not getattr(self, "combos", None)
+                and os.environ.get("DM_KERNEL", "stream") == "stream"):
+            flags, scores, anomalies = self._detect_pipelined(data)
+            n_anom = int(np.count_nonzero(flags))
+        else:
+            flags, scores = self.det.process_lines(data, n_train_lines=remaining, copy=False)
+            n_anom = self.det.last_n_anomalies
         n = int(flags.size)
         base = self.n_seen
         self.n_seen += n
         if self.output_format == "compact":
             return struct.pack("<I", n) + flags.tobytes() + scores.tobytes()
-        if self.det.last_n_anomalies == 0:
+        if n_anom == 0:
             return None
+        if anomalies is None:
+            anomalies = self.det.anomalies()
         out = []
         raw_keys = [m.key for m in self.monitors]
-        for line_idx, mask, offset in self.det.anomalies():
+        for line_idx, mask, offset in anomalies:
             rec = _alerts.record_at(data, offset)
             if self.logformat is not None:
                 _eid, variables, lfv = self.logformat.parse(rec) or (-1, [], {})

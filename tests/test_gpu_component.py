@@ -133,3 +133,38 @@ def test_engine_pipeline_raw_messages(tmp_path):
         assert eng.counters["errors"] == 0 and not any(b for _, _, b in comp._frames)
     sink.close()
     comp.close()
+
+
+def test_large_messages_are_pipelined_and_match_the_oracle():
+    """Messages of 4 MiB and more are cut at record boundaries into pieces that overlap copy and compute
+    (component._detect_pipelined): same flags, scores and alerts as the oracle on the whole message."""
+    from detectmateservice_b200.component import decode_compact
+    from detectmateservice_b200.synth import AuditSynth, MONITORED_KEYS
+    g = AuditSynth(seed=99)
+    train, _ = g.batch(8192, inject=False)
+    msgs = [g.batch(40000, inject=True)[0], g.batch_varlen(30000, inject=True)[0]]        # ~10 MiB each
+    keys = [k.encode() for k in MONITORED_KEYS]
+    base = {"method_type": "new_value_detector", "data_use_training": 8192, "auto_config": False,
+            "global": {"g": {"header_variables": [{"pos": k} for k in MONITORED_KEYS]}}}
+    for fmt in ("compact", "alerts"):
+        orc = NativeOracle(keys)
+        orc.process(train, 8192)
+        comp = _comp({"detectors": {"B200NewValueDetector": dict(base, params={"output_format": fmt, "max_batch_bytes": 32 << 20})}})
+        assert comp.process(train) is None or fmt == "compact"
+        lines_before = 8192
+        for m in msgs:
+            assert len(m) >= comp.PIPE_MIN_BYTES
+            wf, ws, wm = orc.process(m, 0, want_masks=True)
+            out = comp.process(m)
+            if fmt == "compact":
+                f, s = decode_compact(out)
+                assert (f == wf).all() and (s == ws).all()
+            else:
+                alerts = [wire.decode_detector_schema(b) for b in wire.split_delimited(out)]
+                idx = np.flatnonzero(wf)
+                assert [int(a["logIDs"][0]) - lines_before for a in alerts] == idx.tolist()
+                assert [a["score"] for a in alerts] == ws[idx].tolist()
+                for a, i in zip(alerts, idx):
+                    assert sorted(a["alertsObtain"]) == sorted(f"Global - {MONITORED_KEYS[b]}" for b in range(5) if wm[i] >> b & 1)
+            lines_before += wf.size
+        comp.close()

@@ -26,7 +26,8 @@ import pynng  # noqa: E402
 from oracle import schemas as oschemas  # noqa: E402
 from oracle.native import NativeOracle  # noqa: E402
 
-REF_SRC = "/root/reference/src"
+REF_SRC = next((p for p in (os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref"),
+                             "/root/reference/src") if os.path.isdir(os.path.join(p, "service"))), "/root/reference/src")
 
 
 # ------------------------------------------------------------------------------------------
@@ -367,7 +368,7 @@ def test_component_config_validation():
 # ------------------------------------------------------------------------------------------
 # the UNMODIFIED reference service, with the shims, loading the B200 component
 # ------------------------------------------------------------------------------------------
-@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference checkout not present (GPU box)")
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="the reference service is neither in baseline/_ref nor in /root/reference/src")
 def test_reference_service_loads_b200_component(tmp_path, monkeypatch, golden_dir):
     import yaml
     monkeypatch.syspath_prepend(REF_SRC)
