@@ -343,8 +343,12 @@ class B200NewValueDetector(CoreComponent):
         merged = b"".join(o for o in outs if o)
         return merged or None
 
-    PIPE_MIN_BYTES = 4 << 20       # messages at least this large are cut into pieces that overlap copy and compute
-    PIPE_PIECE_BYTES = 4 << 20
+    # Messages at least this large are cut into pieces that overlap copy and compute.  Measured on a B200 / PCIe 5 box
+    # (scripts/e2e_pieces.py): a piece costs ~150-280 us of latency (copy + kernel + two small copies back, each with a
+    # host synchronisation), so pieces below ~12 MiB LOSE against one call (16 MiB message: 0.42 ms in one call, 0.51 /
+    # 0.67 / 1.09 ms in 8 / 4 / 2 MiB pieces); from two 12 MiB pieces on the link stays busy (0.21 G records/s).
+    PIPE_MIN_BYTES = 24 << 20
+    PIPE_PIECE_BYTES = 12 << 20
 
     def _detect_pipelined(self, data):
         """Detection-only message, key=value records: cut it at record boundaries into ~4 MiB pieces and run them

@@ -136,7 +136,7 @@ def test_engine_pipeline_raw_messages(tmp_path):
 
 
 def test_large_messages_are_pipelined_and_match_the_oracle():
-    """Messages of 4 MiB and more are cut at record boundaries into pieces that overlap copy and compute
+    """Large messages are cut at record boundaries into pieces that overlap copy and compute
     (component._detect_pipelined): same flags, scores and alerts as the oracle on the whole message."""
     from detectmateservice_b200.component import decode_compact
     from detectmateservice_b200.synth import AuditSynth, MONITORED_KEYS
@@ -150,6 +150,7 @@ def test_large_messages_are_pipelined_and_match_the_oracle():
         orc = NativeOracle(keys)
         orc.process(train, 8192)
         comp = _comp({"detectors": {"B200NewValueDetector": dict(base, params={"output_format": fmt, "max_batch_bytes": 32 << 20})}})
+        comp.PIPE_MIN_BYTES = comp.PIPE_PIECE_BYTES = 4 << 20          # (the defaults only cut much larger messages)
         assert comp.process(train) is None or fmt == "compact"
         lines_before = 8192
         for m in msgs:
