@@ -25,6 +25,12 @@ void dmo_destroy(dmo* d);
 uint64_t dmo_process(dmo* d, const uint8_t* buf, uint64_t n, uint64_t n_train_lines, uint8_t* flags, float* scores, uint32_t* masks);
 
 typedef struct {
+    /* what the worker needs to build ITS detector on ITS core (first touch: the state lands on the worker's NUMA node) */
+    int n_keys;
+    const uint8_t* keys_blob;
+    const uint32_t* key_lens;
+    const uint8_t* train;
+    uint64_t train_bytes;
     dmo* det;
     const uint8_t* shard;
     uint64_t shard_bytes;
@@ -50,6 +56,14 @@ static void* worker_main(void* arg) {
         CPU_ZERO(&set);
         CPU_SET(w->cpu, &set);
         pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
+    if (!w->det) {
+        w->det = dmo_create(w->n_keys, w->keys_blob, w->key_lens);
+        if (w->train && w->train_bytes) dmo_process(w->det, w->train, w->train_bytes, ~0ull, NULL, NULL, NULL);
+        w->flags = (uint8_t*)malloc((256u << 10) + 4096);
+        w->scores = (float*)malloc(((256u << 10) + 4096) * sizeof(float));
+        memset(w->flags, 0, (256u << 10) + 4096);
+        memset(w->scores, 0, ((256u << 10) + 4096) * sizeof(float));
     }
     pthread_barrier_wait(w->start);
     uint64_t lines = 0, anomalies = 0;
@@ -96,8 +110,8 @@ int dmo_bench_threads(int n_keys, const uint8_t* keys_blob, const uint32_t* key_
     pthread_barrier_t start;
     uint64_t cut = 0;
     for (int t = 0; t < n_threads; t++) {
-        w[t].det = dmo_create(n_keys, keys_blob, key_lens);
-        if (train && train_bytes) dmo_process(w[t].det, train, train_bytes, ~0ull, NULL, NULL, NULL);
+        w[t].n_keys = n_keys; w[t].keys_blob = keys_blob; w[t].key_lens = key_lens;
+        w[t].train = train; w[t].train_bytes = train_bytes;
         uint64_t end = t + 1 == n_threads ? detect_bytes : detect_bytes * (uint64_t)(t + 1) / (uint64_t)n_threads;
         if (end < detect_bytes) {
             const uint8_t* nl = (const uint8_t*)memchr(detect + end, '\n', detect_bytes - end);
@@ -107,8 +121,6 @@ int dmo_bench_threads(int n_keys, const uint8_t* keys_blob, const uint32_t* key_
         w[t].shard = detect + cut;
         w[t].shard_bytes = end - cut;
         cut = end;
-        w[t].flags = (uint8_t*)malloc((256u << 10) + 4096);
-        w[t].scores = (float*)malloc(((256u << 10) + 4096) * sizeof(float));
         w[t].cpu = n_cpus > 0 ? cpus[t % n_cpus] : -1;
         w[t].stop = &stop;
         w[t].start = &start;
@@ -118,7 +130,7 @@ int dmo_bench_threads(int n_keys, const uint8_t* keys_blob, const uint32_t* key_
         stop = 0;
         pthread_barrier_init(&start, NULL, (unsigned)n_threads + 1);
         for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, worker_main, &w[t]);
-        pthread_barrier_wait(&start);
+        pthread_barrier_wait(&start);              /* (in the first sample the workers build and train their detectors first) */
         const double t0 = now_s();
         while (now_s() - t0 < min_seconds) usleep(2000);
         stop = 1;
