@@ -123,6 +123,7 @@ SYMBOLS = {
     "dm_get_global_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "dm_profile_enable": (C.c_int, [_P, C.c_int]),
     "dm_set_overlap": (C.c_int, [_P, C.c_int]),
+    "dm_window_pending_keys": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "dm_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 

@@ -119,16 +119,20 @@ __device__ __forceinline__ bool dm_table_contains_volatile(const DmTable& t, uin
     return false;
 }
 
-// Returns true if this call inserted the key (it was not present).
-__device__ __forceinline__ bool dm_table_insert(const DmTable& t, uint64_t key, unsigned int* err) {
+// Returns true if this call inserted the key (it was not present).  learnt = the key was learnt from this rank's own
+// records: it is appended to the novel list, which the window exchange ships to the other ranks (keys that arrive
+// from peers or from dm_import_known are not shipped again).
+__device__ __forceinline__ bool dm_table_insert(const DmTable& t, uint64_t key, unsigned int* err, bool learnt = true) {
     uint32_t i = dm_slot_of(key, t.mask);
     for (uint32_t probes = 0; probes <= t.mask; ++probes) {
         unsigned long long v = atomicCAS(t.slots + i, 0ull, (unsigned long long)key);
         if (v == 0ull) {
             unsigned long long c = atomicAdd(t.count, 1ull);
             if (c + 1 > t.limit) atomicOr(err, DM_DEVERR_TABLE_FULL);
-            unsigned long long j = atomicAdd(t.novel_count, 1ull);
-            if (j < t.novel_cap) t.novel[j] = key; else atomicOr(err, DM_DEVERR_NOVEL_OVERFLOW);
+            if (learnt) {
+                unsigned long long j = atomicAdd(t.novel_count, 1ull);
+                if (j < t.novel_cap) t.novel[j] = key; else atomicOr(err, DM_DEVERR_NOVEL_OVERFLOW);
+            }
             return true;
         }
         if (v == key) return false;

@@ -80,6 +80,7 @@ struct dm_handle {
     unsigned long long* h_stats = nullptr;         // pinned
     DmTable table;
     uint64_t novel_exported = 0;         // novel keys already shipped in a window
+    uint64_t novel_pending = 0;          // novel keys the last window could not carry (more than DM_WINDOW_KEYS learnt)
     DmRowsScratch rows;                  // row / record index scratch (K_A: lanes and log_format kernels)
     DmxScratch dmx;                      // stream-variant scratch (default kernel)
     uint64_t last_nbytes = 0;
@@ -888,7 +889,7 @@ extern "C" int dm_get_global_stats(dm_handle* h, dm_stats_t* out) {
 __global__ void dm_k_insert_keys(DmTable t, const unsigned long long* __restrict__ keys, uint64_t n, unsigned int* err) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         unsigned long long k = keys[i];
-        if (k) dm_table_insert(t, k, err);
+        if (k) dm_table_insert(t, k, err, false);
     }
 }
 
@@ -896,17 +897,16 @@ extern "C" int dm_export_known(dm_handle* h, uint64_t* keys_out, uint64_t cap, u
     if (!h || !n_out) return dm_fail(DM_ERR_ARG, "NULL argument");
     DM_CUDA(cudaSetDevice(h->device));
     DM_CUDA(cudaStreamSynchronize(h->last_stream));
-    unsigned long long cnt[2];
-    DM_CUDA(cudaMemcpy(cnt, h->table.count, sizeof(cnt), cudaMemcpyDeviceToHost));
-    // the novel list holds every key in insertion order (bounded by DM_NOVEL_CAP, checked at insert)
-    const uint64_t n = std::min<uint64_t>(cnt[1], h->table.novel_cap);
+    // every key of the table (own records, peers, dm_import_known): the slots themselves are read back
+    const uint64_t slots = (uint64_t)h->table.mask + 1;
+    std::vector<unsigned long long> tmp(slots);
+    DM_CUDA(cudaMemcpy(tmp.data(), h->table.slots, slots * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < slots; ++i)
+        if (tmp[i]) tmp[n++] = tmp[i];
+    std::sort(tmp.begin(), tmp.begin() + n);
     *n_out = n;
-    if (keys_out && cap) {
-        std::vector<unsigned long long> tmp(n);
-        if (n) DM_CUDA(cudaMemcpy(tmp.data(), h->table.novel, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        std::sort(tmp.begin(), tmp.end());
-        memcpy(keys_out, tmp.data(), std::min<uint64_t>(n, cap) * sizeof(uint64_t));
-    }
+    if (keys_out && cap) memcpy(keys_out, tmp.data(), std::min<uint64_t>(n, cap) * sizeof(uint64_t));
     return DM_OK;
 }
 
@@ -935,6 +935,7 @@ extern "C" int dm_reset(dm_handle* h) {
     DM_CUDA(cudaMemset(h->d_stats, 0, 3 * DM_STATS_WORDS * sizeof(unsigned long long)));
     DM_CUDA(cudaMemset(h->d_hdr, 0, sizeof(DmBatchHeader)));
     h->novel_exported = 0;
+    h->novel_pending = 0;
     return DM_OK;
 }
 
@@ -984,7 +985,7 @@ __global__ void dm_k_window_import(const unsigned long long* __restrict__ in, ui
         const uint64_t cnt = in[seg];
         for (uint64_t j = tid; j < cnt && j < DM_WINDOW_KEYS; j += nth) {
             unsigned long long k = in[seg + 1 + j];
-            if (k) dm_table_insert(t, k, err);
+            if (k) dm_table_insert(t, k, err, false);
         }
     }
 }
@@ -1001,9 +1002,10 @@ extern "C" int dm_window_export(dm_handle* h, uint64_t* dev_buf, uint32_t rank, 
         DM_CUDA(cudaMemcpyAsync(cnt, h->table.count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         DM_CUDA(cudaStreamSynchronize(st));
         novel_to = std::min<uint64_t>(cnt[1], h->table.novel_cap);
-        if (novel_to - h->novel_exported > DM_WINDOW_KEYS)
-            return dm_fail(DM_ERR_CAPACITY, "%llu keys learnt in one window, at most %u can be exchanged; shorten the training window",
-                           (unsigned long long)(novel_to - h->novel_exported), DM_WINDOW_KEYS);
+        // at most DM_WINDOW_KEYS keys travel per window; the rest goes with the next one (dm_window_pending_keys).
+        // Failing here instead would leave the other ranks waiting in the all-reduce.
+        if (novel_to - h->novel_exported > DM_WINDOW_KEYS) novel_to = h->novel_exported + DM_WINDOW_KEYS;
+        h->novel_pending = std::min<uint64_t>(cnt[1], h->table.novel_cap) - novel_to;
     }
     const uint64_t n_words = dm_window_words(h, world, with_keys);
     const uint64_t seg_off = (uint64_t)DM_STATS_WORDS + (uint64_t)rank * (1ull + DM_WINDOW_KEYS);
@@ -1015,6 +1017,12 @@ extern "C" int dm_window_export(dm_handle* h, uint64_t* dev_buf, uint32_t rank, 
     return DM_OK;
 }
 
+extern "C" int dm_window_pending_keys(dm_handle* h, uint64_t* n_out) {
+    if (!h || !n_out) return dm_fail(DM_ERR_ARG, "NULL argument");
+    *n_out = h->novel_pending;
+    return DM_OK;
+}
+
 extern "C" int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream_) {
     if (!h || !dev_buf || rank >= world) return dm_fail(DM_ERR_ARG, "bad window arguments");
     DM_CUDA(cudaSetDevice(h->device));
@@ -1023,13 +1031,7 @@ extern "C" int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t 
     dm_k_window_import<<<with_keys ? 256 : 1, 256, 0, st>>>((const unsigned long long*)dev_buf, world, rank,
                                                           h->d_stats_global, h->table, &h->d_hdr->error, with_keys);
     DM_CUDA(cudaGetLastError());
-    if (with_keys) {
-        // keys received from peers are in the table now but must not be re-exported
-        unsigned long long cnt[2];
-        DM_CUDA(cudaMemcpyAsync(cnt, h->table.count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-        DM_CUDA(cudaStreamSynchronize(st));
-        h->novel_exported = std::min<uint64_t>(cnt[1], h->table.novel_cap);
-    }
+    // (keys received from peers are inserted without joining the novel list: they are not shipped again)
     return DM_OK;
 }
 

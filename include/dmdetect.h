@@ -228,6 +228,10 @@ uint64_t dm_table_key(uint32_t field, const uint8_t* value, uint32_t len);
 uint64_t dm_window_words(dm_handle* h, uint32_t world, int with_keys);
 int dm_window_export(dm_handle* h, uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream);
 int dm_window_import(dm_handle* h, const uint64_t* dev_buf, uint32_t rank, uint32_t world, int with_keys, void* stream);
+/* A window carries at most 65536 newly learnt keys per rank.  After an export with keys: how many of this rank's
+ * learnt keys are still waiting (0 in all but pathological training windows).  When any rank reports > 0 the caller
+ * runs another exchange with keys before detection starts (all ranks call the collective the same number of times). */
+int dm_window_pending_keys(dm_handle* h, uint64_t* n_out);
 
 /* The same exchange done by the library itself: export, ncclAllReduce(sum, uint64) over the
  * handle's own communicator, import -- enqueued on `stream` by ONE call (no host work per
