@@ -102,6 +102,7 @@ SYMBOLS = {
     "dm_host_cache_flush": (C.c_int, [_P, C.c_uint64]),
     "dm_debug_rows_timeline": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint32)]),
     "dm_set_format": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p)]),
+    "dm_set_format_ex": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32]),
     "dm_process_records": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64,
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dm_submit_lines": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint32]),
@@ -143,8 +144,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.dm_abi_version() != 3:
-        raise RuntimeError(f"libdmdetect ABI version {lib.dm_abi_version()} != 3")
+    if lib.dm_abi_version() != 4:
+        raise RuntimeError(f"libdmdetect ABI version {lib.dm_abi_version()} != 4")
     _lib = lib
     return lib
 

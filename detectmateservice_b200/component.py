@@ -149,10 +149,10 @@ class B200NewValueDetector(CoreComponent):
             templates = list(cfg.get("templates") or [])
             if cfg.get("path_templates"):
                 templates += load_templates(str(cfg["path_templates"]))
-            for k in ("remove_spaces", "remove_punctuation", "lowercase"):
-                if cfg.get(k):
-                    raise ValueError(f"{k}: true is not supported by the fused matcher (templates are matched verbatim)")
-            self.logformat = LogFormat(cfg["log_format"], templates, str(cfg.get("content_name", "Content")))
+            from .logformat import norm_flags
+            # R-norm (params.remove_spaces / remove_punctuation / lowercase, ibid. lines 82-84)
+            flags = norm_flags(bool(cfg.get("remove_spaces")), bool(cfg.get("remove_punctuation")), bool(cfg.get("lowercase")))
+            self.logformat = LogFormat(cfg["log_format"], templates, str(cfg.get("content_name", "Content")), flags)
         self.device = int(cfg.get("device", 0))
         self.max_batch_bytes = int(cfg.get("max_batch_bytes", 64 << 20))
         self.table_log2_slots = int(cfg.get("table_log2_slots", 20))
@@ -174,7 +174,7 @@ class B200NewValueDetector(CoreComponent):
             self._det.set_monitors([{"event_id": m.event_id, "source": m.source, "pos": m.pos} for m in self.monitors])
             if self.logformat is not None:
                 lf = self.logformat
-                self._det.set_format(lf.source, lf.template_sources, lf.content_name)
+                self._det.set_format(lf.source, lf.template_sources, lf.content_name, lf.flags)
         return self._det
 
     # ------------------------------------------------------------------ receive buffers (lent to the transport)

@@ -28,7 +28,21 @@ struct FmtBuilder {
         return true;
     }
 
+    // R-norm on one literal of a template: the bytes DmFormat.norm_drop names are
+    // dropped, upper-case ASCII letters are folded when DM_NORM_LOWERCASE is set
+    std::string normalised(const std::string& lit) const {
+        if (!f.norm_flags) return lit;
+        std::string o;
+        for (unsigned char c : lit) {
+            if ((f.norm_drop[c >> 5] >> (c & 31)) & 1u) continue;
+            if ((f.norm_flags & DM_NORM_LOWERCASE) && c >= 'A' && c <= 'Z') c = (unsigned char)(c + 32);
+            o.push_back((char)c);
+        }
+        return o;
+    }
+
     // text = L0 C0 L1 C1 ...; named: captures are <Name> (name = [A-Za-z0-9_]+), else the token <*>
+    // (templates, named == false, are normalised literal by literal)
     bool add_chain(const std::string& text, bool named, std::vector<std::string>* names) {
         const uint32_t c = f.n_chains;
         if (c >= DM_FMT_MAX_CHAINS) { err = "too many templates (at most 63)"; return false; }
@@ -51,6 +65,8 @@ struct FmtBuilder {
             }
             if (cap_end == std::string::npos) { lit.push_back(text[i]); ++i; last_was_capture = false; continue; }
             if (last_was_capture) { err = "two captures with nothing between them"; return false; }
+            if (!named) lit = normalised(lit);
+            if (lits_here > 0 && lit.empty()) { err = "normalisation leaves nothing between two wildcards"; return false; }
             if (!add_literal(lit)) return false;                   // the literal in front of this capture (L0 may be empty)
             ++lits_here;
             lit.clear();
@@ -58,8 +74,9 @@ struct FmtBuilder {
             last_was_capture = true;
             i = cap_end;
         }
-        if (last_was_capture) {
-            f.chain_endcap[c] = 1;
+        if (!named) lit = normalised(lit);
+        if (last_was_capture || (!named && f.norm_flags && lits_here > 0 && lit.empty())) {
+            f.chain_endcap[c] = 1;                                 // (`... <*>'` normalised: the last wildcard runs to the end)
         } else {
             if (!add_literal(lit)) return false;                   // the final literal (or the whole text)
             ++lits_here;
@@ -75,9 +92,18 @@ struct FmtBuilder {
 
 // Returns false and sets *err on a configuration error.
 inline bool dm_format_build(const char* log_format, const char* content_name, uint32_t n_templates,
-                            const char* const* templates, const DmMonitors& hm, DmFormat* out, std::string* err) {
+                            const char* const* templates, uint32_t norm_flags, const DmMonitors& hm, DmFormat* out,
+                            std::string* err) {
     dm_format_detail::FmtBuilder b;
     memset(&b.f, 0, sizeof(DmFormat));
+    if (norm_flags & ~(DM_NORM_REMOVE_SPACES | DM_NORM_REMOVE_PUNCTUATION | DM_NORM_LOWERCASE)) { *err = "unknown normalisation flag"; return false; }
+    b.f.norm_flags = norm_flags;
+    for (unsigned c = 0; c < 128; ++c) {
+        const bool space = (c >= 0x09 && c <= 0x0D) || c == 0x20;
+        const bool punct = (c >= 0x21 && c <= 0x2F) || (c >= 0x3A && c <= 0x40) || (c >= 0x5B && c <= 0x60) || (c >= 0x7B && c <= 0x7E);
+        if ((space && (norm_flags & DM_NORM_REMOVE_SPACES)) || (punct && (norm_flags & DM_NORM_REMOVE_PUNCTUATION)))
+            b.f.norm_drop[c >> 5] |= 1u << (c & 31);
+    }
     if (!b.add_chain(log_format, true, &b.header_names)) { *err = std::string("log_format: ") + b.err; return false; }
     for (size_t i = 0; i < b.header_names.size(); ++i)
         for (size_t j = 0; j < i; ++j)

@@ -49,15 +49,32 @@ struct DmFormat {
     // a lane keeps only those, in slot popc(need & ((1 << capture) - 1))
     uint32_t chain_need[DM_FMT_MAX_CHAINS];
     uint32_t max_slots;                               // max over chains of popc(chain_need)
-    uint32_t pad2_[3];
+    // R-norm (MatcherParser params.remove_spaces / remove_punctuation / lowercase): the Content text
+    // is rewritten without the bytes of norm_drop (a 256-bit set), letters folded, before the
+    // template chains -- whose literals the host normalised the same way -- are matched against it
+    uint32_t norm_flags;
+    uint32_t pad2_[2];
+    uint32_t norm_drop[8];
 };
+#ifndef DM_NORM_LOWERCASE                             // (the same bits as include/dmdetect.h)
+#define DM_NORM_REMOVE_SPACES 1u
+#define DM_NORM_REMOVE_PUNCTUATION 2u
+#define DM_NORM_LOWERCASE 4u
+#endif
 
 // 4 text bytes starting at any byte offset (little endian).  Reads the two aligned words
 // around it: up to 7 bytes past `p`, covered by the slack every message buffer carries.
-__device__ __forceinline__ uint32_t dm_fmt_load4(const uint8_t* __restrict__ buf, uint32_t p) {
+// NC: the text is read-only for the whole kernel (the message) and goes through the non-coherent
+// path; !NC: it is the normalised copy the SAME thread wrote earlier in this kernel (R-norm), which
+// ld.global.nc must not be used on -- those loads are L2-coherent (ld.global.cg).
+template <bool NC>
+__device__ __forceinline__ uint32_t dm_fmt_ldw(const uint32_t* w) { return NC ? __ldg(w) : __ldcg(w); }
+
+template <bool NC = true>
+__device__ __forceinline__ uint32_t dm_fmt_load4(const uint8_t* buf, uint32_t p) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(buf) + p;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3u) * 8u);
+    return __funnelshift_r(dm_fmt_ldw<NC>(w), dm_fmt_ldw<NC>(w + 1), (uint32_t)(a & 3u) * 8u);
 }
 
 __device__ __forceinline__ uint32_t dm_fmt_tail_mask(uint32_t nbytes) {     // nbytes in 1..4
@@ -65,11 +82,12 @@ __device__ __forceinline__ uint32_t dm_fmt_tail_mask(uint32_t nbytes) {     // n
 }
 
 // dm_fp64 of text[p, p+n) with word loads
-__device__ __forceinline__ uint64_t dm_fmt_fp64(const uint8_t* __restrict__ buf, uint32_t p, uint32_t n) {
+template <bool NC = true>
+__device__ __forceinline__ uint64_t dm_fmt_fp64(const uint8_t* buf, uint32_t p, uint32_t n) {
     DmHashState st;
     dm_hash_init(st);
     for (uint32_t i = 0; i < n; i += 4) {
-        uint32_t w = dm_fmt_load4(buf, p + i);
+        uint32_t w = dm_fmt_load4<NC>(buf, p + i);
         if (n - i < 4) w &= dm_fmt_tail_mask(n - i);
         dm_hash_word(st, w);
     }
@@ -89,7 +107,8 @@ __device__ __forceinline__ uint64_t dm_fmt_fp64(const uint8_t* __restrict__ buf,
 // earliest q in [pos, e - len] with text[q, q+len) == literal (len >= 1), else DM_FMT_NOT_FOUND.
 // Four start positions per step (one aligned word): the four compares are independent, which
 // matters because a lane is one long dependent chain and only ~14 warps per SM hide latency.
-__device__ __forceinline__ uint32_t dm_fmtl_find(const uint8_t* __restrict__ buf, uint32_t pos, uint32_t e,
+template <bool NC>
+__device__ __forceinline__ uint32_t dm_fmtl_find(const uint8_t* buf, uint32_t pos, uint32_t e,
                                                  const uint32_t* lit, uint32_t len) {
     if (e < pos + len) return DM_FMT_NOT_FOUND;
     const uint32_t last = e - len;
@@ -99,7 +118,7 @@ __device__ __forceinline__ uint32_t dm_fmtl_find(const uint8_t* __restrict__ buf
     const uint32_t mis = (uint32_t)(base_addr & 3u);               // buf is word aligned in the product (mis == 0)
     uint32_t q0 = ((pos + mis) & ~3u) - mis;                       // position of the aligned word that holds pos (may be pos-3..pos)
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(base_addr + q0);
-    uint32_t lo = __ldg(wp), hi = __ldg(wp + 1), nx = __ldg(wp + 2);
+    uint32_t lo = dm_fmt_ldw<NC>(wp), hi = dm_fmt_ldw<NC>(wp + 1), nx = dm_fmt_ldw<NC>(wp + 2);
     uint32_t found = DM_FMT_NOT_FOUND;
     for (;;) {
         const uint32_t x1 = __funnelshift_r(lo, hi, 8), x2 = __funnelshift_r(lo, hi, 16), x3 = __funnelshift_r(lo, hi, 24);
@@ -113,21 +132,22 @@ __device__ __forceinline__ uint32_t dm_fmtl_find(const uint8_t* __restrict__ buf
             bool ok = true;
             for (uint32_t j = 4; j < len; j += 4) {
                 const uint32_t lm = len - j >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len - j);
-                if (((dm_fmt_load4(buf, q + j) ^ lit[j >> 2]) & lm) != 0) { ok = false; break; }
+                if (((dm_fmt_load4<NC>(buf, q + j) ^ lit[j >> 2]) & lm) != 0) { ok = false; break; }
             }
             if (ok) { found = q; break; }
         }
         if (found != DM_FMT_NOT_FOUND || q0 + 4u > last) break;
         q0 += 4;
-        lo = hi; hi = nx; ++wp; nx = __ldg(wp + 2);
+        lo = hi; hi = nx; ++wp; nx = dm_fmt_ldw<NC>(wp + 2);
     }
     return found;
 }
 
-__device__ __forceinline__ bool dm_fmtl_match_at(const uint8_t* __restrict__ buf, uint32_t q, const uint32_t* lit, uint32_t len) {
+template <bool NC>
+__device__ __forceinline__ bool dm_fmtl_match_at(const uint8_t* buf, uint32_t q, const uint32_t* lit, uint32_t len) {
     for (uint32_t j = 0; j < len; j += 4) {
         const uint32_t m = len - j >= 4 ? 0xFFFFFFFFu : dm_fmt_tail_mask(len - j);
-        if (((dm_fmt_load4(buf, q + j) ^ lit[j >> 2]) & m) != 0) return false;
+        if (((dm_fmt_load4<NC>(buf, q + j) ^ lit[j >> 2]) & m) != 0) return false;
     }
     return true;
 }
@@ -138,7 +158,8 @@ __device__ __forceinline__ bool dm_fmtl_match_at(const uint8_t* __restrict__ buf
 // that is inactive or has already failed just idles): the __syncwarp() after each literal is
 // what keeps the 32 records of a warp in lockstep -- without it the lanes drift apart through
 // the data-dependent search loops and the warp degenerates to 3 active threads per instruction.
-__device__ uint32_t dm_fmtl_match_chain(const DmFormat& f, uint32_t c, const uint8_t* __restrict__ buf, uint32_t s,
+template <bool NC>
+__device__ uint32_t dm_fmtl_match_chain(const DmFormat& f, uint32_t c, const uint8_t* buf, uint32_t s,
                                         uint32_t e, uint2* caps, bool active) {
     const uint32_t first = f.chain_first[c];
     const uint32_t n = (uint32_t)f.chain_first[c + 1] - first;
@@ -152,11 +173,11 @@ __device__ uint32_t dm_fmtl_match_chain(const DmFormat& f, uint32_t c, const uin
             const uint32_t* lit = f.pool + f.lit_off[first + i];
             uint32_t q = DM_FMT_NOT_FOUND;
             if (i == 0) {
-                if (e >= pos + len && dm_fmtl_match_at(buf, pos, lit, len)) q = pos;
+                if (e >= pos + len && dm_fmtl_match_at<NC>(buf, pos, lit, len)) q = pos;
             } else if (i == n - 1 && !endcap) {
-                if (e >= pos + len && dm_fmtl_match_at(buf, e - len, lit, len)) q = e - len;
+                if (e >= pos + len && dm_fmtl_match_at<NC>(buf, e - len, lit, len)) q = e - len;
             } else {
-                q = dm_fmtl_find(buf, pos, e, lit, len);
+                q = dm_fmtl_find<NC>(buf, pos, e, lit, len);
             }
             if (q == DM_FMT_NOT_FOUND) {
                 ok = false;
@@ -179,8 +200,41 @@ __device__ uint32_t dm_fmtl_match_chain(const DmFormat& f, uint32_t c, const uin
     return n ? n - 1 : 0;
 }
 
-template <bool TRAIN>
-__global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArgs a, const DmFormat* __restrict__ gfmt) {
+// R-norm: text[s, s+len) without the bytes of f.norm_drop, letters folded, written to nbuf at
+// the SAME offset (the copy is never longer, so the records of a message cannot collide).
+// Aligned words are stored whole; the first and last partial word byte by byte, because the
+// rest of those words belongs to a neighbouring record another lane may be writing.
+// Returns the normalised length.
+__device__ __forceinline__ uint32_t dm_fmtl_normalise(const DmFormat& f, const uint8_t* __restrict__ buf, uint8_t* nbuf,
+                                                      uint32_t s, uint32_t len) {
+    const bool fold = (f.norm_flags & DM_NORM_LOWERCASE) != 0;
+    uint32_t o = s, acc = 0;
+    for (uint32_t i = 0; i < len; i += 4) {
+        const uint32_t w = dm_fmt_load4(buf, s + i);
+        const uint32_t nb = len - i < 4u ? len - i : 4u;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint32_t c = (w >> (8u * j)) & 0xFFu;
+            if (j >= nb || ((f.norm_drop[c >> 5] >> (c & 31u)) & 1u)) continue;
+            if (fold && c - 0x41u < 26u) c += 0x20u;
+            acc |= c << ((o & 3u) * 8u);
+            ++o;
+            if ((o & 3u) == 0) {
+                if (o - 4u >= s) *reinterpret_cast<uint32_t*>(nbuf + (o - 4u)) = acc;
+                else for (uint32_t b = s; b < o; ++b) nbuf[b] = (uint8_t)(acc >> ((b & 3u) * 8u));
+                acc = 0;
+            }
+        }
+    }
+    const uint32_t w0 = o & ~3u;
+    for (uint32_t b = w0 > s ? w0 : s; b < o; ++b) nbuf[b] = (uint8_t)(acc >> ((b & 3u) * 8u));
+    return o - s;
+}
+
+// NORM: R-norm is configured; the templates then run on `nbuf`, the per-message normalised copy.
+template <bool TRAIN, bool NORM>
+__global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArgs a, const DmFormat* __restrict__ gfmt,
+                                                                     uint8_t* nbuf) {
     // [2][max_slots][DM_FMTL_THREADS]: header captures, template captures
 #ifdef DM_EMU
     uint2* s_caps = reinterpret_cast<uint2*>(g_emu_dyn_smem.data());
@@ -223,15 +277,20 @@ __global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArg
         const bool act = line < hi;
         const uint32_t s = act ? a.line_start[line] : 0u;
         const uint32_t e = act ? a.line_start[line + 1] - 1 : 0u;
-        const uint32_t n_hcaps = dm_fmtl_match_chain(sf, 0, buf, s, e, hcap, act);
+        const uint32_t n_hcaps = dm_fmtl_match_chain<true>(sf, 0, buf, s, e, hcap, act);
         const bool hok = n_hcaps != 0xFFFFFFFFu;
         int32_t eid = -1;
         uint32_t n_vars = 0;
         if (sf.content_capture != DM_FMT_NONE) {
             uint2 cc = make_uint2(0, 0);
             if (hok) cc = hcap[(uint32_t)__popc(sf.chain_need[0] & ((1u << sf.content_capture) - 1u)) * DM_FMTL_THREADS];
+            if (NORM) {
+                if (hok) cc.y = dm_fmtl_normalise(sf, buf, nbuf, cc.x, cc.y);
+                __syncwarp();
+            }
+            const uint8_t* tbuf = NORM ? nbuf : buf;
             for (uint32_t t = 1; t < sf.n_chains; ++t) {
-                const uint32_t nv = dm_fmtl_match_chain(sf, t, buf, cc.x, cc.x + cc.y, vcap, hok && eid < 0);
+                const uint32_t nv = dm_fmtl_match_chain<!NORM>(sf, t, tbuf, cc.x, cc.x + cc.y, vcap, hok && eid < 0);
                 if (nv != 0xFFFFFFFFu) { eid = (int32_t)t - 1; n_vars = nv; }
             }
         }
@@ -250,7 +309,9 @@ __global__ void __launch_bounds__(DM_FMTL_THREADS) dm_k_format_lanes(DmDetectArg
                 }
             }
             if (use) {
-                const uint64_t key = dm_make_key(dm_fmt_fp64(buf, cap.x, cap.y), dm_field_salt(k));
+                const uint64_t fp = (NORM && sf.mon_source[k]) ? dm_fmt_fp64<false>(nbuf, cap.x, cap.y)
+                                                               : dm_fmt_fp64<true>(buf, cap.x, cap.y);
+                const uint64_t key = dm_make_key(fp, dm_field_salt(k));
                 if (TRAIN) dm_table_insert(a.table, key, &a.hdr->error);
                 else if (!dm_table_contains(a.table, key)) unknown |= 1u << k;
             }

@@ -91,6 +91,8 @@ struct dm_handle {
     bool mons_set = false;
     DmMonitors h_mons;             // host copy (dm_set_monitors + dm_set_combos)
     DmFormat* d_fmt = nullptr;     // log_format + templates (dm_set_format)
+    uint8_t* d_norm = nullptr;     // R-norm: the message's normalised Content text (dm_set_format_ex with flags)
+    uint32_t fmt_norm = 0;
     void* nccl_comm[2] = {nullptr, nullptr};   // own NCCL communicators (dm_nccl_init): windows alternate between them
     uint32_t nccl_n = 0, nccl_rank = 0, nccl_world = 1;
     unsigned long long* d_win[2] = {nullptr, nullptr};   // window exchange buffers of dm_window_allreduce
@@ -305,7 +307,7 @@ extern "C" int dm_destroy(dm_handle* h) {
     cudaFree(h->d_line_start); cudaFree(h->d_flags); cudaFree(h->d_scores); cudaFree(h->d_hdr);
     cudaFreeHost(h->h_hdr); cudaFree(h->d_anoms); cudaFree(h->d_stats); cudaFreeHost(h->h_stats);
     cudaFree(h->table.slots); cudaFree(h->table.novel); cudaFree(h->table.count);
-    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons); cudaFree(h->d_fmt);
+    cudaFree(h->d_vals); cudaFree(h->d_masks); cudaFree(h->d_mons); cudaFree(h->d_fmt); cudaFree(h->d_norm);
     for (int k = 0; k < 2; ++k) {
         cudaFree(h->d_win[k]);
         if (h->ev_win_done[k]) cudaEventDestroy(h->ev_win_done[k]);
@@ -403,13 +405,16 @@ extern "C" int dm_process_lines(dm_handle* h, const uint8_t* buf, uint64_t nbyte
             const uint64_t want = (max_recs + DM_FMTL_THREADS - 1) / DM_FMTL_THREADS;
             const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->sm_count * 32));
             const size_t smem = (size_t)2 * h->fmt_slots * DM_FMTL_THREADS * sizeof(uint2);
+            const bool norm = h->fmt_norm != 0;
             if (n_train_lines > 0) {
                 a.line_lo = 0; a.line_hi = n_train_lines;
-                dm_launch_pdl_smem(dm_k_format_lanes<true>, (unsigned)grid, DM_FMTL_THREADS, smem, st, false, a, (const DmFormat*)h->d_fmt);
+                dm_launch_pdl_smem(norm ? dm_k_format_lanes<true, true> : dm_k_format_lanes<true, false>, (unsigned)grid,
+                                   DM_FMTL_THREADS, smem, st, false, a, (const DmFormat*)h->d_fmt, h->d_norm);
             }
             a.line_lo = n_train_lines; a.line_hi = ~0ull;
             dm_prof_mark(h, st, 0);
-            dm_launch_pdl_smem(dm_k_format_lanes<false>, (unsigned)grid, DM_FMTL_THREADS, smem, st, false, a, (const DmFormat*)h->d_fmt);
+            dm_launch_pdl_smem(norm ? dm_k_format_lanes<false, true> : dm_k_format_lanes<false, false>, (unsigned)grid,
+                               DM_FMTL_THREADS, smem, st, false, a, (const DmFormat*)h->d_fmt, h->d_norm);
             dm_prof_mark(h, st, 1);
             h->launches += 2 + (n_train_lines > 0 ? 1 : 0);
         }
@@ -587,6 +592,11 @@ extern "C" int dm_set_combos(dm_handle* h, uint32_t n_combos, const uint32_t* me
 
 extern "C" int dm_set_format(dm_handle* h, const char* log_format, const char* content_name, uint32_t n_templates,
                              const char* const* templates) {
+    return dm_set_format_ex(h, log_format, content_name, n_templates, templates, 0);
+}
+
+extern "C" int dm_set_format_ex(dm_handle* h, const char* log_format, const char* content_name, uint32_t n_templates,
+                                const char* const* templates, uint32_t norm_flags) {
     if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
     if (!log_format) {                                             // back to key=value tokenisation
         h->fmt_set = false;
@@ -598,17 +608,19 @@ extern "C" int dm_set_format(dm_handle* h, const char* log_format, const char* c
     if (!f) return dm_fail(DM_ERR_CUDA, "out of host memory");
     std::string err;
     int rc = DM_OK;
-    if (!dm_format_build(log_format, content_name, n_templates, templates, h->h_mons, f, &err)) {
+    if (!dm_format_build(log_format, content_name, n_templates, templates, norm_flags, h->h_mons, f, &err)) {
         rc = dm_fail(DM_ERR_ARG, "%s", err.c_str());
     } else {
         cudaError_t e = cudaSetDevice(h->device);
         if (e == cudaSuccess && !h->d_fmt) e = cudaMalloc(&h->d_fmt, sizeof(DmFormat));
+        if (e == cudaSuccess && norm_flags && n_templates && !h->d_norm) e = cudaMalloc(&h->d_norm, h->max_batch_bytes + 256);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->last_stream);
         if (e == cudaSuccess) e = cudaMemcpy(h->d_fmt, f, sizeof(DmFormat), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = dm_fail(DM_ERR_CUDA, "dm_set_format: %s", cudaGetErrorString(e));
         else {
             h->fmt_set = true;
             h->fmt_slots = f->max_slots;
+            h->fmt_norm = n_templates ? norm_flags : 0;             // (without templates there is nothing to normalise)
         }
     }
     delete f;
@@ -687,7 +699,12 @@ extern "C" int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nby
         a.hdr = h->d_hdr; a.stats = h->d_stats;
         const int grid = (int)std::min<uint32_t>((n_records + 127) / 128, (uint32_t)h->sm_count * 16);
         if (n_train_records > 0) { dm_k_records<<<grid, 128, 0, st>>>(a, 0); h->launches++; }
-        if (n_train_records < n_records) { dm_k_records<<<grid, 128, 0, st>>>(a, 1); h->launches++; }
+        if (n_train_records < n_records) {
+            dm_prof_mark(h, st, 0);
+            dm_k_records<<<grid, 128, 0, st>>>(a, 1);
+            dm_prof_mark(h, st, 1);
+            h->launches++;
+        }
         DM_CUDA(cudaGetLastError());
     }
     DM_CUDA(cudaMemcpyAsync(h->h_hdr, h->d_hdr, sizeof(DmBatchHeader), cudaMemcpyDeviceToHost, st));

@@ -218,17 +218,19 @@ class DeviceDetector:
         a_mem = (C.c_uint32 * max(1, len(flat)))(*flat)
         _lib.check(self._lib.dm_set_combos(self._h, len(combos), a_off, a_mem, int(member_only_mask)))
 
-    def set_format(self, log_format: Optional[str], templates=(), content_name: str = "Content") -> None:
+    def set_format(self, log_format: Optional[str], templates=(), content_name: str = "Content", norm_flags: int = 0) -> None:
         """Tokenise process_lines() input with a MatcherParser log_format (+ `<*>` templates
         matched against the capture `content_name`) instead of key=value fields.  The
         monitors of set_monitors() bind to it by capture name / wildcard index / EventID.
+        norm_flags: logformat.NORM_* (remove_spaces / remove_punctuation / lowercase).
         None switches back."""
         if log_format is None:
             _lib.check(self._lib.dm_set_format(self._h, None, None, 0, None))
             return
         ts = [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in templates]
         arr = (C.c_char_p * max(1, len(ts)))(*ts)
-        _lib.check(self._lib.dm_set_format(self._h, log_format.encode("utf-8"), content_name.encode("utf-8"), len(ts), arr))
+        _lib.check(self._lib.dm_set_format_ex(self._h, log_format.encode("utf-8"), content_name.encode("utf-8"), len(ts), arr,
+                                              int(norm_flags)))
 
     def process_records(self, buf: bytes, n_train_records: int = 0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """A batch of varint-length-delimited ParserSchema records, decoded and scored on the

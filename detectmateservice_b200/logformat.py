@@ -17,6 +17,23 @@ _NAME_CHARS = frozenset(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz01
 MAX_TEMPLATES = 63
 MAX_CAPTURES = 32
 
+# R-norm: MatcherParser's params.remove_spaces / remove_punctuation / lowercase.  The same
+# bits are passed to dm_set_format_ex; the device drops / folds the same bytes (DmFormat.norm_drop).
+NORM_REMOVE_SPACES, NORM_REMOVE_PUNCTUATION, NORM_LOWERCASE = 1, 2, 4
+_SPACES = bytes(range(0x09, 0x0E)) + b" "
+_PUNCT = b"!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~"
+_FOLD = bytes.maketrans(bytes(range(0x41, 0x5B)), bytes(range(0x61, 0x7B)))
+
+
+def norm_flags(remove_spaces: bool = False, remove_punctuation: bool = False, lowercase: bool = False) -> int:
+    return ((NORM_REMOVE_SPACES if remove_spaces else 0) | (NORM_REMOVE_PUNCTUATION if remove_punctuation else 0)
+            | (NORM_LOWERCASE if lowercase else 0))
+
+
+def normalise(text: bytes, flags: int) -> bytes:
+    drop = (_SPACES if flags & NORM_REMOVE_SPACES else b"") + (_PUNCT if flags & NORM_REMOVE_PUNCTUATION else b"")
+    return text.translate(_FOLD if flags & NORM_LOWERCASE else None, drop) if flags else text
+
 
 class Chain:
     """L0 C0 L1 C1 ... L(n-1) [C(n-1)]"""
@@ -93,18 +110,32 @@ def _parse(text: bytes, named: bool) -> Chain:
     return Chain(lits, last_cap, names)
 
 
+def _normalised(ch: Chain, flags: int, source: bytes) -> Chain:
+    """R-norm on a template: every literal is normalised, the wildcards stay."""
+    if not flags:
+        return ch
+    lits = [normalise(l, flags) for l in ch.literals]
+    inner = lits[1:] if ch.ends_with_capture else lits[1:-1]
+    if any(l == b"" for l in inner):
+        raise ValueError("normalisation leaves nothing between two wildcards of %r" % source.decode("utf-8", "replace"))
+    if not ch.ends_with_capture and len(lits) > 1 and lits[-1] == b"":
+        return Chain(lits[:-1], True, ch.names)                  # `... <*>'` -> the last wildcard runs to the end
+    return Chain(lits, ch.ends_with_capture, ch.names)
+
+
 def _b(x) -> bytes:
     return x if isinstance(x, bytes) else str(x).encode("utf-8")
 
 
 class LogFormat:
-    def __init__(self, log_format, templates: Sequence = (), content_name: str = "Content") -> None:
+    def __init__(self, log_format, templates: Sequence = (), content_name: str = "Content", flags: int = 0) -> None:
         self.source = _b(log_format).decode("utf-8")
         self.template_sources = [_b(t) for t in templates]
+        self.flags = int(flags)
         self.header = _parse(_b(log_format), named=True)
         if len(set(self.header.names)) != len(self.header.names):
             raise ValueError("log_format: a capture name appears twice")
-        self.templates = [_parse(_b(t), named=False) for t in templates]
+        self.templates = [_normalised(_parse(_b(t), named=False), self.flags, _b(t)) for t in templates]
         if len(self.templates) > MAX_TEMPLATES:
             raise ValueError(f"{len(self.templates)} templates, the device holds {MAX_TEMPLATES}")
         self.content_name = content_name
@@ -119,6 +150,7 @@ class LogFormat:
         lfv = dict(zip(self.header.names, caps))
         content = lfv.get(self.content_name)
         if content is not None:
+            content = normalise(content, self.flags)             # variables are slices of the normalised text
             for t, ch in enumerate(self.templates):
                 v = ch.match(content)
                 if v is not None:

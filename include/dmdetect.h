@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 3
+#define DM_ABI_VERSION 4
 #define DM_MAX_KEYS 32      /* monitored fields per detector                         */
 #define DM_MAX_KEYLEN 32    /* bytes per monitored key                                */
 
@@ -175,6 +175,18 @@ int dm_set_combos(dm_handle* h, uint32_t n_combos, const uint32_t* member_off, c
  * log_format = NULL switches back.  At most 63 templates, 32 captures per chain. */
 int dm_set_format(dm_handle* h, const char* log_format, const char* content_name, uint32_t n_templates,
                   const char* const* templates);
+/* dm_set_format + MatcherParser's params.remove_spaces / remove_punctuation / lowercase
+ * (tests/library_integration/test_pipe_filereader_matcher_nvd.py:82-84 sets all three).
+ * norm_flags = OR of DM_NORM_*: before template matching the Content text and the literal
+ * parts of every template (the `<*>` stay) lose ASCII white space (0x09-0x0D, 0x20) and/or the
+ * 32 ASCII punctuation bytes, and/or have 'A'-'Z' folded to lower case; variables[i] are then
+ * slices of the normalised Content.  Header captures are never normalised.  (DESIGN.md R-norm;
+ * the library is not vendored in the reference, so this rule is unpinned.) */
+#define DM_NORM_REMOVE_SPACES 1u
+#define DM_NORM_REMOVE_PUNCTUATION 2u
+#define DM_NORM_LOWERCASE 4u
+int dm_set_format_ex(dm_handle* h, const char* log_format, const char* content_name, uint32_t n_templates,
+                     const char* const* templates, uint32_t norm_flags);
 /* Host utility: write a host buffer back to memory and evict it from the CPU caches (x86:
  * clflush), so that device DMA streams it from DRAM instead of snooping dirty cache lines. */
 int dm_host_cache_flush(const void* p, uint64_t nbytes);

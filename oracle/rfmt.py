@@ -20,16 +20,40 @@ R-match templates = lines of the templates file; each is literal text with `<*>`
         matches the capture named Content iff ^S0(.*?)S1(.*?)...$ matches it.  The first
         matching template (file order) gives EventID = its 0-based index and variables =
         its wildcard captures; no match: EventID -1, no variables.
-        (The preprocessing switches remove_spaces / remove_punctuation / lowercase of the
-        reference test config are NOT restated: their exact effect is not visible in the
-        reference; all three are treated as false, as in docs/getting_started.md:409-412.)
+R-norm  params.remove_spaces / remove_punctuation / lowercase (all true in the reference's audit
+        config, test_pipe_filereader_matcher_nvd.py:82-84; all false in docs/getting_started.md:
+        411-413 and container/config/parser_config.yaml:8-10).  The reference shows the switches
+        but not their effect, so this is a restatement of the library's documented intent, PARITY
+        UNPINNED: before template matching, the Content text AND every literal segment of every
+        template (the `<*>` wildcards survive) are normalised byte-wise --
+          remove_spaces       drop 0x09-0x0D and 0x20            (ASCII white space)
+          remove_punctuation  drop the 32 bytes of string.punctuation
+          lowercase           'A'-'Z' -> 'a'-'z'                  (ASCII only; other bytes untouched)
+        -- and R-match then runs on the normalised text: `variables` are slices of the normalised
+        Content.  The header extraction (R-fmt) and logFormatVariables stay verbatim.  A template
+        whose normalisation leaves nothing between two wildcards is a configuration error.
 """
 from __future__ import annotations
 
 import re
+import string
 from typing import Dict, List, Optional, Tuple
 
 _CAPTURE = re.compile(rb"<([A-Za-z0-9_]+)>")
+
+_SPACES = bytes(range(0x09, 0x0E)) + b" "
+_PUNCT = string.punctuation.encode("ascii")
+_UPPER = bytes(range(0x41, 0x5B))
+_LOWER = bytes(range(0x61, 0x7B))
+
+
+def normaliser(remove_spaces: bool = False, remove_punctuation: bool = False, lowercase: bool = False):
+    """R-norm as a bytes -> bytes function."""
+    drop = (_SPACES if remove_spaces else b"") + (_PUNCT if remove_punctuation else b"")
+    table = bytes.maketrans(_UPPER, _LOWER) if lowercase else None
+    if not drop and table is None:
+        return lambda text: text
+    return lambda text: text.translate(table, drop)
 
 
 def _chain_regex(literals: List[bytes], ends_with_capture: bool) -> "re.Pattern[bytes]":
@@ -54,8 +78,8 @@ def compile_log_format(fmt: bytes) -> Tuple["re.Pattern[bytes]", List[str]]:
     return _chain_regex(lits[:-1] if ends else lits, ends), names
 
 
-def compile_template(t: bytes) -> "re.Pattern[bytes]":
-    segs = t.split(b"<*>")
+def compile_template(t: bytes, norm=lambda x: x) -> "re.Pattern[bytes]":
+    segs = [norm(s) for s in t.split(b"<*>")]
     if any(s == b"" for s in segs[1:-1]):
         raise ValueError("two wildcards with nothing between them")
     ends = len(segs) > 1 and segs[-1] == b""
@@ -63,10 +87,12 @@ def compile_template(t: bytes) -> "re.Pattern[bytes]":
 
 
 class FormatParser:
-    def __init__(self, log_format, templates=(), content_name: str = "Content") -> None:
+    def __init__(self, log_format, templates=(), content_name: str = "Content", remove_spaces: bool = False,
+                 remove_punctuation: bool = False, lowercase: bool = False) -> None:
         b = lambda x: x if isinstance(x, bytes) else str(x).encode("utf-8")
+        self.norm = normaliser(remove_spaces, remove_punctuation, lowercase)
         self.regex, self.names = compile_log_format(b(log_format))
-        self.templates = [compile_template(b(t)) for t in templates]
+        self.templates = [compile_template(b(t), self.norm) for t in templates]
         self.content_name = content_name
 
     def parse_line(self, line: bytes) -> Optional[dict]:
@@ -79,6 +105,7 @@ class FormatParser:
         eid, variables = -1, []
         content = lfv.get(self.content_name)
         if content is not None:
+            content = self.norm(content)
             for t, rx in enumerate(self.templates):
                 tm = rx.match(content)
                 if tm is not None:

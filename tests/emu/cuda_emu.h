@@ -160,6 +160,7 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) {
     return (unsigned)((v << (sh & 31)) >> 32);
 }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline uint4 __ldg(const uint4* p) { uint4 r; std::memcpy(&r, p, 16); return r; }
 
 // ---- atomics (GCC builtins on plain memory) ----------------------------------------------

@@ -226,13 +226,13 @@ static DmFormat g_fmt;
 static bool g_fmt_set = false;
 static char g_fmt_err[256];
 extern "C" const char* emu_set_format(const DmMonitor* mons, uint32_t n_mons, const char* log_format, const char* content_name,
-                                      uint32_t n_templates, const char* const* templates) {
+                                      uint32_t n_templates, const char* const* templates, uint32_t norm_flags) {
     static DmMonitors hm;
     memset(&hm, 0, sizeof(hm));
     hm.n = n_mons;
     for (uint32_t i = 0; i < n_mons; ++i) hm.m[i] = mons[i];
     std::string err;
-    g_fmt_set = dm_format_build(log_format, content_name, n_templates, templates, hm, &g_fmt, &err);
+    g_fmt_set = dm_format_build(log_format, content_name, n_templates, templates, norm_flags, hm, &g_fmt, &err);
     snprintf(g_fmt_err, sizeof(g_fmt_err), "%s", err.c_str());
     return g_fmt_set ? nullptr : g_fmt_err;
 }
@@ -259,8 +259,21 @@ extern "C" int emu_process_format(EmuHandle* h, const uint8_t* msg, uint64_t nby
     a.stats = h->stats; a.combos = nullptr; a.nbytes = nbytes;
     const uint64_t nt = std::min<uint64_t>(n_train, n);
     g_emu_dyn_smem.assign((size_t)2 * g_fmt.max_slots * DM_FMTL_THREADS * sizeof(uint2), 0);
-    if (nt > 0) { a.line_lo = 0; a.line_hi = nt; emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<true>(a, &g_fmt); }); }
-    if (nt < n) { a.line_lo = nt; a.line_hi = ~0ull; emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<false>(a, &g_fmt); }); }
+    // R-norm scratch: hostile content (the kernel may only read back what it wrote itself)
+    const bool norm = g_fmt.norm_flags != 0 && g_fmt.n_chains > 1;
+    uint8_t* nbuf = (uint8_t*)aligned_alloc(64, ((nbytes + 256 + 63) / 64) * 64);
+    memset(nbuf, 0xA5, nbytes + 256);
+    if (nt > 0) {
+        a.line_lo = 0; a.line_hi = nt;
+        if (norm) emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<true, true>(a, &g_fmt, nbuf); });
+        else emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<true, false>(a, &g_fmt, nbuf); });
+    }
+    if (nt < n) {
+        a.line_lo = nt; a.line_hi = ~0ull;
+        if (norm) emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<false, true>(a, &g_fmt, nbuf); });
+        else emu_launch_grid(3, DM_FMTL_THREADS, [&] { dm_k_format_lanes<false, false>(a, &g_fmt, nbuf); });
+    }
+    free(nbuf);
     *n_lines = n;
     *n_anoms = h->hdr.n_anomalies;
     return 0;

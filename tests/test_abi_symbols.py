@@ -25,7 +25,7 @@ def test_header_symbols_all_exported():
         assert hasattr(lib, n), f"{n} declared in dmdetect.h but not exported"
         assert n in _lib.SYMBOLS, f"{n} has no ctypes prototype"
     assert set(_lib.SYMBOLS) == set(names)
-    assert lib.dm_abi_version() == 3
+    assert lib.dm_abi_version() == 4
 
 
 def test_sass_is_sm100a_only():

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from detectmateservice_b200 import wire
-from detectmateservice_b200.logformat import LogFormat, load_templates
+from detectmateservice_b200.logformat import LogFormat, load_templates, norm_flags
 from oracle.nvd import NewValueDetectorOracle
 from oracle.rfmt import FormatParser
 
@@ -32,8 +32,8 @@ def audit_templates(golden_dir):
 class FormatOracle:
     """FormatParser (regex) + NewValueDetectorOracle: the CPU restatement of parser + detector."""
 
-    def __init__(self, cfg, log_format, templates=()):
-        self.parser = FormatParser(log_format, templates)
+    def __init__(self, cfg, log_format, templates=(), norm=(False, False, False)):
+        self.parser = FormatParser(log_format, templates, remove_spaces=norm[0], remove_punctuation=norm[1], lowercase=norm[2])
         self.nvd = NewValueDetectorOracle(config=cfg, clock=lambda: 1773848383)
 
     def process_lines(self, buf):
@@ -125,6 +125,77 @@ def test_sequential_matcher_equals_regex_fuzz():
     assert n_match > 2000
 
 
+NORMS = [(True, True, True), (True, False, False), (False, True, False), (False, False, True), (True, False, True)]
+
+
+def norm_fuzz_template(r):
+    """A template over an alphabet with spaces, punctuation and capitals, whose literals keep at least one
+    letter (so that normalisation never empties the text between two wildcards)."""
+    alpha = b"aB =:c-"
+    k = int(r.integers(1, 4))
+    lits = []
+    for _ in range(k + 1):
+        raw = bytes(alpha[int(i)] for i in r.integers(0, len(alpha), int(r.integers(1, 4))))
+        at = int(r.integers(0, len(raw) + 1))
+        lits.append(raw[:at] + (b"a", b"B", b"c")[int(r.integers(0, 3))] + raw[at:])
+    if r.random() < 0.3:
+        lits[0] = b""
+    ends = r.random() < 0.5
+    if not ends and r.random() < 0.3:
+        lits[-1] = b"'"                                          # punctuation only: vanishes under remove_punctuation
+    return lits, ends
+
+
+def norm_fuzz_text(r, lits, ends):
+    alpha = b"aB =:c-xY\t.A"
+    t = b""
+    for i, lit in enumerate(lits):
+        t += lit if r.random() < 0.8 else lit.swapcase().replace(b" ", b"  ")
+        if i < len(lits) - 1 or ends:
+            t += bytes(alpha[int(j)] for j in r.integers(0, len(alpha), int(r.integers(0, 9))))
+    if r.random() < 0.2:
+        t = bytes(alpha[int(i)] for i in r.integers(0, len(alpha), int(r.integers(0, 24))))
+    return t
+
+
+def test_normalisation_switches_host_mirror_equals_regex(golden_dir):
+    """R-norm (remove_spaces / remove_punctuation / lowercase): the sequential matcher on the normalised
+    text against Python's re on the same; then the reference's audit templates with all three on."""
+    from detectmateservice_b200.logformat import normalise
+    assert normalise(b" A-b\tC\r\n.d_E ", norm_flags(True, True, True)) == b"abcde"
+    assert normalise(b" A-b\tC ", norm_flags(True, False, False)) == b"A-bC"
+    assert normalise(b" A-b\tC\x80\xc3\x84", norm_flags(False, True, True)) == b" ab\tc\x80\xc3\x84"
+    r = np.random.Generator(np.random.PCG64(7))
+    n_match = 0
+    for it in range(300):
+        lits, ends = norm_fuzz_template(r)
+        norm = NORMS[it % len(NORMS)]
+        tmpl = b"<*>".join(lits) + (b"<*>" if ends else b"")
+        ta = FormatParser("<Content>", [tmpl], remove_spaces=norm[0], remove_punctuation=norm[1], lowercase=norm[2])
+        tb = LogFormat("<Content>", [tmpl], flags=norm_flags(*norm))
+        for _ in range(40):
+            text = norm_fuzz_text(r, lits, ends)
+            va, vb = ta.parse_line(text), tb.parse(text)
+            assert (va["EventID"], va["variables"]) == (vb[0], vb[1]), (tmpl, text, norm)
+            n_match += va["EventID"] == 0
+    assert n_match > 3000
+    tm = audit_templates(golden_dir)
+    a, b = FormatParser(AUDIT, tm, remove_spaces=True, remove_punctuation=True, lowercase=True), LogFormat(AUDIT, tm, flags=7)
+    plain = LogFormat(AUDIT, tm)
+    for ln in open(os.path.join(golden_dir, "audit_sample.log"), "rb").read().split(b"\n")[:-1]:
+        x, y = a.parse_line(ln), b.parse(ln)
+        assert (x["EventID"], x["variables"], x["logFormatVariables"]) == y
+        assert y[0] == plain.parse(ln)[0] and y[2] == plain.parse(ln)[2]     # same template, verbatim header
+    first = b.parse(b"type=USER_ACCT msg=audit(1642723741.072:375): pid=10125 uid=0 auid=4294967295 ses=4294967295 "
+                    b"msg='op=PAM:accounting acct=\"root\" exe=\"/usr/sbin/cron\" hostname=? addr=? terminal=cron res=success'")
+    assert first[1] == [b"10125", b"0", b"4294967295", b"4294967295", b"pamaccounting", b"root", b"usrsbincron", b"", b"",
+                        b"cron", b"success"]
+    with pytest.raises(ValueError, match="nothing between"):
+        LogFormat("<Content>", ["a<*> - <*>b"], flags=norm_flags(True, True, False))
+    with pytest.raises(ValueError):
+        FormatParser("<Content>", ["a<*> - <*>b"], remove_spaces=True, remove_punctuation=True)
+
+
 def test_config_errors():
     with pytest.raises(ValueError):
         LogFormat("<A><B> x")
@@ -166,7 +237,7 @@ def emu_kernel(request):
 
 
 class EmuFormat:
-    def __init__(self, cfg, log_format, templates=(), name="NewValueDetector"):
+    def __init__(self, cfg, log_format, templates=(), name="NewValueDetector", norm=(False, False, False)):
         import emu_harness
         from detectmateservice_b200.component import parse_monitors, select_component_config
         self.mons = parse_monitors(select_component_config(cfg, name))
@@ -174,12 +245,13 @@ class EmuFormat:
         self.det = emu_harness.EmuDetector([m.key for m in self.mons], table_log2=12)
         L = self.lib
         L.emu_set_format.restype = C.c_char_p
-        L.emu_set_format.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p)]
+        L.emu_set_format.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32]
         L.emu_process_format.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         ts = [t if isinstance(t, bytes) else t.encode() for t in templates]
         fmt = log_format if isinstance(log_format, bytes) else log_format.encode()
-        err = L.emu_set_format(_monitor_array(self.mons), len(self.mons), fmt, b"Content", len(ts), (C.c_char_p * max(1, len(ts)))(*ts))
+        err = L.emu_set_format(_monitor_array(self.mons), len(self.mons), fmt, b"Content", len(ts), (C.c_char_p * max(1, len(ts)))(*ts),
+                               norm_flags(*norm))
         if err:
             raise ValueError(err.decode())
 
@@ -285,7 +357,58 @@ def test_emu_kernel_synthetic_header_and_variable_monitors(emu_kernel):
     assert len({m for m in masks.values()}) >= 3                  # several different monitors fired
 
 
+AUDIT_NORM_CFG = {"detectors": {"NewValueDetector": {
+    "method_type": "new_value_detector", "data_use_training": 250, "auto_config": False,
+    "global": {"g": {"header_variables": [{"pos": "type"}]}},
+    "events": {0: {"pam": {"variables": [{"pos": 4, "name": "op"}, {"pos": 6, "name": "exe"}, {"pos": 9, "name": "terminal"}]}},
+               1: {"unit": {"variables": [{"pos": 4, "name": "unit"}]}},
+               2: {"login": {"variables": [{"pos": 3, "name": "auid"}, {"pos": 7, "name": "res"}]}}}}}}
+# records that differ from trained ones only in what R-norm removes (no alert) or in more (alert)
+AUDIT_NORM_TAIL = (
+    b"type=USER_ACCT msg=audit(1642723741.072:375): pid=10125 uid=0 auid=4294967295 ses=4294967295 "
+    b"msg='op=pam:ACCOUNTING acct=\"root\" exe=\"/usr/sbin/CRON\" hostname=? addr=? terminal=cron res=success'\n"
+    b"type=USER_ACCT msg=audit(1642723741.072:375): pid=10125   uid=0 AUID=4294967295 ses=4294967295 "
+    b"msg='op=PAM:accounting acct=\"root\" exe=\"/usr/sbin/cron2\" hostname=? addr=? terminal=cron res=success'\n"
+    b"type=LOGIN msg=audit(1642723741.076:377): pid=1 uid=0 old-auid=4294967295 auid=77777 tty=(none) old-ses=4294967295 ses=65 res=9")
+
+
+def test_emu_kernel_normalisation_switches(golden_dir, emu_kernel):
+    """R-norm on the device path: the reference's audit templates with all three switches on
+    (tests/library_integration/test_pipe_filereader_matcher_nvd.py:82-84), then random templates
+    under every switch combination, against the regular-expression oracle."""
+    tm = audit_templates(golden_dir)
+    buf = open(os.path.join(golden_dir, "audit_sample.log"), "rb").read() + AUDIT_NORM_TAIL
+    norm = (True, True, True)
+    wf, ws, wa, bad = FormatOracle(AUDIT_NORM_CFG, AUDIT, tm, norm).process_lines(buf)
+    emu = EmuFormat(AUDIT_NORM_CFG, AUDIT, tm, norm=norm)
+    f, s, masks = emu.process(buf, 250)
+    assert f == wf and s == ws and bad == 0
+    assert masks == {i: _mask_of(a, emu.mons) for i, a in enumerate(wa) if a}
+    assert wf[-3:] == [0, 1, 1] and wa[-2] == {"EventID 0 - exe": "Unknown value: 'usrsbincron2'"}
+    r = np.random.Generator(np.random.PCG64(29))
+    checked = 0
+    for it in range(20):
+        lits, ends = norm_fuzz_template(r)
+        norm = NORMS[it % len(NORMS)]
+        n_caps = len(lits) - (0 if ends else 1)
+        tmpl = b"<*>".join(lits) + (b"<*>" if ends else b"")
+        cfg = {"detectors": {"NewValueDetector": {"method_type": "new_value_detector", "data_use_training": 30,
+               "global": {"g": {"header_variables": [{"pos": "h"}]}},
+               "events": {0: {"e": {"variables": [{"pos": i} for i in range(n_caps)]}}}}}}
+        lines = [b"%d|" % int(r.integers(0, 3)) + norm_fuzz_text(r, lits, ends) for _ in range(120)]
+        buf = b"\n".join(lines) + b"\n"
+        wf, ws, wa, _ = FormatOracle(cfg, "<h>|<Content>", [tmpl], norm).process_lines(buf)
+        emu = EmuFormat(cfg, "<h>|<Content>", [tmpl], norm=norm)
+        f, s, masks = emu.process(buf, 30)
+        assert f == wf and s == ws, (tmpl, norm)
+        assert masks == {i: _mask_of(a, emu.mons) for i, a in enumerate(wa) if a}, (tmpl, norm)
+        checked += sum(wf)
+    assert checked > 100
+
+
 def test_emu_set_format_errors():
+    with pytest.raises(ValueError, match="nothing between"):
+        EmuFormat(NGINX_CFG, "<Content>", ["a<*> - <*>b"], norm=(True, True, False))
     with pytest.raises(ValueError, match="nothing between"):
         EmuFormat(NGINX_CFG, "<A><B>")
     with pytest.raises(ValueError, match="twice"):
@@ -352,6 +475,54 @@ def test_gpu_audit_templates_component_vs_oracle(golden_dir):
     f, s = decode_compact(comp.process(buf))
     assert f.tolist() == wf and s.tolist() == ws
     comp.close()
+
+
+@pytest.mark.gpu
+def test_gpu_normalisation_switches(golden_dir):
+    """The reference's audit parser config as it stands -- remove_spaces, remove_punctuation, lowercase all
+    true (tests/library_integration/test_pipe_filereader_matcher_nvd.py:74-88) -- through the component,
+    then random templates under every switch combination through the C-ABI, against the oracle."""
+    from detectmateservice_b200.detector import DeviceDetector
+    from detectmateservice_b200.component import parse_monitors, select_component_config
+    tm = audit_templates(golden_dir)
+    buf = open(os.path.join(golden_dir, "audit_sample.log"), "rb").read() + AUDIT_NORM_TAIL + b"\n"
+    norm = (True, True, True)
+    wf, ws, wa, bad = FormatOracle(AUDIT_NORM_CFG, AUDIT, tm, norm).process_lines(buf)
+    comp = _component(AUDIT_NORM_CFG, {"log_format": AUDIT, "path_templates": os.path.join(golden_dir, "audit_templates.txt"),
+                                       "remove_spaces": True, "remove_punctuation": True, "lowercase": True})
+    cut = buf.index(b"\n", len(buf) // 2) + 1
+    got = []
+    for part in (buf[:cut], buf[cut:]):
+        out = comp.process(part)
+        got += [wire.decode_detector_schema(b) for b in wire.split_delimited(out)] if out else []
+    want = [(i, a) for i, a in enumerate(wa) if a]
+    assert [(int(x["logIDs"][0]), x["alertsObtain"]) for x in got] == want and len(want) >= 5
+    assert want[-2][1] == {"EventID 0 - exe": "Unknown value: 'usrsbincron2'"}
+    assert comp.stats()["bad_records"] == bad == 0
+    comp.close()
+    r = np.random.Generator(np.random.PCG64(31))
+    checked = 0
+    for it in range(40):
+        lits, ends = norm_fuzz_template(r)
+        norm = NORMS[it % len(NORMS)]
+        n_caps = len(lits) - (0 if ends else 1)
+        tmpl = b"<*>".join(lits) + (b"<*>" if ends else b"")
+        cfg = {"detectors": {"NewValueDetector": {"method_type": "new_value_detector", "data_use_training": 100,
+               "global": {"g": {"header_variables": [{"pos": "h"}]}},
+               "events": {0: {"e": {"variables": [{"pos": i} for i in range(n_caps)]}}}}}}
+        mons = parse_monitors(select_component_config(cfg, "NewValueDetector"))
+        lines = [b"%d|" % int(r.integers(0, 3)) + norm_fuzz_text(r, lits, ends) for _ in range(500)]
+        buf = b"\n".join(lines) + b"\n"
+        wf, ws, wa, _ = FormatOracle(cfg, "<h>|<Content>", [tmpl], norm).process_lines(buf)
+        det = DeviceDetector([m.key for m in mons], max_batch_bytes=1 << 20)
+        det.set_monitors([{"event_id": m.event_id, "source": m.source, "pos": m.pos} for m in mons])
+        det.set_format("<h>|<Content>", [tmpl], norm_flags=norm_flags(*norm))
+        f, s = det.process_lines(buf, n_train_lines=100)
+        assert f.tolist() == wf and s.tolist() == ws, (tmpl, norm)
+        assert {a[0]: a[1] for a in det.anomalies()} == {i: _mask_of(a, mons) for i, a in enumerate(wa) if a}
+        checked += sum(wf)
+        det.close()
+    assert checked > 300
 
 
 @pytest.mark.gpu
