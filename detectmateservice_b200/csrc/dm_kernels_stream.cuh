@@ -401,6 +401,281 @@ __device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ bu
 }
 
 // ---------------------------------------------------------------------------------------
+// Chained re-check of a whole batch of queued fields (the field phase's slow path).
+//
+// dmx_verify_thread walks a candidate's record back to its first byte: fine when candidates are rare
+// (one in a thousand records), quadratic when a long record holds dozens of them -- BASELINE config 5,
+// where every `kN="v .. res=quoted x"` filler carries a quoted look-alike of a monitored key.  The
+// queue already holds EVERY '=' that ends a monitored key, so what a candidate needs is only what lies
+// between consecutive entries: each lane scans the bytes between its predecessor's '=' and its own
+// (last '\n', parity of '"' behind it), a segmented scan over the lanes turns that into (first byte of
+// the record, quote parity at the '=') per entry, and a second one ORs the keys of the true fields
+// (parity 0) seen earlier in the same record -- R-tok L2, L4, L6 for all 32 entries at once.  The
+// state behind the last entry is carried to the next batch (DmxCarry): a long record is walked once,
+// not once per candidate.
+//
+// What the queue guarantees: entries are in message order at the granularity of a lane's 32 bytes; the
+// (up to four) '=' of one lane come out in bit order of the unordered mask, and a lane with more than
+// four puts the rest behind everybody else's (`dense` rows).  So: the batch is sorted first (an entry is
+// at most three places off); batches that touch a dense row fall back as a whole; and because the
+// entries of one 32-byte chunk may be split over two batches, a candidate in the LAST chunk of a batch
+// (a sibling with a smaller offset may still be queued) and, without carried state, the records that
+// start in its FIRST chunk (a sibling with a larger offset may already be gone) are not decided
+// here.  Whatever is not decided here goes to dmx_verify_thread, which is always exact.
+// ---------------------------------------------------------------------------------------
+// (inlined: as a real call the function's own register demand counts against the kernel's 64 and ptxas spills in the
+// row loop; inlined the rare path costs the detect kernel nothing -- 63 registers, no spills)
+#ifndef DM_NOINLINE
+#define DM_NOINLINE __forceinline__
+#endif
+#ifdef DM_EMU
+static unsigned long long g_emu_chain_stats[8];      // candidates decided by the chain / by the fall-back / in batches not chained
+#endif
+struct DmxCarry {
+    uint32_t qh_next;        // queue index of the entry right behind the batch this state describes
+    uint32_t last_q;         // the largest '=' offset of that batch
+    uint32_t ls;             // first byte of the record it lies in
+    uint32_t par;            // bit 0: quote parity at last_q; bit 1: `seen` is complete for that record
+    uint32_t seen;           // keys of the true fields of that record up to and including last_q
+    int dense_row;           // last row (of this warp's) in which a lane had more than four '=': its entries are out of order
+    uint8_t perm[32];        // scratch: lane that holds the entry of sorted rank r
+};
+
+// bytes [lb, q): offset behind the last '\n' (found) and the parity of '"' behind it (else of the whole interval)
+__device__ __forceinline__ void dmx_scan_back(const uint8_t* __restrict__ buf, uint32_t lb, uint32_t q, bool& found, uint32_t& ls,
+                                              uint32_t& par) {
+    found = false; ls = lb; par = 0;
+    if (q <= lb) return;
+    for (long long c = (long long)((q - 1u) >> 4); c >= (long long)(lb >> 4); --c) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(buf + c * 16));
+        const uint32_t cb = (uint32_t)c * 16u;
+        uint32_t keep = 0xFFFFu;
+        if (q - cb < 16u) keep = (1u << (q - cb)) - 1u;
+        if (cb < lb) keep &= ~((1u << (lb - cb)) - 1u);
+        const uint32_t nl = dm_chunk_mask(v, 0x0A0A0A0Au) & keep;
+        if (nl) {
+            const uint32_t top = 31u - (uint32_t)__clz((int)nl);
+            ls = cb + top + 1u;
+            keep &= ~((2u << top) - 1u);
+            found = true;
+        }
+        par ^= (uint32_t)__popc(dm_chunk_mask(v, 0x22222222u) & keep) & 1u;
+        if (found) break;
+    }
+}
+
+// Warp-collective: the record that holds byte q0 - 1 (q0 = an '=' offset): *ls = its first byte, *par_q0 = parity of '"' in
+// [ls, q0), return value = keys of its true fields (R-tok L2/L4/L5) whose '=' lies in [ls, x_end).  Two passes over the
+// bytes themselves, 512 per step: backwards for the last '\n' in front of q0, then forwards with the running parity.
+__device__ __forceinline__ uint32_t dmx_history(const uint8_t* __restrict__ buf, const DmxKeyTab* gk, uint32_t q0, uint32_t x_end, uint32_t* ls_out,
+                                                uint32_t* par_q0) {
+    const uint32_t lane = threadIdx.x & 31, full = 0xffffffffu;
+    const uint4* b16 = reinterpret_cast<const uint4*>(buf);
+    uint32_t ls = 0;
+    {
+        const long long ctop = (long long)((q0 - 1u) >> 4);                  // (q0 > 0: an '=' is never the first byte of a key)
+        for (long long c0 = ctop; c0 >= 0; c0 -= 32) {
+            const long long c = c0 - (31 - (long long)lane);
+            uint32_t nl = 0;
+            if (c >= 0) {
+                nl = dm_chunk_mask(__ldg(b16 + c), 0x0A0A0A0Au);
+                if (c == ctop && (q0 & 15u)) nl &= (1u << (q0 & 15u)) - 1u;
+            }
+            const uint32_t has = __ballot_sync(full, nl != 0u);
+            if (has) {
+                const int top = 31 - __clz((int)has);
+                const uint32_t bits = __shfl_sync(full, nl, top);
+                ls = (uint32_t)(c0 - (31 - top)) * 16u + (31u - (uint32_t)__clz((int)bits)) + 1u;
+                break;
+            }
+        }
+    }
+    uint32_t seen = 0, pq0 = 0, run = 0;
+    const uint32_t nk = gk->n;
+    for (uint32_t cb0 = ls & ~15u; cb0 < x_end; cb0 += 512u) {
+        const uint32_t cb = cb0 + 16u * lane;
+        uint32_t dq = 0, eq = 0, nl = 0;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        uint32_t keep = 0u;
+        if (cb < x_end) {
+            v = __ldg(b16 + (cb >> 4));
+            keep = 0xFFFFu;
+            if (cb < ls) keep &= ~((1u << (ls - cb)) - 1u);
+            if (x_end - cb < 16u) keep &= (1u << (x_end - cb)) - 1u;
+            nl = dm_chunk_mask(v, 0x0A0A0A0Au) & keep;                      // (behind q0: the record may end in front of x_end)
+        }
+        const uint32_t ends = __ballot_sync(full, nl != 0u);
+        if (ends) {
+            const int first = __ffs((int)ends) - 1;
+            const uint32_t at = (uint32_t)__ffs((int)__shfl_sync(full, nl, first)) - 1u;
+            if ((int)lane > first) keep = 0u;
+            else if ((int)lane == first) keep &= (1u << at) - 1u;
+            x_end = cb0 + 16u * (uint32_t)first + at;                       // the loop ends with this step
+        }
+        if (keep) {
+            dq = dm_chunk_mask(v, 0x22222222u) & keep;
+            eq = dm_chunk_mask(v, 0x3D3D3D3Du) & keep;
+            uint32_t below = dq;
+            if (cb >= q0) below = 0u;
+            else if (q0 - cb < 16u) below &= (1u << (q0 - cb)) - 1u;
+            pq0 ^= (uint32_t)__popc(below) & 1u;
+        }
+        const uint32_t odd = __ballot_sync(full, (__popc(dq) & 1) != 0);
+        const uint32_t par_in = run ^ ((uint32_t)__popc(odd & dm_lanemask_lt()) & 1u);
+        while (eq) {
+            const uint32_t j = (uint32_t)__ffs(eq) - 1u;
+            eq &= eq - 1u;
+            if ((par_in ^ ((uint32_t)__popc(dq & ((1u << j) - 1u)) & 1u)) != 0u) continue;     // inside double quotes
+            const uint32_t e = cb + j;
+            for (uint32_t k = 0; k < nk; ++k) {
+                const uint32_t L = gk->len[k];
+                if (e < ls + L) continue;
+                const uint32_t ks = e - L;
+                bool ok = ks == ls || dmx_is_delim(dm_ld8(buf, ks - 1u));
+                for (uint32_t i = L; ok && i > 0; --i) ok = dm_ld8(buf, ks + i - 1u) == gk->bytes[k][i - 1u];
+                if (ok) { seen |= 1u << k; break; }
+            }
+        }
+        run ^= (uint32_t)__popc(odd) & 1u;
+        __syncwarp();
+    }
+    *ls_out = ls;
+    *par_q0 = __reduce_xor_sync(full, pq0);
+    return __reduce_or_sync(full, seen);
+}
+
+// Warp-collective.  Lane i < n holds queue entry i of the batch: '=' at qpos_in, key k_in (-1: no monitored key ends
+// there, or the record is not this pass's), cand_in = its value is not in the table.  `chainable` = no entry of a dense
+// row; pend_min = the smallest offset among the '=' still queued right behind the batch (~0: none): a candidate in front
+// of it has no sibling left in the queues.  Returns (ok << 32) | ls: ok = 1 for the candidates that are the first true field with their key in their record,
+// ls = first byte of that record.
+__device__ DM_NOINLINE unsigned long long dmx_verify_chain(const uint8_t* __restrict__ buf, const DmxKeyTab* gk, DmxCarry* cy, uint32_t qh,
+                                                           uint32_t n, bool chainable, uint32_t pend_min, uint32_t qpos_in, int k_in, bool cand_in) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t full = 0xffffffffu;
+    bool ok = false;
+    uint32_t ls = 0;
+    if (!chainable) {
+        if (cand_in && k_in >= 0) {
+            ok = dmx_verify_thread(buf, qpos_in, (uint32_t)k_in, gk, &ls);
+#ifdef DM_EMU
+            __atomic_fetch_add(&g_emu_chain_stats[2], 1ull, __ATOMIC_RELAXED);
+#endif
+        }
+        if (lane == 0) cy->qh_next = 0xFFFFFFFFu;
+        __syncwarp();
+        return ((unsigned long long)(ok ? 1u : 0u) << 32) | ls;
+    }
+    // ---- sort by offset: an entry is at most 3 places away from its rank ----
+    const uint32_t key = lane < n ? qpos_in : 0xFFFFFFFFu;
+    uint32_t rank = lane;
+#pragma unroll
+    for (int d = 1; d <= 3; ++d) {
+        const uint32_t up = __shfl_down_sync(full, key, d);               // entry d places behind this one
+        const uint32_t dn = __shfl_up_sync(full, key, d);                 // entry d places in front of it
+        if (lane + d < 32u && up < key) ++rank;
+        if ((int)lane >= d && dn > key) --rank;
+    }
+    cy->perm[rank & 31u] = (uint8_t)lane;
+    __syncwarp();
+    const uint32_t src = cy->perm[lane];
+    const uint32_t qpos = __shfl_sync(full, key, src);
+    const int k = __shfl_sync(full, k_in, src);
+    const bool cand = __shfl_sync(full, cand_in ? 1u : 0u, src) != 0u;
+    const bool inq = lane < n;                                            // (the n entries sort in front of the empty lanes)
+    const uint32_t q_first = __shfl_sync(full, qpos, 0);
+    const bool cont = cy->qh_next == qh && cy->last_q < q_first;
+    uint32_t c_q = cy->last_q, c_ls = cy->ls, c_par = cy->par, c_seen = cy->seen;
+    uint32_t prev = __shfl_up_sync(full, qpos, 1);
+    const bool sorted = !__any_sync(full, inq && lane > 0 && prev >= qpos) && __popc(__ballot_sync(full, qpos != 0xFFFFFFFFu)) == (int)n;
+    if (sorted) {
+        // ---- nothing carried over: the record the batch starts in is read from its first byte (history) up to the end
+        // of the batch's first 32-byte chunk x_end -- entries in front of x_end may have siblings that left the queue
+        // earlier, so there the bytes speak, not the queue; from x_end on, the queue does ----
+        uint32_t x_end = 0;
+        if (!cont) {
+            x_end = (q_first | 31u) + 1u;
+            uint32_t h_par = 0;
+            c_seen = dmx_history(buf, gk, q_first, x_end, &c_ls, &h_par);
+            c_par = h_par | 2u;
+            c_q = 0xFFFFFFFFu;
+        }
+        if (lane == 0) prev = c_q;
+        // ---- per entry: the bytes between the previous '=' and this one ----
+        bool found = false;
+        uint32_t par = 0;
+        if (inq && !(lane == 0 && !cont)) dmx_scan_back(buf, prev + 1u, qpos, found, ls, par);
+        __syncwarp();
+        bool abs_ = inq && (found || lane == 0);                          // (ls, par) already count from the record's first byte
+        if (lane == 0 && !found) { ls = c_ls; par ^= c_par & 1u; }
+        // ---- segmented scan: (first byte of the record, parity at the '=') of every entry ----
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(full, (par << 1) | (abs_ ? 1u : 0u), d);
+            const uint32_t yl = __shfl_up_sync(full, ls, d);
+            if ((int)lane >= d && !abs_) { par ^= y >> 1; ls = yl; abs_ = (y & 1u) != 0u; }
+        }
+        // ---- keys of the true fields seen earlier in the same record ----
+        const uint32_t ls_prev = __shfl_up_sync(full, ls, 1);
+        const bool head = lane == 0 ? c_ls != ls : ls_prev != ls;                 // no earlier entry of this record in the batch / the carry
+        const uint32_t heads = __ballot_sync(full, head && inq);
+        const bool in_first = (heads & ((2u << lane) - 1u) & ~1u) == 0u;           // same record as the first entry
+        // (the true fields in front of x_end of the batch's first record are in the history already)
+        const uint32_t bit = (inq && k >= 0 && par == 0u && !(in_first && qpos < x_end)) ? 1u << k : 0u;
+        uint32_t incl = bit | ((lane == 0 && !head) ? c_seen : 0u);
+        bool hd = head;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(full, incl, d);
+            const uint32_t yh = __shfl_up_sync(full, hd ? 1u : 0u, d);
+            if ((int)lane >= d && !hd) { incl |= y; hd = yh != 0u; }
+        }
+        uint32_t before = __shfl_up_sync(full, incl, 1);
+        if (lane == 0) before = head ? 0u : c_seen;
+        else if (head) before = 0u;
+        // ---- which entries know all of their record's earlier fields ----
+        const uint32_t chunk_first = q_first >> 5;
+        // the first entry's record: carried over completely / read from its bytes, or begun behind the carried state's
+        // last entry; without carried state a record that starts inside the first chunk may have lost a sibling, and
+        // a candidate in front of x_end would find later fields in the history
+        const bool known0 = __shfl_sync(full, (c_ls != ls || (c_par & 2u) != 0u) ? 1u : 0u, 0) != 0u;
+        const bool known = in_first ? (known0 && qpos >= x_end) : (cont || (ls >> 5) != chunk_first);
+        if (cand && k >= 0) {
+            const bool decide = known && qpos < pend_min;
+            if (decide) ok = par == 0u && !(before & (1u << k));
+            else ok = dmx_verify_thread(buf, qpos, (uint32_t)k, gk, &ls);
+#ifdef DM_EMU
+            __atomic_fetch_add(&g_emu_chain_stats[decide ? 0 : 1], 1ull, __ATOMIC_RELAXED);
+            if (!decide) __atomic_fetch_add(&g_emu_chain_stats[known ? 3 : (in_first ? (cont ? 4 : 5) : 6)], 1ull, __ATOMIC_RELAXED);
+            if (lane == 0 && !cont) __atomic_fetch_add(&g_emu_chain_stats[7], 1ull, __ATOMIC_RELAXED);
+#endif
+        }
+        __syncwarp();
+        // ---- what the next batch needs ----
+        if (lane == n - 1u) {
+            cy->qh_next = qh + n;
+            cy->last_q = qpos;
+            cy->ls = ls;
+            cy->par = (par & 1u) | (known ? 2u : 0u);
+            cy->seen = incl;
+        }
+    } else {
+        if (cand && k >= 0) {
+            ok = dmx_verify_thread(buf, qpos, (uint32_t)k, gk, &ls);
+#ifdef DM_EMU
+            __atomic_fetch_add(&g_emu_chain_stats[2], 1ull, __ATOMIC_RELAXED);
+#endif
+        }
+        if (lane == 0) cy->qh_next = 0xFFFFFFFFu;
+    }
+    __syncwarp();
+    // back to the lanes the entries came from
+    const uint32_t ls_o = __shfl_sync(full, ls, rank & 31u);
+    const uint32_t ok_o = __shfl_sync(full, ok ? 1u : 0u, rank & 31u);
+    return ((unsigned long long)ok_o << 32) | ls_o;
+}
+
+// ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
 // zero-fill of output entries [lo, hi): 16-byte stores where the caller's buffers allow it
@@ -450,7 +725,7 @@ struct DmxDrainCtx {
 // apart for the rest of the function and every later instruction is issued several times for a few lanes each.
 template <bool TRAIN>
 __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab& sk, const uint8_t* ring, const uint32_t* q, uint32_t qh,
-                                          uint32_t n, uint32_t seg_base, uint32_t bound) {
+                                          uint32_t n, uint32_t seg_base, uint32_t bound, DmxCarry* carry, uint32_t qn, const uint32_t* pq, uint32_t ph, uint32_t pn) {
     const uint32_t lane = threadIdx.x & 31;
     const uint8_t* __restrict__ buf = a.buf;
     const uint64_t nbytes = a.nbytes;
@@ -536,9 +811,21 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
         cand = !(TRAIN ? dm_table_contains_volatile(a.table, ckey) : dm_table_contains(a.table, ckey));
     }
     if (__any_sync(0xffffffffu, cand)) {
+        const bool chainable = !__any_sync(0xffffffffu, lane < n && (int)((qpos - seg_base) >> DMX_ROW_LOG2) <= carry->dense_row);
+        // the smallest offset among the next three '=' still queued behind the batch (field queue, then position queue):
+        // the only ones that can be siblings of the batch's last entries
+        uint32_t pend = 0xFFFFFFFFu;
+        if (lane < 3u) {
+            const uint32_t rest = qn - n;
+            if (lane < rest) pend = seg_base + (q[(qh + n + lane) & (DMX_QCAP - 1)] >> 7);
+            else if (lane - rest < pn) pend = seg_base + pq[(ph + lane - rest) & (DMX_PCAP - 1)];
+        }
+        pend = __reduce_min_sync(0xffffffffu, pend);
+        const unsigned long long vr_ = dmx_verify_chain(buf, a.gk, carry, qh, n, chainable, pend, qpos, k, cand);
+        const uint32_t ls = (uint32_t)vr_;
+        const bool ok = (vr_ >> 32) != 0ull;
         if (cand) {
-            uint32_t ls = 0;
-            if (dmx_verify_thread(buf, qpos, (uint32_t)k, a.gk, &ls)) {
+            if (ok) {
                 if (TRAIN) {
                     dm_table_insert(a.table, ckey, a.err);
                 } else {
@@ -578,6 +865,7 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
     __shared__ unsigned long long s_bound;
     __shared__ int s_last;
     __shared__ DmxDrainCtx s_ctx;
+    __shared__ DmxCarry s_carry[DMX_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = dm_lanemask_lt();
     dm_pdl_launch_dependents();                       // the next launch may be scheduled as soon as there is room
@@ -601,6 +889,8 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
     }
     if (lane == 0) {
         s_cnt[warp] = 0;
+        s_carry[warp].qh_next = 0xFFFFFFFFu;
+        s_carry[warp].dense_row = -1;
 #ifndef DM_EMU
         for (uint32_t s = 0; s < DMX_SLOTS; ++s) dmx_mbar_init(dmx_smem_u32(&s_bar[warp][s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -682,6 +972,10 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
             uint32_t g = (dmx_chunk_bits(va, 0x3D3D3D3Du) << (4u * c_first)) | (dmx_chunk_bits(vb, 0x3D3D3D3Du) << (4u * (1u - c_first)));
             const uint32_t qrel = i * DMX_ROW + lane * 32u;
             const bool last = i + 1 == n_own;
+            if (__any_sync(0xffffffffu, __popc(g) > 4)) {           // (see dmx_verify_chain)
+                if (lane == 0) s_carry[warp].dense_row = (int)i;
+                __syncwarp();
+            }
             bool row_done;
             do {
                 // ---- every '=' goes to the position queue: up to 4 per lane and round (prefix over the lanes, then
@@ -715,7 +1009,7 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
                 for (;;) {
                     if (qn >= 32u || (qn && row_done && ((last && !pn) || (q[qh & (DMX_QCAP - 1)] >> (7 + DMX_ROW_LOG2)) + (DMX_SLOTS - 2u) <= i))) {
                         const uint32_t n = qn < 32u ? qn : 32u;
-                        dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound);
+                        dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound, &s_carry[warp], qn, pq, ph, pn);
                         qh += n;
                         qn -= n;
                         continue;

@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--lines", type=int, default=65536)
     ap.add_argument("--msgs", type=int, default=16)
     ap.add_argument("--varlen", action="store_true")
-    ap.add_argument("cfgs", nargs="*", default=["stream:1", "stream:0", "rows:0"])
+    ap.add_argument("cfgs", nargs="*", default=["stream:1", "stream:0", "lanes:0"])
     args = ap.parse_args()
     import torch
     from detectmateservice_b200.detector import DeviceDetector

@@ -22,6 +22,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define DM_NOINLINE __attribute__((noinline))
 #define __shared__ static
 #define __restrict__
 #define __launch_bounds__(...)
@@ -105,6 +106,11 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned d) 
     T got = emu_exchange(v, l >= d ? l - d : l);
     return l >= d ? got : v;
 }
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
+    unsigned l = emu_lane();
+    T got = emu_exchange(v, l + d < 32 ? l + d : l);
+    return l + d < 32 ? got : v;
+}
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, emu_lane() ^ (unsigned)m); }
 static inline unsigned __ballot_sync(unsigned, int pred) {
     EmuWarp& w = emu_warp();
@@ -137,6 +143,15 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
     return r;
 }
 static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return emu_reduce(v, 1); }
+static inline unsigned __reduce_xor_sync(unsigned, unsigned v) {
+    EmuWarp& w = emu_warp();
+    w.slot[emu_lane()] = v;
+    w.bar.sync(32);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r ^= (unsigned)w.slot[i];
+    w.bar.sync(32);
+    return r;
+}
 static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     EmuWarp& w = emu_warp();
     w.slot[emu_lane()] = v;

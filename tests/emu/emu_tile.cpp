@@ -220,6 +220,10 @@ extern "C" int emu_process_records(EmuHandle* h, const DmMonitor* mons, uint32_t
     return 0;
 }
 
+extern "C" void emu_chain_stats(unsigned long long* out, int reset) {
+    for (int i = 0; i < 8; ++i) { out[i] = g_emu_chain_stats[i]; if (reset) g_emu_chain_stats[i] = 0; }
+}
+
 // log_format / template mode: mirrors dm_set_format + the fmt branch of dm_process_lines (line
 // starts are computed here on the host; the device's index kernels are the v1 ones, GPU-tested).
 static DmFormat g_fmt;

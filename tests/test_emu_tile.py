@@ -12,7 +12,7 @@ import pytest
 import emu_harness
 from oracle import fingerprint
 from oracle.native import NativeOracle
-from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines
+from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines, lookalike_lines
 
 
 @pytest.fixture(params=["stream", "lanes"], autouse=True)
@@ -142,6 +142,27 @@ def test_emu_varlen():
     _check(det, o, train, 1500)
     f, _ = _check(det, o, msg, 0)
     assert f.sum() > 10
+    det.close()
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_emu_lookalikes_and_duplicates(seed):
+    """Long records with dozens of candidates each: quoted look-alikes, duplicates, parity flips (the chained
+    re-check of the stream kernel and its fall-backs)."""
+    keys = [b"key", b"type", b"res"]
+    o = NativeOracle(keys)
+    det = EmuDetector(keys)
+    _check(det, o, lookalike_lines(seed, 300), 120)
+    import ctypes as C
+    lib = C.CDLL(emu_harness.build())
+    st = (C.c_ulonglong * 8)()
+    lib.emu_chain_stats(st, 1)
+    f, _ = _check(det, o, lookalike_lines(seed + 50, 500), 0)
+    assert 20 < f.sum() < f.size
+    if VARIANT == "stream":
+        lib.emu_chain_stats(st, 1)
+        chain, fallback, unordered = st[0], st[1], st[2]
+        assert chain > fallback and chain > 1000 and unordered > 0, (chain, fallback, unordered)
     det.close()
 
 
