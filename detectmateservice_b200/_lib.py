@@ -14,7 +14,7 @@ from typing import List
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-SO_PATH = os.path.join(PKG_DIR, "libdmdetect.so")
+SO_PATH = os.environ.get("DM_LIB_PATH") or os.path.join(PKG_DIR, "libdmdetect.so")   # (DM_LIB_PATH: A/B builds side by side)
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "dmdetect.h")
 
 NVCC_FLAGS = [
@@ -39,6 +39,8 @@ def _sources() -> List[str]:
 
 
 def needs_build() -> bool:
+    if os.environ.get("DM_LIB_PATH"):
+        return False                                              # a hand-built variant: never rebuilt behind the user's back
     if not os.path.exists(SO_PATH):
         return True
     so_m = os.path.getmtime(SO_PATH)
@@ -102,6 +104,7 @@ SYMBOLS = {
     "dm_host_cache_flush": (C.c_int, [_P, C.c_uint64]),
     "dm_debug_rows_timeline": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint32)]),
     "dm_set_format": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p)]),
+    "dm_stream_recheck_chained": (C.c_int, [_P]),
     "dm_set_format_ex": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32]),
     "dm_process_records": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64,
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -88,6 +88,7 @@ struct DmxShared {
     unsigned long long epi_done_seq;         // sequence number of the last launch whose epilogue is complete
     unsigned long long zero_bound[DMX_NPAR]; // [seq % NPAR]: records of detect message seq-NPAR: launch seq's CTAs zero-fill
                                              // that many output entries between them, its epilogue does the rest (if any)
+    unsigned int slow_batches[DMX_NPAR];     // [seq % NPAR]: field-phase batches of launch seq that held a candidate
 };
 
 struct DmxArgs {
@@ -122,6 +123,7 @@ struct DmxArgs {
     uint32_t keep_error;                     // the epilogue ORs into hdr->error instead of assigning it
     unsigned long long* timeline;            // diagnostics (DM_STREAM_TIMELINE=1): per CTA {smid, t_start, t_rows_done, t_exit},
                                              // then 8 epilogue stamps (globaltimer ns); else NULL
+    unsigned long long* hint;                // (host-mapped) written by the detect epilogue: (batches with a candidate << 32) | rows
 };
 
 __device__ __forceinline__ unsigned long long dmx_now() {
@@ -723,9 +725,10 @@ struct DmxDrainCtx {
 // Field phase: n (<= 32) queued fields, one per lane.  Called from ONE place in the kernel (one copy of the code);
 // the lanes are brought back together (__syncwarp) after every data-dependent stretch: without that they drift
 // apart for the rest of the function and every later instruction is issued several times for a few lanes each.
-template <bool TRAIN>
+template <bool TRAIN, bool CHAIN>
 __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab& sk, const uint8_t* ring, const uint32_t* q, uint32_t qh,
-                                          uint32_t n, uint32_t seg_base, uint32_t bound, DmxCarry* carry, uint32_t qn, const uint32_t* pq, uint32_t ph, uint32_t pn) {
+                                          uint32_t n, uint32_t seg_base, uint32_t bound, DmxCarry* carry, uint32_t* s_slow, uint32_t qn, const uint32_t* pq, uint32_t ph,
+                                          uint32_t pn) {
     const uint32_t lane = threadIdx.x & 31;
     const uint8_t* __restrict__ buf = a.buf;
     const uint64_t nbytes = a.nbytes;
@@ -811,19 +814,27 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
         cand = !(TRAIN ? dm_table_contains_volatile(a.table, ckey) : dm_table_contains(a.table, ckey));
     }
     if (__any_sync(0xffffffffu, cand)) {
-        const bool chainable = !__any_sync(0xffffffffu, lane < n && (int)((qpos - seg_base) >> DMX_ROW_LOG2) <= carry->dense_row);
-        // the smallest offset among the next three '=' still queued behind the batch (field queue, then position queue):
-        // the only ones that can be siblings of the batch's last entries
-        uint32_t pend = 0xFFFFFFFFu;
-        if (lane < 3u) {
-            const uint32_t rest = qn - n;
-            if (lane < rest) pend = seg_base + (q[(qh + n + lane) & (DMX_QCAP - 1)] >> 7);
-            else if (lane - rest < pn) pend = seg_base + pq[(ph + lane - rest) & (DMX_PCAP - 1)];
+        // (how often this happens decides which instantiation the host launches next: see dmx_launch)
+        if (lane == 0) s_slow[threadIdx.x >> 5] += 1u;
+        uint32_t ls = 0;
+        bool ok = false;
+        if (CHAIN) {
+            const bool chainable = !__any_sync(0xffffffffu, lane < n && (int)((qpos - seg_base) >> DMX_ROW_LOG2) <= carry->dense_row);
+            // the smallest offset among the next three '=' still queued behind the batch (field queue, then position queue):
+            // the only ones that can be siblings of the batch's last entries
+            uint32_t pend = 0xFFFFFFFFu;
+            if (lane < 3u) {
+                const uint32_t rest = qn - n;
+                if (lane < rest) pend = seg_base + (q[(qh + n + lane) & (DMX_QCAP - 1)] >> 7);
+                else if (lane - rest < pn) pend = seg_base + pq[(ph + lane - rest) & (DMX_PCAP - 1)];
+            }
+            pend = __reduce_min_sync(0xffffffffu, pend);
+            const unsigned long long vr_ = dmx_verify_chain(buf, a.gk, carry, qh, n, chainable, pend, qpos, k, cand);
+            ls = (uint32_t)vr_;
+            ok = (vr_ >> 32) != 0ull;
+        } else {
+            ok = cand && dmx_verify_thread(buf, qpos, (uint32_t)k, a.gk, &ls);      // every candidate walks its own record back
         }
-        pend = __reduce_min_sync(0xffffffffu, pend);
-        const unsigned long long vr_ = dmx_verify_chain(buf, a.gk, carry, qh, n, chainable, pend, qpos, k, cand);
-        const uint32_t ls = (uint32_t)vr_;
-        const bool ok = (vr_ >> 32) != 0ull;
         if (cand) {
             if (ok) {
                 if (TRAIN) {
@@ -849,7 +860,10 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
     }
 }
 
-template <bool TRAIN>
+// CHAIN: candidates are re-checked batch-wise (dmx_verify_chain) instead of one by one.  Same results; the chained code
+// costs the row loop about 5 % more instructions (its register demand makes ptxas rematerialise loop state), so it is a
+// separate instantiation that the host picks for streams in which candidates are frequent (dmx_launch).
+template <bool TRAIN, bool CHAIN>
 __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs a) {
 #ifdef DM_EMU
     uint8_t* s_dyn = g_emu_dyn_smem.data();
@@ -866,6 +880,7 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
     __shared__ int s_last;
     __shared__ DmxDrainCtx s_ctx;
     __shared__ DmxCarry s_carry[DMX_WARPS];
+    __shared__ uint32_t s_slow[DMX_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = dm_lanemask_lt();
     dm_pdl_launch_dependents();                       // the next launch may be scheduled as soon as there is room
@@ -889,8 +904,8 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
     }
     if (lane == 0) {
         s_cnt[warp] = 0;
-        s_carry[warp].qh_next = 0xFFFFFFFFu;
-        s_carry[warp].dense_row = -1;
+        s_slow[warp] = 0;
+        if (CHAIN) { s_carry[warp].qh_next = 0xFFFFFFFFu; s_carry[warp].dense_row = -1; }
 #ifndef DM_EMU
         for (uint32_t s = 0; s < DMX_SLOTS; ++s) dmx_mbar_init(dmx_smem_u32(&s_bar[warp][s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -972,9 +987,11 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
             uint32_t g = (dmx_chunk_bits(va, 0x3D3D3D3Du) << (4u * c_first)) | (dmx_chunk_bits(vb, 0x3D3D3D3Du) << (4u * (1u - c_first)));
             const uint32_t qrel = i * DMX_ROW + lane * 32u;
             const bool last = i + 1 == n_own;
-            if (__any_sync(0xffffffffu, __popc(g) > 4)) {           // (see dmx_verify_chain)
-                if (lane == 0) s_carry[warp].dense_row = (int)i;
-                __syncwarp();
+            if (CHAIN) {
+                if (__any_sync(0xffffffffu, __popc(g) > 4)) {       // (see dmx_verify_chain)
+                    if (lane == 0) s_carry[warp].dense_row = (int)i;
+                    __syncwarp();
+                }
             }
             bool row_done;
             do {
@@ -1009,7 +1026,7 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
                 for (;;) {
                     if (qn >= 32u || (qn && row_done && ((last && !pn) || (q[qh & (DMX_QCAP - 1)] >> (7 + DMX_ROW_LOG2)) + (DMX_SLOTS - 2u) <= i))) {
                         const uint32_t n = qn < 32u ? qn : 32u;
-                        dmx_drain<TRAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound, &s_carry[warp], qn, pq, ph, pn);
+                        dmx_drain<TRAIN, CHAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound, &s_carry[warp], s_slow, qn, pq, ph, pn);
                         qh += n;
                         qn -= n;
                         continue;
@@ -1043,7 +1060,10 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
                 }
             } while (!row_done);
         }
-        if (lane == 0) s_cnt[warp] = nl_w;
+        if (lane == 0) {
+            s_cnt[warp] = nl_w;
+            if (s_slow[warp]) atomicAdd(&a.sh->slow_batches[a.seq % DMX_NPAR], s_slow[warp]);
+        }
     }
 
     // ---- end of the CTA's rows ----
@@ -1236,6 +1256,9 @@ __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long lon
         if (tl && tid == 0) tl[4] = dmx_now();
     }
     if (tid == 0) {
+        const unsigned int sb = *((volatile unsigned int*)&a.sh->slow_batches[a.seq % DMX_NPAR]);
+        a.sh->slow_batches[a.seq % DMX_NPAR] = 0;
+        if (!TRAIN && a.hint) *((volatile unsigned long long*)a.hint) = ((unsigned long long)sb << 32) | a.n_rows;
         *a.alert_count = 0;
         a.sh->done_ctr[a.seq % (2 * DMX_NPAR)] = 0;
         __threadfence();
@@ -1316,6 +1339,10 @@ struct DmxScratch {
     cudaStream_t chain_stream = nullptr;        // stream of the last launch, if it was a plain detect launch (else NULL)
     unsigned long long* d_timeline = nullptr;   // DM_STREAM_TIMELINE=1
     unsigned last_grid = 0;
+    // which instantiation re-checks candidates: 0 = one by one, 1 = chained, 2 = by what the last finished message looked like
+    int recheck_mode = 2;
+    unsigned long long* h_hint = nullptr;       // pinned, device-mapped: (batches with a candidate << 32) | rows of that message
+    bool last_chained = false;
 };
 
 static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t max_batch_bytes, uint32_t alert_cap, int sm_count) {
@@ -1329,10 +1356,22 @@ static inline int dmx_scratch_create(DmxScratch* s, const DmKeys& keys, uint64_t
     if (e != cudaSuccess) return DM_ERR_CUDA;
     s->max_rows = (max_batch_bytes + DMB_ROW - 1) / DMB_ROW + 64;
     s->alert_cap = alert_cap;
-    if (cudaFuncSetAttribute(dm_k_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
-    if (cudaFuncSetAttribute(dm_k_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_stream<false>, DMX_THREADS, s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaFuncSetAttribute(dm_k_stream<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaFuncSetAttribute(dm_k_stream<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaFuncSetAttribute(dm_k_stream<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaFuncSetAttribute(dm_k_stream<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
+    int per_sm = 0, per_sm_c = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dm_k_stream<false, false>, DMX_THREADS, s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, dm_k_stream<false, true>, DMX_THREADS, s->dyn_smem) != cudaSuccess) return DM_ERR_CUDA;
+    if (per_sm_c < per_sm) per_sm = per_sm_c;                // (one geometry for both instantiations)
+    {
+        const char* m = getenv("DM_STREAM_RECHECK");         // thread | chain | auto (default)
+        if (m && !strcmp(m, "thread")) s->recheck_mode = 0;
+        else if (m && !strcmp(m, "chain")) s->recheck_mode = 1;
+        else if (m && strcmp(m, "auto") && *m) return DM_ERR_ARG;
+        if (cudaHostAlloc((void**)&s->h_hint, sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess) return DM_ERR_CUDA;
+        *s->h_hint = 0;
+    }
     if (per_sm < 1) per_sm = 1;
     const char* cap = getenv("DM_STREAM_CTAS_PER_SM");     // tuning knob
     if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
@@ -1362,6 +1401,7 @@ static inline void dmx_scratch_destroy(DmxScratch* s) {
     cudaFree(s->d_keys);
     for (unsigned b = 0; b < DMX_NPAR; ++b) { cudaFree(s->d_row_cnt[b]); cudaFree(s->d_cta_cnt[b]); cudaFree(s->d_alerts[b]); }
     cudaFree(s->d_bound_cnt); cudaFree(s->d_alert_count); cudaFree(s->d_bound); cudaFree(s->d_shared); cudaFree(s->d_timeline);
+    if (s->h_hint) cudaFreeHost(s->h_hint);
     *s = DmxScratch();
 }
 
@@ -1380,6 +1420,15 @@ static inline int dmx_launch(DmxScratch* s, const uint8_t* d_buf, uint64_t nbyte
     a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap; a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap;
     a.hdr = d_hdr; a.stats = d_stats; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
     a.sh = s->d_shared; a.alert_cap = s->alert_cap; a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = s->d_timeline; a.ring_smem = DMX_RING_SMEM;
+    a.hint = s->h_hint;                                      // (unified addressing: the mapped host pointer is the device pointer)
+    // chained re-check when, in the last message whose epilogue has run, at least every fourth row had a batch with a
+    // candidate (both instantiations give the same results; this only picks the faster one for the stream at hand)
+    bool chained = s->recheck_mode == 1;
+    if (s->recheck_mode == 2) {
+        const unsigned long long hint = *((volatile unsigned long long*)s->h_hint);
+        chained = (hint & 0xFFFFFFFFull) != 0 && (hint >> 32) * 4ull >= (hint & 0xFFFFFFFFull);
+    }
+    s->last_chained = chained;
     // geometry: every warp gets the same number of contiguous rows
     const unsigned long long warps_max = (unsigned long long)s->max_grid * DMX_WARPS;
     const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
@@ -1401,13 +1450,13 @@ static inline int dmx_launch(DmxScratch* s, const uint8_t* d_buf, uint64_t nbyte
         dm_k_bound<<<1, 256, 0, st>>>(d_buf, nbytes, b_rows, s->d_bound_cnt, n_train_lines, s->d_bound, d_hdr);
         a.bound_ptr = s->d_bound; a.keep_error = 1;
         bind();
-        dm_launch_pdl_smem(dm_k_stream<true>, grid, DMX_THREADS, (size_t)s->dyn_smem, st, false, a);
+        dm_launch_pdl_smem(chained ? dm_k_stream<true, true> : dm_k_stream<true, false>, grid, DMX_THREADS, (size_t)s->dyn_smem, st, false, a);
         launched += 3;
     }
     bind();
     const bool pdl = allow_overlap && n_train_lines == 0 && s->chain_stream == st;
     if (mark) mark(mark_ctx, st, 0);
-    dm_launch_pdl_smem(dm_k_stream<false>, grid, DMX_THREADS, (size_t)s->dyn_smem, st, pdl, a);
+    dm_launch_pdl_smem(chained ? dm_k_stream<false, true> : dm_k_stream<false, false>, grid, DMX_THREADS, (size_t)s->dyn_smem, st, pdl, a);
     if (mark) mark(mark_ctx, st, 1);
     s->chain_stream = st;
     ++launched;

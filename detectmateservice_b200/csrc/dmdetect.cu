@@ -208,6 +208,7 @@ static int dm_create_fill(dm_handle* h, int device, const cudaDeviceProp& prop, 
     int rc = dm_rows_scratch_create(&h->rows, max_batch_bytes, h->sm_count);
     if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "row index scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     rc = dmx_scratch_create(&h->dmx, h->h_keys, max_batch_bytes, h->anomaly_cap, h->sm_count);
+    if (rc == DM_ERR_ARG) return dm_fail(DM_ERR_ARG, "DM_STREAM_RECHECK=%s: thread, chain or auto", getenv("DM_STREAM_RECHECK"));
     if (rc != DM_OK) { return dm_fail(DM_ERR_CUDA, "stream scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     { const char* ov = getenv("DM_OVERLAP"); if (ov) h->dmx.overlap = atoi(ov) != 0; }
     const char* env = getenv("DM_KERNEL");
@@ -625,6 +626,11 @@ extern "C" int dm_set_format_ex(dm_handle* h, const char* log_format, const char
     }
     delete f;
     return rc;
+}
+
+extern "C" int dm_stream_recheck_chained(dm_handle* h) {
+    if (!h) return dm_fail(DM_ERR_ARG, "handle is NULL");
+    return h->dmx.last_chained ? 1 : 0;
 }
 
 // diagnostics: start / end times of the K_B warps of the last rows launch (DM_ROWS_TIMELINE=1)

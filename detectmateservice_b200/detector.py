@@ -297,6 +297,13 @@ class DeviceDetector:
         the caller promises not to rewrite a call's input with a kernel enqueued between calls)."""
         _lib.check(self._lib.dm_set_overlap(self._h, int(on)))
 
+    def stream_recheck_chained(self) -> bool:
+        """Did the last key=value message go through the stream kernel's batch-wise re-check of candidates?"""
+        rc = self._lib.dm_stream_recheck_chained(self._h)
+        if rc < 0:
+            _lib.check(rc)
+        return rc == 1
+
     def profile_enable(self, on: bool = True) -> None:
         _lib.check(self._lib.dm_profile_enable(self._h, int(on)))
 

@@ -187,6 +187,10 @@ int dm_set_format(dm_handle* h, const char* log_format, const char* content_name
 #define DM_NORM_LOWERCASE 4u
 int dm_set_format_ex(dm_handle* h, const char* log_format, const char* content_name, uint32_t n_templates,
                      const char* const* templates, uint32_t norm_flags);
+/* Diagnostics: 1 if the last key=value message was processed by the stream kernel's batch-wise re-check of candidate
+ * fields, 0 if candidates were re-checked one by one.  Both give the same results; unless DM_STREAM_RECHECK=thread|chain
+ * pins it, the library chooses per message from how often the previous message's field batches held a candidate. */
+int dm_stream_recheck_chained(dm_handle* h);
 /* Host utility: write a host buffer back to memory and evict it from the CPU caches (x86:
  * clflush), so that device DMA streams it from DRAM instead of snooping dirty cache lines. */
 int dm_host_cache_flush(const void* p, uint64_t nbytes);

@@ -17,8 +17,13 @@ from detectmateservice_b200.detector import DeviceDetector
 from detectmateservice_b200.synth import MONITORED_KEYS
 
 overlap = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-msgs = _make_messages(0, n_msgs=6)
-det = DeviceDetector(MONITORED_KEYS, max_batch_bytes=len(msgs[0]) + 4096, max_lines=LINES_PER_MSG + 16, table_log2_slots=16)
+if len(sys.argv) > 2 and sys.argv[2] == "varlen":            # BASELINE config 5 record lengths
+    from detectmateservice_b200.synth import AuditSynth, SEED
+    g = AuditSynth(SEED + 3)
+    msgs = [g.batch_varlen(LINES_PER_MSG, inject=False)[0]] + [g.batch_varlen(LINES_PER_MSG, inject=True)[0] for _ in range(5)]
+else:
+    msgs = _make_messages(0, n_msgs=6)
+det = DeviceDetector(MONITORED_KEYS, max_batch_bytes=max(len(m) for m in msgs) + 4096, max_lines=LINES_PER_MSG + 16, table_log2_slots=16)
 det.set_overlap(bool(overlap))
 d = []
 for m in msgs:
@@ -29,7 +34,7 @@ st = torch.cuda.Stream()
 sp = st.cuda_stream
 det.enqueue_device(d[0].data_ptr(), len(msgs[0]), LINES_PER_MSG, 0, 0, 0, sp)
 for i in range(12):
-    det.enqueue_device(d[1 + i % 5].data_ptr(), len(msgs[0]), 0, 0, 0, 0, sp)
+    det.enqueue_device(d[1 + i % 5].data_ptr(), len(msgs[1 + i % 5]), 0, 0, 0, 0, sp)
 det.sync()
 n = C.c_uint32()
 _lib.check(det._lib.dm_debug_rows_timeline(det._h, None, 0, C.byref(n)))

@@ -106,12 +106,13 @@ struct EmuStream {
     std::vector<unsigned int> cta_cnt[DMX_NPAR];
     std::vector<dm_anomaly_t> alerts[DMX_NPAR];
     unsigned int alert_count[DMX_NPAR] = {};
-    unsigned long long bound = 0, seq = 0;
+    unsigned long long bound = 0, seq = 0, hint = 0;
     bool ready = false;
 };
+static unsigned long long g_emu_last_hint = 0;
 void emu_stream_free(EmuStream* x) { delete x; }
-extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
-                                  float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+static int emu_stream_run(EmuHandle* h, bool chained, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                          float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
     if (!h->xs) {
         h->xs = new EmuStream();
         if (!dmx_keytab_build(h->keys, &h->xs->tab)) return -7;
@@ -137,6 +138,7 @@ extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nby
     a.flags = flags; a.scores = scores; a.out_cap = cap; a.anomalies = h->anoms.data(); a.anomaly_cap = (uint32_t)h->anoms.size();
     a.hdr = &h->hdr; a.stats = h->stats; a.n_train_lines = n_train; a.max_lines = h->max_lines;
     a.sh = &g_xs.sh; a.alert_cap = (uint32_t)h->anoms.size(); a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = nullptr; a.ring_smem = DMX_RING_SMEM;
+    a.hint = &g_xs.hint;
     const unsigned long long warps_max = (unsigned long long)g_emu_stream_ctas * DMX_WARPS;
     const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
     const unsigned long long warps = (n_rows + rpw - 1) / rpw;
@@ -156,16 +158,31 @@ extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nby
         emu_launch(256, [&] { dm_k_bound(buf, nbytes, b_rows, g_xs.bound_cnt.data(), n_train, &g_xs.bound, &h->hdr); });
         a.bound_ptr = &g_xs.bound; a.keep_error = 1;
         bind();
-        emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<true>(a); });
+        if (chained) emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<true, true>(a); });
+        else emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<true, false>(a); });
     }
     bind();
-    emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<false>(a); });
+    if (chained) emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<false, true>(a); });
+    else emu_launch_grid(grid, DMX_THREADS, [&] { dm_k_stream<false, false>(a); });
+    g_emu_last_hint = g_xs.hint;
     free(buf);
     *n_lines = h->hdr.n_lines;
     *n_anoms = h->hdr.n_anomalies;
     *err = h->hdr.error;
     return 0;
 }
+
+// the two instantiations of the stream kernel: candidates re-checked one by one / batch-wise (dmx_verify_chain)
+extern "C" int emu_process_stream(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                  float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    return emu_stream_run(h, false, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err);
+}
+extern "C" int emu_process_stream_chain(EmuHandle* h, const uint8_t* msg, uint64_t nbytes, uint64_t n_train, uint8_t* flags,
+                                        float* scores, uint64_t cap, uint64_t* n_lines, uint64_t* n_anoms, uint32_t* err) {
+    return emu_stream_run(h, true, msg, nbytes, n_train, flags, scores, cap, n_lines, n_anoms, err);
+}
+// what the last detect launch told the host: (batches with a candidate << 32) | rows
+extern "C" unsigned long long emu_stream_hint(void) { return g_emu_last_hint; }
 
 // Record mode on the device: mirrors dm_process_records (framing walk on the host, then
 // dm_k_records train pass + detect pass).  `mons` uses the dm_monitor_t layout.

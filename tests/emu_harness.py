@@ -43,6 +43,8 @@ class EmuDetector:
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_process_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.emu_process_stream_chain.argtypes = L.emu_process_stream.argtypes
+        L.emu_stream_hint.restype = C.c_uint64
         L.emu_create.restype = C.c_void_p
         L.emu_create.argtypes = [C.c_uint32, C.c_char_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint64, C.c_uint64]
         L.emu_destroy.argtypes = [C.c_void_p]
@@ -67,7 +69,8 @@ class EmuDetector:
         flags = np.full(cap, 7, dtype=np.uint8)
         scores = np.full(cap, -1, dtype=np.float32)
         n_lines, n_anom, err = C.c_uint64(), C.c_uint64(), C.c_uint32()
-        fn = {"lanes": self.lib.emu_process_lanes, "stream": self.lib.emu_process_stream}[self.variant]
+        fn = {"lanes": self.lib.emu_process_lanes, "stream": self.lib.emu_process_stream,
+              "chain": self.lib.emu_process_stream_chain}[self.variant]
         rc = fn(self.h, msg, len(msg), n_train, flags.ctypes.data, scores.ctypes.data, cap,
                                   C.byref(n_lines), C.byref(n_anom), C.byref(err))
         assert rc == 0 and err.value == 0, (rc, err.value)

@@ -16,13 +16,17 @@ from util import FUZZ_KEYS, FUZZ_KEYS_FEW, fuzz_lines
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = ["stream", "lanes"]
+# stream = the default kernel with candidates re-checked one by one, chain = the same kernel's batch-wise re-check
+# (DM_STREAM_RECHECK; left alone the library picks per message), lanes = one thread per record
+VARIANTS = ["stream", "chain", "lanes"]
 SCORE_TOL = 1e-5
 
 
 @pytest.fixture(params=VARIANTS)
 def variant(request, monkeypatch):
-    monkeypatch.setenv("DM_KERNEL", request.param)
+    monkeypatch.setenv("DM_KERNEL", "lanes" if request.param == "lanes" else "stream")
+    if request.param != "lanes":
+        monkeypatch.setenv("DM_STREAM_RECHECK", "chain" if request.param == "chain" else "thread")
     return request.param
 
 
@@ -163,6 +167,39 @@ def test_varlen_config5(variant):
         _check(det, o, train, 20000)
         f, _ = _check(det, o, msg, 0)
         assert f.sum() > 0
+
+
+def test_recheck_mode_follows_the_stream(monkeypatch):
+    """Left alone (DM_STREAM_RECHECK unset) the library re-checks one by one while candidates are rare and switches to the
+    batch-wise re-check when most batches hold one (config-5 look-alikes) -- with the oracle's results either way."""
+    from detectmateservice_b200.synth import AuditSynth, MONITORED_KEYS
+    from util import lookalike_lines
+    monkeypatch.setenv("DM_KERNEL", "stream")
+    monkeypatch.delenv("DM_STREAM_RECHECK", raising=False)
+    keys = [k.encode() for k in MONITORED_KEYS]
+    g = AuditSynth(seed=77)
+    o = NativeOracle(keys)
+    with _det(keys) as det:
+        _check(det, o, g.batch(20000, inject=False)[0], 20000)
+        modes = []
+        for i in range(3):
+            _check(det, o, g.batch(20000, inject=True)[0], 0)
+            modes.append(det.stream_recheck_chained())
+        for i in range(4):
+            _check(det, o, g.batch_varlen(20000, inject=True)[0], 0)
+            modes.append(det.stream_recheck_chained())
+        for i in range(3):
+            _check(det, o, g.batch(20000, inject=True)[0], 0)
+            modes.append(det.stream_recheck_chained())
+        # (the choice for a message rests on the message before it)
+        assert modes == [False, False, False, False, True, True, True, True, False, False], modes
+    keys2 = [b"key", b"type", b"res"]
+    o2 = NativeOracle(keys2)
+    with _det(keys2) as det:
+        _check(det, o2, lookalike_lines(5, 3000), 1000)
+        for seed in (6, 7, 8):
+            _check(det, o2, lookalike_lines(seed, 3000), 0)
+        assert det.stream_recheck_chained()
 
 
 def test_full_size_properties(variant):
