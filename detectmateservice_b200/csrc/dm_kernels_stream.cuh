@@ -433,6 +433,7 @@ __device__ __forceinline__ bool dmx_verify_thread(const uint8_t* __restrict__ bu
 #ifdef DM_EMU
 static unsigned long long g_emu_chain_stats[8];      // candidates decided by the chain / by the fall-back / in batches not chained
 #endif
+#define DMX_LATE 16u                         // (a field takes at least 3 bytes: at most 10 in 32)
 struct DmxCarry {
     uint32_t qh_next;        // queue index of the entry right behind the batch this state describes
     uint32_t last_q;         // the largest '=' offset of that batch
@@ -441,6 +442,10 @@ struct DmxCarry {
     uint32_t seen;           // keys of the true fields of that record up to and including last_q
     int dense_row;           // last row (of this warp's) in which a lane had more than four '=': its entries are out of order
     uint8_t perm[32];        // scratch: lane that holds the entry of sorted rank r
+    // scratch of a batch without carried state: the true fields in its first 32-byte chunk, read from the bytes
+    uint32_t n_late;
+    uint32_t late_pos[DMX_LATE];
+    uint8_t late_key[DMX_LATE];
 };
 
 // bytes [lb, q): offset behind the last '\n' (found) and the parity of '"' behind it (else of the whole interval)
@@ -466,11 +471,24 @@ __device__ __forceinline__ void dmx_scan_back(const uint8_t* __restrict__ buf, u
     }
 }
 
+// Which monitored key ends right before the '=' at e, starting at a field start of the record that begins at ls (-1: none)?
+// Byte-wise from global memory: the slow paths' counterpart of dmx_resolve_key.
+__device__ __forceinline__ int dmx_key_at(const uint8_t* __restrict__ buf, const DmxKeyTab* gk, uint32_t nk, uint32_t e, uint32_t ls) {
+    for (uint32_t k = 0; k < nk; ++k) {
+        const uint32_t L = gk->len[k];
+        if (e < ls + L) continue;
+        const uint32_t ks = e - L;
+        bool ok = ks == ls || dmx_is_delim(dm_ld8(buf, ks - 1u));
+        for (uint32_t i = L; ok && i > 0; --i) ok = dm_ld8(buf, ks + i - 1u) == gk->bytes[k][i - 1u];
+        if (ok) return (int)k;
+    }
+    return -1;
+}
+
 // Warp-collective: the record that holds byte q0 - 1 (q0 = an '=' offset): *ls = its first byte, *par_q0 = parity of '"' in
-// [ls, q0), return value = keys of its true fields (R-tok L2/L4/L5) whose '=' lies in [ls, x_end).  Two passes over the
+// [ls, q0), return value = keys of its true fields (R-tok L2/L4/L5) whose '=' lies in [ls, q0).  Two passes over the
 // bytes themselves, 512 per step: backwards for the last '\n' in front of q0, then forwards with the running parity.
-__device__ __forceinline__ uint32_t dmx_history(const uint8_t* __restrict__ buf, const DmxKeyTab* gk, uint32_t q0, uint32_t x_end, uint32_t* ls_out,
-                                                uint32_t* par_q0) {
+__device__ __forceinline__ uint32_t dmx_history(const uint8_t* __restrict__ buf, const DmxKeyTab* gk, uint32_t q0, uint32_t* ls_out, uint32_t* par_q0) {
     const uint32_t lane = threadIdx.x & 31, full = 0xffffffffu;
     const uint4* b16 = reinterpret_cast<const uint4*>(buf);
     uint32_t ls = 0;
@@ -492,35 +510,18 @@ __device__ __forceinline__ uint32_t dmx_history(const uint8_t* __restrict__ buf,
             }
         }
     }
-    uint32_t seen = 0, pq0 = 0, run = 0;
+    uint32_t seen = 0, run = 0;
     const uint32_t nk = gk->n;
-    for (uint32_t cb0 = ls & ~15u; cb0 < x_end; cb0 += 512u) {
+    for (uint32_t cb0 = ls & ~15u; cb0 < q0; cb0 += 512u) {
         const uint32_t cb = cb0 + 16u * lane;
-        uint32_t dq = 0, eq = 0, nl = 0;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        uint32_t keep = 0u;
-        if (cb < x_end) {
-            v = __ldg(b16 + (cb >> 4));
-            keep = 0xFFFFu;
+        uint32_t dq = 0, eq = 0;
+        if (cb < q0) {
+            const uint4 v = __ldg(b16 + (cb >> 4));
+            uint32_t keep = 0xFFFFu;
             if (cb < ls) keep &= ~((1u << (ls - cb)) - 1u);
-            if (x_end - cb < 16u) keep &= (1u << (x_end - cb)) - 1u;
-            nl = dm_chunk_mask(v, 0x0A0A0A0Au) & keep;                      // (behind q0: the record may end in front of x_end)
-        }
-        const uint32_t ends = __ballot_sync(full, nl != 0u);
-        if (ends) {
-            const int first = __ffs((int)ends) - 1;
-            const uint32_t at = (uint32_t)__ffs((int)__shfl_sync(full, nl, first)) - 1u;
-            if ((int)lane > first) keep = 0u;
-            else if ((int)lane == first) keep &= (1u << at) - 1u;
-            x_end = cb0 + 16u * (uint32_t)first + at;                       // the loop ends with this step
-        }
-        if (keep) {
+            if (q0 - cb < 16u) keep &= (1u << (q0 - cb)) - 1u;
             dq = dm_chunk_mask(v, 0x22222222u) & keep;
             eq = dm_chunk_mask(v, 0x3D3D3D3Du) & keep;
-            uint32_t below = dq;
-            if (cb >= q0) below = 0u;
-            else if (q0 - cb < 16u) below &= (1u << (q0 - cb)) - 1u;
-            pq0 ^= (uint32_t)__popc(below) & 1u;
         }
         const uint32_t odd = __ballot_sync(full, (__popc(dq) & 1) != 0);
         const uint32_t par_in = run ^ ((uint32_t)__popc(odd & dm_lanemask_lt()) & 1u);
@@ -528,22 +529,33 @@ __device__ __forceinline__ uint32_t dmx_history(const uint8_t* __restrict__ buf,
             const uint32_t j = (uint32_t)__ffs(eq) - 1u;
             eq &= eq - 1u;
             if ((par_in ^ ((uint32_t)__popc(dq & ((1u << j) - 1u)) & 1u)) != 0u) continue;     // inside double quotes
-            const uint32_t e = cb + j;
-            for (uint32_t k = 0; k < nk; ++k) {
-                const uint32_t L = gk->len[k];
-                if (e < ls + L) continue;
-                const uint32_t ks = e - L;
-                bool ok = ks == ls || dmx_is_delim(dm_ld8(buf, ks - 1u));
-                for (uint32_t i = L; ok && i > 0; --i) ok = dm_ld8(buf, ks + i - 1u) == gk->bytes[k][i - 1u];
-                if (ok) { seen |= 1u << k; break; }
-            }
+            const int k = dmx_key_at(buf, gk, nk, cb + j, ls);
+            if (k >= 0) seen |= 1u << k;
         }
         run ^= (uint32_t)__popc(odd) & 1u;
         __syncwarp();
     }
     *ls_out = ls;
-    *par_q0 = __reduce_xor_sync(full, pq0);
+    *par_q0 = run;
     return __reduce_or_sync(full, seen);
+}
+
+// ONE lane: the true fields whose '=' lies in [q0, x_end) (at most 32 bytes), byte by byte, given the record start and
+// the quote parity at q0; records may end and begin on the way.  They go to cy->late_*.
+__device__ __forceinline__ void dmx_first_chunk(const uint8_t* __restrict__ buf, const DmxKeyTab* gk, DmxCarry* cy, uint32_t q0, uint32_t x_end,
+                                                uint32_t ls, uint32_t par) {
+    const uint32_t nk = gk->n;
+    uint32_t n = 0;
+    for (uint32_t p = q0; p < x_end; ++p) {
+        const uint32_t c = dm_ld8(buf, p);
+        if (c == 0x0Au) { par = 0; ls = p + 1u; }
+        else if (c == 0x22u) par ^= 1u;
+        else if (c == 0x3Du && !par) {
+            const int k = dmx_key_at(buf, gk, nk, p, ls);
+            if (k >= 0 && n < DMX_LATE) { cy->late_pos[n] = p; cy->late_key[n] = (uint8_t)k; ++n; }
+        }
+    }
+    cy->n_late = n;
 }
 
 // Warp-collective.  Lane i < n holds queue entry i of the batch: '=' at qpos_in, key k_in (-1: no monitored key ends
@@ -552,7 +564,7 @@ __device__ __forceinline__ uint32_t dmx_history(const uint8_t* __restrict__ buf,
 // of it has no sibling left in the queues.  Returns (ok << 32) | ls: ok = 1 for the candidates that are the first true field with their key in their record,
 // ls = first byte of that record.
 __device__ DM_NOINLINE unsigned long long dmx_verify_chain(const uint8_t* __restrict__ buf, const DmxKeyTab* gk, DmxCarry* cy, uint32_t qh,
-                                                           uint32_t n, bool chainable, uint32_t pend_min, uint32_t qpos_in, int k_in, bool cand_in) {
+                                                           uint32_t n, bool chainable, uint32_t pend_min, uint64_t nbytes, uint32_t qpos_in, int k_in, bool cand_in) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t full = 0xffffffffu;
     bool ok = false;
@@ -591,14 +603,17 @@ __device__ DM_NOINLINE unsigned long long dmx_verify_chain(const uint8_t* __rest
     uint32_t prev = __shfl_up_sync(full, qpos, 1);
     const bool sorted = !__any_sync(full, inq && lane > 0 && prev >= qpos) && __popc(__ballot_sync(full, qpos != 0xFFFFFFFFu)) == (int)n;
     if (sorted) {
-        // ---- nothing carried over: the record the batch starts in is read from its first byte (history) up to the end
-        // of the batch's first 32-byte chunk x_end -- entries in front of x_end may have siblings that left the queue
-        // earlier, so there the bytes speak, not the queue; from x_end on, the queue does ----
+        // ---- nothing carried over: the record the batch starts in is read from its first byte up to the batch's first
+        // '=' (history), and so is the rest of that '=''s 32-byte chunk, up to x_end (late list): there, entries may have
+        // siblings that left the queue earlier, so the bytes speak, not the queue; from x_end on the queue does ----
         uint32_t x_end = 0;
         if (!cont) {
             x_end = (q_first | 31u) + 1u;
+            if ((uint64_t)x_end > nbytes) x_end = (uint32_t)nbytes;
             uint32_t h_par = 0;
-            c_seen = dmx_history(buf, gk, q_first, x_end, &c_ls, &h_par);
+            c_seen = dmx_history(buf, gk, q_first, &c_ls, &h_par);
+            if (lane == 0) dmx_first_chunk(buf, gk, cy, q_first, x_end, c_ls, h_par);
+            __syncwarp();
             c_par = h_par | 2u;
             c_q = 0xFFFFFFFFu;
         }
@@ -622,8 +637,8 @@ __device__ DM_NOINLINE unsigned long long dmx_verify_chain(const uint8_t* __rest
         const bool head = lane == 0 ? c_ls != ls : ls_prev != ls;                 // no earlier entry of this record in the batch / the carry
         const uint32_t heads = __ballot_sync(full, head && inq);
         const bool in_first = (heads & ((2u << lane) - 1u) & ~1u) == 0u;           // same record as the first entry
-        // (the true fields in front of x_end of the batch's first record are in the history already)
-        const uint32_t bit = (inq && k >= 0 && par == 0u && !(in_first && qpos < x_end)) ? 1u << k : 0u;
+        // (the true fields in front of x_end are in the late list)
+        const uint32_t bit = (inq && k >= 0 && par == 0u && qpos >= x_end) ? 1u << k : 0u;
         uint32_t incl = bit | ((lane == 0 && !head) ? c_seen : 0u);
         bool hd = head;
 #pragma unroll
@@ -635,21 +650,28 @@ __device__ DM_NOINLINE unsigned long long dmx_verify_chain(const uint8_t* __rest
         uint32_t before = __shfl_up_sync(full, incl, 1);
         if (lane == 0) before = head ? 0u : c_seen;
         else if (head) before = 0u;
-        // ---- which entries know all of their record's earlier fields ----
-        const uint32_t chunk_first = q_first >> 5;
-        // the first entry's record: carried over completely / read from its bytes, or begun behind the carried state's
-        // last entry; without carried state a record that starts inside the first chunk may have lost a sibling, and
-        // a candidate in front of x_end would find later fields in the history
+        uint32_t late_incl = 0;                                                   // late fields of this entry's record up to the entry itself
+        if (!cont && inq) {
+            const uint32_t nl_ = cy->n_late;
+            for (uint32_t j = 0; j < nl_; ++j) {
+                const uint32_t lp = cy->late_pos[j];
+                if (lp >= ls && lp <= qpos) {
+                    late_incl |= 1u << cy->late_key[j];
+                    if (lp < qpos) before |= 1u << cy->late_key[j];
+                }
+            }
+        }
+        // ---- which entries know all of their record's earlier fields: all but those of a record the carried state
+        // knows only in part ----
         const bool known0 = __shfl_sync(full, (c_ls != ls || (c_par & 2u) != 0u) ? 1u : 0u, 0) != 0u;
-        const bool known = in_first ? (known0 && qpos >= x_end) : (cont || (ls >> 5) != chunk_first);
+        const bool known = !in_first || known0;
         if (cand && k >= 0) {
             const bool decide = known && qpos < pend_min;
             if (decide) ok = par == 0u && !(before & (1u << k));
             else ok = dmx_verify_thread(buf, qpos, (uint32_t)k, gk, &ls);
 #ifdef DM_EMU
             __atomic_fetch_add(&g_emu_chain_stats[decide ? 0 : 1], 1ull, __ATOMIC_RELAXED);
-            if (!decide) __atomic_fetch_add(&g_emu_chain_stats[known ? 3 : (in_first ? (cont ? 4 : 5) : 6)], 1ull, __ATOMIC_RELAXED);
-            if (lane == 0 && !cont) __atomic_fetch_add(&g_emu_chain_stats[7], 1ull, __ATOMIC_RELAXED);
+            if (!decide) __atomic_fetch_add(&g_emu_chain_stats[known ? 3 : (cont ? 4 : 5)], 1ull, __ATOMIC_RELAXED);
 #endif
         }
         __syncwarp();
@@ -659,7 +681,7 @@ __device__ DM_NOINLINE unsigned long long dmx_verify_chain(const uint8_t* __rest
             cy->last_q = qpos;
             cy->ls = ls;
             cy->par = (par & 1u) | (known ? 2u : 0u);
-            cy->seen = incl;
+            cy->seen = incl | late_incl;
         }
     } else {
         if (cand && k >= 0) {
@@ -829,7 +851,7 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
                 else if (lane - rest < pn) pend = seg_base + pq[(ph + lane - rest) & (DMX_PCAP - 1)];
             }
             pend = __reduce_min_sync(0xffffffffu, pend);
-            const unsigned long long vr_ = dmx_verify_chain(buf, a.gk, carry, qh, n, chainable, pend, qpos, k, cand);
+            const unsigned long long vr_ = dmx_verify_chain(buf, a.gk, carry, qh, n, chainable, pend, nbytes, qpos, k, cand);
             ls = (uint32_t)vr_;
             ok = (vr_ >> 32) != 0ull;
         } else {

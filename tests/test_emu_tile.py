@@ -171,6 +171,14 @@ def test_emu_lookalikes_and_duplicates(seed):
         chain, fallback, unordered = st[0], st[1], st[2]
         assert chain > 10 * fallback and chain > 1000 and unordered > 0, (chain, fallback, unordered)
     if VARIANT != "lanes":
+        # many short warp segments (the GPU's geometry: a few rows per warp): nearly every batch starts without carried state
+        for ctas in (40, 150):
+            lib.emu_stream_ctas(ctas)
+            try:
+                _check(det, o, lookalike_lines(seed + 70 + ctas, 400), 0)
+            finally:
+                lib.emu_stream_ctas(3)
+        _check(det, o, lookalike_lines(seed + 50, 500), 0)
         # what the host's choice of instantiation rests on: most batches of this message held a candidate
         lib.emu_stream_hint.restype = C.c_uint64
         hint = lib.emu_stream_hint()
