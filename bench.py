@@ -71,13 +71,15 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+KERNEL_SOURCES = ("dm_kernels_stream.cuh", "dm_kernels_index.cuh", "dm_device.cuh", "dm_hash.h")
+
+
 def _csrc_sha() -> str:
-    """Fingerprint of the kernel sources: ties profiles/ numbers to the binary they were taken on."""
+    """Fingerprint of the sources of the dominant kernel (dm_k_stream and what it includes): ties the ncu numbers under
+    profiles/ to the code they were taken on."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "detectmateservice_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if not f.endswith((".cu", ".cuh", ".h")):
-            continue
+    for f in KERNEL_SOURCES:
         h.update(f.encode())
         h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
@@ -551,6 +553,10 @@ def run_gpu(args):
             v_steps = 24
             for k in range(4):
                 vdet.enqueue_device(vd[1 + k % 4].data_ptr(), len(vmsgs[1 + k % 4]), 0, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
+            # (the library picks the candidate re-check per message from the last message it has SEEN finish: let the
+            # warm-up finish, as a stream that arrives over time would)
+            vdet.sync()
+            vdet.enqueue_device(vd[1].data_ptr(), len(vmsgs[1]), 0, d_flags.data_ptr(), d_scores.data_ptr(), cap, sp)
             barrier()
             v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             v0.record(stream)
@@ -569,6 +575,7 @@ def run_gpu(args):
             extra["configs"]["config5_varlen"] = {
                 "lines_per_s": world * v_steps * LINES_PER_MSG / (vms * 1e-3), "n_gpus": world,
                 "mean_record_bytes": float(np.mean([len(m) for m in vmsgs[1:]])) / LINES_PER_MSG,
+                "candidate_recheck": "chained" if vdet.stream_recheck_chained() else "one by one",
                 "roofline": {"bound": "hbm", "achieved": vb / (vms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": vb / (vms * 1e-3) / 1e9 / peak},
                 "workload": "64k records per message, lengths 32 B - 4 KB (70/25/5 % log-uniform mixture), quoted values with "

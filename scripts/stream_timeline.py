@@ -7,6 +7,8 @@ import sys
 
 os.environ["DM_STREAM_TIMELINE"] = "1"
 os.environ.setdefault("DM_KERNEL", "stream")
+if len(sys.argv) > 2 and sys.argv[2] == "varlen":
+    os.environ.setdefault("DM_STREAM_RECHECK", "chain")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
