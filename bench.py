@@ -452,7 +452,7 @@ def run_gpu(args):
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel": "dm_k_stream<false> (one launch per 64k-record message)",
+                "kernel": "dm_k_stream<false,false> (one launch per 64k-record message)",
                 "kernel_ms": kernel_ms, "kernel_ms_definition": "timed region / launches (consecutive launches overlap)",
                 "kernel_ms_isolated": (k_ms / k_n) if k_n else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "csrc_sha": _csrc_sha()}
