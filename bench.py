@@ -402,24 +402,23 @@ def run_gpu(args):
     barrier()
     ms = e0.elapsed_time(e1)
     _, _, launches1 = det.profile_read()
-    # The timed region is a few milliseconds, shorter than one NVML query: the same steps are kept running for
-    # another quarter of a second (untimed) under the sampler, so that clocks / throttle reasons are seen under load
-    t_soak = time.perf_counter()
-    k = 0
-    while time.perf_counter() - t_soak < 0.25:
-        step(k)
-        k += 1
-        if k % 8 == 0:
-            stream.synchronize()
-    torch.cuda.synchronize()
-    clocks = sampler.finish()
-    clocks["window"] = "timed region + 0.25 s of the same steps"
-    n_anom_last = det.sync()[1]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(lines_timed)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    # The timed region is a few milliseconds, shorter than one NVML query: the same steps are kept running for
+    # about another quarter of a second (untimed) under the sampler, so that clocks / throttle reasons are seen under
+    # load.  Every rank runs the SAME number of steps (each ends in a collective), derived from the agreed step time.
+    n_soak = int(min(20000, max(8, 250.0 / max(float(t.item()) / args.steps, 1e-3))))
+    for k in range(n_soak):
+        step(k)
+        if k % 8 == 7:
+            stream.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.finish()
+    clocks["window"] = f"timed region + {n_soak} more of the same steps (~0.25 s)"
+    n_anom_last = det.sync()[1]
     ms_max, lines_all = float(t.item()), float(tot.item())
     value = lines_all / (ms_max * 1e-3)
 
@@ -627,6 +626,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-extra", action="store_true", help="skip the config 3 / config 5 legs")
     args = ap.parse_args()
+    if os.environ.get("DM_BENCH_WATCHDOG"):                    # a hung run says where: all threads' stacks every N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["DM_BENCH_WATCHDOG"]), repeat=True, file=sys.stderr)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
