@@ -231,6 +231,33 @@ class B200NewValueDetector(CoreComponent):
             self._det.close()
             self._det = None
 
+    def reconfigure(self, config: Optional[Any]) -> bool:
+        """Take a new detector configuration (what Service.reconfigure has just put into its config manager,
+        /root/reference/src/service/core.py:299-345 -- the reference updates the manager and leaves the loaded
+        component alone; the B200 service subclass of service.py forwards it here).  Scalar parameters
+        (data_use_training, output_format, start_id ...) apply in place and the known sets stay.  If the monitored
+        fields, the log_format / templates or the device geometry change, the device handle is dropped and rebuilt
+        on the next message: table keys are salted by the monitor's position, so the learnt state cannot be carried
+        over and training starts again (n_seen = 0).  Returns True if the device configuration was rebuilt.
+        Call it from the thread that calls process()."""
+        new = type(self)(name=self.name, config=config)
+        sig = lambda c: ([(m.event_id, m.source, m.pos, m.key) for m in c.monitors],
+                         None if c.logformat is None else (c.logformat.source, c.logformat.template_sources,
+                                                           c.logformat.content_name, c.logformat.flags),
+                         c.device, c.max_batch_bytes, c.table_log2_slots, getattr(c, "combos", None))
+        rebuild = sig(new) != sig(self)
+        keep = ("_det", "_frames", "_frame_lock", "n_seen", "n_alerts", "clock")
+        for k, v in vars(new).items():
+            if k not in keep:
+                setattr(self, k, v)
+        if rebuild:
+            self.close()
+            self.n_seen = 0
+            if self._frames and new.max_batch_bytes > len(self._frames[0][1]) - 64:
+                with self._frame_lock:
+                    self._frames = None                          # re-created at the new size on the next alloc_frame()
+        return rebuild
+
     # ------------------------------------------------------------------ the plugin entry point
     def process(self, data: bytes) -> Optional[bytes]:
         if not data:

@@ -173,6 +173,20 @@ def b200_detector_service():
         def process(self, raw_message: bytes):
             # keep the base class's metrics (core.py:184-200) by routing through it
             self.library_component = self.detector
+            if self._pending_config is not None:             # (applied on the engine thread, between two messages)
+                cfg, self._pending_config = self._pending_config, None
+                self.detector.reconfigure(cfg)
             return super().process(raw_message)
+
+        _pending_config = None
+
+        def reconfigure(self, config_data, persist: bool = False) -> str:
+            # the reference validates + stores the new configuration (core.py:299-345); the detector takes it over
+            # before the next message
+            out = super().reconfigure(config_data, persist=persist)
+            if out == "reconfigure: ok" and self.config_manager is not None:
+                got = self.config_manager.get()
+                self._pending_config = got.model_dump() if hasattr(got, "model_dump") else got
+            return out
 
     return B200DetectorService

@@ -169,3 +169,27 @@ def test_large_messages_are_pipelined_and_match_the_oracle():
                     assert sorted(a["alertsObtain"]) == sorted(f"Global - {MONITORED_KEYS[b]}" for b in range(5) if wm[i] >> b & 1)
             lines_before += wf.size
         comp.close()
+
+
+def test_reconfigure_rebuilds_the_device_configuration(golden_dir):
+    """Service.reconfigure -> component.reconfigure (core.py:299-345): new monitored fields take effect on the
+    next message, with fresh training; scalar changes keep the learnt state."""
+    from detectmateservice_b200.component import decode_compact
+    def cfg(keys, n_train):
+        return {"detectors": {"B200NewValueDetector": {"method_type": "new_value_detector", "data_use_training": n_train,
+                "global": {"g": {"header_variables": [{"pos": k} for k in keys]}}, "params": {"output_format": "compact"}}}}
+    train = b"type=A res=ok\ntype=B res=ok\n"
+    probe = b"type=A res=bad\ntype=C res=ok\n"
+    comp = _comp(cfg(["type"], 2))
+    comp.process(train)
+    assert decode_compact(comp.process(probe))[0].tolist() == [0, 1]
+    assert comp.reconfigure(cfg(["type"], 2)) is False           # nothing changed: state kept
+    assert decode_compact(comp.process(probe))[0].tolist() == [0, 1]
+    assert comp.reconfigure(cfg(["type", "res"], 2)) is True     # a new monitored field: rebuilt, trains again
+    comp.process(train)
+    f, s = decode_compact(comp.process(probe))
+    assert f.tolist() == [1, 1] and s.tolist() == [1.0, 1.0]
+    o = NativeOracle([b"type", b"res"])
+    o.process(train, 2)
+    assert o.process(probe, 0)[0].tolist() == [1, 1]
+    comp.close()

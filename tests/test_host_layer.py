@@ -229,12 +229,16 @@ def test_engine_mirror_reply_none_exception_and_fanout(tmp_path):
 class FakeDevice:
     """Stands in for DeviceDetector on a box without a GPU (tests only)."""
 
+    def close(self):
+        self.closed = True
+
     def __init__(self, keys):
         self.keys = [bytes(k) for k in keys]
         self.oracle = NativeOracle([k if not k.startswith(b"\x01") else b"\x02unused%d" % i for i, k in enumerate(self.keys)])
         self.known = [set() for _ in self.keys]
         self.last_n_anomalies = 0
         self._an = []
+        self.closed = False
 
     def process_lines(self, buf, n_train_lines=0, copy=True):
         f, s, m = self.oracle.process(bytes(buf), n_train_lines, want_masks=True)
@@ -363,6 +367,69 @@ def test_component_config_validation():
     assert mons[0].key == b"type" and mons[1].key.startswith(b"\x01") and mons[2].key.startswith(b"\x01")
     from detectmatelibrary.common.core import CoreComponent
     assert isinstance(B200NewValueDetector(config={}), CoreComponent)
+
+
+def test_component_reconfigure_decides_what_has_to_be_rebuilt():
+    """reconfigure(): scalar parameters apply in place, a change of the monitored fields / log_format / geometry asks
+    for a new device configuration (no device is touched here: the handle is created lazily)."""
+    from detectmateservice_b200.component import B200NewValueDetector
+    base = {"method_type": "new_value_detector", "data_use_training": 5,
+            "global": {"g": {"header_variables": [{"pos": "type"}, {"pos": "res"}]}}}
+    c = B200NewValueDetector(config={"detectors": {"B200NewValueDetector": base}})
+    c.n_seen = 3
+    assert c.reconfigure({"detectors": {"B200NewValueDetector": dict(base, data_use_training=9,
+                                                                       params={"output_format": "compact"})}}) is False
+    assert (c.data_use_training, c.output_format, c.n_seen) == (9, "compact", 3)
+    assert c.reconfigure({"detectors": {"B200NewValueDetector": dict(base, **{"global": {"g": {"header_variables": [{"pos": "type"}]}}})}}) is True
+    assert [m.pos for m in c.monitors] == ["type"] and c.n_seen == 0 and c.data_use_training == 5
+    assert c.reconfigure({"detectors": {"B200NewValueDetector": dict(base, **{"global": {"g": {"header_variables": [{"pos": "type"}]}}},
+                                                                       params={"log_format": "type=<type> <Content>"})}}) is True
+    assert c.logformat is not None
+    with pytest.raises(ValueError):
+        c.reconfigure({"detectors": {"B200NewValueDetector": {"auto_config": True}}})
+    assert c.logformat is not None                               # a rejected configuration changes nothing
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="the reference service is neither in baseline/_ref nor in /root/reference/src")
+def test_service_subclass_forwards_reconfigure(tmp_path, monkeypatch):
+    """Service.reconfigure (core.py:299-345) stores the new configuration; the B200 subclass hands it to the
+    detector before the next message (the device handle is a double here)."""
+    import yaml
+    monkeypatch.syspath_prepend(REF_SRC)
+    from service.settings import ServiceSettings
+    from detectmateservice_b200.service import b200_detector_service
+    def det_cfg(keys, n_train):
+        return {"detectors": {"B200NewValueDetector": {"method_type": "new_value_detector", "auto_config": False,
+                "data_use_training": n_train, "global": {"g": {"header_variables": [{"pos": k} for k in keys]}}}}}
+    cfg_file = tmp_path / "detector_config.yaml"
+    cfg_file.write_text(yaml.safe_dump(det_cfg(["type"], 1)))
+    Svc = b200_detector_service()
+    svc = Svc(settings=ServiceSettings(component_name="b200-reconf", engine_addr=f"ipc://{tmp_path}/r.ipc", config_file=cfg_file,
+                                       log_dir=tmp_path / "logs", log_to_file=False, log_to_console=False, http_port=18127,
+                                       engine_autostart=False))
+    try:
+        assert [m.pos for m in svc.detector.monitors] == ["type"]
+        svc.detector._det = FakeDevice([m.key for m in svc.detector.monitors])
+        assert svc.process(b"type=A res=ok\n") is None                       # training record
+        assert svc.reconfigure(det_cfg(["type", "res"], 1), persist=True) == "reconfigure: ok"
+        assert [m.pos for m in svc.detector.monitors] == ["type"]            # not before the next message
+        real_reconf = svc.detector.reconfigure
+
+        def reconf(cfg):
+            rebuilt = real_reconf(cfg)
+            svc.detector._det = FakeDevice([m.key for m in svc.detector.monitors])
+            return rebuilt
+        svc.detector.reconfigure = reconf
+        assert svc.process(b"type=A res=ok\n") is None                       # rebuilt: trains again
+        assert [m.pos for m in svc.detector.monitors] == ["type", "res"] and svc._pending_config is None
+        out = svc.process(b"type=A res=bad\n")
+        assert wire.decode_detector_schema(out)["alertsObtain"] == {"Global - res": "Unknown value: 'bad'"}
+        assert "res" in cfg_file.read_text()                                 # persisted by the reference's manager
+    finally:
+        try:
+            svc.stop()
+        except Exception:
+            pass
 
 
 # ------------------------------------------------------------------------------------------
