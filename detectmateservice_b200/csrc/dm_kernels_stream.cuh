@@ -728,6 +728,18 @@ __device__ __forceinline__ uint32_t dmx_chunk_bits(const uint4& v, uint32_t pat)
     return (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
 }
 
+// The same for '=' with the three-instruction zero-byte test, which is exact except that a run of '<' (0x3C = '=' ^ 1)
+// right behind an '=' in the same 32-bit word is flagged as well (the borrow of the subtraction).  Harmless: the bytes
+// in front of such a position hold that '=' within the last three, an '=' is part of no monitored key (dm_create rejects
+// it) and is no field-start delimiter, so the key lookup of the position fails like that of any other '=' that ends no
+// monitored key.  ('\n' is counted, so it keeps the exact test.)
+__device__ __forceinline__ uint32_t dmx_eq_bits(const uint4& v) {
+    const uint32_t x0 = v.x ^ 0x3D3D3D3Du, x1 = v.y ^ 0x3D3D3D3Du, x2 = v.z ^ 0x3D3D3D3Du, x3 = v.w ^ 0x3D3D3D3Du;
+    const uint32_t f0 = (x0 - 0x01010101u) & ~x0 & 0x80808080u, f1 = (x1 - 0x01010101u) & ~x1 & 0x80808080u;
+    const uint32_t f2 = (x2 - 0x01010101u) & ~x2 & 0x80808080u, f3 = (x3 - 0x01010101u) & ~x3 & 0x80808080u;
+    return (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
+}
+
 template <bool TRAIN>
 __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_pre);
 
@@ -770,29 +782,27 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
     const uint32_t vpos = qpos + 1u;
     const uint32_t vr = ra + 1u;                              // the value's place in the ring
     uint32_t w[8];
-    uint32_t m = 0, lim = 0;
-    if (act) {
-        const uint32_t base = vr & ~3u;
-        const uint32_t sh = (vr & 3u) * 8u;
-        uint32_t lo = dmx_ld32(ring, base);
+    uint32_t lim = 0, lo = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 8; ++i) w[i] = 0;
+    const uint32_t base = vr & ~3u;
+    const uint32_t sh = (vr & 3u) * 8u;
+    uint32_t nv = 0xFFFFFFFFu, par = 0;
+    // the first 16 bytes of the window decide for nearly every value; the other 16 are fetched only if some lane needs them
+    if (act) {
+        lo = dmx_ld32(ring, base);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
             const uint32_t hi = dmx_ld32(ring, base + 4u * (i + 1));
             w[i] = __funnelshift_r(lo, hi, sh);
             lo = hi;
         }
         const uint64_t avail = nbytes > vpos ? nbytes - vpos : 0;
         lim = avail < DMX_WIN ? (uint32_t)avail : DMX_WIN;
+        uint32_t m = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
-        if (lim < DMX_WIN) m &= (1u << lim) - 1u;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = 0;
-    }
-    uint32_t nv = 0xFFFFFFFFu;
-    {
-        uint32_t par = 0;
+        for (int i = 0; i < 4; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
+        if (lim < 16u) m &= (1u << lim) - 1u;
         while (m) {
             const uint32_t j = (uint32_t)__ffs(m) - 1u;
             m &= m - 1u;
@@ -802,6 +812,29 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
         }
     }
     __syncwarp();
+    const bool more = act && nv == 0xFFFFFFFFu && lim > 16u;
+    if (__any_sync(0xffffffffu, more)) {
+        if (more) {
+#pragma unroll
+            for (int i = 4; i < 8; ++i) {
+                const uint32_t hi = dmx_ld32(ring, base + 4u * (i + 1));
+                w[i] = __funnelshift_r(lo, hi, sh);
+                lo = hi;
+            }
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 4; i < 8; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
+            if (lim < DMX_WIN) m &= (1u << lim) - 1u;
+            while (m) {
+                const uint32_t j = (uint32_t)__ffs(m) - 1u;
+                m &= m - 1u;
+                const uint32_t c = ring[vr + j];
+                if (c == 0x0Au || (c == 0x20u && !par)) { nv = j; break; }
+                if (c == 0x22u) par ^= 1u;
+            }
+        }
+        __syncwarp();
+    }
     bool slow = false;
     if (act && nv == 0xFFFFFFFFu) {
         if (lim < DMX_WIN) nv = lim;                      // the message ends inside the window: that ends the value
@@ -1006,7 +1039,7 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
                 nl_w += tot;
             }
             // the '=' of this lane's 32 bytes: bit 8b + 4c + w = byte b of word w of chunk c
-            uint32_t g = (dmx_chunk_bits(va, 0x3D3D3D3Du) << (4u * c_first)) | (dmx_chunk_bits(vb, 0x3D3D3D3Du) << (4u * (1u - c_first)));
+            uint32_t g = (dmx_eq_bits(va) << (4u * c_first)) | (dmx_eq_bits(vb) << (4u * (1u - c_first)));
             const uint32_t qrel = i * DMX_ROW + lane * 32u;
             const bool last = i + 1 == n_own;
             if (CHAIN) {
@@ -1046,16 +1079,25 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
                 // ---- full passes; at the end of a row also whatever is left of rows up to (i + 2 - SLOTS): the next
                 // iteration loads row i+2 into that row's slot ----
                 for (;;) {
-                    if (qn >= 32u || (qn && row_done && ((last && !pn) || (q[qh & (DMX_QCAP - 1)] >> (7 + DMX_ROW_LOG2)) + (DMX_SLOTS - 2u) <= i))) {
-                        const uint32_t n = qn < 32u ? qn : 32u;
+                    // cheap tests first; what has to leave because its row's slot is about to be reused (or because
+                    // the warp's rows end) is only looked at once both queues are below a full pass
+                    uint32_t n_drain = 0, n_look = 0;
+                    if (qn >= 32u) n_drain = 32u;
+                    else if (pn >= 32u) n_look = 32u;
+                    else if (row_done) {
+                        if (pn && (last || (pq[ph & (DMX_PCAP - 1)] >> DMX_ROW_LOG2) + (DMX_SLOTS - 2u) <= i)) n_look = pn;
+                        else if (qn && (last || (q[qh & (DMX_QCAP - 1)] >> (7 + DMX_ROW_LOG2)) + (DMX_SLOTS - 2u) <= i)) n_drain = qn;
+                    }
+                    if (n_drain) {
+                        const uint32_t n = n_drain;
                         dmx_drain<TRAIN, CHAIN>(s_ctx, sk, ring, q, qh, n, seg_base, bound, &s_carry[warp], s_slow, qn, pq, ph, pn);
                         qh += n;
                         qn -= n;
                         continue;
                     }
-                    if (pn >= 32u || (pn && row_done && (last || (pq[ph & (DMX_PCAP - 1)] >> DMX_ROW_LOG2) + (DMX_SLOTS - 2u) <= i))) {
+                    if (n_look) {
                         // one '=' per lane: the 4 bytes in front of it (shared memory, any alignment) -> level-1 table
-                        const uint32_t n = pn < 32u ? pn : 32u;
+                        const uint32_t n = n_look;
                         bool hit = false;
                         uint32_t e = 0;
                         if (lane < n) {

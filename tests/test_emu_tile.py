@@ -110,6 +110,16 @@ def test_emu_edge_cases():
     _check(det2, o2, b"k=second\nk=inquote\nk=first\nk=real\ntype=U\ntype=T\n", 0)
     det.close()
     det2.close()
+    # '<' right behind an '=': the stream kernel's '=' mask flags such bytes too (dmx_eq_bits); they must never turn into
+    # fields, not even with keys made of '<'
+    keys3 = [b"<", b"<<", b"k", b"a<<"]
+    o3 = NativeOracle(keys3)
+    det3 = EmuDetector(keys3)
+    _check(det3, o3, b"k=<1 <=2 <<=3 a<<=4\n", 1)
+    for c in [b"k=<< <=<\n", b"k==< <<=<< a<<=<<<\n", b"x=<=5 =<<=6 k=<<<<=7\n", b"<=<=<=< k=<\n" * 40,
+              b"a<<=<<< a<<=1\n", b"'<=9 '<<=9 'a<<=9\n", b"=<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<<=1 <=u\n"]:
+        _check(det3, o3, c, 0)
+    det3.close()
 
 
 def test_emu_synthetic_and_split():
