@@ -733,13 +733,13 @@ __device__ __forceinline__ uint32_t dmx_chunk_bits(const uint4& v, uint32_t pat)
 // in front of such a position hold that '=' within the last three, an '=' is part of no monitored key (dm_create rejects
 // it) and is no field-start delimiter, so the key lookup of the position fails like that of any other '=' that ends no
 // monitored key.  ('\n' is counted, so it keeps the exact test.)
-__device__ __forceinline__ uint32_t dmx_eq_bits(const uint4& v) {
-    const uint32_t x0 = v.x ^ 0x3D3D3D3Du, x1 = v.y ^ 0x3D3D3D3Du, x2 = v.z ^ 0x3D3D3D3Du, x3 = v.w ^ 0x3D3D3D3Du;
+__device__ __forceinline__ uint32_t dmx_loose_bits(const uint4& v, uint32_t pat) {
+    const uint32_t x0 = v.x ^ pat, x1 = v.y ^ pat, x2 = v.z ^ pat, x3 = v.w ^ pat;
     const uint32_t f0 = (x0 - 0x01010101u) & ~x0 & 0x80808080u, f1 = (x1 - 0x01010101u) & ~x1 & 0x80808080u;
     const uint32_t f2 = (x2 - 0x01010101u) & ~x2 & 0x80808080u, f3 = (x3 - 0x01010101u) & ~x3 & 0x80808080u;
     return (f0 >> 7) | (f1 >> 6) | (f2 >> 5) | (f3 >> 4);
 }
-
+__device__ __forceinline__ uint32_t dmx_eq_bits(const uint4& v) { return dmx_loose_bits(v, 0x3D3D3D3Du); }
 template <bool TRAIN>
 __device__ __forceinline__ void dmx_epilogue(const DmxArgs& a, unsigned long long* s_pre);
 
@@ -782,27 +782,29 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
     const uint32_t vpos = qpos + 1u;
     const uint32_t vr = ra + 1u;                              // the value's place in the ring
     uint32_t w[8];
-    uint32_t lim = 0, lo = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = 0;
-    const uint32_t base = vr & ~3u;
-    const uint32_t sh = (vr & 3u) * 8u;
-    uint32_t nv = 0xFFFFFFFFu, par = 0;
-    // the first 16 bytes of the window decide for nearly every value; the other 16 are fetched only if some lane needs them
+    uint32_t m = 0, lim = 0;
     if (act) {
-        lo = dmx_ld32(ring, base);
+        const uint32_t base = vr & ~3u;
+        const uint32_t sh = (vr & 3u) * 8u;
+        uint32_t lo = dmx_ld32(ring, base);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const uint32_t hi = dmx_ld32(ring, base + 4u * (i + 1));
             w[i] = __funnelshift_r(lo, hi, sh);
             lo = hi;
         }
         const uint64_t avail = nbytes > vpos ? nbytes - vpos : 0;
         lim = avail < DMX_WIN ? (uint32_t)avail : DMX_WIN;
-        uint32_t m = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
-        if (lim < 16u) m &= (1u << lim) - 1u;
+        for (int i = 0; i < 8; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
+        if (lim < DMX_WIN) m &= (1u << lim) - 1u;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = 0;
+    }
+    uint32_t nv = 0xFFFFFFFFu;
+    {
+        uint32_t par = 0;
         while (m) {
             const uint32_t j = (uint32_t)__ffs(m) - 1u;
             m &= m - 1u;
@@ -812,29 +814,6 @@ __device__ __forceinline__ void dmx_drain(const DmxDrainCtx& a, const DmxKeyTab&
         }
     }
     __syncwarp();
-    const bool more = act && nv == 0xFFFFFFFFu && lim > 16u;
-    if (__any_sync(0xffffffffu, more)) {
-        if (more) {
-#pragma unroll
-            for (int i = 4; i < 8; ++i) {
-                const uint32_t hi = dmx_ld32(ring, base + 4u * (i + 1));
-                w[i] = __funnelshift_r(lo, hi, sh);
-                lo = hi;
-            }
-            uint32_t m = 0;
-#pragma unroll
-            for (int i = 4; i < 8; ++i) m |= dm_flags_to_nib(dmx_stopflags(w[i])) << (4 * i);
-            if (lim < DMX_WIN) m &= (1u << lim) - 1u;
-            while (m) {
-                const uint32_t j = (uint32_t)__ffs(m) - 1u;
-                m &= m - 1u;
-                const uint32_t c = ring[vr + j];
-                if (c == 0x0Au || (c == 0x20u && !par)) { nv = j; break; }
-                if (c == 0x22u) par ^= 1u;
-            }
-        }
-        __syncwarp();
-    }
     bool slow = false;
     if (act && nv == 0xFFFFFFFFu) {
         if (lim < DMX_WIN) nv = lim;                      // the message ends inside the window: that ends the value
