@@ -50,6 +50,7 @@ for S in $STAGES; do
       timeout 200 python scripts/stream_bench.py stream:1 stream:0 lanes:0 > "$OUT/stream_bench_config2.jsonl" 2>&1
       timeout 300 python scripts/stream_bench.py --varlen stream:1 stream:0 lanes:0 > "$OUT/stream_bench_config5.jsonl" 2>&1
       DM_STREAM_RECHECK=thread timeout 300 python scripts/stream_bench.py --varlen stream:1 > "$OUT/stream_bench_config5_onebyone.jsonl" 2>&1
+      timeout 120 python scripts/sock_ceiling.py > "$OUT/sock_ceiling.json" 2>&1
       echo "extras done" | tee -a "$OUT/summary.txt" ;;
   esac
 done
