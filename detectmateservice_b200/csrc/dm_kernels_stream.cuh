@@ -21,9 +21,11 @@
 //     class ("stop bytes" < 0x23: space, '"', '\n', controls) over a 32-byte window, dm_fp64,
 //     table probe;
 //   * quote parity (R-tok L2-L4) and first-occurrence-wins (L6) are NOT tracked on that path: they
-//     can only change the outcome for a value that is not in the table, so exactly those rare
-//     candidates are re-checked exactly, by their own lane, walking the record backwards
-//     (dmx_verify_thread);
+//     can only change the outcome for a value that is not in the table, so exactly those
+//     candidates are re-checked exactly: by their own lane, walking the record backwards
+//     (dmx_verify_thread), or -- second instantiation, for streams in which candidates are
+//     frequent -- a whole batch at a time from what lies between consecutive queue entries
+//     (dmx_verify_chain);
 //   * the record index of a byte is needed for ALERTS only: alerts are staged as (offset of the
 //     record's first byte, field) and the last CTA to finish runs the epilogue -- prefix of the
 //     per-CTA '\n' counts, batch header, record index of each alert, atomics on scores / flags /
@@ -32,8 +34,8 @@
 // CTAs are small (2 warps): a CTA's slot is free again as soon as its two warps are through, and
 // consecutive launches overlap (programmatic dependent launch): a launch never waits for its
 // predecessor kernel; what has to be ordered is ordered by sequence numbers in device memory
-// (DmxShared): scratch buffers alternate between two parities and a launch starts only after the
-// epilogue of the launch two before it has finished; epilogues run one after the other.
+// (DmxShared): scratch buffers rotate over DMX_NPAR sets and a launch starts only after the
+// epilogue of the launch DMX_NPAR before it has finished; epilogues run one after the other.
 #pragma once
 #include "dm_kernels_index.cuh"    // dm_pdl_*, dm_launch_pdl_smem; byte helpers in dm_device.cuh
 
