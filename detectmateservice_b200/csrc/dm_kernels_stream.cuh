@@ -125,6 +125,7 @@ struct DmxArgs {
     uint32_t keep_error;                     // the epilogue ORs into hdr->error instead of assigning it
     unsigned long long* timeline;            // diagnostics (DM_STREAM_TIMELINE=1): per CTA {smid, t_start, t_rows_done, t_exit},
                                              // then 8 epilogue stamps (globaltimer ns); else NULL
+    uint32_t keytab_bytes;                   // bytes of the key table that go to shared memory (multiple of 16)
     unsigned long long* hint;                // (host-mapped) written by the detect epilogue: (batches with a candidate << 32) | rows
 };
 
@@ -932,12 +933,23 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
             a.timeline[4ull * blockIdx.x + 1] = dmx_now();
         }
     }
+#ifdef DMX_KEYTAB_LOOP
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.keys);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_dyn + a.ring_smem);
-        const uint32_t total = (uint32_t)(offsetof(DmxKeyTab, l1) / 4) + 2u * __ldg(&a.keys->l1_slots);
-        for (uint32_t i = threadIdx.x; i < total; i += DMX_THREADS) dst[i] = __ldg(src + i);
+        for (uint32_t i = threadIdx.x; i < a.keytab_bytes / 4u; i += DMX_THREADS) dst[i] = __ldg(src + i);
     }
+#else
+    // the key table comes in with ONE bulk copy issued by thread 0 (waited for right before the rows)
+    __shared__ unsigned long long s_kbar;
+    if (threadIdx.x == 0) {
+        dmx_mbar_init(dmx_smem_u32(&s_kbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        dmx_mbar_expect_tx(dmx_smem_u32(&s_kbar), a.keytab_bytes);
+        dmx_bulk_g2s(dmx_smem_u32(s_dyn + a.ring_smem), a.keys, a.keytab_bytes, dmx_smem_u32(&s_kbar));
+    }
+#endif
     if (lane == 0) {
         s_cnt[warp] = 0;
         s_slow[warp] = 0;
@@ -955,6 +967,9 @@ __global__ void __launch_bounds__(DMX_THREADS, DMX_MIN_CTAS) dm_k_stream(DmxArgs
         s_bound = zb < a.out_cap ? zb : a.out_cap;
     }
     __syncthreads();
+#ifndef DMX_KEYTAB_LOOP
+    dmx_mbar_wait(dmx_smem_u32(&s_kbar), 0u);
+#endif
 
     const uint64_t nbytes = a.nbytes;
     const uint32_t bound = a.bound_ptr ? (uint32_t)(*a.bound_ptr > 0xFFFFFFFFull ? 0xFFFFFFFFull : *a.bound_ptr) : (TRAIN ? 0xFFFFFFFFu : 0u);
@@ -1465,6 +1480,7 @@ static inline int dmx_launch(DmxScratch* s, const uint8_t* d_buf, uint64_t nbyte
     a.flags = d_flags; a.scores = d_scores; a.out_cap = out_cap; a.anomalies = d_anoms; a.anomaly_cap = anomaly_cap;
     a.hdr = d_hdr; a.stats = d_stats; a.n_train_lines = n_train_lines; a.max_lines = max_lines;
     a.sh = s->d_shared; a.alert_cap = s->alert_cap; a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = s->d_timeline; a.ring_smem = DMX_RING_SMEM;
+    a.keytab_bytes = s->dyn_smem - (uint32_t)DMX_RING_SMEM;
     a.hint = s->h_hint;                                      // (unified addressing: the mapped host pointer is the device pointer)
     // chained re-check when, in the last message whose epilogue has run, at least every fourth row had a batch with a
     // candidate (both instantiations give the same results; this only picks the faster one for the stream at hand)

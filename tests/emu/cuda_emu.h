@@ -18,6 +18,7 @@
 #include <vector>
 
 #define DM_EMU 1
+#define DMX_KEYTAB_LOOP 1      // (no bulk-copy engine in the emulator)
 #define __global__
 #define __device__
 #define __host__

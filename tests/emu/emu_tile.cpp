@@ -139,6 +139,7 @@ static int emu_stream_run(EmuHandle* h, bool chained, const uint8_t* msg, uint64
     a.hdr = &h->hdr; a.stats = h->stats; a.n_train_lines = n_train; a.max_lines = h->max_lines;
     a.sh = &g_xs.sh; a.alert_cap = (uint32_t)h->anoms.size(); a.bound_ptr = nullptr; a.keep_error = 0; a.timeline = nullptr; a.ring_smem = DMX_RING_SMEM;
     a.hint = &g_xs.hint;
+    a.keytab_bytes = (uint32_t)((DMX_KEYTAB_HOT(g_xs.tab.l1_slots) + 15) & ~(size_t)15);
     const unsigned long long warps_max = (unsigned long long)g_emu_stream_ctas * DMX_WARPS;
     const uint32_t rpw = (uint32_t)((n_rows + warps_max - 1) / warps_max);
     const unsigned long long warps = (n_rows + rpw - 1) / rpw;
