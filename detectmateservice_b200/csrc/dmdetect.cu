@@ -633,7 +633,7 @@ extern "C" int dm_stream_recheck_chained(dm_handle* h) {
     return h->dmx.last_chained ? 1 : 0;
 }
 
-// diagnostics: start / end times of the K_B warps of the last rows launch (DM_ROWS_TIMELINE=1)
+// diagnostics: per-CTA time stamps of the last stream-kernel launch (DM_STREAM_TIMELINE=1)
 extern "C" int dm_debug_rows_timeline(dm_handle* h, unsigned long long* out, uint64_t cap_words, uint32_t* n_warps_out) {
     if (!h || !n_warps_out) return dm_fail(DM_ERR_ARG, "NULL argument");
     if (h->dmx.d_timeline) {

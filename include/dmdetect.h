@@ -195,8 +195,9 @@ int dm_stream_recheck_chained(dm_handle* h);
  * clflush), so that device DMA streams it from DRAM instead of snooping dirty cache lines. */
 int dm_host_cache_flush(const void* p, uint64_t nbytes);
 
-/* Diagnostics: {smid, t_first, t_work_end, t_exit} (globaltimer ns) of every warp of the last
- * rows-variant detect kernel; only for handles created with DM_ROWS_TIMELINE=1 in the environment. */
+/* Diagnostics: {smid, t_start, t_rows_done, t_exit} (globaltimer ns) of every CTA of the last stream-kernel
+ * launch, followed by 8 time stamps of its epilogue; *n_warps_out = number of CTAs.  Only for handles created
+ * with DM_STREAM_TIMELINE=1 in the environment (scripts/stream_timeline.py).  The name is historical. */
 int dm_debug_rows_timeline(dm_handle* h, unsigned long long* out, uint64_t cap_words, uint32_t* n_warps_out);
 int dm_process_records(dm_handle* h, const uint8_t* buf, uint64_t nbytes, uint32_t n_train_records,
                        uint8_t* flags_out, float* scores_out, uint32_t* masks_out, uint64_t out_cap,
