@@ -74,3 +74,9 @@ def record_at(msg: bytes, offset: int) -> bytes:
 
 def alert_text(value: bytes) -> str:
     return "Unknown value: '%s'" % value.decode("utf-8", "replace")
+
+
+def count_records(data) -> int:
+    """Records of a raw-line message (R-tok L1): every '\n' ends one, a non-empty tail is one."""
+    b = bytes(data)
+    return b.count(b"\n") + (1 if b and not b.endswith(b"\n") else 0)

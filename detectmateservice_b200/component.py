@@ -324,7 +324,11 @@ class B200NewValueDetector(CoreComponent):
         matching, hashing and scoring happen on the device; the host only decodes the (rare)
         anomalous records to word their alerts."""
         remaining = max(0, self.data_use_training - self.n_seen)
-        flags, scores, masks = self.det.process_records(data, n_train_records=remaining)
+        try:
+            flags, scores, masks = self.det.process_records(data, n_train_records=remaining)
+        except Exception as e:
+            self._count_dropped_training(e, remaining, lambda: len(wire.split_delimited(data)))
+            raise
         n = int(flags.size)
         self.n_seen += n
         if self.output_format == "compact":
@@ -421,7 +425,11 @@ class B200NewValueDetector(CoreComponent):
             flags, scores, anomalies = self._detect_pipelined(data)
             n_anom = int(np.count_nonzero(flags))
         else:
-            flags, scores = self.det.process_lines(data, n_train_lines=remaining, copy=False)
+            try:
+                flags, scores = self.det.process_lines(data, n_train_lines=remaining, copy=False)
+            except Exception as e:
+                self._count_dropped_training(e, remaining, lambda: _alerts.count_records(data))
+                raise
             n_anom = self.det.last_n_anomalies
         n = int(flags.size)
         base = self.n_seen
@@ -451,6 +459,18 @@ class B200NewValueDetector(CoreComponent):
         if not out:
             return None
         return out[0] if (n == 1 and not force_delimited) else wire.frame_delimited(out)
+
+    def _count_dropped_training(self, err: Exception, remaining: int, count) -> None:
+        """A training message the device refused because the known-set table is full (DM_ERR_TABLE_FULL) is dropped by
+        the engine like any failing message (engine.py:192-194) -- but its records still count as seen, otherwise the
+        training window would never end and every later message would fail the same way (the reference's Python sets
+        are unbounded; a larger params.table_log2_slots is the cure)."""
+        from ._lib import DM_ERR_TABLE_FULL
+        if remaining > 0 and getattr(err, "code", None) == DM_ERR_TABLE_FULL:
+            try:
+                self.n_seen += int(count())
+            except Exception:
+                self.n_seen += remaining
 
     def _line_alerts(self, rec: bytes, mask: int, raw_keys: List[bytes]) -> Dict[str, str]:
         """alertsObtain of one anomalous raw record from the device's unknown-field mask."""
@@ -576,6 +596,18 @@ class B200NewValueComboDetector(B200NewValueDetector):
         if out is None or self.output_format == "compact":
             return out
         return wire.split_delimited(out)[0]                                 # one record in, one bare alert out
+
+    def _count_dropped_training(self, err: Exception, remaining: int, count) -> None:
+        """A training message the device refused because the known-set table is full (DM_ERR_TABLE_FULL) is dropped by
+        the engine like any failing message (engine.py:192-194) -- but its records still count as seen, otherwise the
+        training window would never end and every later message would fail the same way (the reference's Python sets
+        are unbounded; a larger params.table_log2_slots is the cure)."""
+        from ._lib import DM_ERR_TABLE_FULL
+        if remaining > 0 and getattr(err, "code", None) == DM_ERR_TABLE_FULL:
+            try:
+                self.n_seen += int(count())
+            except Exception:
+                self.n_seen += remaining
 
     def _line_alerts(self, rec: bytes, mask: int, raw_keys: List[bytes]) -> Dict[str, str]:
         """Raw key=value records (one thread per record on the device, dm_kernels_lanes.cuh): a

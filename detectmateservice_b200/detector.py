@@ -235,13 +235,18 @@ class DeviceDetector:
     def process_records(self, buf: bytes, n_train_records: int = 0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """A batch of varint-length-delimited ParserSchema records, decoded and scored on the
         device.  Returns (flags u8, scores f32, unknown-field masks u32), one entry per record."""
-        cap = max(1, len(buf) // 2 + 1)
-        flags = np.zeros(cap, dtype=np.uint8)
-        scores = np.zeros(cap, dtype=np.float32)
-        masks = np.zeros(cap, dtype=np.uint32)
-        n_rec, n_anom = C.c_uint64(), C.c_uint64()
-        _lib.check(self._lib.dm_process_records(self._h, bytes(buf), len(buf), int(n_train_records), flags.ctypes.data,
-                                                scores.ctypes.data, masks.ctypes.data, cap, C.byref(n_rec), C.byref(n_anom)))
+        # a record takes its length prefix and, nearly always, at least one more byte; a batch of (mostly) EMPTY records --
+        # one zero byte each -- gets a second try with room for one record per byte
+        for cap in (max(1, len(buf) // 2 + 1), len(buf) + 1):
+            flags = np.zeros(cap, dtype=np.uint8)
+            scores = np.zeros(cap, dtype=np.float32)
+            masks = np.zeros(cap, dtype=np.uint32)
+            n_rec, n_anom = C.c_uint64(), C.c_uint64()
+            rc = self._lib.dm_process_records(self._h, bytes(buf), len(buf), int(n_train_records), flags.ctypes.data,
+                                              scores.ctypes.data, masks.ctypes.data, cap, C.byref(n_rec), C.byref(n_anom))
+            if rc != _lib.DM_ERR_CAPACITY or cap == len(buf) + 1:
+                break
+        _lib.check(rc)
         self.last_n_anomalies = n_anom.value
         k = n_rec.value
         return flags[:k], scores[:k], masks[:k]

@@ -369,6 +369,64 @@ def test_component_config_validation():
     assert isinstance(B200NewValueDetector(config={}), CoreComponent)
 
 
+def test_process_records_retries_with_room_for_empty_records():
+    """DeviceDetector.process_records sizes its outputs for records of >= 2 bytes and tries again, one entry per byte,
+    when the library reports that the batch holds more (a batch of empty ParserSchema records: one zero byte each)."""
+    import ctypes as C
+    from detectmateservice_b200 import _lib
+    from detectmateservice_b200.detector import DeviceDetector
+    calls = []
+
+    class StubLib:
+        def dm_process_records(self, h, buf, nbytes, n_train, flags_p, scores_p, masks_p, cap, n_rec, n_anom):
+            calls.append(cap)
+            n = buf.count(b"\0")                                  # (every record of the stub batch is empty)
+            if n > cap:
+                return _lib.DM_ERR_CAPACITY
+            C.cast(n_rec, C.POINTER(C.c_uint64))[0] = n
+            C.cast(n_anom, C.POINTER(C.c_uint64))[0] = 0
+            return _lib.DM_OK
+
+    d = object.__new__(DeviceDetector)
+    d._lib, d._h = StubLib(), None
+    f, s_, m = d.process_records(b"\0" * 10)
+    assert calls == [6, 11] and f.size == 10 and s_.size == 10 and m.size == 10
+    calls.clear()
+    f, _, _ = d.process_records(b"\0\0")
+    assert calls == [2] and f.size == 2
+
+
+def test_training_window_ends_even_when_the_table_is_full():
+    """DM_ERR_TABLE_FULL on a training message: the engine drops the message (the exception propagates), but its
+    records count as seen, so the training window ends instead of failing forever."""
+    from detectmateservice_b200._lib import DmError, DM_ERR_TABLE_FULL, DM_ERR_CUDA
+    from detectmateservice_b200.component import B200NewValueDetector
+
+    class FullDevice(FakeDevice):
+        def __init__(self, keys, code):
+            super().__init__(keys)
+            self.code = code
+
+        def process_lines(self, *a, **k):
+            raise DmError(self.code, "known-set table over its load limit")
+
+    cfg = {"detectors": {"B200NewValueDetector": {"method_type": "new_value_detector", "data_use_training": 3,
+                                                  "global": {"g": {"header_variables": [{"pos": "type"}]}}}}}
+    c = B200NewValueDetector(config=cfg)
+    c._det = FullDevice([m.key for m in c.monitors], DM_ERR_TABLE_FULL)
+    with pytest.raises(DmError):
+        c.process(b"type=A\ntype=B\n")
+    assert c.n_seen == 2
+    with pytest.raises(DmError):
+        c.process(b"type=C\ntype=D")
+    assert c.n_seen == 4                                          # training (3 records) is over
+    c._det = FullDevice([m.key for m in c.monitors], DM_ERR_CUDA)
+    c.n_seen = 0
+    with pytest.raises(DmError):
+        c.process(b"type=A\n")
+    assert c.n_seen == 0                                          # any other failure: the message simply did not happen
+
+
 def test_component_reconfigure_decides_what_has_to_be_rebuilt():
     """reconfigure(): scalar parameters apply in place, a change of the monitored fields / log_format / geometry asks
     for a new device configuration (no device is touched here: the handle is created lazily)."""
