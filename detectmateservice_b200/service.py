@@ -43,6 +43,10 @@ class DetectorEngine:
         self._thread: Optional[threading.Thread] = None
         self._sock = pynng.Pair0()
         self._sock.recv_timeout = recv_timeout_ms
+        try:
+            self._sock.recv_max_size = 0           # batches are multi-MiB messages: no receive limit (NNG's default is 1 MiB)
+        except Exception:                          # (a pynng build without the option: keep its default)
+            pass
         # shim-only hint (ignored by real pynng): hand big frames over as a bytearray filled in
         # place; the component takes any bytes-like object, and this halves the receive cost
         self._sock.large_frames_as_bytearray = bool(getattr(processor, "accepts_bytes_like", False))
